@@ -1,0 +1,999 @@
+// block.cu -- the C ABI (include/idefix_b200.h): block life cycle, geometry set-up,
+// the granular entry points mirroring the reference's call sites, and the fused
+// TimeIntegrator::Cycle path.
+//
+// Host-side geometry follows src/dataBlock/makeGeometry.cpp:16-217 and
+// src/fluid/RiemannSolver/extrapolateToFaces.hpp:43-71 expression by expression (same
+// libm, same association) so that the separable 1-D factors reproduce the reference's
+// 3-D dV / A arrays bit for bit.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/idefix_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string &msg) {
+  g_error = msg;
+  return 1;
+}
+
+#define CUDA_TRY(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                        \
+  } while (0)
+
+#define KTRY(call)                                                                            \
+  do {                                                                                        \
+    int e_ = (call);                                                                          \
+    if (e_ == -1) return fail(std::string(#call) + ": configuration not instantiated");       \
+    if (e_ != 0) return fail(std::string(#call) + ": " + cudaGetErrorString((cudaError_t)e_)); \
+  } while (0)
+
+}  // namespace
+
+struct IdfxBlock {
+  IdfxBlockDesc desc;
+  PhysCfg cfg;
+  DevGrid g;
+  DevEmf emf;
+  double *Vc = nullptr, *Uc = nullptr, *Vs = nullptr, *Uc0 = nullptr, *Vs0 = nullptr, *invDt = nullptr;
+  long long nCells = 0, nVs = 0;
+  double *state = nullptr;                  // device: t, dt, t0, tstop
+  unsigned long long *redBits = nullptr;    // device: [0] dt-min bits, [1] divB-max bits
+  long long *ncyclesDev = nullptr;
+  int *statusDev = nullptr, *nanDev = nullptr;
+  double *hostState = nullptr;              // pinned mirror (4 doubles + scratch)
+  cudaStream_t stream = nullptr;
+  std::vector<void *> allocs;
+  long long launches = 0;
+  int nproc[3] = {1, 1, 1};
+  bool haveUserdef = false;
+  bool fused = true;
+  IdfxUserBoundaryFn userBc = nullptr;
+  void *userBcData = nullptr;
+  IdfxHaloFn haloFn = nullptr;
+  void *haloData = nullptr;
+  double *haloSend[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  double *haloRecv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  double *haloPeer[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  std::vector<std::vector<double>> hostCoords;  // owned copies of the descriptor's coordinate arrays
+  double wc[2] = {0, 0}, w0[2] = {0, 0};
+};
+
+namespace {
+
+template <typename T>
+int devAlloc(IdfxBlock *b, T **p, long long n) {
+  if (n <= 0) n = 1;
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), b->stream);
+  if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+  b->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+int upload1D(IdfxBlock *b, const double **dst, const std::vector<double> &v) {
+  double *p = nullptr;
+  if (devAlloc(b, &p, (long long)v.size())) return 1;
+  CUDA_TRY(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  *dst = p;
+  return 0;
+}
+
+// DataBlock::MakeGeometry + ExtrapolateToFaces::ComputePLMweights on the host
+int buildGeometry(IdfxBlock *b) {
+  const IdfxBlockDesc &d = b->desc;
+  DevGrid &g = b->g;
+  const int geo = d.geometry;
+  const int nd = d.ndim;
+  int nx[3];
+  for (int dir = 0; dir < 3; dir++) nx[dir] = g.nx[dir];
+  const double *x1 = d.x[0], *x2 = d.x[1], *x3 = d.x[2];
+  const double *x1m = d.xl[0], *x2m = d.xl[1];
+  const double *x1p = d.xr[0], *x2p = d.xr[1];
+  const double *dx1 = d.dx[0], *dx2 = d.dx[1], *dx3 = d.dx[2];
+  (void)x3;
+
+  std::vector<double> xgc[3], vol[3], area[3][3];
+  std::vector<double> rt(nx[0], 0.0), sinx2m(nx[1] + 1, 0.0), tanx2m(nx[1], 0.0), sinx2(nx[1], 0.0),
+      tanx2(nx[1], 0.0), dmu(nx[1], 0.0);
+  for (int dir = 0; dir < 3; dir++) {
+    xgc[dir].assign(nx[dir], 0.0);
+    vol[dir].assign(nx[dir], 1.0);
+    for (int e = 0; e < 3; e++) area[dir][e].assign(nx[e] + 1, 1.0);
+  }
+  // volumes (makeGeometry.cpp:66-84)
+  for (int i = 0; i < nx[0]; i++) {
+    if (geo == IDFX_CARTESIAN) vol[0][i] = dx1[i];
+    else if (geo == IDFX_CYLINDRICAL || geo == IDFX_POLAR) vol[0][i] = std::fabs(x1p[i] * x1p[i] - x1m[i] * x1m[i]) / 2.0;
+    else vol[0][i] = std::fabs(x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / 3.0;
+  }
+  if (nd >= 2) {
+    for (int j = 0; j < nx[1]; j++) {
+      if (geo == IDFX_SPHERICAL) vol[1][j] = std::fabs(std::cos(x2m[j]) - std::cos(x2p[j]));
+      else vol[1][j] = dx2[j];
+    }
+  }
+  if (nd == 3) {
+    for (int k = 0; k < nx[2]; k++) vol[2][k] = (geo == IDFX_CYLINDRICAL) ? 1.0 : dx3[k];
+  }
+  // geometrical centres and spherical helpers (makeGeometry.cpp:91-130)
+  for (int i = 0; i < nx[0]; i++) {
+    if (geo == IDFX_CARTESIAN) {
+      xgc[0][i] = x1[i];
+    } else if (geo == IDFX_CYLINDRICAL || geo == IDFX_POLAR) {
+      xgc[0][i] = x1[i] + dx1[i] * dx1[i] / (12.0 * x1[i]);
+    } else {
+      xgc[0][i] = x1[i] + 2.0 * x1[i] * dx1[i] * dx1[i] / (12.0 * x1[i] * x1[i] + dx1[i] * dx1[i]);
+      rt[i] = (x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / (x1p[i] * x1p[i] - x1m[i] * x1m[i]) / 1.5;
+    }
+  }
+  for (int j = 0; j < nx[1]; j++) {
+    if (geo != IDFX_SPHERICAL) {
+      xgc[1][j] = x2[j];
+    } else {
+      const double xL = x2m[j], xR = x2p[j];
+      xgc[1][j] = (std::sin(xR) - std::sin(xL) + xL * std::cos(xL) - xR * std::cos(xR)) / (std::cos(xL) - std::cos(xR));
+      sinx2m[j] = std::sin(xL);
+      tanx2m[j] = std::tan(xL);
+      sinx2[j] = std::sin(x2[j]);
+      tanx2[j] = std::tan(x2[j]);
+      dmu[j] = std::fabs(std::cos(xL) - std::cos(xR));
+    }
+  }
+  if (geo == IDFX_SPHERICAL) sinx2m[nx[1]] = std::sin(x2p[nx[1] - 1]);  // used by evolveMagField at j+1 only below np_tot
+  for (int k = 0; k < nx[2]; k++) xgc[2][k] = d.x[2][k];
+
+  // areas (makeGeometry.cpp:139-211); factor e of A[dir] multiplies along dimension e, D_EXPAND order
+  // A1
+  for (int i = 0; i <= nx[0]; i++) {
+    double f;
+    const bool last = (i == nx[0]);
+    if (geo == IDFX_CARTESIAN) f = 1.0;
+    else if (geo == IDFX_CYLINDRICAL || geo == IDFX_POLAR) f = last ? std::fabs(x1p[i - 1]) : std::fabs(x1m[i]);
+    else f = last ? x1p[i - 1] * x1p[i - 1] : x1m[i] * x1m[i];
+    area[0][0][i] = f;
+  }
+  if (nd >= 2)
+    for (int j = 0; j < nx[1]; j++) area[0][1][j] = (geo == IDFX_SPHERICAL) ? std::fabs(std::cos(x2m[j]) - std::cos(x2p[j])) : dx2[j];
+  if (nd == 3)
+    for (int k = 0; k < nx[2]; k++) area[0][2][k] = (geo == IDFX_CYLINDRICAL) ? 1.0 : dx3[k];
+  // A2
+  for (int i = 0; i < nx[0]; i++) {
+    double f;
+    if (geo == IDFX_CARTESIAN || geo == IDFX_POLAR) f = dx1[i];
+    else if (geo == IDFX_CYLINDRICAL) f = (nd >= 2) ? std::fabs(x1[i]) * dx1[i] : std::fabs(x1[i]);
+    else f = x1[i] * dx1[i];
+    area[1][0][i] = f;
+  }
+  if (nd >= 2) {
+    for (int j = 0; j <= nx[1]; j++) {
+      double f = 1.0;
+      if (geo == IDFX_SPHERICAL) f = (j == nx[1]) ? std::fabs(std::sin(x2p[j - 1])) : std::fabs(std::sin(x2m[j]));
+      area[1][1][j] = f;
+    }
+  }
+  if (nd == 3)
+    for (int k = 0; k < nx[2]; k++) area[1][2][k] = (geo == IDFX_CYLINDRICAL) ? 1.0 : dx3[k];
+  // A3
+  for (int i = 0; i < nx[0]; i++) {
+    double f;
+    if (geo == IDFX_CARTESIAN) f = dx1[i];
+    else if (geo == IDFX_CYLINDRICAL) f = 1.0;
+    else f = x1[i] * dx1[i];
+    area[2][0][i] = f;
+  }
+  if (nd >= 2)
+    for (int j = 0; j < nx[1]; j++) area[2][1][j] = (geo == IDFX_CYLINDRICAL) ? 1.0 : dx2[j];
+  // area[2][2] stays 1
+
+  for (int dir = 0; dir < 3; dir++) {
+    std::vector<double> vx(d.x[dir], d.x[dir] + nx[dir]), vl(d.xl[dir], d.xl[dir] + nx[dir] ),
+        vr(d.xr[dir], d.xr[dir] + nx[dir]), vd(d.dx[dir], d.dx[dir] + nx[dir]);
+    // one extra entry so that x1m(i+1) style accesses at the last index stay in bounds
+    vx.push_back(vx.back());
+    vl.push_back(vr.back());
+    vr.push_back(vr.back());
+    vd.push_back(vd.back());
+    if (upload1D(b, &g.x[dir], vx) || upload1D(b, &g.xl[dir], vl) || upload1D(b, &g.xr[dir], vr) ||
+        upload1D(b, &g.dx[dir], vd) || upload1D(b, &g.xgc[dir], xgc[dir]) || upload1D(b, &g.vol[dir], vol[dir]))
+      return 1;
+    for (int e = 0; e < 3; e++)
+      if (upload1D(b, &g.area[dir][e], area[dir][e])) return 1;
+  }
+  if (upload1D(b, &g.rt, rt) || upload1D(b, &g.sinx2m, sinx2m) || upload1D(b, &g.tanx2m, tanx2m) ||
+      upload1D(b, &g.sinx2, sinx2) || upload1D(b, &g.tanx2, tanx2) || upload1D(b, &g.dmu, dmu))
+    return 1;
+
+  // irregular-grid PLM weights (extrapolateToFaces.hpp:43-71)
+  for (int dir = 0; dir < 3; dir++) {
+    const int n = nx[dir];
+    std::vector<double> wp(n, 0.0), wm(n, 0.0), cp(n, 0.0), cm(n, 0.0), dp(n, 0.0), dm(n, 0.0);
+    if (!d.regular_grid && dir < nd) {
+      const double *dx = d.dx[dir], *xr = d.xr[dir];
+      const std::vector<double> &gc = xgc[dir];
+      for (int i = 1; i < n - 1; i++) {
+        wp[i] = dx[i] / (gc[i + 1] - gc[i]);
+        wm[i] = dx[i] / (gc[i] - gc[i - 1]);
+        cp[i] = (gc[i + 1] - gc[i]) / (xr[i] - gc[i]);
+        cm[i] = (gc[i] - gc[i - 1]) / (gc[i] - xr[i - 1]);
+        dp[i] = (xr[i] - gc[i]) / dx[i];
+        dm[i] = (gc[i] - xr[i - 1]) / dx[i];
+      }
+    }
+    if (upload1D(b, &g.wp[dir], wp) || upload1D(b, &g.wm[dir], wm) || upload1D(b, &g.cp[dir], cp) ||
+        upload1D(b, &g.cm[dir], cm) || upload1D(b, &g.dp[dir], dp) || upload1D(b, &g.dm[dir], dm))
+      return 1;
+  }
+  return 0;
+}
+
+int setupPhys(IdfxBlock *b) {
+  const IdfxBlockDesc &d = b->desc;
+  PhysCfg &c = b->cfg;
+  c.ndim = d.ndim;
+  c.ncomp = d.ncomp;
+  c.mhd = d.mhd ? 1 : 0;
+  c.iso = d.isothermal ? 1 : 0;
+  c.order = d.order;
+  c.solver = d.solver;
+  c.emf = d.emf;
+  const int energy = c.iso ? 0 : 1;
+  c.RHO = 0;
+  c.MX1 = 1;
+  c.MX2 = (c.ncomp >= 2 ? 2 : 255);
+  c.MX3 = (c.ncomp == 3 ? 3 : 254);
+  c.ENG = energy ? c.ncomp + 1 : 250;
+  c.BX1 = c.mhd ? c.ncomp + 1 + energy : 253;
+  c.BX2 = (c.mhd && c.ncomp >= 2) ? c.BX1 + 1 : 252;
+  c.BX3 = (c.mhd && c.ncomp == 3) ? c.BX1 + 2 : 251;
+  c.nvar = 1 + c.ncomp + energy + (c.mhd ? c.ncomp : 0);
+  return 0;
+}
+
+int validate(const IdfxBlockDesc &d) {
+  if (d.ndim < 1 || d.ndim > 3) return fail("ndim must be 1..3");
+  if (d.ncomp < d.ndim || d.ncomp > 3) return fail("ncomp must satisfy ndim <= ncomp <= 3");
+  if (d.order < 1 || d.order > 4) return fail("order must be 1..4");
+  if (d.nstages < 1 || d.nstages > 3) return fail("nstages must be 1..3");
+  if (d.geometry < IDFX_CARTESIAN || d.geometry > IDFX_SPHERICAL) return fail("unknown geometry");
+  if (d.geometry == IDFX_CYLINDRICAL && d.ndim == 3) return fail("CYLINDRICAL is 2-D only; use POLAR");
+  if (d.mhd) {
+    if (d.solver != IDFX_TVDLF && d.solver != IDFX_HLL && d.solver != IDFX_HLLD && d.solver != IDFX_ROE)
+      return fail("hllc Riemann solver requires a HD fluid");
+    if (d.emf < IDFX_EMF_ARITHMETIC || d.emf > IDFX_EMF_UCT_HLLD) return fail("Unknown EMF averaging scheme");
+    if (d.emf == IDFX_EMF_UCT_HLLD && (d.solver == IDFX_HLL || d.solver == IDFX_TVDLF))
+      return fail("HLLD EMF reconstruction is only compatible with HLLD or ROE Riemann solvers");
+  } else {
+    if (d.solver == IDFX_HLLD) return fail("hlld Riemann solver requires a MHD fluid");
+    if (d.solver == IDFX_ROE) return fail("roe HD solver is not available in this build");
+  }
+  for (int dir = 0; dir < d.ndim; dir++) {
+    const int need = (d.order == 4) ? 3 : 2;
+    if (d.nghost[dir] < need) return fail("nghost too small for the reconstruction order");
+    if (d.np_int[dir] < 1) return fail("np_int must be >= 1");
+    const int lb = d.lbound[dir], rb = d.rbound[dir];
+    for (int t : {lb, rb}) {
+      if (t == IDFX_BC_SHEARINGBOX || t == IDFX_BC_AXIS)
+        return fail("shearingbox / axis boundaries are outside the scope of this build");
+      if (t < 0 || t >= IDFX_BC_UNDEFINED) return fail("undefined boundary condition");
+    }
+  }
+  for (int dir = 0; dir < 3; dir++)
+    if (!d.x[dir] || !d.xl[dir] || !d.xr[dir] || !d.dx[dir]) return fail("coordinate arrays must be provided");
+  return 0;
+}
+
+SweepArgs baseSweepArgs(IdfxBlock *b) {
+  SweepArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.g = b->g;
+  a.emf = b->emf;
+  a.Vc = b->Vc;
+  a.Uc = b->Uc;
+  a.Vs = b->Vs;
+  a.invDt = b->invDt;
+  a.dt = b->state + 1;
+  a.gamma = b->desc.gamma;
+  a.csiso = b->desc.csiso;
+  a.emfMode = b->cfg.emf;
+  a.perpExt = 0;
+  if (b->cfg.mhd) {
+    a.perpExt = 1;
+    // HLL / HLLD widen the face box for the UCT-HLLx stencils; Roe and TVDLF never do
+    // (hlldMHD.hpp:32-37, hllMHD.hpp:30-35 vs roeMHD.hpp:63-73, tvdlfMHD.hpp:31)
+    if ((b->cfg.emf == EMF_UCT_HLL || b->cfg.emf == EMF_UCT_HLLD) &&
+        (b->cfg.solver == SOLVER_HLL || b->cfg.solver == SOLVER_HLLD))
+      a.perpExt = -1;  // resolved per direction: nghost[dir]
+  }
+  a.doInvDt = 1;
+  return a;
+}
+
+int launchSweepDir(IdfxBlock *b, int dir, SweepArgs a) {
+  if (a.perpExt == -1) a.perpExt = b->desc.nghost[dir];
+  int rc;
+  const PhysCfg &c = b->cfg;
+  if (!c.mhd) {
+    rc = idfxk::sweepHD(c, dir, a, b->stream);
+  } else {
+    switch (c.solver) {
+      case SOLVER_TVDLF: rc = idfxk::sweepMhdTvdlf(c, dir, a, b->stream); break;
+      case SOLVER_HLL: rc = idfxk::sweepMhdHll(c, dir, a, b->stream); break;
+      case SOLVER_HLLD: rc = idfxk::sweepMhdHlld(c, dir, a, b->stream); break;
+      case SOLVER_ROE: rc = idfxk::sweepMhdRoe(c, dir, a, b->stream); break;
+      default: rc = -1;
+    }
+  }
+  b->launches++;
+  return rc;
+}
+
+// host copy of (t, dt); synchronises the stream
+int readState(IdfxBlock *b) {
+  CUDA_TRY(cudaMemcpyAsync(b->hostState, b->state, 4 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+bool needsExchange(const IdfxBlock *b, int dir) { return b->nproc[dir] > 1; }
+
+// Boundary::SetBoundaries without the final ReconstructVcField (boundary.hpp:252-275)
+int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
+  const IdfxBlockDesc &d = b->desc;
+  for (int dir = 0; dir < d.ndim; dir++) {
+    if (needsExchange(b, dir)) {
+      if (!b->haloFn) return fail("nproc > 1 in a direction but no halo exchange has been enrolled");
+      b->haloFn(b, dir, b->haloData);
+    }
+    for (int side = 0; side < 2; side++) {
+      const int type = side == 0 ? d.lbound[dir] : d.rbound[dir];
+      switch (type) {
+        case IDFX_BC_INTERNAL: break;
+        case IDFX_BC_PERIODIC:
+          if (needsExchange(b, dir)) break;  // periodicity enforced by the exchange
+          KTRY(idfxk::enforcePhysicalBoundary(b->cfg, b->g, b->Vc, b->Vs, dir, side, BC_PERIODIC, b->stream, &b->launches));
+          break;
+        case IDFX_BC_REFLECTIVE:
+          KTRY(idfxk::enforcePhysicalBoundary(b->cfg, b->g, b->Vc, b->Vs, dir, side, BC_REFLECTIVE, b->stream, &b->launches));
+          break;
+        case IDFX_BC_OUTFLOW:
+          KTRY(idfxk::enforcePhysicalBoundary(b->cfg, b->g, b->Vc, b->Vs, dir, side, BC_OUTFLOW, b->stream, &b->launches));
+          break;
+        case IDFX_BC_USERDEF: {
+          if (!b->userBc)
+            return fail("No function has been enrolled to define your own boundary conditions");
+          double tt = t;
+          if (!tKnown) {
+            if (readState(b)) return 1;
+            tt = b->hostState[0];
+          } else {
+            CUDA_TRY(cudaStreamSynchronize(b->stream));
+          }
+          b->userBc(b, dir, side, tt, b->userBcData);
+          CUDA_TRY(cudaDeviceSynchronize());
+          break;
+        }
+        default: return fail("Boundary condition type is not yet implemented");
+      }
+    }
+    if (b->cfg.mhd) {
+      const int left = !(d.lbound[dir] == IDFX_BC_PERIODIC || d.lbound[dir] == IDFX_BC_INTERNAL);
+      const int right = !(d.rbound[dir] == IDFX_BC_PERIODIC || d.rbound[dir] == IDFX_BC_INTERNAL);
+      KTRY(idfxk::reconstructNormalField(b->cfg, b->g, b->Vs, dir, left, right, b->stream, &b->launches));
+    }
+  }
+  return 0;
+}
+
+int reconstructVc(IdfxBlock *b, double *V) {
+  if (!b->cfg.mhd) return 0;
+  KTRY(idfxk::reconstructVcField(b->cfg, b->g, b->Vs, V, b->stream));
+  b->launches++;
+  return 0;
+}
+
+// Fluid::EvolveStage (evolveStage.hpp:41-90); fusedStage < 0 : reference-like behaviour
+int evolveStageImpl(IdfxBlock *b, int fusedStage) {
+  const IdfxBlockDesc &d = b->desc;
+  const bool fused = fusedStage >= 0;
+  const bool multi = d.nstages > 1;
+  for (int dir = 0; dir < d.ndim; dir++) {
+    SweepArgs a = baseSweepArgs(b);
+    a.doSource = (dir == d.ndim - 1 && d.geometry != IDFX_CARTESIAN) ? 1 : 0;
+    if (fused) {
+      a.doInvDt = (fusedStage == 0) ? 1 : 0;
+      a.invDtInit = (dir == 0) ? 1 : 0;
+      a.fusedP2C = (dir == 0) ? 1 : 0;
+      a.Uc0 = (dir == 0 && fusedStage == 0 && multi) ? b->Uc0 : nullptr;
+    }
+    KTRY(launchSweepDir(b, dir, a));
+  }
+  if (b->cfg.mhd && d.ndim >= 2) {
+    KTRY(idfxk::calcCornerEmf(b->g, b->emf, b->Vc, b->Vs, b->cfg.emf, b->cfg.order, b->cfg.ncomp, b->cfg.MX1,
+                              b->cfg.BX1, b->stream, &b->launches));
+    int mode = 0;
+    double wc = 0, w0 = 0;
+    if (fused && multi) {
+      mode = (fusedStage == 0) ? 1 : 2;
+      if (fusedStage > 0) {
+        wc = b->wc[fusedStage - 1];
+        w0 = b->w0[fusedStage - 1];
+      }
+    }
+    KTRY(idfxk::evolveMagField(b->g, b->emf, b->Vs, b->Vs0, b->state + 1, 0, mode, wc, w0, b->stream, &b->launches));
+    if (!fused) {
+      if (reconstructVc(b, b->Uc)) return 1;
+    }
+  }
+  return 0;
+}
+
+int timestepReduceImpl(IdfxBlock *b) {
+  KTRY(idfxk::timestepReduce(b->g, b->invDt, b->redBits, b->stream));
+  b->launches++;
+  return 0;
+}
+
+// TimeIntegrator::Cycle as a sequence of the reference's own steps (timeIntegrator.cpp:246-414)
+int cycleReferenceOrder(IdfxBlock *b) {
+  const IdfxBlockDesc &d = b->desc;
+  KTRY(idfxk::dtControlBegin(b->state, b->redBits, b->stream));
+  KTRY(idfxk::fill(b->invDt, b->nCells, 0.0, b->stream));
+  b->launches += 2;
+  for (int stage = 0; stage < d.nstages; stage++) {
+    if (setBoundariesCore(b, 0.0, false)) return 1;
+    if (reconstructVc(b, b->Vc)) return 1;
+    KTRY(idfxk::primToCons(b->cfg, b->g, b->Vc, b->Uc, d.gamma, b->stream));
+    b->launches++;
+    if (d.nstages > 1 && stage == 0) {
+      KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * b->cfg.nvar, b->stream));
+      b->launches++;
+      if (b->cfg.mhd) {
+        KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * d.ndim, b->stream));
+        b->launches++;
+      }
+    }
+    if (evolveStageImpl(b, -1)) return 1;
+    const double wc = stage > 0 ? b->wc[stage - 1] : 0.0, w0 = stage > 0 ? b->w0[stage - 1] : 0.0;
+    KTRY(idfxk::stageTimeAdvance(b->state, stage, wc, w0, b->stream));
+    b->launches++;
+    if (stage == 0 && !(d.fixed_dt > 0.0)) {
+      if (timestepReduceImpl(b)) return 1;
+    }
+    if (stage > 0) {
+      KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * b->cfg.nvar, wc, w0, b->stream));
+      b->launches++;
+      if (b->cfg.mhd) {
+        KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * d.ndim, wc, w0, b->stream));
+        b->launches++;
+      }
+    }
+    if (reconstructVc(b, b->Uc)) return 1;
+    KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, d.gamma, b->stream));
+    b->launches++;
+  }
+  KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
+                           b->stream));
+  b->launches++;
+  return 0;
+}
+
+// The same cycle with the point-wise steps folded into the sweeps / CT / one epilogue.
+int cycleFused(IdfxBlock *b) {
+  const IdfxBlockDesc &d = b->desc;
+  KTRY(idfxk::dtControlBegin(b->state, b->redBits, b->stream));
+  b->launches++;
+  for (int stage = 0; stage < d.nstages; stage++) {
+    if (setBoundariesCore(b, 0.0, false)) return 1;
+    if (reconstructVc(b, b->Vc)) return 1;
+    if (evolveStageImpl(b, stage)) return 1;
+    const double wc = stage > 0 ? b->wc[stage - 1] : 0.0, w0 = stage > 0 ? b->w0[stage - 1] : 0.0;
+    KTRY(idfxk::stageTimeAdvance(b->state, stage, wc, w0, b->stream));
+    b->launches++;
+    if (stage == 0 && !(d.fixed_dt > 0.0)) {
+      if (timestepReduceImpl(b)) return 1;
+    }
+    KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, 1,
+                              b->stream));
+    b->launches++;
+  }
+  KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
+                           b->stream));
+  b->launches++;
+  return 0;
+}
+
+int fieldPtr(IdfxBlock *b, int field, double **p, int dims[4]) {
+  const DevGrid &g = b->g;
+  dims[1] = g.nx[2];
+  dims[2] = g.nx[1];
+  dims[3] = g.nx[0];
+  dims[0] = 1;
+  switch (field) {
+    case IDFX_FIELD_VC: *p = b->Vc; dims[0] = b->cfg.nvar; break;
+    case IDFX_FIELD_UC: *p = b->Uc; dims[0] = b->cfg.nvar; break;
+    case IDFX_FIELD_UC0: *p = b->Uc0; dims[0] = b->cfg.nvar; break;
+    case IDFX_FIELD_VS:
+    case IDFX_FIELD_VS0:
+      *p = (field == IDFX_FIELD_VS) ? b->Vs : b->Vs0;
+      dims[0] = b->cfg.mhd ? b->desc.ndim : 0;
+      dims[1] = g.nx[2] + g.off[2];
+      dims[2] = g.nx[1] + g.off[1];
+      dims[3] = g.nx[0] + g.off[0];
+      break;
+    case IDFX_FIELD_INVDT: *p = b->invDt; break;
+    case IDFX_FIELD_EX: *p = b->emf.ex; break;
+    case IDFX_FIELD_EY: *p = b->emf.ey; break;
+    case IDFX_FIELD_EZ: *p = b->emf.ez; break;
+    default: return fail("unknown field id");
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char *idfx_last_error(void) { return g_error.c_str(); }
+const char *idfx_version(void) { return "idefix_b200 0.1 (sm_100a, FP64, fmad=false)"; }
+
+int idfx_device_count(int *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = n;
+  return 0;
+}
+
+int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
+  if (!desc || !out) return fail("null argument");
+  *out = nullptr;
+  if (validate(*desc)) return 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available: idefix_b200 has no CPU fallback");
+  if (desc->device < 0 || desc->device >= ndev) return fail("invalid device ordinal");
+  CUDA_TRY(cudaSetDevice(desc->device));
+
+  IdfxBlock *b = new IdfxBlock();
+  b->desc = *desc;
+  // own the coordinate arrays
+  b->hostCoords.resize(12);
+  for (int dir = 0; dir < 3; dir++) {
+    const int n = desc->np_int[dir] + 2 * desc->nghost[dir];
+    const double *src[4] = {desc->x[dir], desc->xl[dir], desc->xr[dir], desc->dx[dir]};
+    for (int q = 0; q < 4; q++) b->hostCoords[dir * 4 + q].assign(src[q], src[q] + n);
+    b->desc.x[dir] = b->hostCoords[dir * 4 + 0].data();
+    b->desc.xl[dir] = b->hostCoords[dir * 4 + 1].data();
+    b->desc.xr[dir] = b->hostCoords[dir * 4 + 2].data();
+    b->desc.dx[dir] = b->hostCoords[dir * 4 + 3].data();
+  }
+  setupPhys(b);
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+
+  DevGrid &g = b->g;
+  std::memset(&g, 0, sizeof(g));
+  g.ndim = desc->ndim;
+  g.geometry = desc->geometry;
+  g.regular = desc->regular_grid ? 1 : 0;
+  for (int dir = 0; dir < 3; dir++) {
+    g.ng[dir] = desc->nghost[dir];
+    g.nx[dir] = desc->np_int[dir] + 2 * desc->nghost[dir];
+    g.beg[dir] = desc->nghost[dir];
+    g.end[dir] = desc->nghost[dir] + desc->np_int[dir];
+    g.off[dir] = dir < desc->ndim ? 1 : 0;
+  }
+  g.sj = g.nx[0];
+  g.sk = (long long)g.nx[0] * g.nx[1];
+  g.sn = g.sk * g.nx[2];
+  g.vsj = g.nx[0] + g.off[0];
+  g.vsk = g.vsj * (g.nx[1] + g.off[1]);
+  g.vsn = g.vsk * (g.nx[2] + g.off[2]);
+  b->nCells = g.sn;
+  b->nVs = g.vsn;
+
+  int rc = 0;
+  rc |= buildGeometry(b);
+  const int nv = b->cfg.nvar;
+  rc = rc || devAlloc(b, &b->Vc, b->nCells * nv);
+  rc = rc || devAlloc(b, &b->Uc, b->nCells * nv);
+  rc = rc || devAlloc(b, &b->invDt, b->nCells);
+  if (desc->nstages > 1) rc = rc || devAlloc(b, &b->Uc0, b->nCells * nv);
+  std::memset(&b->emf, 0, sizeof(b->emf));
+  if (b->cfg.mhd) {
+    rc = rc || devAlloc(b, &b->Vs, b->nVs * desc->ndim);
+    if (desc->nstages > 1) rc = rc || devAlloc(b, &b->Vs0, b->nVs * desc->ndim);
+    DevEmf &e = b->emf;
+    const long long n = b->nCells;
+    const int nd = desc->ndim;
+    if (nd >= 2) {
+      rc = rc || devAlloc(b, &e.ez, n) || devAlloc(b, &e.ezi, n) || devAlloc(b, &e.ezj, n);
+      if (nd == 3 || desc->ncomp == 3) rc = rc || devAlloc(b, &e.eyi, n) || devAlloc(b, &e.exj, n);
+      if (nd == 3)
+        rc = rc || devAlloc(b, &e.ex, n) || devAlloc(b, &e.ey, n) || devAlloc(b, &e.exk, n) || devAlloc(b, &e.eyk, n);
+      if (desc->emf == IDFX_EMF_UCT0 || desc->emf == IDFX_EMF_UCT_CONTACT) {
+        rc = rc || devAlloc(b, &e.Ex3, n);
+        if (nd == 3) rc = rc || devAlloc(b, &e.Ex1, n) || devAlloc(b, &e.Ex2, n);
+      }
+      if (desc->emf == IDFX_EMF_UCT_CONTACT) {
+        rc = rc || devAlloc(b, &e.svx, n) || devAlloc(b, &e.svy, n);
+        if (nd == 3) rc = rc || devAlloc(b, &e.svz, n);
+      }
+      if (desc->emf == IDFX_EMF_UCT_HLL || desc->emf == IDFX_EMF_UCT_HLLD) {
+        rc = rc || devAlloc(b, &e.axL, n) || devAlloc(b, &e.axR, n) || devAlloc(b, &e.dxL, n) || devAlloc(b, &e.dxR, n);
+        rc = rc || devAlloc(b, &e.ayL, n) || devAlloc(b, &e.ayR, n) || devAlloc(b, &e.dyL, n) || devAlloc(b, &e.dyR, n);
+        if (nd == 3)
+          rc = rc || devAlloc(b, &e.azL, n) || devAlloc(b, &e.azR, n) || devAlloc(b, &e.dzL, n) || devAlloc(b, &e.dzR, n);
+      }
+    } else {
+      // 1-D MHD: the sweep still stores the transverse EMFs; give them somewhere to go
+      rc = rc || devAlloc(b, &e.ezi, n) || devAlloc(b, &e.eyi, n) || devAlloc(b, &e.svx, n);
+      rc = rc || devAlloc(b, &e.axL, n) || devAlloc(b, &e.axR, n) || devAlloc(b, &e.dxL, n) || devAlloc(b, &e.dxR, n);
+    }
+  }
+  rc = rc || devAlloc(b, &b->state, 4);
+  rc = rc || devAlloc(b, &b->redBits, 2);
+  rc = rc || devAlloc(b, &b->ncyclesDev, 1);
+  rc = rc || devAlloc(b, &b->statusDev, 1);
+  rc = rc || devAlloc(b, &b->nanDev, 1);
+  if (rc) {
+    idfx_block_destroy(b);
+    return 1;
+  }
+  if (cudaMallocHost((void **)&b->hostState, 16 * sizeof(double)) != cudaSuccess) {
+    idfx_block_destroy(b);
+    return fail("cudaMallocHost failed");
+  }
+  // TimeIntegrator ctor (timeIntegrator.cpp:23-85)
+  if (desc->nstages == 2) {
+    b->wc[0] = 0.5;
+    b->w0[0] = 0.5;
+  }
+  if (desc->nstages == 3) {
+    b->wc[0] = 0.25;
+    b->w0[0] = 0.75;
+    b->wc[1] = 2.0 / 3.0;
+    b->w0[1] = 1.0 / 3.0;
+  }
+  b->hostState[0] = 0.0;
+  b->hostState[1] = desc->fixed_dt > 0.0 ? desc->fixed_dt : desc->first_dt;
+  b->hostState[2] = 0.0;
+  b->hostState[3] = -1.0;
+  cudaMemcpyAsync(b->state, b->hostState, 4 * sizeof(double), cudaMemcpyHostToDevice, b->stream);
+  for (int dir = 0; dir < desc->ndim; dir++)
+    if (desc->lbound[dir] == IDFX_BC_USERDEF || desc->rbound[dir] == IDFX_BC_USERDEF) b->haveUserdef = true;
+  b->fused = !b->haveUserdef;
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    idfx_block_destroy(b);
+    return fail("device initialisation failed");
+  }
+  *out = b;
+  return 0;
+}
+
+int idfx_block_destroy(IdfxBlock *b) {
+  if (!b) return 0;
+  cudaSetDevice(b->desc.device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (void *p : b->allocs) cudaFree(p);
+  if (b->hostState) cudaFreeHost(b->hostState);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+  return 0;
+}
+
+int idfx_sync(IdfxBlock *b) {
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_field_info(IdfxBlock *b, int field, double **dev, int dims[4]) {
+  double *p = nullptr;
+  if (fieldPtr(b, field, &p, dims)) return 1;
+  if (dev) *dev = p;
+  return 0;
+}
+
+int idfx_upload(IdfxBlock *b, int field, const double *host) {
+  double *p = nullptr;
+  int dims[4];
+  if (fieldPtr(b, field, &p, dims)) return 1;
+  if (!p) return fail("field is not allocated in this configuration");
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
+  CUDA_TRY(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_download(IdfxBlock *b, int field, double *host) {
+  double *p = nullptr;
+  int dims[4];
+  if (fieldPtr(b, field, &p, dims)) return 1;
+  if (!p) return fail("field is not allocated in this configuration");
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
+  CUDA_TRY(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_set_time(IdfxBlock *b, double t, double dt) {
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  b->hostState[8] = t;
+  b->hostState[9] = dt;
+  CUDA_TRY(cudaMemcpyAsync(b->state, b->hostState + 8, 2 * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_get_time(IdfxBlock *b, double *t, double *dt) {
+  if (readState(b)) return 1;
+  if (t) *t = b->hostState[0];
+  if (dt) *dt = b->hostState[1];
+  return 0;
+}
+
+int idfx_set_tstop(IdfxBlock *b, double tstop) {
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  b->hostState[10] = tstop;
+  CUDA_TRY(cudaMemcpyAsync(b->state + 3, b->hostState + 10, sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_get_ncycles(IdfxBlock *b, long long *n) {
+  CUDA_TRY(cudaMemcpyAsync(b->hostState + 12, b->ncyclesDev, sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  std::memcpy(n, b->hostState + 12, sizeof(long long));
+  return 0;
+}
+
+int idfx_launch_count(IdfxBlock *b, long long *count) {
+  *count = b->launches;
+  return 0;
+}
+
+int idfx_set_nproc(IdfxBlock *b, const int nproc[3]) {
+  for (int d = 0; d < 3; d++) b->nproc[d] = nproc[d] < 1 ? 1 : nproc[d];
+  return 0;
+}
+
+// ---- granular entry points -----------------------------------------------------------------
+int idfx_reset_stage(IdfxBlock *b) {
+  KTRY(idfxk::fill(b->invDt, b->nCells, 0.0, b->stream));
+  b->launches++;
+  return 0;
+}
+
+int idfx_enforce_boundary_dir(IdfxBlock *b, double t, int dir) {
+  (void)t;
+  (void)dir;
+  return fail("idfx_enforce_boundary_dir: use idfx_set_boundaries");
+}
+
+int idfx_set_boundaries(IdfxBlock *b, double t) {
+  if (setBoundariesCore(b, t, true)) return 1;
+  return reconstructVc(b, b->Vc);
+}
+
+int idfx_reconstruct_vc_field(IdfxBlock *b, int field) {
+  if (field == IDFX_FIELD_VC) return reconstructVc(b, b->Vc);
+  if (field == IDFX_FIELD_UC) return reconstructVc(b, b->Uc);
+  return fail("idfx_reconstruct_vc_field: field must be VC or UC");
+}
+
+int idfx_prim_to_cons(IdfxBlock *b) {
+  KTRY(idfxk::primToCons(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
+  b->launches++;
+  return 0;
+}
+
+int idfx_cons_to_prim(IdfxBlock *b) {
+  if (reconstructVc(b, b->Uc)) return 1;
+  KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
+  b->launches++;
+  return 0;
+}
+
+int idfx_state_copy(IdfxBlock *b) {
+  if (!b->Uc0) return fail("states[\"begin\"] exists only when nstages > 1");
+  KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * b->cfg.nvar, b->stream));
+  b->launches++;
+  if (b->cfg.mhd) {
+    KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * b->desc.ndim, b->stream));
+    b->launches++;
+  }
+  return 0;
+}
+
+int idfx_state_add_and_store(IdfxBlock *b, double wc, double w0) {
+  if (!b->Uc0) return fail("states[\"begin\"] exists only when nstages > 1");
+  KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * b->cfg.nvar, wc, w0, b->stream));
+  b->launches++;
+  if (b->cfg.mhd) {
+    KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * b->desc.ndim, wc, w0, b->stream));
+    b->launches++;
+  }
+  return 0;
+}
+
+int idfx_evolve_stage(IdfxBlock *b, double t, double dt) {
+  (void)t;
+  // dt lives on the device; only touch it when the caller's value differs from the mirror
+  if (readState(b)) return 1;
+  if (b->hostState[1] != dt) {
+    b->hostState[9] = dt;
+    CUDA_TRY(cudaMemcpyAsync(b->state + 1, b->hostState + 9, sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  }
+  return evolveStageImpl(b, -1);
+}
+
+int idfx_compute_timestep(IdfxBlock *b, double *dt_min) {
+  b->hostState[11] = INFINITY;
+  CUDA_TRY(cudaMemcpyAsync(b->redBits, b->hostState + 11, sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  if (timestepReduceImpl(b)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(b->hostState + 11, b->redBits, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  *dt_min = b->hostState[11];
+  return 0;
+}
+
+int idfx_check_divb(IdfxBlock *b, double *divb_max) {
+  if (!b->cfg.mhd) {
+    *divb_max = 0.0;
+    return 0;
+  }
+  CUDA_TRY(cudaMemsetAsync(b->redBits + 1, 0, sizeof(double), b->stream));
+  KTRY(idfxk::checkDivB(b->cfg, b->g, b->Vs, b->redBits + 1, b->stream));
+  b->launches++;
+  CUDA_TRY(cudaMemcpyAsync(b->hostState + 13, b->redBits + 1, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  *divb_max = b->hostState[13];
+  return 0;
+}
+
+int idfx_check_nan(IdfxBlock *b, int *nan_count) {
+  CUDA_TRY(cudaMemsetAsync(b->nanDev, 0, sizeof(int), b->stream));
+  KTRY(idfxk::checkNan(b->cfg, b->g, b->Vc, b->Vs, b->nanDev, b->stream));
+  b->launches += b->cfg.mhd ? 2 : 1;
+  CUDA_TRY(cudaMemcpyAsync(b->hostState + 14, b->nanDev, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  int n;
+  std::memcpy(&n, b->hostState + 14, sizeof(int));
+  *nan_count = n;
+  return 0;
+}
+
+// ---- fused path -------------------------------------------------------------------------------
+int idfx_cycles(IdfxBlock *b, int ncycles) {
+  for (int n = 0; n < ncycles; n++) {
+    if (b->fused) {
+      if (cycleFused(b)) return 1;
+    } else {
+      if (cycleReferenceOrder(b)) return 1;
+    }
+  }
+  return 0;
+}
+
+int idfx_cycle(IdfxBlock *b, double *t, double *dt, int *status_flags) {
+  if (idfx_cycles(b, 1)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(b->hostState, b->state, 4 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(b->hostState + 14, b->statusDev, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  if (t) *t = b->hostState[0];
+  if (dt) *dt = b->hostState[1];
+  int s;
+  std::memcpy(&s, b->hostState + 14, sizeof(int));
+  if (status_flags) *status_flags = s;
+  return 0;
+}
+
+// selects the reference-ordered (un-fused) kernel sequence; used by the parity tests
+int idfx_set_fused(IdfxBlock *b, int fused) {
+  if (fused && b->haveUserdef) return fail("the fused path is not available with user-defined boundaries");
+  b->fused = fused != 0;
+  return 0;
+}
+
+// ---- callbacks -----------------------------------------------------------------------------------
+int idfx_enroll_userdef_boundary(IdfxBlock *b, IdfxUserBoundaryFn fn, void *user) {
+  b->userBc = fn;
+  b->userBcData = user;
+  return 0;
+}
+int idfx_enroll_halo_exchange(IdfxBlock *b, IdfxHaloFn fn, void *user) {
+  b->haloFn = fn;
+  b->haloData = user;
+  return 0;
+}
+
+// ---- halo exchange building blocks ------------------------------------------------------------------
+int idfx_halo_buffer_size(IdfxBlock *b, int dir, size_t *ndoubles) {
+  if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
+  *ndoubles = (size_t)idfxk::haloBufferSize(b->cfg, b->g, dir);
+  return 0;
+}
+
+static int ensureHaloBuffers(IdfxBlock *b, int dir) {
+  if (b->haloSend[dir][0]) return 0;
+  const long long n = idfxk::haloBufferSize(b->cfg, b->g, dir);
+  for (int s = 0; s < 2; s++) {
+    if (devAlloc(b, &b->haloSend[dir][s], n)) return 1;
+    if (devAlloc(b, &b->haloRecv[dir][s], n)) return 1;
+  }
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_halo_buffers(IdfxBlock *b, int dir, int side, double **send, double **recv) {
+  if (dir < 0 || dir >= b->desc.ndim || side < 0 || side > 1) return fail("invalid direction / side");
+  if (ensureHaloBuffers(b, dir)) return 1;
+  if (send) *send = b->haloSend[dir][side];
+  if (recv) *recv = b->haloRecv[dir][side];
+  return 0;
+}
+
+int idfx_halo_pack(IdfxBlock *b, int dir) {
+  if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
+  if (ensureHaloBuffers(b, dir)) return 1;
+  for (int side = 0; side < 2; side++) {
+    // with a bound peer the slab is written straight into the neighbour's receive buffer (NVLink P2P store)
+    double *dst = b->haloPeer[dir][side] ? b->haloPeer[dir][side] : b->haloSend[dir][side];
+    KTRY(idfxk::haloPack(b->cfg, b->g, b->Vc, b->Vs, dir, side, dst, b->stream, &b->launches));
+  }
+  return 0;
+}
+
+int idfx_halo_unpack(IdfxBlock *b, int dir) {
+  if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
+  if (ensureHaloBuffers(b, dir)) return 1;
+  for (int side = 0; side < 2; side++)
+    KTRY(idfxk::haloUnpack(b->cfg, b->g, b->Vc, b->Vs, dir, side, b->haloRecv[dir][side], b->stream, &b->launches));
+  return 0;
+}
+
+int idfx_halo_bind_peer(IdfxBlock *b, int dir, int side, double *peer_recv) {
+  if (dir < 0 || dir >= b->desc.ndim || side < 0 || side > 1) return fail("invalid direction / side");
+  b->haloPeer[dir][side] = peer_recv;
+  return 0;
+}
+
+int idfx_halo_ipc_handle(IdfxBlock *b, int dir, int side, void *handle64) {
+  if (dir < 0 || dir >= b->desc.ndim || side < 0 || side > 1) return fail("invalid direction / side");
+  if (ensureHaloBuffers(b, dir)) return 1;
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, b->haloRecv[dir][side]));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int idfx_halo_open_ipc(IdfxBlock *b, const void *handle64, double **ptr) {
+  (void)b;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = (double *)p;
+  return 0;
+}
+
+}  // extern "C"

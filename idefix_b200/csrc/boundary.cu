@@ -1,0 +1,316 @@
+// boundary.cu -- physical boundary conditions, normal-field reconstruction in the
+// ghost zones and the halo pack / unpack kernels of the multi-GPU exchange.
+//
+// Reference: src/fluid/boundary/boundary.hpp:577-809 (periodic / reflective / outflow),
+// :408-530 (ReconstructNormalField), :969-1100 (loop bounds of BoundaryForAll/X1s/X2s/X3s);
+// src/mpi.cpp:247-846 and src/mpi.hpp:49-172 (which slabs travel between neighbours).
+#include "kernels.h"
+
+namespace {
+
+constexpr int TBX = 64, TBY = 4;
+
+struct Box {
+  int lo[3], hi[3];
+};
+inline dim3 boxGrid(const Box &b, int nz = 1) {
+  int n0 = b.hi[0] - b.lo[0], n1 = b.hi[1] - b.lo[1], n2 = b.hi[2] - b.lo[2];
+  if (n0 < 1) n0 = 1;
+  if (n1 < 1) n1 = 1;
+  if (n2 < 1) n2 = 1;
+  return dim3((n0 + TBX - 1) / TBX, (n1 + TBY - 1) / TBY, n2 * nz);
+}
+inline bool emptyBox(const Box &b) {
+  return b.hi[0] <= b.lo[0] || b.hi[1] <= b.lo[1] || b.hi[2] <= b.lo[2];
+}
+
+// ghost slab of direction dir / side for an array whose active extent along `stag` is
+// one larger (stag = -1: cell centred).  boundary.hpp:969-1100.
+Box ghostSlab(const DevGrid &g, int dir, int side, int stag) {
+  Box b;
+  for (int d = 0; d < 3; d++) {
+    const int nint = (g.end[d] - g.beg[d]) + (d == stag ? 1 : 0);
+    const int ntot = g.nx[d] + (d == stag ? 1 : 0);
+    if (d == dir) {
+      b.lo[d] = side * (g.ng[d] + nint);
+      b.hi[d] = g.ng[d] + side * (g.ng[d] + nint);
+    } else {
+      b.lo[d] = 0;
+      b.hi[d] = ntot;
+    }
+  }
+  return b;
+}
+
+// One kernel serves the three standard boundary types for any array (cell-centred variable
+// or staggered component): out(k,j,i) = sign * in(ref), with the reference index along dir.
+//   type periodic  : ref = ng + (x + ng*(n-1)) % n                 (boundary.hpp:591-603)
+//   type reflective: ref = 2*(ng + side*n) - x - 1                  (boundary.hpp:693-699)
+//   type outflow   : ref = ng + side*(n-1)                          (boundary.hpp:757-769)
+// n is the number of ACTIVE CELLS (np_int) along dir in all cases, as in the reference.
+__global__ void ghostFillKernel(double *__restrict__ q, long long sj, long long sk, Box b, int nvars,
+                                long long sn, int dir, int side, int type, int ng, int nint, int signMask,
+                                int zeroInflowVar) {
+  const int i = b.lo[0] + blockIdx.x * TBX + threadIdx.x;
+  const int j = b.lo[1] + blockIdx.y * TBY + threadIdx.y;
+  const int nk = b.hi[2] - b.lo[2];
+  const int k = b.lo[2] + (int)(blockIdx.z % nk);
+  const int n = (int)(blockIdx.z / nk);
+  if (i >= b.hi[0] || j >= b.hi[1] || n >= nvars) return;
+  int x = (dir == 0) ? i : (dir == 1 ? j : k);
+  int ref;
+  if (type == BC_PERIODIC) {
+    ref = ng + (x + ng * (nint - 1)) % nint;
+  } else if (type == BC_REFLECTIVE) {
+    ref = 2 * (ng + side * nint) - x - 1;
+  } else {
+    ref = ng + side * (nint - 1);
+  }
+  const int ir = (dir == 0) ? ref : i, jr = (dir == 1) ? ref : j, kr = (dir == 2) ? ref : k;
+  const long long dst = n * sn + (long long)k * sk + (long long)j * sj + i;
+  const long long src = n * sn + (long long)kr * sk + (long long)jr * sj + ir;
+  double v = q[src];
+  if (type == BC_REFLECTIVE) {
+    if ((signMask >> n) & 1) v = -1.0 * v;
+    else v = 1.0 * v;
+  } else if (type == BC_OUTFLOW) {
+    // no inflow through an outflow boundary (boundary.hpp:763-767)
+    const int sign = 1 - 2 * side;
+    if (n == zeroInflowVar && (sign * v >= 0.0)) v = 0.0;
+  }
+  q[dst] = v;
+}
+
+// boundary.hpp:434-527: march outwards from the last active face so that div B = 0 in the ghosts
+__global__ void reconstructNormalKernel(DevGrid g, double *__restrict__ Vs, int dir, int left, int right,
+                                        int signLeft, int signRight) {
+  // thread owns a line along dir; (a,b) index the two perpendicular directions
+  const int p0 = (dir == 0) ? 1 : 0;
+  const int p1 = (dir == 2) ? 1 : 2;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y * blockDim.y + threadIdx.y;
+  if (a >= g.nx[p0] || b >= g.nx[p1]) return;
+  const int nd = g.ndim;
+  double *B1 = Vs, *B2 = Vs + g.vsn, *B3 = Vs + 2 * g.vsn;
+  auto S = [&](int k, int j, int i) { return sidx(g, k, j, i); };
+  auto div2 = [&](int k, int j, int i, int skip) -> double {
+    // sum of the perpendicular flux differences, in the reference's order
+    double s = 0.0;
+    if (skip == 0) {
+      if (nd >= 2) s = s + faceAreaDir(g, 1, k, j + 1, i) * B2[S(k, j + 1, i)] - faceAreaDir(g, 1, k, j, i) * B2[S(k, j, i)];
+      if (nd == 3) s = s + faceAreaDir(g, 2, k + 1, j, i) * B3[S(k + 1, j, i)] - faceAreaDir(g, 2, k, j, i) * B3[S(k, j, i)];
+    }
+    return s;
+  };
+  if (dir == 0) {
+    const int j = a, k = b;
+    if (left) {
+      for (int i = g.beg[0] - 1; i >= 0; i--) {
+        B1[S(k, j, i)] = 1.0 / faceAreaDir(g, 0, k, j, i) *
+                         (faceAreaDir(g, 0, k, j, i + 1) * B1[S(k, j, i + 1)] + (div2(k, j, i, 0)));
+      }
+    }
+    if (right) {
+      for (int i = g.end[0]; i < g.nx[0]; i++) {
+        B1[S(k, j, i + 1)] = 1.0 / faceAreaDir(g, 0, k, j, i + 1) *
+                             (faceAreaDir(g, 0, k, j, i) * B1[S(k, j, i)] - (div2(k, j, i, 0)));
+      }
+    }
+  } else if (dir == 1) {
+    const int i = a, k = b;
+    if (left) {
+      for (int j = g.beg[1] - 1; j >= 0; j--) {
+        double s = faceAreaDir(g, 0, k, j, i + 1) * B1[S(k, j, i + 1)] - faceAreaDir(g, 0, k, j, i) * B1[S(k, j, i)];
+        if (nd == 3)
+          s = s + signLeft * (faceAreaDir(g, 2, k + 1, j, i) * B3[S(k + 1, j, i)] -
+                              faceAreaDir(g, 2, k, j, i) * B3[S(k, j, i)]);
+        B2[S(k, j, i)] = 1.0 / faceAreaDir(g, 1, k, j, i) * (faceAreaDir(g, 1, k, j + 1, i) * B2[S(k, j + 1, i)] + (s));
+      }
+    }
+    if (right) {
+      for (int j = g.end[1]; j < g.nx[1]; j++) {
+        double s = faceAreaDir(g, 0, k, j, i + 1) * B1[S(k, j, i + 1)] - faceAreaDir(g, 0, k, j, i) * B1[S(k, j, i)];
+        if (nd == 3)
+          s = s + signRight * (faceAreaDir(g, 2, k + 1, j, i) * B3[S(k + 1, j, i)] -
+                               faceAreaDir(g, 2, k, j, i) * B3[S(k, j, i)]);
+        B2[S(k, j + 1, i)] =
+            1.0 / faceAreaDir(g, 1, k, j + 1, i) * (faceAreaDir(g, 1, k, j, i) * B2[S(k, j, i)] - (s));
+      }
+    }
+  } else {
+    const int i = a, j = b;
+    if (left) {
+      for (int k = g.beg[2] - 1; k >= 0; k--) {
+        const double s = faceAreaDir(g, 0, k, j, i + 1) * B1[S(k, j, i + 1)] - faceAreaDir(g, 0, k, j, i) * B1[S(k, j, i)] +
+                         faceAreaDir(g, 1, k, j + 1, i) * B2[S(k, j + 1, i)] - faceAreaDir(g, 1, k, j, i) * B2[S(k, j, i)];
+        B3[S(k, j, i)] = 1.0 / faceAreaDir(g, 2, k, j, i) * (faceAreaDir(g, 2, k + 1, j, i) * B3[S(k + 1, j, i)] + (s));
+      }
+    }
+    if (right) {
+      for (int k = g.end[2]; k < g.nx[2]; k++) {
+        const double s = faceAreaDir(g, 0, k, j, i + 1) * B1[S(k, j, i + 1)] - faceAreaDir(g, 0, k, j, i) * B1[S(k, j, i)] +
+                         faceAreaDir(g, 1, k, j + 1, i) * B2[S(k, j + 1, i)] - faceAreaDir(g, 1, k, j, i) * B2[S(k, j, i)];
+        B3[S(k + 1, j, i)] =
+            1.0 / faceAreaDir(g, 2, k + 1, j, i) * (faceAreaDir(g, 2, k, j, i) * B3[S(k, j, i)] - (s));
+      }
+    }
+  }
+}
+
+// ---- halo pack / unpack ----------------------------------------------------------------------
+struct VarList {
+  int n;
+  int v[16];
+};
+
+template <bool PACK>
+__global__ void haloCopyKernel(double *__restrict__ q, long long sj, long long sk, long long sn, VarList vars, Box b,
+                               double *__restrict__ buf) {
+  const int n0 = b.hi[0] - b.lo[0], n1 = b.hi[1] - b.lo[1], n2 = b.hi[2] - b.lo[2];
+  const int ii = blockIdx.x * TBX + threadIdx.x;
+  const int jj = blockIdx.y * TBY + threadIdx.y;
+  const int kk = (int)(blockIdx.z % n2);
+  const int n = (int)(blockIdx.z / n2);
+  if (ii >= n0 || jj >= n1 || n >= vars.n) return;
+  const long long a = vars.v[n] * sn + (long long)(b.lo[2] + kk) * sk + (long long)(b.lo[1] + jj) * sj + (b.lo[0] + ii);
+  const long long p = (((long long)n * n2 + kk) * n1 + jj) * n0 + ii;
+  if (PACK) buf[p] = q[a];
+  else q[a] = buf[p];
+}
+
+inline long long boxCount(const Box &b) {
+  if (emptyBox(b)) return 0;
+  return (long long)(b.hi[0] - b.lo[0]) * (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+}
+
+// variables of Vc that travel: everything except the CT-evolved field components (boundary.hpp:164-186)
+VarList haloVars(const PhysCfg &c) {
+  VarList l;
+  l.n = 0;
+  for (int n = 0; n < c.nvar; n++) {
+    if (c.mhd && n >= c.BX1 && n < c.BX1 + c.ndim) continue;
+    l.v[l.n++] = n;
+  }
+  return l;
+}
+
+// box of cells/faces sent (pack) or received (unpack) in direction dir on `side`
+// comp = -1 for cell-centred data, 0..2 for the staggered component.  mpi.cpp:269-320,469-520,666-716
+Box haloBox(const DevGrid &g, int dir, int side, int comp, bool pack) {
+  Box b;
+  for (int d = 0; d < 3; d++) {
+    if (d == dir) {
+      const int ng = g.ng[d];
+      const int shift = (comp == d) ? 1 : 0;  // the shared face is not exchanged
+      if (pack) {
+        if (side == 0) { b.lo[d] = ng + shift; b.hi[d] = 2 * ng + shift; }
+        else           { b.lo[d] = g.end[d] - ng; b.hi[d] = g.end[d]; }
+      } else {
+        if (side == 0) { b.lo[d] = 0; b.hi[d] = ng; }
+        else           { b.lo[d] = g.end[d] + shift; b.hi[d] = g.end[d] + ng + shift; }
+      }
+    } else if (d < dir) {
+      // directions already exchanged: whole extent, ghosts included (corners ride along)
+      b.lo[d] = 0;
+      b.hi[d] = g.nx[d] + ((comp == d) ? 1 : 0);
+    } else {
+      b.lo[d] = g.beg[d];
+      b.hi[d] = g.end[d] + ((comp == d && d < g.ndim) ? 1 : 0);
+    }
+  }
+  return b;
+}
+
+template <bool PACK>
+int haloTransfer(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side, double *buf,
+                 cudaStream_t st, long long *launches) {
+  const dim3 block(TBX, TBY, 1);
+  long long offset = 0;
+  {
+    const VarList vars = haloVars(c);
+    const Box b = haloBox(g, dir, side, -1, PACK);
+    if (!emptyBox(b) && vars.n > 0) {
+      haloCopyKernel<PACK><<<boxGrid(b, vars.n), block, 0, st>>>(Vc, g.sj, g.sk, g.sn, vars, b, buf + offset);
+      (*launches)++;
+      offset += boxCount(b) * vars.n;
+    }
+  }
+  if (c.mhd) {
+    for (int comp = 0; comp < g.ndim; comp++) {
+      VarList one;
+      one.n = 1;
+      one.v[0] = comp;
+      const Box b = haloBox(g, dir, side, comp, PACK);
+      if (emptyBox(b)) continue;
+      haloCopyKernel<PACK><<<boxGrid(b, 1), block, 0, st>>>(Vs, g.vsj, g.vsk, g.vsn, one, b, buf + offset);
+      (*launches)++;
+      offset += boxCount(b);
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+long long idfxk::haloBufferSize(const PhysCfg &c, const DevGrid &g, int dir) {
+  long long n = boxCount(haloBox(g, dir, 0, -1, true)) * haloVars(c).n;
+  if (c.mhd)
+    for (int comp = 0; comp < g.ndim; comp++) n += boxCount(haloBox(g, dir, 0, comp, true));
+  return n;
+}
+
+int idfxk::haloPack(const PhysCfg &c, const DevGrid &g, const double *Vc, const double *Vs, int dir, int side,
+                    double *buf, cudaStream_t st, long long *launches) {
+  return haloTransfer<true>(c, g, const_cast<double *>(Vc), const_cast<double *>(Vs), dir, side, buf, st, launches);
+}
+int idfxk::haloUnpack(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side,
+                      const double *buf, cudaStream_t st, long long *launches) {
+  return haloTransfer<false>(c, g, Vc, Vs, dir, side, const_cast<double *>(buf), st, launches);
+}
+
+// Boundary::EnforcePeriodic / EnforceReflective / EnforceOutflow for one side
+int idfxk::enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side,
+                                   int type, cudaStream_t st, long long *launches) {
+  const dim3 block(TBX, TBY, 1);
+  const int nint = g.end[dir] - g.beg[dir];
+  const int ng = g.ng[dir];
+  {
+    // cell-centred variables (BoundaryForAll)
+    const Box b = ghostSlab(g, dir, side, -1);
+    int signMask = 0;
+    if (type == BC_REFLECTIVE) {
+      // normal velocity and tangential field components change sign (boundary.hpp:697)
+      for (int n = 0; n < c.nvar; n++) {
+        const bool flip = (n == c.MX1 + dir) || (c.mhd && n >= c.BX1 && n < c.BX1 + c.ncomp && n != c.BX1 + dir);
+        if (flip) signMask |= (1 << n);
+      }
+    }
+    ghostFillKernel<<<boxGrid(b, c.nvar), block, 0, st>>>(Vc, g.sj, g.sk, b, c.nvar, g.sn, dir, side, type, ng, nint,
+                                                          signMask, c.MX1 + dir);
+    (*launches)++;
+  }
+  if (c.mhd) {
+    for (int comp = 0; comp < g.ndim; comp++) {
+      // reflective / outflow leave the normal component to ReconstructNormalField (boundary.hpp:702-736)
+      if (type != BC_PERIODIC && comp == dir) continue;
+      const Box b = ghostSlab(g, dir, side, comp);
+      const int signMask = (type == BC_REFLECTIVE) ? 1 : 0;
+      ghostFillKernel<<<boxGrid(b, 1), block, 0, st>>>(Vs + comp * g.vsn, g.vsj, g.vsk, b, 1, 0, dir, side, type, ng,
+                                                       nint, signMask, -1);
+      (*launches)++;
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+int idfxk::reconstructNormalField(const PhysCfg &c, const DevGrid &g, double *Vs, int dir, int left, int right,
+                                  cudaStream_t st, long long *launches) {
+  if (!c.mhd || (!left && !right)) return 0;
+  const int p0 = (dir == 0) ? 1 : 0;
+  const int p1 = (dir == 2) ? 1 : 2;
+  const dim3 block(32, 4, 1);
+  const dim3 grid((g.nx[p0] + 31) / 32, (g.nx[p1] + 3) / 4, 1);
+  reconstructNormalKernel<<<grid, block, 0, st>>>(g, Vs, dir, left, right, 1, 1);
+  (*launches)++;
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,76 @@
+// kernels.h -- host-callable launchers of the CUDA kernels (internal interface
+// between block.cu, which implements the C ABI, and the kernel translation units).
+#ifndef IDFX_KERNELS_H_
+#define IDFX_KERNELS_H_
+
+#include "common.cuh"
+
+// Run-time image of the compile-time configuration of the reference
+struct PhysCfg {
+  int ndim, ncomp, mhd, iso;
+  int nvar;
+  int order, solver, emf;
+  // variable indices (255.. when absent)
+  int RHO, MX1, MX2, MX3, ENG, BX1, BX2, BX3;
+};
+
+namespace idfxk {
+
+// ---- sweeps (sweep_*.cu) ----------------------------------------------------
+// returns cudaError_t as int; -1 when the (physics, solver, order) combination is not instantiated
+int sweepHD(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepMhdTvdlf(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepMhdHll(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepMhdHlld(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepMhdHlldIso(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepMhdRoe(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepMhdRoeIso(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+
+// ---- constrained transport (ct.cu) ------------------------------------------
+int calcCornerEmf(const DevGrid &g, const DevEmf &e, const double *Vc, const double *Vs, int emfMode, int order,
+                  int ncomp, int vx1, int bx1, cudaStream_t st, long long *launches);
+// mode 0: Vs += rhs (reference behaviour); 1: additionally save the old Vs into Vs0 (first stage of the
+// fused path); 2: Vs <- wc*(Vs+rhs) + w0*Vs0 (later stages of the fused path)
+int evolveMagField(const DevGrid &g, const DevEmf &e, double *Vs, double *Vs0, const double *dt, int haveAxis,
+                   int mode, double wc, double w0, cudaStream_t st, long long *launches);
+
+// ---- point-wise kernels (pointwise.cu) ---------------------------------------
+struct Eos2 { double gamma, csiso; };
+int primToCons(const PhysCfg &c, const DevGrid &g, const double *Vc, double *Uc, double gamma, cudaStream_t st);
+int consToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, double gamma, cudaStream_t st);
+// cell-centred field from the staggered one over the whole block (boundary.hpp:389-404)
+int reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st);
+int fill(double *p, long long n, double value, cudaStream_t st);
+int copy(double *dst, const double *src, long long n, cudaStream_t st);
+// dst = wl*dst + wr*src (stateContainer.cpp:91-98)
+int addAndStore(double *dst, const double *src, long long n, double wl, double wr, cudaStream_t st);
+// fused stage epilogue over the interior: RK combine of Uc, Uc(B) <- Vs, Vc <- C2P(Uc)
+int stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs, const double *Uc0,
+                  double gamma, int combine, double wc, double w0, int keepUc, cudaStream_t st);
+
+// ---- boundaries (boundary.cu) -------------------------------------------------
+int enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side, int type,
+                            cudaStream_t st, long long *launches);
+int reconstructNormalField(const PhysCfg &c, const DevGrid &g, double *Vs, int dir, int left, int right,
+                           cudaStream_t st, long long *launches);
+// halo pack / unpack (mpi.hpp:49-172, mpi.cpp:79-134)
+long long haloBufferSize(const PhysCfg &c, const DevGrid &g, int dir);
+int haloPack(const PhysCfg &c, const DevGrid &g, const double *Vc, const double *Vs, int dir, int side, double *buf,
+             cudaStream_t st, long long *launches);
+int haloUnpack(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side, const double *buf,
+               cudaStream_t st, long long *launches);
+
+// ---- reductions (reduce.cu) ----------------------------------------------------
+// min over the interior of 1/InvDt, written as ordered bits to *outBits (must be preset to +inf bits)
+int timestepReduce(const DevGrid &g, const double *invDt, unsigned long long *outBits, cudaStream_t st);
+// device-side dt control (timeIntegrator.cpp:313-323,380-408); state: [0]=t [1]=dt [2]=t0 [3]=tstop
+int dtControlBegin(double *state, unsigned long long *dtMinBits, cudaStream_t st);
+int dtControlEnd(double *state, unsigned long long *dtMinBits, double cfl, double cflMaxVar, double fixedDt,
+                 long long *ncycles, int *status, cudaStream_t st);
+int stageTimeAdvance(double *state, int stage, double wc, double w0, cudaStream_t st);
+int checkDivB(const PhysCfg &c, const DevGrid &g, const double *Vs, unsigned long long *outBits, cudaStream_t st);
+int checkNan(const PhysCfg &c, const DevGrid &g, const double *Vc, const double *Vs, int *count, cudaStream_t st);
+
+}  // namespace idfxk
+
+#endif  // IDFX_KERNELS_H_

@@ -1,0 +1,183 @@
+// pointwise.cu -- per-cell kernels: conservative<->primitive conversion, cell-centred
+// field reconstruction, Runge-Kutta state combination, and their fused stage
+// prologue / epilogue forms.
+//
+// Reference: src/fluid/convertConsToPrim.hpp:106-189 (array loops),
+// src/fluid/boundary/boundary.hpp:389-404 (ReconstructVcField),
+// src/dataBlock/stateContainer.cpp:19-37,75-104 (CopyFrom / AddAndStore),
+// src/fluid/enroll.hpp:116-129 (ResetStage).
+#include "kernels.h"
+#include "phys.cuh"
+
+namespace {
+
+constexpr int TB = 256;
+
+inline int blocksFor(long long n) { return (int)((n + TB - 1) / TB); }
+
+// run F<P>::run(args...) for the Phys matching c
+#define PHYS_CASE(ND, NC, MHDF, ISOF, CALL)                                                  \
+  if (c.ndim == ND && c.ncomp == NC && (c.mhd != 0) == MHDF && (c.iso != 0) == ISOF) {       \
+    using P = Phys<ND, NC, MHDF, ISOF>;                                                      \
+    CALL;                                                                                    \
+    return (int)cudaGetLastError();                                                          \
+  }
+#define PHYS_DISPATCH(CALL)                \
+  PHYS_CASE(1, 1, false, false, CALL)      \
+  PHYS_CASE(1, 3, false, false, CALL)      \
+  PHYS_CASE(2, 2, false, false, CALL)      \
+  PHYS_CASE(2, 3, false, false, CALL)      \
+  PHYS_CASE(3, 3, false, false, CALL)      \
+  PHYS_CASE(1, 1, false, true, CALL)       \
+  PHYS_CASE(1, 3, false, true, CALL)       \
+  PHYS_CASE(2, 2, false, true, CALL)       \
+  PHYS_CASE(2, 3, false, true, CALL)       \
+  PHYS_CASE(3, 3, false, true, CALL)       \
+  PHYS_CASE(1, 3, true, false, CALL)       \
+  PHYS_CASE(2, 2, true, false, CALL)       \
+  PHYS_CASE(2, 3, true, false, CALL)       \
+  PHYS_CASE(3, 3, true, false, CALL)       \
+  PHYS_CASE(1, 3, true, true, CALL)        \
+  PHYS_CASE(2, 2, true, true, CALL)        \
+  PHYS_CASE(2, 3, true, true, CALL)        \
+  PHYS_CASE(3, 3, true, true, CALL)        \
+  return -1;
+
+template <class P>
+__global__ void primToConsKernel(DevGrid g, const double *__restrict__ Vc, double *__restrict__ Uc, Eos eos,
+                                 long long n) {
+  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
+  if (c >= n) return;
+  double v[P::nvar], u[P::nvar];
+#pragma unroll
+  for (int nv = 0; nv < P::nvar; nv++) v[nv] = Vc[nv * g.sn + c];
+  primToCons<P>(u, v, eos);
+#pragma unroll
+  for (int nv = 0; nv < P::nvar; nv++) Uc[nv * g.sn + c] = u[nv];
+}
+
+template <class P>
+__global__ void consToPrimKernel(DevGrid g, double *__restrict__ Vc, double *__restrict__ Uc, Eos eos, long long n) {
+  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
+  if (c >= n) return;
+  double v[P::nvar], u[P::nvar];
+#pragma unroll
+  for (int nv = 0; nv < P::nvar; nv++) u[nv] = Uc[nv * g.sn + c];
+  const bool fixed = consToPrim<P>(v, u, eos);
+#pragma unroll
+  for (int nv = 0; nv < P::nvar; nv++) Vc[nv * g.sn + c] = v[nv];
+  if constexpr (P::energy) {
+    if (fixed) Uc[P::ENG * g.sn + c] = u[P::ENG];
+  }
+}
+
+// V(BXn) = 0.5*(Vs(n,.) + Vs(n,.+1)) for the CT components, over the whole block
+__global__ void reconstructVcFieldKernel(DevGrid g, const double *__restrict__ Vs, double *__restrict__ V, int bx1,
+                                         long long n) {
+  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
+  if (c >= n) return;
+  const int i = (int)(c % g.nx[0]);
+  const int j = (int)((c / g.nx[0]) % g.nx[1]);
+  const int k = (int)(c / ((long long)g.nx[0] * g.nx[1]));
+  const long long s = sidx(g, k, j, i);
+  V[(bx1 + 0) * g.sn + c] = 0.5 * (Vs[s] + Vs[s + 1]);
+  if (g.ndim >= 2) V[(bx1 + 1) * g.sn + c] = 0.5 * (Vs[g.vsn + s] + Vs[g.vsn + s + g.vsj]);
+  if (g.ndim == 3) V[(bx1 + 2) * g.sn + c] = 0.5 * (Vs[2 * g.vsn + s] + Vs[2 * g.vsn + s + g.vsk]);
+}
+
+__global__ void fillKernel(double *p, long long n, double v) {
+  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
+  if (c < n) p[c] = v;
+}
+__global__ void copyKernel(double *__restrict__ d, const double *__restrict__ s, long long n) {
+  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
+  if (c < n) d[c] = s[c];
+}
+__global__ void addAndStoreKernel(double *__restrict__ d, const double *__restrict__ s, long long n, double wl,
+                                  double wr) {
+  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
+  if (c < n) d[c] = wl * d[c] + wr * s[c];
+}
+
+// ---- fused stage epilogue -----------------------------------------------------------------
+// One pass over the INTERIOR cells (the fused path is only used when every ghost cell is
+// refilled by the next SetBoundaries, i.e. no user-defined boundary):
+//   stages >= 1: u <- wc*Uc + w0*Uc0                                  (StateContainer::AddAndStore)
+//   u(B_ct) <- face average of Vs (already combined by evolveMagField)  (ReconstructVcField(Uc))
+//   Vc <- ConsToPrim(u)                                                 (Fluid::ConvertConsToPrim)
+// Uc is written back only when keepUc is set (it is rebuilt from Vc by the next stage anyway).
+template <class P>
+__global__ void stageEpilogueKernel(DevGrid g, double *__restrict__ Vc, double *__restrict__ Uc,
+                                    const double *__restrict__ Vs, const double *__restrict__ Uc0, Eos eos,
+                                    int combine, double wc, double w0, int keepUc) {
+  const int ni = g.end[0] - g.beg[0], nj = g.end[1] - g.beg[1], nk = g.end[2] - g.beg[2];
+  const long long t = (long long)blockIdx.x * TB + threadIdx.x;
+  if (t >= (long long)ni * nj * nk) return;
+  const int i = g.beg[0] + (int)(t % ni);
+  const int j = g.beg[1] + (int)((t / ni) % nj);
+  const int k = g.beg[2] + (int)(t / ((long long)ni * nj));
+  const long long c = cidx(g, k, j, i);
+  double u[P::nvar], v[P::nvar];
+  if constexpr (P::mhd) {
+    const long long s = sidx(g, k, j, i);
+    u[P::BX1] = 0.5 * (Vs[s] + Vs[s + 1]);
+    if constexpr (P::ndim >= 2) u[P::BX2] = 0.5 * (Vs[g.vsn + s] + Vs[g.vsn + s + g.vsj]);
+    if constexpr (P::ndim == 3) u[P::BX3] = 0.5 * (Vs[2 * g.vsn + s] + Vs[2 * g.vsn + s + g.vsk]);
+  }
+#pragma unroll
+  for (int nv = 0; nv < P::nvar; nv++) {
+    if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
+    double x = Uc[nv * g.sn + c];
+    if (combine) x = wc * x + w0 * Uc0[nv * g.sn + c];
+    u[nv] = x;
+  }
+  consToPrim<P>(v, u, eos);
+#pragma unroll
+  for (int nv = 0; nv < P::nvar; nv++) {
+    Vc[nv * g.sn + c] = v[nv];
+    if (keepUc) Uc[nv * g.sn + c] = u[nv];
+  }
+}
+
+}  // namespace
+
+int idfxk::primToCons(const PhysCfg &c, const DevGrid &g, const double *Vc, double *Uc, double gamma,
+                      cudaStream_t st) {
+  const long long n = g.sn;
+  const Eos eos{gamma, 0.0};
+  PHYS_DISPATCH((primToConsKernel<P><<<blocksFor(n), TB, 0, st>>>(g, Vc, Uc, eos, n)))
+}
+
+int idfxk::consToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, double gamma, cudaStream_t st) {
+  const long long n = g.sn;
+  const Eos eos{gamma, 0.0};
+  PHYS_DISPATCH((consToPrimKernel<P><<<blocksFor(n), TB, 0, st>>>(g, Vc, Uc, eos, n)))
+}
+
+int idfxk::reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st) {
+  const long long n = g.sn;
+  reconstructVcFieldKernel<<<blocksFor(n), TB, 0, st>>>(g, Vs, V, c.BX1, n);
+  return (int)cudaGetLastError();
+}
+
+int idfxk::fill(double *p, long long n, double value, cudaStream_t st) {
+  fillKernel<<<blocksFor(n), TB, 0, st>>>(p, n, value);
+  return (int)cudaGetLastError();
+}
+int idfxk::copy(double *dst, const double *src, long long n, cudaStream_t st) {
+  copyKernel<<<blocksFor(n), TB, 0, st>>>(dst, src, n);
+  return (int)cudaGetLastError();
+}
+int idfxk::addAndStore(double *dst, const double *src, long long n, double wl, double wr, cudaStream_t st) {
+  addAndStoreKernel<<<blocksFor(n), TB, 0, st>>>(dst, src, n, wl, wr);
+  return (int)cudaGetLastError();
+}
+
+int idfxk::stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs,
+                         const double *Uc0, double gamma, int combine, double wc, double w0, int keepUc,
+                         cudaStream_t st) {
+  const long long n = (long long)(g.end[0] - g.beg[0]) * (g.end[1] - g.beg[1]) * (g.end[2] - g.beg[2]);
+  const Eos eos{gamma, 0.0};
+  PHYS_DISPATCH((stageEpilogueKernel<P><<<blocksFor(n), TB, 0, st>>>(g, Vc, Uc, Vs, Uc0, eos, combine, wc, w0,
+                                                                      keepUc)))
+}

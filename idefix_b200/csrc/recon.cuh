@@ -1,0 +1,203 @@
+// recon.cuh -- slope limiters and face reconstruction (one variable at a time).
+//
+// Reference: src/fluid/RiemannSolver/slopeLimiter.hpp:16-191 and
+// src/fluid/RiemannSolver/extrapolateToFaces.hpp:75-309.
+// Interface i-1/2 separates cell i-1 (left state vL) from cell i (right state vR).
+// `q` points at cell i of the variable, `s` is the element stride along the sweep.
+#ifndef IDFX_RECON_CUH_
+#define IDFX_RECON_CUH_
+
+#include "common.cuh"
+
+namespace lim {
+
+// slopeLimiter.hpp:16-23 -- the reference's MinMod shadows its result and therefore
+// always returns zero; reproduced on purpose.
+IDFX_HD double minmodRef(double, double) { return 0.0; }
+
+// slopeLimiter.hpp:54-57
+IDFX_HD double vanLeer(double dvp, double dvm) {
+  return (dvp * dvm > 0.0 ? 2.0 * dvp * dvm / (dvp + dvm) : 0.0);
+}
+// slopeLimiter.hpp:60-65 (non-uniform spacing)
+IDFX_HD double vanLeer(double dvp, double dvm, double cp, double cm) {
+  return (dvp * dvm > 0.0
+              ? dvp * dvm * (cp * dvm + cm * dvp) / (dvp * dvp + dvm * dvm + (cp + cm - 2.0) * dvp * dvm)
+              : 0.0);
+}
+// slopeLimiter.hpp:67-75
+IDFX_HD double mc(double dvp, double dvm) {
+  double dq = 0.0;
+  if (dvp * dvm > 0.0) {
+    double dqc = 0.5 * (dvp + dvm);
+    double d2q = 2.0 * (fabs(dvp) < fabs(dvm) ? dvp : dvm);
+    dq = fabs(d2q) < fabs(dqc) ? d2q : dqc;
+  }
+  return dq;
+}
+// slopeLimiter.hpp:25-52
+IDFX_HD double limO3(double dvp, double dvm, double dx) {
+  const double r = 0.1;
+  const double eps = 1.e-12;
+  double th = dvm / (dvp + 1.e-16);
+  double q = (2.0 + th) / 3.0;
+  double a = fmin(1.5, 2.0 * th);
+  a = fmin(q, a);
+  double b = fmax(-0.5 * th, a);
+  double c = fmin(q, b);
+  double psi = fmax(0.0, c);
+  double eta = r * dx;
+  eta = (dvm * dvm + dvp * dvp) / (eta * eta);
+  double l;
+  if (eta <= 1.0 - eps) {
+    l = q;
+  } else if (eta >= 1.0 + eps) {
+    l = psi;
+  } else {
+    psi = (1.0 - (eta - 1.0) / eps) * q + (1.0 + (eta - 1.0) / eps) * psi;
+    l = 0.5 * psi;
+  }
+  return l;
+}
+
+IDFX_HD int sgn(double v) { return (0.0 < v) - (v < 0.0); }
+
+// slopeLimiter.hpp:121-140
+IDFX_HD void ppmLimitFace(double vm1, double v0, double vp1, double vp2, double &vph) {
+  if ((vp1 - vph) * (vph - v0) < 0.0) {
+    const double deltaL = (vm1 - 2 * v0 + vp1);
+    const double deltaC = 3 * (v0 - 2 * vph + vp1);
+    const double deltaR = (v0 - 2 * vp1 + vp2);
+    double delta = 0.0;
+    if (sgn(deltaL) == sgn(deltaC) && sgn(deltaR) == sgn(deltaC)) {
+      const double C = 1.25;
+      delta = C * fmin(fabs(deltaL), fabs(deltaR));
+      delta = sgn(deltaC) * fmin(delta, fabs(deltaC));
+    }
+    vph = 0.5 * (v0 + vp1) - delta / 6.0;
+  }
+}
+
+// slopeLimiter.hpp:142-190: limited parabola in cell "0"; vl / vr are its left / right face values
+IDFX_HD void ppmStates(double vm2, double vm1, double v0, double vp1, double vp2, double &vl, double &vr) {
+  const int n = 2;
+  vr = 7.0 / 12.0 * (v0 + vp1) - 1.0 / 12.0 * (vm1 + vp2);
+  vl = 7.0 / 12.0 * (vm1 + v0) - 1.0 / 12.0 * (vm2 + vp1);
+  ppmLimitFace(vm2, vm1, v0, vp1, vl);
+  ppmLimitFace(vm1, v0, vp1, vp2, vr);
+
+  double d2qf = 6.0 * (vl + vr - 2.0 * v0);
+  double d2qc0 = vm1 + vp1 - 2.0 * v0;
+  double d2qcp1 = v0 + vp2 - 2.0 * vp1;
+  double d2qcm1 = vm2 + v0 - 2.0 * vm1;
+  double d2q = 0.0;
+  if (sgn(d2qf) == sgn(d2qc0) && sgn(d2qf) == sgn(d2qcp1) && sgn(d2qf) == sgn(d2qcm1)) {
+    const double C = 1.25;
+    d2q = fmin(fabs(d2qc0), fabs(d2qcp1));
+    d2q = C * fmin(fabs(d2qcm1), d2q);
+    d2q = sgn(d2qf) * fmin(fabs(d2qf), d2q);
+  }
+  double qmax = fmax(fmax(fabs(vm1), fabs(v0)), fabs(vp1));
+  double rho = 0.0;
+  if (fabs(d2qf) > 1e-12 * qmax) rho = d2q / d2qf;
+
+  if (((vr - v0) * (v0 - vl) <= 0) || (vm1 - v0) * (v0 - vp1) <= 0) {
+    if (rho <= (1.0 - 1e-12)) {
+      vl = v0 - rho * (v0 - vl);
+      vr = v0 + rho * (vr - v0);
+    }
+  } else {
+    if (fabs(vr - v0) >= n * fabs(v0 - vl)) vr = v0 + n * (v0 - vl);
+    if (fabs(vl - v0) >= n * fabs(v0 - vr)) vl = v0 + n * (v0 - vr);
+  }
+}
+}  // namespace lim
+
+// Irregular-grid PLM weights of one direction, already offset to the face index
+struct PlmWeights {
+  const double *wp, *wm, *cp, *cm, *dp, *dm;
+};
+
+// positive = variable for which the face value must stay positive (RHO, PRS)
+template <int ORDER>
+IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool positive, bool regular,
+                           const PlmWeights &w, const double *__restrict__ dx, int index,
+                           double &vL, double &vR) {
+  if constexpr (ORDER == 1) {
+    vL = q[-s];
+    vR = q[0];
+  } else if constexpr (ORDER == 2) {
+    const double qm2 = q[-2 * s], qm1 = q[-s], q0 = q[0], qp1 = q[s];
+    if (regular) {
+      // extrapolateToFaces.hpp:89-124
+      double dvm = qm1 - qm2;
+      double dvp = q0 - qm1;
+      double dv = lim::vanLeer(dvp, dvm);
+      vL = qm1 + 0.5 * dv;
+      dvm = dvp;
+      dvp = qp1 - q0;
+      dv = lim::vanLeer(dvp, dvm);
+      vR = q0 - 0.5 * dv;
+    } else {
+      // extrapolateToFaces.hpp:125-171
+      double dvm = qm1 - qm2;
+      double dvp = q0 - qm1;
+      dvm *= w.wm[index - 1];
+      dvp *= w.wp[index - 1];
+      double dv = lim::vanLeer(dvp, dvm, w.cp[index - 1], w.cm[index - 1]);
+      vL = qm1 + w.dp[index - 1] * dv;
+      dvm = q0 - qm1;
+      dvp = qp1 - q0;
+      dvm *= w.wm[index];
+      dvp *= w.wp[index];
+      dv = lim::vanLeer(dvp, dvm, w.cp[index], w.cm[index]);
+      vR = q0 - w.dm[index] * dv;
+    }
+  } else if constexpr (ORDER == 3) {
+    // extrapolateToFaces.hpp:173-246
+    const double qm2 = q[-2 * s], qm1 = q[-s], q0 = q[0], qp1 = q[s];
+    double dvm = qm1 - qm2;
+    double dvp = q0 - qm1;
+    double dv = dvp * lim::limO3(dvp, dvm, dx[index - 1]);
+    vL = qm1 + 0.5 * dv;
+    if (positive && vL <= 0.0) {
+      dv = lim::minmodRef(dvp, dvm);
+      vL = qm1 + 0.5 * dv;
+    }
+    dvm = dvp;
+    dvp = qp1 - q0;
+    dv = dvm * lim::limO3(dvm, dvp, dx[index]);
+    vR = q0 - 0.5 * dv;
+    if (positive && vR <= 0.0) {
+      dv = lim::minmodRef(dvp, dvm);
+      vR = q0 - 0.5 * dv;
+    }
+  } else {
+    // extrapolateToFaces.hpp:247-307
+    double vm2 = q[-3 * s];
+    double vm1 = q[-2 * s];
+    double v0 = q[-s];
+    double vp1 = q[0];
+    double vp2 = q[s];
+    double vl, vr;
+    lim::ppmStates(vm2, vm1, v0, vp1, vp2, vl, vr);
+    if (positive && vr <= 0.0) {
+      double dv = lim::vanLeer(vp1 - v0, v0 - vm1);
+      vr = v0 + 0.5 * dv;
+    }
+    vL = vr;
+    vm2 = vm1;
+    vm1 = v0;
+    v0 = vp1;
+    vp1 = vp2;
+    vp2 = q[2 * s];
+    lim::ppmStates(vm2, vm1, v0, vp1, vp2, vl, vr);
+    if (positive && vl <= 0.0) {
+      double dv = lim::vanLeer(vp1 - v0, v0 - vm1);
+      vl = v0 - 0.5 * dv;
+    }
+    vR = vl;
+  }
+}
+
+#endif  // IDFX_RECON_CUH_

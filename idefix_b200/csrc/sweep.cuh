@@ -1,0 +1,351 @@
+// sweep.cuh -- one directional sweep of the Godunov update as a single kernel.
+//
+// It fuses what the reference runs as three kernels per direction with two
+// DRAM round trips of the 8-variable flux array:
+//   K8  CalcRiemannFlux  (e.g. hlldMHD.hpp:147)   reconstruct + Riemann solver + EMF storage
+//   K9  Correct Flux     (calcRightHandSide.hpp:16-196)
+//   K10 CalcRightHandSide(calcRightHandSide.hpp:201-551)  flux divergence, InvDt, Uc update
+// (+ K11 AddSourceTerms, addSourceTerms.hpp:16-195, after the last direction).
+//
+// Work decomposition: a CTA owns a BX x BY tile of interfaces.  Each thread
+// reconstructs and solves ONE interface, publishes the area-weighted flux and the
+// signal speed in shared memory, and after one barrier updates the cell to the right
+// of its interface with the flux difference.  Tiles overlap by one interface along the
+// sweep direction, so the flux array never exists in HBM.  Threads run along i (unit
+// stride) in every direction, which keeps all global accesses coalesced.
+#ifndef IDFX_SWEEP_CUH_
+#define IDFX_SWEEP_CUH_
+
+#include "common.cuh"
+#include "phys.cuh"
+#include "recon.cuh"
+#include "riemann_hd.cuh"
+#include "riemann_mhd.cuh"
+#include "riemann_roe.cuh"
+#include "emf_store.cuh"
+
+template <class P, int SOLVER, int DIR>
+IDFX_D void riemannDispatch(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+  if constexpr (P::mhd) {
+    if constexpr (SOLVER == SOLVER_TVDLF) riemannTvdlfMHD<P, DIR>(vL, vR, eos, F, aux);
+    if constexpr (SOLVER == SOLVER_HLL) riemannHllMHD<P, DIR>(vL, vR, eos, F, aux);
+    if constexpr (SOLVER == SOLVER_HLLD) riemannHlldMHD<P, DIR>(vL, vR, eos, F, aux);
+    if constexpr (SOLVER == SOLVER_ROE) riemannRoeMHD<P, DIR>(vL, vR, eos, F, aux);
+  } else {
+    if constexpr (SOLVER == SOLVER_TVDLF) riemannTvdlfHD<P, DIR>(vL, vR, eos, F, aux);
+    if constexpr (SOLVER == SOLVER_HLL) riemannHllHD<P, DIR>(vL, vR, eos, F, aux);
+    if constexpr (SOLVER == SOLVER_HLLC) riemannHllcHD<P, DIR>(vL, vR, eos, F, aux);
+  }
+}
+
+// Index of the azimuthal momentum / field for the curvilinear corrections (idefix.hpp:129-187)
+template <class P>
+struct CurvIdx {
+  // returns -1 when the component does not exist
+  static IDFX_HD int mphi(int geo) {
+    if (geo == GEO_CYLINDRICAL) return (P::ncomp == 3 ? P::MX3 : -1);
+    if (geo == GEO_POLAR) return (P::ncomp >= 2 ? P::MX2 : -1);
+    if (geo == GEO_SPHERICAL) return (P::ncomp == 3 ? P::MX3 : -1);
+    return -1;
+  }
+  static IDFX_HD int bphi(int geo) {
+    if (!P::mhd) return -1;
+    if (geo == GEO_CYLINDRICAL) return (P::ncomp == 3 ? P::BX3 : -1);
+    if (geo == GEO_POLAR) return (P::ncomp >= 2 ? P::BX2 : -1);
+    if (geo == GEO_SPHERICAL) return (P::ncomp == 3 ? P::BX3 : -1);
+    return -1;
+  }
+  static IDFX_HD int bth(int geo) {
+    if (!P::mhd) return -1;
+    if (geo == GEO_SPHERICAL) return (P::ncomp >= 2 ? P::BX2 : -1);
+    return -1;
+  }
+};
+
+// Geometrical source terms of one cell (addSourceTerms.hpp:96-192), rotation/Fargo excluded.
+template <class P>
+IDFX_D void geometricSource(const DevGrid &g, const double *v, const Eos &eos, double dt, int j, int i,
+                            double &s1, double &s2) {
+  s1 = 0.0;
+  s2 = 0.0;
+  const int geo = g.geometry;
+  [[maybe_unused]] double c2iso = eos.csiso * eos.csiso;
+  if (geo == GEO_CYLINDRICAL) {
+    if constexpr (P::ncomp == 3) {
+      double vphi = v[P::MX3];
+      double Sm = v[P::RHO] * vphi * vphi;
+      if constexpr (P::iso) Sm += v[P::RHO] * c2iso;
+      else Sm += v[P::PRS];
+      if constexpr (P::mhd) {
+        Sm -= v[P::BX3] * v[P::BX3];
+        Sm += 0.5 * (v[P::BX1] * v[P::BX1] + v[P::BX2] * v[P::BX2] + v[P::BX3] * v[P::BX3]);
+      }
+      s1 = dt * Sm / g.x[0][i];
+    }
+  } else if (geo == GEO_POLAR) {
+    if constexpr (P::ncomp >= 2) {
+      double vphi = v[P::MX2] + 0.0;
+      double Sm = v[P::RHO] * vphi * vphi;
+      if constexpr (P::iso) Sm += v[P::RHO] * c2iso;
+      else Sm += v[P::PRS];
+      if constexpr (P::mhd) {
+        Sm -= v[P::BX2] * v[P::BX2];
+        double b2 = v[P::BX1] * v[P::BX1];
+        b2 = b2 + v[P::BX2] * v[P::BX2];
+        if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
+        Sm += 0.5 * b2;
+      }
+      s1 = dt * Sm / g.x[0][i];
+    }
+  } else if (geo == GEO_SPHERICAL) {
+    double vphi = 0.0;
+    if constexpr (P::ncomp == 3) vphi = v[P::MX3];
+    vphi = vphi + 0.0;
+    double vv = 0.0;
+    if constexpr (P::ncomp >= 2) vv = vv + v[P::MX2] * v[P::MX2];
+    if constexpr (P::ncomp == 3) vv = vv + vphi * vphi;
+    double Sm = v[P::RHO] * vv;
+    if constexpr (P::iso) Sm += 2.0 * v[P::RHO] * c2iso;
+    else Sm += 2.0 * v[P::PRS];
+    if constexpr (P::mhd) {
+      double hs = 0.0;
+      if constexpr (P::ncomp >= 2) hs = hs + v[P::BX2] * v[P::BX2];
+      if constexpr (P::ncomp == 3) hs = hs + v[P::BX3] * v[P::BX3];
+      Sm -= hs;
+      double b2 = v[P::BX1] * v[P::BX1];
+      if constexpr (P::ncomp >= 2) b2 = b2 + v[P::BX2] * v[P::BX2];
+      if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
+      Sm += b2;
+    }
+    s1 = dt * Sm / g.rt[i];
+    if constexpr (P::ncomp >= 2) {
+      const double ct = 1.0 / g.tanx2[j];
+      double cc = 0.0;
+      cc = cc - v[P::MX2] * v[P::MX1];
+      if constexpr (P::ncomp == 3) cc = cc + ct * vphi * vphi;
+      Sm = v[P::RHO] * cc;
+      if constexpr (P::iso) Sm += ct * c2iso * v[P::RHO];
+      else Sm += ct * v[P::PRS];
+      if constexpr (P::mhd) {
+        double hs = 0.0;
+        hs = hs + v[P::BX2] * v[P::BX1];
+        if constexpr (P::ncomp == 3) hs = hs - ct * v[P::BX3] * v[P::BX3];
+        Sm += hs;
+        double b2 = v[P::BX1] * v[P::BX1];
+        b2 = b2 + v[P::BX2] * v[P::BX2];
+        if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
+        Sm += 0.5 * ct * b2;
+      }
+      s2 = dt * Sm / g.rt[i];
+    }
+  }
+}
+
+template <class P, int SOLVER, int ORDER, int DIR, int BX, int BY>
+__global__ void __launch_bounds__(BX *BY) sweepKernel(const SweepArgs a) {
+  constexpr int NV = P::nvar;
+  using D = Dirs<P, DIR>;
+  __shared__ double sF[NV + 1][BY][BX];
+
+  const DevGrid &g = a.g;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ext = a.perpExt;
+
+  // ---- index mapping -------------------------------------------------------
+  int i, j, k;
+  {
+    const int ilo = (DIR == IDIR) ? g.beg[0] : g.beg[0] - ((P::ndim > 0) ? ext : 0);
+    const int jlo = (DIR == JDIR) ? g.beg[1] : g.beg[1] - ((P::ndim > 1) ? ext : 0);
+    const int klo = (DIR == KDIR) ? g.beg[2] : g.beg[2] - ((P::ndim > 2) ? ext : 0);
+    if constexpr (DIR == IDIR) {
+      i = ilo + blockIdx.x * (BX - 1) + tx;
+      j = jlo + blockIdx.y * BY + ty;
+      k = klo + blockIdx.z;
+    } else if constexpr (DIR == JDIR) {
+      i = ilo + blockIdx.x * BX + tx;
+      j = jlo + blockIdx.y * (BY - 1) + ty;
+      k = klo + blockIdx.z;
+    } else {
+      i = ilo + blockIdx.x * BX + tx;
+      k = klo + blockIdx.y * (BY - 1) + ty;
+      j = jlo + blockIdx.z;
+    }
+  }
+  const int ihi = (DIR == IDIR) ? g.end[0] + 1 : g.end[0] + ((P::ndim > 0) ? ext : 0);
+  const int jhi = (DIR == JDIR) ? g.end[1] + 1 : g.end[1] + ((P::ndim > 1) ? ext : 0);
+  const int khi = (DIR == KDIR) ? g.end[2] + 1 : g.end[2] + ((P::ndim > 2) ? ext : 0);
+  const bool faceValid = (i < ihi) && (j < jhi) && (k < khi);
+
+  const long long cell = cidx(g, k, j, i);
+  const long long stride = (DIR == IDIR) ? 1 : (DIR == JDIR ? g.sj : g.sk);
+  const int idir = (DIR == IDIR) ? i : (DIR == JDIR ? j : k);  // 1-D index along the sweep
+  const Eos eos{a.gamma, a.csiso};
+  const double dt = *a.dt;
+
+  // ---- interface phase -----------------------------------------------------
+  if (faceValid) {
+    double vL[NV], vR[NV];
+    PlmWeights w{g.wp[DIR], g.wm[DIR], g.cp[DIR], g.cm[DIR], g.dp[DIR], g.dm[DIR]};
+    const bool regular = (g.regular != 0);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      if (P::mhd && nv == D::BXn) continue;  // replaced by the face-centred field below
+      const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
+      reconstructVar<ORDER>(a.Vc + nv * g.sn + cell, stride, positive, regular, w, g.dx[DIR], idir, vL[nv], vR[nv]);
+    }
+    if constexpr (P::mhd) {
+      const double bn = a.Vs[DIR * g.vsn + sidx(g, k, j, i)];
+      vL[D::BXn] = bn;
+      vR[D::BXn] = bn;
+    }
+
+    double F[NV];
+    RiemannAux aux;
+    riemannDispatch<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+
+    if constexpr (P::mhd) {
+      const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
+      storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
+    }
+
+    // area weighting and curvilinear factors (calcRightHandSide.hpp:152-195)
+    const double A0 = faceArea<DIR>(g, k, j, i);
+    const int geo = g.geometry;
+    const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      double Ax = A0;
+      if (geo != GEO_CARTESIAN) {
+        if constexpr (DIR == IDIR) {
+          if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
+            if (nv == mphi) Ax *= fabs(g.xl[0][i]);
+            if (nv == bphi) Ax = 1.0;
+          } else if (geo == GEO_SPHERICAL) {
+            if (nv == mphi) Ax *= fabs(g.xl[0][i]);
+            if (nv == bth || nv == bphi) Ax = g.xl[0][i];
+          }
+        } else if constexpr (DIR == JDIR) {
+          if (geo == GEO_SPHERICAL && P::ncomp == 3) {
+            if (nv == mphi) Ax *= fabs(g.sinx2m[j]);
+            if (nv == bphi) Ax = 1.0;
+          }
+        }
+      }
+      sF[nv][ty][tx] = F[nv] * Ax;
+    }
+    sF[NV][ty][tx] = aux.cmax;
+  }
+  __syncthreads();
+
+  // ---- cell phase ------------------------------------------------------------
+  const bool neighbour = (DIR == IDIR) ? (tx < BX - 1) : (ty < BY - 1);
+  const bool cellValid = neighbour && (i >= g.beg[0]) && (i < g.end[0]) && (j >= g.beg[1]) && (j < g.end[1]) &&
+                         (k >= g.beg[2]) && (k < g.end[2]);
+  if (!cellValid) return;
+  const int txr = (DIR == IDIR) ? tx + 1 : tx;
+  const int tyr = (DIR == IDIR) ? ty : ty + 1;
+
+  const double dtdV = dt / cellVolume(g, k, j, i);
+  double rhs[NV];
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (sF[nv][tyr][txr] - sF[nv][ty][tx]);
+
+  const int geo = g.geometry;
+  if (geo != GEO_CARTESIAN) {
+    const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
+    if constexpr (DIR == IDIR) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        if (nv == mphi) rhs[nv] = rhs[nv] / g.x[0][i];
+        if constexpr (P::mhd) {
+          if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
+            if (nv == bphi) rhs[nv] = -dt / g.dx[0][i] * (sF[nv][tyr][txr] - sF[nv][ty][tx]);
+          } else if (geo == GEO_SPHERICAL) {
+            if (nv == bth || nv == bphi) {
+              const double q = dt / (g.x[0][i] * g.dx[0][i]);
+              rhs[nv] = -q * ((sF[nv][tyr][txr] - sF[nv][ty][tx]));
+            }
+          }
+        }
+      }
+    } else if constexpr (DIR == JDIR) {
+      if (geo == GEO_SPHERICAL && P::ncomp == 3) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) {
+          if (nv == mphi) rhs[nv] /= fabs(g.sinx2[j]);
+          if constexpr (P::mhd) {
+            if (nv == bphi) rhs[nv] = -dt / (g.rt[i] * g.dx[1][j]) * (sF[nv][tyr][txr] - sF[nv][ty][tx]);
+          }
+        }
+      }
+    }
+  }
+
+  // time-step control (calcRightHandSide.hpp:426-531)
+  if (a.doInvDt) {
+    double dl = g.dx[DIR][idir];
+    if (geo == GEO_POLAR) {
+      if constexpr (DIR == JDIR) dl = dl * g.x[0][i];
+    } else if (geo == GEO_SPHERICAL) {
+      if constexpr (DIR == JDIR) dl = dl * g.rt[i];
+      if constexpr (DIR == KDIR) dl = dl * g.rt[i] * g.dmu[j] / g.dx[1][j];
+    }
+    // invDtInit: first sweep after ResetStage, the accumulator is known to be zero
+    const double prev = a.invDtInit ? 0.0 : a.invDt[cell];
+    a.invDt[cell] = prev + 0.5 * (sF[NV][tyr][txr] + sF[NV][ty][tx]) / (dl);
+  }
+
+  // conservative update; CT-evolved field components are skipped (calcRightHandSide.hpp:541-549)
+  double s1 = 0.0, s2 = 0.0;
+  double ucell[NV];
+  if (a.doSource || a.fusedP2C) {
+    double v[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) v[nv] = a.Vc[nv * g.sn + cell];
+    if (a.doSource) geometricSource<P>(g, v, eos, dt, j, i, s1, s2);
+    // fused path: the conservative state of the cell is rebuilt from the primitives
+    // (Fluid::ConvertPrimToCons) instead of being read back, and optionally saved as the
+    // "begin" state of the Runge-Kutta cycle (StateContainer::CopyFrom)
+    if (a.fusedP2C) primToCons<P>(ucell, v, eos);
+  }
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
+    double u0 = a.fusedP2C ? ucell[nv] : a.Uc[nv * g.sn + cell];
+    if (a.fusedP2C && a.Uc0 != nullptr) a.Uc0[nv * g.sn + cell] = u0;
+    double u = u0 + rhs[nv];
+    if (a.doSource) {
+      if (nv == P::MX1) u += s1;
+      if (P::ncomp >= 2 && nv == P::MX2) u += s2;
+    }
+    a.Uc[nv * g.sn + cell] = u;
+  }
+}
+
+// ---- host-side launcher ------------------------------------------------------
+template <class P, int SOLVER, int ORDER, int DIR>
+inline cudaError_t launchSweep(const SweepArgs &a, cudaStream_t stream) {
+  constexpr int BX = (DIR == IDIR) ? 64 : 32;
+  constexpr int BY = (DIR == IDIR) ? 4 : 8;
+  const DevGrid &g = a.g;
+  const int ext = a.perpExt;
+  int n[3];
+  for (int d = 0; d < 3; d++) {
+    const int e = (d < P::ndim && d != DIR) ? ext : 0;
+    n[d] = g.end[d] - g.beg[d] + 2 * e + (d == DIR ? 1 : 0);
+  }
+  dim3 block(BX, BY, 1), grid;
+  if (DIR == IDIR) {
+    grid = dim3((n[0] - 1 + BX - 2) / (BX - 1), (n[1] + BY - 1) / BY, n[2]);
+  } else if (DIR == JDIR) {
+    grid = dim3((n[0] + BX - 1) / BX, (n[1] - 1 + BY - 2) / (BY - 1), n[2]);
+  } else {
+    grid = dim3((n[0] + BX - 1) / BX, (n[2] - 1 + BY - 2) / (BY - 1), n[1]);
+  }
+  if (grid.x == 0) grid.x = 1;
+  if (grid.y == 0) grid.y = 1;
+  sweepKernel<P, SOLVER, ORDER, DIR, BX, BY><<<grid, block, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+#endif  // IDFX_SWEEP_CUH_

@@ -1,0 +1,163 @@
+/* idefix_b200.h -- C ABI of the B200-native explicit Godunov (M)HD update.
+ *
+ * One opaque handle (IdfxBlock) per (GPU, sub-domain).  Every entry point
+ * mirrors one call site of the reference's hot loop (cited as file:line under
+ * the reference tree) so that the reference's DataBlock / Fluid /
+ * TimeIntegrator methods can forward to it 1:1.
+ *
+ * Conventions
+ *  - plain C types only; all arrays are FP64; index order (n,k,j,i), i fastest
+ *    (reference layout: src/arrays.hpp:12-19, src/idefix.hpp:20).
+ *  - every function returns 0 on success, non-zero on failure; the message
+ *    is retrievable with idfx_last_error().  No exception crosses the ABI.
+ *  - kernels are enqueued on the block's stream; calls returning host scalars
+ *    synchronise that stream.
+ *  - there is NO CPU fallback: creating a block without a CUDA device fails.
+ */
+#ifndef IDEFIX_B200_H_
+#define IDEFIX_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enumerations (values of the boundary enum follow src/idefix.hpp:220) ---- */
+enum IdfxGeometry { IDFX_CARTESIAN = 1, IDFX_CYLINDRICAL = 2, IDFX_POLAR = 3, IDFX_SPHERICAL = 4 };
+enum IdfxSolver   { IDFX_TVDLF = 0, IDFX_HLL = 1, IDFX_HLLC = 2, IDFX_HLLD = 3, IDFX_ROE = 4 };
+enum IdfxEmf      { IDFX_EMF_ARITHMETIC = 0, IDFX_EMF_UCT0 = 1, IDFX_EMF_UCT_CONTACT = 2,
+                    IDFX_EMF_UCT_HLL = 3, IDFX_EMF_UCT_HLLD = 4 };
+enum IdfxBoundary { IDFX_BC_INTERNAL = 0, IDFX_BC_PERIODIC = 1, IDFX_BC_REFLECTIVE = 2,
+                    IDFX_BC_OUTFLOW = 3, IDFX_BC_SHEARINGBOX = 4, IDFX_BC_AXIS = 5,
+                    IDFX_BC_USERDEF = 6, IDFX_BC_UNDEFINED = 7 };
+
+/* Field identifiers for idfx_field_info / idfx_upload / idfx_download. */
+enum IdfxField {
+  IDFX_FIELD_VC = 0,     /* primitive variables        (nvar, n3, n2, n1)              */
+  IDFX_FIELD_UC = 1,     /* conservative variables     (nvar, n3, n2, n1)              */
+  IDFX_FIELD_VS = 2,     /* staggered field            (ndim, n3+o3, n2+o2, n1+1)      */
+  IDFX_FIELD_INVDT = 3,  /* inverse time-step          (n3, n2, n1)                    */
+  IDFX_FIELD_EX = 4,     /* corner EMFs                (n3, n2, n1)                    */
+  IDFX_FIELD_EY = 5,
+  IDFX_FIELD_EZ = 6,
+  IDFX_FIELD_UC0 = 7,    /* states["begin"] copy of Uc                                  */
+  IDFX_FIELD_VS0 = 8     /* states["begin"] copy of Vs                                  */
+};
+
+/* Compile-time configuration of the reference (definitions.hpp macros and CMake
+ * options, CMakeLists.txt:12-33) expressed as a run-time descriptor. */
+typedef struct IdfxBlockDesc {
+  int ndim;            /* DIMENSIONS 1..3                                               */
+  int ncomp;           /* COMPONENTS 1..3 (>= ndim)                                     */
+  int mhd;             /* Idefix_MHD                                                    */
+  int isothermal;      /* ISOTHERMAL defined (constant cs only)                         */
+  int geometry;        /* enum IdfxGeometry                                             */
+  int order;           /* Idefix_RECONSTRUCTION: 1 constant, 2 PLM, 3 LimO3, 4 PPM      */
+  int solver;          /* [Hydro] solver   (riemannSolver.hpp:100-140)                  */
+  int emf;             /* [Hydro] emf      (constrainedTransport.hpp:157-178)           */
+  int nstages;         /* [TimeIntegrator] nstages 1..3                                 */
+  int np_int[3];       /* interior cells of THIS block                                  */
+  int nghost[3];       /* ghost depth (0 in unused dims; grid.cpp:55-66)                */
+  int lbound[3];       /* enum IdfxBoundary, left side per direction                    */
+  int rbound[3];       /* enum IdfxBoundary, right side per direction                   */
+  int regular_grid;    /* Grid::isRegularCartesian (grid.cpp:49-51, gridHost.cpp:89)    */
+  int device;          /* CUDA device ordinal                                           */
+  double gamma;        /* [Hydro] gamma (eos_adiabatic.hpp:21)                          */
+  double csiso;        /* [Hydro] csiso constant <value>                                */
+  double cfl;          /* [TimeIntegrator] CFL                                          */
+  double cfl_max_var;  /* [TimeIntegrator] CFL_max_var (default 1.1)                    */
+  double first_dt;     /* [TimeIntegrator] first_dt                                     */
+  double fixed_dt;     /* [TimeIntegrator] fixed_dt, <= 0 when absent                   */
+  /* cell coordinates of this block incl. ghosts, HOST pointers, length
+   * np_int[d]+2*nghost[d] (DataBlock::x/xl/xr/dx, dataBlock.cpp:68-84). */
+  const double *x[3];
+  const double *xl[3];
+  const double *xr[3];
+  const double *dx[3];
+} IdfxBlockDesc;
+
+typedef struct IdfxBlock IdfxBlock;
+
+/* ---- life cycle ------------------------------------------------------------ */
+const char *idfx_last_error(void);
+const char *idfx_version(void);
+int idfx_device_count(int *count);
+/* replaces DataBlock::DataBlock + Fluid ctor allocation (dataBlock.cpp:22-160, fluid.hpp:529-577) */
+int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out);
+int idfx_block_destroy(IdfxBlock *blk);
+int idfx_sync(IdfxBlock *blk);
+
+/* ---- field access ----------------------------------------------------------- */
+/* dims[4] receives (n, n3, n2, n1); dev receives the device pointer (may be NULL). */
+int idfx_field_info(IdfxBlock *blk, int field, double **dev, int dims[4]);
+/* DataBlockHost::SyncToDevice / SyncFromDevice (dataBlockHost.cpp:108-190) */
+int idfx_upload(IdfxBlock *blk, int field, const double *host);
+int idfx_download(IdfxBlock *blk, int field, double *host);
+int idfx_set_time(IdfxBlock *blk, double t, double dt);
+int idfx_get_time(IdfxBlock *blk, double *t, double *dt);
+
+/* ---- granular entry points: one per reference call site ---------------------- */
+int idfx_reset_stage(IdfxBlock *blk);                 /* Fluid::ResetStage        enroll.hpp:116-129            */
+int idfx_set_boundaries(IdfxBlock *blk, double t);    /* Boundary::SetBoundaries  boundary.hpp:240-282          */
+int idfx_enforce_boundary_dir(IdfxBlock *blk, double t, int dir);  /* boundary.hpp:287-385 (+ReconstructNormalField) */
+int idfx_reconstruct_vc_field(IdfxBlock *blk, int field);          /* boundary.hpp:389-404; field = VC or UC */
+int idfx_prim_to_cons(IdfxBlock *blk);                /* Fluid::ConvertPrimToCons convertConsToPrim.hpp:153-189 */
+int idfx_cons_to_prim(IdfxBlock *blk);                /* Fluid::ConvertConsToPrim convertConsToPrim.hpp:106-149 */
+int idfx_state_copy(IdfxBlock *blk);                  /* StateContainer::CopyFrom stateContainer.cpp:19-37      */
+int idfx_state_add_and_store(IdfxBlock *blk, double wc, double w0);  /* stateContainer.cpp:75-104              */
+int idfx_evolve_stage(IdfxBlock *blk, double t, double dt);          /* Fluid::EvolveStage evolveStage.hpp:41-90 */
+int idfx_compute_timestep(IdfxBlock *blk, double *dt_min);           /* DataBlock::ComputeTimestep dataBlock.cpp:333-364 */
+int idfx_check_divb(IdfxBlock *blk, double *divb_max);               /* Fluid::CheckDivB checkDivB.hpp:15-68     */
+int idfx_check_nan(IdfxBlock *blk, int *nan_count);                  /* Fluid::CheckNan  checkNan.hpp:15-131     */
+
+/* ---- fused path: TimeIntegrator::Cycle (timeIntegrator.cpp:246-414) ---------- */
+/* Runs ncycles full RK cycles with the dt control logic evaluated on the device
+ * (no host round trip); results are identical to the granular sequence. */
+int idfx_cycles(IdfxBlock *blk, int ncycles);
+/* One cycle, host-synchronous: returns the new t and dt like Cycle() leaves them
+ * in DataBlock::t/dt.  status_flags: bit0 dt<1e-15, bit1 first_dt too large. */
+int idfx_cycle(IdfxBlock *blk, double *t, double *dt, int *status_flags);
+/* Limit dt so that the run ends at tstop (main.cpp:191). Negative disables. */
+int idfx_set_tstop(IdfxBlock *blk, double tstop);
+/* fused = 0 runs the cycle as the reference's own kernel sequence (one kernel per reference
+ * kernel, whole-array point-wise passes); fused = 1 (default unless a boundary is userdef)
+ * folds the point-wise passes into the sweeps.  Both give bit-identical Vc / Vs. */
+int idfx_set_fused(IdfxBlock *blk, int fused);
+int idfx_get_ncycles(IdfxBlock *blk, long long *ncycles);
+/* number of kernels launched by this block since creation (bench "gpu_launches") */
+int idfx_launch_count(IdfxBlock *blk, long long *count);
+
+/* ---- callbacks --------------------------------------------------------------- */
+/* UserDefBoundaryFunc (boundary.hpp:28-35): invoked for sides declared userdef.
+ * side: 0 left, 1 right.  The block's stream is synchronised around the call. */
+typedef void (*IdfxUserBoundaryFn)(IdfxBlock *blk, int dir, int side, double t, void *user);
+int idfx_enroll_userdef_boundary(IdfxBlock *blk, IdfxUserBoundaryFn fn, void *user);
+/* Halo exchange hook, replaces Mpi::ExchangeX1/X2/X3 (mpi.cpp:247,449,646) for
+ * sides declared internal or periodic with more than one block in `dir`.
+ * Called from idfx_set_boundaries / idfx_cycles once per direction. */
+typedef void (*IdfxHaloFn)(IdfxBlock *blk, int dir, void *user);
+int idfx_enroll_halo_exchange(IdfxBlock *blk, IdfxHaloFn fn, void *user);
+
+/* ---- halo exchange building blocks (mpi.cpp:79-134 buffer layout) ------------ */
+/* Number of doubles in the send/recv buffer of direction dir. */
+int idfx_halo_buffer_size(IdfxBlock *blk, int dir, size_t *ndoubles);
+/* Device pointers of the block-owned send/recv buffers; side 0 = left, 1 = right. */
+int idfx_halo_buffers(IdfxBlock *blk, int dir, int side, double **send, double **recv);
+/* Pack the two send buffers of `dir` (Buffer::Pack, mpi.hpp:49-110). */
+int idfx_halo_pack(IdfxBlock *blk, int dir);
+/* Unpack the two recv buffers of `dir` into the ghost zones (mpi.hpp:112-172). */
+int idfx_halo_unpack(IdfxBlock *blk, int dir);
+/* Peer-to-peer variant: bind the neighbour's recv buffer (a device pointer valid in
+ * this process, e.g. from cudaIpcOpenMemHandle) so that idfx_halo_pack writes
+ * straight into it over NVLink. side = side of THIS block that faces the peer. */
+int idfx_halo_bind_peer(IdfxBlock *blk, int dir, int side, double *peer_recv);
+int idfx_halo_ipc_handle(IdfxBlock *blk, int dir, int side, void *handle64);
+int idfx_halo_open_ipc(IdfxBlock *blk, const void *handle64, double **ptr);
+/* tell the block that `dir` has more than one block (nproc[dir] > 1) */
+int idfx_set_nproc(IdfxBlock *blk, const int nproc[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* IDEFIX_B200_H_ */
