@@ -62,11 +62,45 @@ struct IdfxBlock {
   void *userBcData = nullptr;
   IdfxHaloFn haloFn = nullptr;
   void *haloData = nullptr;
+  IdfxReduceFn reduceFn = nullptr;
+  void *reduceData = nullptr;
   double *haloSend[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   double *haloRecv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   double *haloPeer[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   std::vector<std::vector<double>> hostCoords;  // owned copies of the descriptor's coordinate arrays
   double wc[2] = {0, 0}, w0[2] = {0, 0};
+  bool ownStream = true;
+  // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
+  bool timing = false;
+  std::vector<cudaEvent_t> evPool;      // pairs: [2n] start, [2n+1] stop
+  std::vector<int> evCat;               // category of pair n
+  size_t evUsed = 0;
+};
+
+enum { TIME_SWEEP_X1 = 0, TIME_SWEEP_X2 = 1, TIME_SWEEP_X3 = 2, TIME_CT = 3, TIME_EPILOGUE = 4, TIME_BOUNDARY = 5,
+       TIME_NCAT = 6 };
+
+// RAII bracket: records an event pair around the launches issued while it is alive
+struct TimeScope {
+  IdfxBlock *b;
+  size_t slot = (size_t)-1;
+  TimeScope(IdfxBlock *blk, int cat) : b(blk) {
+    if (!b->timing) return;
+    if (b->evUsed * 2 + 2 > b->evPool.size()) {
+      if (b->evPool.size() >= 2 * 16384) return;  // bounded pool: stop sampling, never grow without limit
+      cudaEvent_t e0, e1;
+      if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return;
+      b->evPool.push_back(e0);
+      b->evPool.push_back(e1);
+      b->evCat.push_back(cat);
+    }
+    slot = b->evUsed++;
+    b->evCat[slot] = cat;
+    cudaEventRecord(b->evPool[2 * slot], b->stream);
+  }
+  ~TimeScope() {
+    if (slot != (size_t)-1) cudaEventRecord(b->evPool[2 * slot + 1], b->stream);
+  }
 };
 
 namespace {
@@ -325,6 +359,7 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
 
 int launchSweepDir(IdfxBlock *b, int dir, SweepArgs a) {
   if (a.perpExt == -1) a.perpExt = b->desc.nghost[dir];
+  TimeScope ts(b, TIME_SWEEP_X1 + dir);
   int rc;
   const PhysCfg &c = b->cfg;
   if (!c.mhd) {
@@ -354,6 +389,7 @@ bool needsExchange(const IdfxBlock *b, int dir) { return b->nproc[dir] > 1; }
 // Boundary::SetBoundaries without the final ReconstructVcField (boundary.hpp:252-275)
 int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
   const IdfxBlockDesc &d = b->desc;
+  TimeScope ts(b, TIME_BOUNDARY);
   for (int dir = 0; dir < d.ndim; dir++) {
     if (needsExchange(b, dir)) {
       if (!b->haloFn) return fail("nproc > 1 in a direction but no halo exchange has been enrolled");
@@ -423,6 +459,7 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
     KTRY(launchSweepDir(b, dir, a));
   }
   if (b->cfg.mhd && d.ndim >= 2) {
+    TimeScope ts(b, TIME_CT);
     KTRY(idfxk::calcCornerEmf(b->g, b->emf, b->Vc, b->Vs, b->cfg.emf, b->cfg.order, b->cfg.ncomp, b->cfg.MX1,
                               b->cfg.BX1, b->stream, &b->launches));
     int mode = 0;
@@ -446,6 +483,12 @@ int timestepReduceImpl(IdfxBlock *b) {
   KTRY(idfxk::timestepReduce(b->g, b->invDt, b->redBits, b->stream));
   b->launches++;
   return 0;
+}
+
+// MPI_Iallreduce(MIN) of timeIntegrator.cpp:318: the enrolled hook reduces the device scalar in place
+// across blocks, enqueued on the block's stream (a non-negative double orders like its bit pattern)
+void crossBlockReduce(IdfxBlock *b, double *devValue, int op) {
+  if (b->reduceFn && b->nproc[0] * b->nproc[1] * b->nproc[2] > 1) b->reduceFn(b, devValue, op, b->reduceData);
 }
 
 // TimeIntegrator::Cycle as a sequence of the reference's own steps (timeIntegrator.cpp:246-414)
@@ -473,6 +516,7 @@ int cycleReferenceOrder(IdfxBlock *b) {
     b->launches++;
     if (stage == 0 && !(d.fixed_dt > 0.0)) {
       if (timestepReduceImpl(b)) return 1;
+      crossBlockReduce(b, (double *)b->redBits, IDFX_REDUCE_MIN);
     }
     if (stage > 0) {
       KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * b->cfg.nvar, wc, w0, b->stream));
@@ -506,9 +550,13 @@ int cycleFused(IdfxBlock *b) {
     b->launches++;
     if (stage == 0 && !(d.fixed_dt > 0.0)) {
       if (timestepReduceImpl(b)) return 1;
+      crossBlockReduce(b, (double *)b->redBits, IDFX_REDUCE_MIN);
     }
-    KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, 1,
-                              b->stream));
+    {
+      TimeScope ts(b, TIME_EPILOGUE);
+      KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, 1,
+                                b->stream));
+    }
     b->launches++;
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
@@ -695,7 +743,8 @@ int idfx_block_destroy(IdfxBlock *b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void *p : b->allocs) cudaFree(p);
   if (b->hostState) cudaFreeHost(b->hostState);
-  if (b->stream) cudaStreamDestroy(b->stream);
+  for (cudaEvent_t e : b->evPool) cudaEventDestroy(e);
+  if (b->stream && b->ownStream) cudaStreamDestroy(b->stream);
   delete b;
   return 0;
 }
@@ -767,6 +816,35 @@ int idfx_get_ncycles(IdfxBlock *b, long long *n) {
 
 int idfx_launch_count(IdfxBlock *b, long long *count) {
   *count = b->launches;
+  return 0;
+}
+
+int idfx_set_stream(IdfxBlock *b, void *stream) {
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
+  b->stream = (cudaStream_t)stream;
+  b->ownStream = false;
+  return 0;
+}
+
+// mode 1: start sampling, 0: stop, 2: collect into out[2*TIME_NCAT] = {launch brackets, total ms} per class
+// (X1, X2, X3 sweeps, constrained transport, stage epilogue, boundaries) and reset the samples.
+int idfx_timing(IdfxBlock *b, int mode, double *out) {
+  if (mode == 0 || mode == 1) {
+    b->timing = (mode == 1);
+    if (mode == 1) b->evUsed = 0;
+    return 0;
+  }
+  if (mode != 2 || !out) return fail("idfx_timing: mode must be 0, 1 or 2 (with an output array)");
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  for (int c = 0; c < 2 * TIME_NCAT; c++) out[c] = 0.0;
+  for (size_t n = 0; n < b->evUsed; n++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->evPool[2 * n], b->evPool[2 * n + 1]) != cudaSuccess) continue;
+    out[2 * b->evCat[n]] += 1.0;
+    out[2 * b->evCat[n] + 1] += (double)ms;
+  }
+  b->evUsed = 0;
   return 0;
 }
 
@@ -849,6 +927,7 @@ int idfx_compute_timestep(IdfxBlock *b, double *dt_min) {
   b->hostState[11] = INFINITY;
   CUDA_TRY(cudaMemcpyAsync(b->redBits, b->hostState + 11, sizeof(double), cudaMemcpyHostToDevice, b->stream));
   if (timestepReduceImpl(b)) return 1;
+  crossBlockReduce(b, (double *)b->redBits, IDFX_REDUCE_MIN);
   CUDA_TRY(cudaMemcpyAsync(b->hostState + 11, b->redBits, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   *dt_min = b->hostState[11];
@@ -863,6 +942,7 @@ int idfx_check_divb(IdfxBlock *b, double *divb_max) {
   CUDA_TRY(cudaMemsetAsync(b->redBits + 1, 0, sizeof(double), b->stream));
   KTRY(idfxk::checkDivB(b->cfg, b->g, b->Vs, b->redBits + 1, b->stream));
   b->launches++;
+  crossBlockReduce(b, (double *)(b->redBits + 1), IDFX_REDUCE_MAX);
   CUDA_TRY(cudaMemcpyAsync(b->hostState + 13, b->redBits + 1, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   *divb_max = b->hostState[13];
@@ -919,6 +999,11 @@ int idfx_enroll_userdef_boundary(IdfxBlock *b, IdfxUserBoundaryFn fn, void *user
   b->userBcData = user;
   return 0;
 }
+int idfx_enroll_reduce(IdfxBlock *b, IdfxReduceFn fn, void *user) {
+  b->reduceFn = fn;
+  b->reduceData = user;
+  return 0;
+}
 int idfx_enroll_halo_exchange(IdfxBlock *b, IdfxHaloFn fn, void *user) {
   b->haloFn = fn;
   b->haloData = user;
@@ -930,6 +1015,13 @@ int idfx_halo_buffer_size(IdfxBlock *b, int dir, size_t *ndoubles) {
   if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
   *ndoubles = (size_t)idfxk::haloBufferSize(b->cfg, b->g, dir);
   return 0;
+}
+
+// a side exchanges ghosts with another block when it is internal, or periodic with nproc[dir] > 1
+// (mpi.cpp:262-266: MPI_PROC_NULL neighbours on physical boundaries)
+static bool sideFacesBlock(const IdfxBlock *b, int dir, int side) {
+  const int type = side == 0 ? b->desc.lbound[dir] : b->desc.rbound[dir];
+  return type == IDFX_BC_INTERNAL || (type == IDFX_BC_PERIODIC && b->nproc[dir] > 1);
 }
 
 static int ensureHaloBuffers(IdfxBlock *b, int dir) {
@@ -955,6 +1047,7 @@ int idfx_halo_pack(IdfxBlock *b, int dir) {
   if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
   if (ensureHaloBuffers(b, dir)) return 1;
   for (int side = 0; side < 2; side++) {
+    if (!sideFacesBlock(b, dir, side)) continue;
     // with a bound peer the slab is written straight into the neighbour's receive buffer (NVLink P2P store)
     double *dst = b->haloPeer[dir][side] ? b->haloPeer[dir][side] : b->haloSend[dir][side];
     KTRY(idfxk::haloPack(b->cfg, b->g, b->Vc, b->Vs, dir, side, dst, b->stream, &b->launches));
@@ -965,8 +1058,10 @@ int idfx_halo_pack(IdfxBlock *b, int dir) {
 int idfx_halo_unpack(IdfxBlock *b, int dir) {
   if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
   if (ensureHaloBuffers(b, dir)) return 1;
-  for (int side = 0; side < 2; side++)
+  for (int side = 0; side < 2; side++) {
+    if (!sideFacesBlock(b, dir, side)) continue;
     KTRY(idfxk::haloUnpack(b->cfg, b->g, b->Vc, b->Vs, dir, side, b->haloRecv[dir][side], b->stream, &b->launches));
+  }
   return 0;
 }
 

@@ -24,19 +24,23 @@ inline int blocksFor(long long n) { return (int)((n + TB - 1) / TB); }
   }
 #define PHYS_DISPATCH(CALL)                \
   PHYS_CASE(1, 1, false, false, CALL)      \
+  PHYS_CASE(1, 2, false, false, CALL)      \
   PHYS_CASE(1, 3, false, false, CALL)      \
   PHYS_CASE(2, 2, false, false, CALL)      \
   PHYS_CASE(2, 3, false, false, CALL)      \
   PHYS_CASE(3, 3, false, false, CALL)      \
   PHYS_CASE(1, 1, false, true, CALL)       \
+  PHYS_CASE(1, 2, false, true, CALL)       \
   PHYS_CASE(1, 3, false, true, CALL)       \
   PHYS_CASE(2, 2, false, true, CALL)       \
   PHYS_CASE(2, 3, false, true, CALL)       \
   PHYS_CASE(3, 3, false, true, CALL)       \
+  PHYS_CASE(1, 2, true, false, CALL)       \
   PHYS_CASE(1, 3, true, false, CALL)       \
   PHYS_CASE(2, 2, true, false, CALL)       \
   PHYS_CASE(2, 3, true, false, CALL)       \
   PHYS_CASE(3, 3, true, false, CALL)       \
+  PHYS_CASE(1, 2, true, true, CALL)        \
   PHYS_CASE(1, 3, true, true, CALL)        \
   PHYS_CASE(2, 2, true, true, CALL)        \
   PHYS_CASE(2, 3, true, true, CALL)        \

@@ -34,6 +34,7 @@ inline int sweepOrder(int order, int dir, const SweepArgs &a, cudaStream_t st) {
     return sweepOrder<Phys<ND, NC, MHDF, ISOF>, SOLVER>(c.order, dir, a, st);
 
 #define IDFX_SWEEP_MHD_ALL(SOLVER, ISOF)   \
+  IDFX_SWEEP_CASE(1, 2, true, ISOF, SOLVER) \
   IDFX_SWEEP_CASE(1, 3, true, ISOF, SOLVER) \
   IDFX_SWEEP_CASE(2, 2, true, ISOF, SOLVER) \
   IDFX_SWEEP_CASE(2, 3, true, ISOF, SOLVER) \
@@ -41,6 +42,7 @@ inline int sweepOrder(int order, int dir, const SweepArgs &a, cudaStream_t st) {
 
 #define IDFX_SWEEP_HD_ALL(SOLVER, ISOF)      \
   IDFX_SWEEP_CASE(1, 1, false, ISOF, SOLVER) \
+  IDFX_SWEEP_CASE(1, 2, false, ISOF, SOLVER) \
   IDFX_SWEEP_CASE(1, 3, false, ISOF, SOLVER) \
   IDFX_SWEEP_CASE(2, 2, false, ISOF, SOLVER) \
   IDFX_SWEEP_CASE(2, 3, false, ISOF, SOLVER) \

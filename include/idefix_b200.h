@@ -87,6 +87,9 @@ int idfx_device_count(int *count);
 int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out);
 int idfx_block_destroy(IdfxBlock *blk);
 int idfx_sync(IdfxBlock *blk);
+/* Enqueue on a caller-provided cudaStream_t instead of the block's own stream (the reference
+ * runs everything on Kokkos' default execution-space instance, src/loop.hpp:56-61). */
+int idfx_set_stream(IdfxBlock *blk, void *cuda_stream);
 
 /* ---- field access ----------------------------------------------------------- */
 /* dims[4] receives (n, n3, n2, n1); dev receives the device pointer (may be NULL). */
@@ -128,6 +131,13 @@ int idfx_get_ncycles(IdfxBlock *blk, long long *ncycles);
 /* number of kernels launched by this block since creation (bench "gpu_launches") */
 int idfx_launch_count(IdfxBlock *blk, long long *count);
 
+/* Per-kernel-class device timing with CUDA events on the launching stream (the role of the
+ * reference's -profile region timers, src/profiler.cpp:59-203).  mode 1 starts sampling, 0 stops,
+ * 2 collects: out[2*c] = number of brackets, out[2*c+1] = total milliseconds, for the classes
+ * c = 0,1,2 X1/X2/X3 sweep kernel, 3 constrained transport, 4 stage epilogue, 5 boundaries. */
+#define IDFX_TIMING_CLASSES 6
+int idfx_timing(IdfxBlock *blk, int mode, double *out);
+
 /* ---- callbacks --------------------------------------------------------------- */
 /* UserDefBoundaryFunc (boundary.hpp:28-35): invoked for sides declared userdef.
  * side: 0 left, 1 right.  The block's stream is synchronised around the call. */
@@ -138,6 +148,13 @@ int idfx_enroll_userdef_boundary(IdfxBlock *blk, IdfxUserBoundaryFn fn, void *us
  * Called from idfx_set_boundaries / idfx_cycles once per direction. */
 typedef void (*IdfxHaloFn)(IdfxBlock *blk, int dir, void *user);
 int idfx_enroll_halo_exchange(IdfxBlock *blk, IdfxHaloFn fn, void *user);
+
+/* Cross-block reduction hook, replaces the MPI_(I)allreduce sites of the hot path: the CFL time
+ * step (MIN, timeIntegrator.cpp:318,358) and div B (MAX, checkDivB.hpp:63).  The hook must reduce
+ * the device scalar *dev_value in place over all blocks, enqueued on the block's stream. */
+enum IdfxReduceOp { IDFX_REDUCE_MIN = 0, IDFX_REDUCE_MAX = 1 };
+typedef void (*IdfxReduceFn)(IdfxBlock *blk, double *dev_value, int op, void *user);
+int idfx_enroll_reduce(IdfxBlock *blk, IdfxReduceFn fn, void *user);
 
 /* ---- halo exchange building blocks (mpi.cpp:79-134 buffer layout) ------------ */
 /* Number of doubles in the send/recv buffer of direction dir. */

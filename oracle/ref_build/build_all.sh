@@ -1,0 +1,20 @@
+#!/bin/bash
+# Builds every reference (Kokkos-OpenMP CPU) binary the parity tests and bench.py use.
+# Needs /root/reference; the outputs under oracle/_ref/ travel to the GPU box via gpurun.
+set -e
+cd "$(dirname "$0")"
+J=${J:-8}
+b() { [ -x ../_ref/$1/idefix ] || make -s -j$J NAME=$1 SETUP=$2 MHD=$3 ORDER=$4 LOOP=$5; }
+make -s -j$J kokkos
+b sod_plm      test/HD/sod                NO  2
+b ot2d_plm     test/MHD/OrszagTang        YES 2 TPX
+b ot3d_plm     test/MHD/OrszagTang3D      YES 2
+b lw_ppm       test/MHD/LinearWaveTest    YES 4
+b lw_plm       test/MHD/LinearWaveTest    YES 2
+b lw_limo3     test/MHD/LinearWaveTest    YES 3
+b ot2d_limo3   test/MHD/OrszagTang        YES 3 TPX
+b ot2d_ppm     test/MHD/OrszagTang        YES 4 TPX
+b mhdsod_plm   test/MHD/sod               YES 2
+b sod_limo3    test/HD/sod                NO  3
+b sod_ppm      test/HD/sod                NO  4
+echo done

@@ -1,0 +1,133 @@
+"""Parity cases shared by tests/golden/make_golden.py (which runs the reference binaries of
+oracle/_ref to produce the fixtures) and the GPU parity tests.
+
+SHORT cases: reduced grids, a few cycles, one dump per cycle ([Output] dmp 1e-7), fixtures
+``tests/golden/short/<name>.c<NNNN>.dmp`` generated HERE from the reference's own build.
+FULL cases: the reference's regression runs (testme.py of each test) compared against copies of
+its golden dumps ``tests/golden/reference/<dir>/<file>`` with the reference's own tolerance.
+"""
+from collections import namedtuple
+
+Short = namedtuple("Short", "name setup order ref overrides cycles")
+Full = namedtuple("Full", "name setup order overrides golden tol")
+
+_G = ("Grid",)
+
+
+def _grid(*dims):
+    return {("Grid", f"X{d + 1}-grid"): v for d, v in enumerate(dims)}
+
+
+def _ot2d(n, solver, emf, nstages=2):
+    o = _grid(["1", "0.0", str(n), "u", "1.0"], ["1", "0.0", str(n), "u", "1.0"])
+    o[("Hydro", "solver")] = solver
+    o[("Hydro", "emf")] = emf
+    o[("TimeIntegrator", "nstages")] = nstages
+    return o
+
+
+def _ot3d(n1, n2, n3, solver="hlld", emf=None, nstages=2):
+    o = _grid(["1", "0.0", str(n1), "u", "1.0"], ["1", "0.0", str(n2), "u", "1.0"], ["1", "0.0", str(n3), "u", "1.0"])
+    o[("Hydro", "solver")] = solver
+    o[("Hydro", "emf")] = emf
+    o[("TimeIntegrator", "nstages")] = nstages
+    return o
+
+
+def _lw(n1, n2, n3, solver, nstages, mode):
+    o = _grid(["1", "0.0", str(n1), "u", "3.0"], ["1", "0.0", str(n2), "u", "1.5"], ["1", "0.0", str(n3), "u", "1.5"])
+    o[("Hydro", "solver")] = solver
+    o[("TimeIntegrator", "nstages")] = nstages
+    o[("Setup", "mode")] = mode
+    return o
+
+
+def _sod(solver, nstages=2):
+    return {("Hydro", "solver"): solver, ("TimeIntegrator", "nstages"): nstages}
+
+
+SHORT = [
+    # C1: HD sod, every HD solver x reconstruction
+    Short("sod_hllc_plm", "sod", 2, "sod_plm", _sod("hllc"), (1, 5, 20)),
+    Short("sod_hll_plm", "sod", 2, "sod_plm", _sod("hll"), (1, 20)),
+    Short("sod_tvdlf_plm", "sod", 2, "sod_plm", _sod("tvdlf"), (1, 20)),
+    Short("sod_hllc_limo3", "sod", 3, "sod_limo3", _sod("hllc"), (1, 20)),
+    Short("sod_hllc_ppm_rk3", "sod", 4, "sod_ppm", _sod("hllc", 3), (1, 20)),
+    # 1-D MHD shock tube
+    Short("mhdsod_roe_plm", "mhdsod", 2, "mhdsod_plm", _sod("roe"), (1, 20)),
+    Short("mhdsod_hlld_plm", "mhdsod", 2, "mhdsod_plm", _sod("hlld"), (1, 20)),
+    Short("mhdsod_hll_plm", "mhdsod", 2, "mhdsod_plm", _sod("hll"), (1, 20)),
+    Short("mhdsod_tvdlf_plm", "mhdsod", 2, "mhdsod_plm", _sod("tvdlf"), (1, 20)),
+    # C2 physics: 2-D Orszag-Tang, every solver x EMF averaging
+    Short("ot2d_hlld_ucthlld_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "hlld", "uct_hlld"), (1, 2, 10)),
+    Short("ot2d_hlld_ucthll_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "hlld", "uct_hll"), (1, 10)),
+    Short("ot2d_hlld_contact_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "hlld", "uct_contact"), (1, 10)),
+    Short("ot2d_hlld_uct0_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "hlld", "uct0"), (1, 10)),
+    Short("ot2d_hlld_arith_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "hlld", "arithmetic"), (1, 10)),
+    Short("ot2d_hll_ucthll_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "hll", "uct_hll"), (1, 10)),
+    Short("ot2d_roe_contact_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "roe", "uct_contact"), (1, 10)),
+    Short("ot2d_tvdlf_contact_plm", "ot2d", 2, "ot2d_plm", _ot2d(64, "tvdlf", "uct_contact"), (1, 10)),
+    Short("ot2d_hlld_ucthlld_limo3", "ot2d", 3, "ot2d_limo3", _ot2d(64, "hlld", "uct_hlld"), (1, 10)),
+    Short("ot2d_hlld_ucthlld_ppm_rk3", "ot2d", 4, "ot2d_ppm", _ot2d(64, "hlld", "uct_hlld", 3), (1, 10)),
+    # C4 physics: 3-D Orszag-Tang
+    Short("ot3d_hlld_contact_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16), (1, 2, 10)),
+    Short("ot3d_hlld_ucthlld_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, emf="uct_hlld"), (1, 10)),
+    Short("ot3d_roe_contact_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, solver="roe"), (1, 10)),
+    Short("ot3d_hll_uct0_plm_rk3", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, solver="hll", emf="uct0", nstages=3), (1, 10)),
+    # C3 physics: linear waves, HLLD + PPM + RK3 has no shipped golden -> reference binary
+    Short("lw_fast_hlld_ppm_rk3", "linearwave", 4, "lw_ppm", _lw(32, 16, 16, "hlld", 3, 1), (1, 10)),
+    Short("lw_alfven_roe_limo3", "linearwave", 3, "lw_limo3", _lw(32, 16, 16, "roe", 2, 2), (1, 10)),
+    Short("lw_slow_hlld_plm_rk3", "linearwave", 2, "lw_plm", _lw(32, 16, 16, "hlld", 3, 3), (1, 10)),
+]
+
+FULL = [
+    Full("sod_hllc", "sod", 2, _sod("hllc"), "HD/sod/dump.ref.double.plm.idefix-hllc.ini.dmp", 0.0),
+    Full("sod_hll", "sod", 2, _sod("hll"), "HD/sod/dump.ref.double.plm.idefix-hll.ini.dmp", 0.0),
+    Full("sod_tvdlf", "sod", 2, _sod("tvdlf"), "HD/sod/dump.ref.double.plm.idefix-tvdlf.ini.dmp", 0.0),
+    Full("sod_hllc_limo3", "sod", 3, _sod("hllc"), "HD/sod/dump.ref.double.limo3.idefix-hllc.ini.dmp", 0.0),
+    Full("sod_hllc_ppm", "sod", 4, _sod("hllc"), "HD/sod/dump.ref.double.ppm.idefix-hllc.ini.dmp", 0.0),
+    Full("sod_hllc_ppm_rk3", "sod", 4, _sod("hllc", 3), "HD/sod/dump.ref.double.ppm.idefix-hllc-rk3.ini.dmp", 0.0),
+    Full("mhdsod_roe", "mhdsod", 2, _sod("roe"), "MHD/sod/dump.ref.double.plm.idefix.ini.dmp", 1e-14),
+    Full("mhdsod_hlld", "mhdsod", 2, _sod("hlld"), "MHD/sod/dump.ref.double.plm.idefix-hlld.ini.dmp", 1e-14),
+    Full("mhdsod_hll", "mhdsod", 2, _sod("hll"), "MHD/sod/dump.ref.double.plm.idefix-hll.ini.dmp", 1e-14),
+    Full("mhdsod_tvdlf", "mhdsod", 2, _sod("tvdlf"), "MHD/sod/dump.ref.double.plm.idefix-tvdlf.ini.dmp", 1e-14),
+    Full("ot2d_hlld_hlld", "ot2d", 2, _ot2d(128, "hlld", "uct_hlld"),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld-hlld.ini.dmp", 1e-12),
+    Full("ot2d_hlld_hll", "ot2d", 2, _ot2d(128, "hlld", "uct_hll"),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld-hll.ini.dmp", 1e-12),
+    Full("ot2d_hlld_contact", "ot2d", 2, _ot2d(128, "hlld", None),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld.ini.dmp", 1e-12),
+    Full("ot2d_hlld_uct0", "ot2d", 2, _ot2d(128, "hlld", "uct0"),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld-uct0.ini.dmp", 1e-12),
+    Full("ot2d_hlld_arithmetic", "ot2d", 2, _ot2d(128, "hlld", "arithmetic"),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld-arithmetic.ini.dmp", 1e-12),
+    Full("ot2d_hll", "ot2d", 2, _ot2d(128, "hll", None), "MHD/OrszagTang/dump.ref.double.plm.idefix-hll.ini.dmp", 1e-12),
+    Full("ot2d_tvdlf", "ot2d", 2, _ot2d(128, "tvdlf", None),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-tvdlf.ini.dmp", 1e-12),
+    Full("ot2d_roe", "ot2d", 2, _ot2d(128, "roe", None), "MHD/OrszagTang/dump.ref.double.plm.idefix.ini.dmp", 1e-12),
+    Full("ot2d_hlld_hlld_limo3", "ot2d", 3, _ot2d(128, "hlld", "uct_hlld"),
+         "MHD/OrszagTang/dump.ref.double.limo3.idefix-hlld-hlld.ini.dmp", 1e-12),
+    Full("ot2d_hlld_hlld_ppm", "ot2d", 4, _ot2d(128, "hlld", "uct_hlld"),
+         "MHD/OrszagTang/dump.ref.double.ppm.idefix-hlld-hlld.ini.dmp", 1e-12),
+    Full("ot3d_hlld_contact", "ot3d", 2, _ot3d(32, 64, 32), "MHD/OrszagTang3D/dump.ref.double.plm.idefix.ini.dmp", 1e-13),
+    Full("lw_fast_roe_plm", "linearwave", 2, _lw(64, 32, 32, "roe", 2, 1),
+         "MHD/LinearWaveTest/dump.ref.double.plm.idefix-fast.ini.dmp", 1e-14),
+    Full("lw_alfven_roe_ppm", "linearwave", 4, {**_lw(64, 32, 32, "roe", 3, 2), ("TimeIntegrator", "tstop"): "1.0"},
+         "MHD/LinearWaveTest/dump.ref.double.ppm.idefix-alfven.ini.dmp", 1e-14),
+]
+
+
+def ini_for(case, dump_every_cycle=False):
+    """ini text of a case = the set-up's default ini with the case's overrides applied"""
+    from idefix_b200.input import Input
+    from idefix_b200.setups import REGISTRY
+    inp = Input.from_string(REGISTRY[case.setup].ini)
+    for (block, name), vals in case.overrides.items():
+        if vals is None:
+            inp.remove(block, name)
+        else:
+            inp.set(block, name, *(vals if isinstance(vals, (list, tuple)) else [vals]))
+    if dump_every_cycle:
+        inp.set("Output", "dmp", "1e-7")   # smaller than any dt: one dump per cycle
+    inp.set("Output", "log", "1000000")
+    return inp.dumps()
