@@ -113,7 +113,9 @@ FULL = [
     Full("lw_fast_roe_plm", "linearwave", 2, _lw(64, 32, 32, "roe", 2, 1),
          "MHD/LinearWaveTest/dump.ref.double.plm.idefix-fast.ini.dmp", 1e-14),
     Full("lw_alfven_roe_ppm", "linearwave", 4, {**_lw(64, 32, 32, "roe", 3, 2), ("TimeIntegrator", "tstop"): "1.0"},
-         "MHD/LinearWaveTest/dump.ref.double.ppm.idefix-alfven.ini.dmp", 1e-14),
+         # the reference's own build in this image scores 3.408e-14 against this shipped golden
+         # (different libm/compiler than the machine that wrote it); our GPU result is that same number
+         "MHD/LinearWaveTest/dump.ref.double.ppm.idefix-alfven.ini.dmp", 5e-14),
 ]
 
 
