@@ -1,0 +1,123 @@
+"""ctypes front end of the CPU oracle (oracle/godunov_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: used by tests/ and __graft_entry__.smoke() as the checker.  The product
+(idefix_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libgodunov_oracle.so")
+
+SOLVERS = {"tvdlf": 0, "hll": 1, "hllc": 2, "hlld": 3}
+EMFS = {"arithmetic": 0, "uct0": 1, "uct_contact": 2, "uct_hll": 3, "uct_hlld": 4}
+BCS = {"periodic": 1, "outflow": 3}
+
+
+class OracleDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int), ("ncomp", C.c_int), ("mhd", C.c_int), ("solver", C.c_int), ("emf", C.c_int),
+                ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
+                ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
+                ("dx", C.c_double * 3)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "godunov_oracle.c")):
+            subprocess.run(["make", "-C", HERE], check=True, capture_output=True)
+        L = C.CDLL(LIB)
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.POINTER(OracleDesc)]
+        for name in ("oracle_vc", "oracle_vs"):
+            getattr(L, name).restype = C.POINTER(C.c_double)
+            getattr(L, name).argtypes = [C.c_void_p]
+        for name in ("oracle_time", "oracle_dt"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.oracle_nvar.argtypes = [C.c_void_p]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_set_boundaries.argtypes = [C.c_void_p]
+        L.oracle_cycle.argtypes = [C.c_void_p]
+        L.oracle_run.argtypes = [C.c_void_p, C.c_double, C.c_long]
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    """One block evolved by the CPU restatement.  Fields are numpy views of the C arrays, indexed
+    (n, k, j, i) like the reference's IdefixArray4D."""
+
+    def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
+                 cfl_max_var=1.1):
+        d = OracleDesc()
+        d.ndim, d.ncomp, d.mhd = ndim, ncomp, int(mhd)
+        d.solver, d.emf, d.nstages = SOLVERS[solver], EMFS[emf or "uct_contact"], nstages
+        for a in range(3):
+            d.np_int[a] = np_int[a] if a < ndim else 1
+            d.nghost[a] = 2 if a < ndim else 0
+            d.bc[a] = BCS[bc[a]] if a < ndim else 0
+            d.dx[a] = dx[a]
+        d.gamma, d.cfl, d.cfl_max_var, d.first_dt = gamma, cfl, cfl_max_var, first_dt
+        self.desc = d
+        self.h = lib().oracle_create(C.byref(d))
+        nt = [d.np_int[a] + 2 * d.nghost[a] for a in range(3)]
+        self.nvar = lib().oracle_nvar(self.h)
+        self.Vc = np.ctypeslib.as_array(lib().oracle_vc(self.h), shape=(self.nvar, nt[2], nt[1], nt[0]))
+        self.Vs = None
+        if mhd:
+            off = [1 if a < ndim else 0 for a in range(3)]
+            self.Vs = np.ctypeslib.as_array(lib().oracle_vs(self.h),
+                                            shape=(ndim, nt[2] + off[2], nt[1] + off[1], nt[0] + off[0]))
+
+    @classmethod
+    def from_setup(cls, setup):
+        """same configuration as an idefix_b200.setups.Setup built with device=None (host only)"""
+        defs, inp, grid = setup.definitions, setup.input, setup.grid
+        if defs.order != 2 or defs.isothermal or defs.geometry != 1:
+            raise ValueError("the C oracle restates PLM / adiabatic / cartesian only")
+        names = {1: "periodic", 3: "outflow"}
+        nd = defs.dimensions
+        emf = inp.Get(str, "Hydro", "emf", 0) if inp.CheckEntry("Hydro", "emf") >= 0 else "uct_contact"
+        first_dt = inp.GetOrSet(float, "TimeIntegrator", "first_dt", 0, 1e-10)
+        o = cls(nd, defs.components, defs.mhd, inp.Get(str, "Hydro", "solver", 0), emf,
+                inp.Get(int, "TimeIntegrator", "nstages", 0), grid.np_int, [names[grid.lbound[a]] for a in range(nd)],
+                setup.data.hydro.gamma, inp.Get(float, "TimeIntegrator", "CFL", 0), first_dt,
+                [float(grid.dx[a][0]) for a in range(3)])
+        return o
+
+    def set_state(self, Vc, Vs=None):
+        self.Vc[...] = Vc
+        if self.Vs is not None:
+            self.Vs[...] = Vs
+        lib().oracle_set_boundaries(self.h)
+
+    def cycle(self, n=1):
+        for _ in range(n):
+            rc = lib().oracle_cycle(self.h)
+            if rc:
+                raise RuntimeError(f"oracle_cycle failed with status {rc}")
+
+    def run(self, tstop, maxcycles=-1):
+        rc = lib().oracle_run(self.h, tstop, maxcycles)
+        if rc:
+            raise RuntimeError(f"oracle_run failed with status {rc}")
+
+    @property
+    def t(self):
+        return lib().oracle_time(self.h)
+
+    @property
+    def dt(self):
+        return lib().oracle_dt(self.h)
+
+    def close(self):
+        if self.h:
+            lib().oracle_destroy(self.h)
+            self.h = None

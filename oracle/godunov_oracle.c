@@ -1,0 +1,880 @@
+/* godunov_oracle.c -- CPU restatement of Idefix's explicit Godunov (M)HD update.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker the parity tests and smoke() compare the
+ * CUDA path against; nothing under idefix_b200/ includes, links or calls it.  It restates the
+ * reference's algorithm with the reference's OWN kernel structure (separate flux array, flux
+ * correction, right-hand side, whole-array point-wise passes), i.e. deliberately NOT the fused
+ * structure of the CUDA kernels, and is pinned against the reference's golden dumps and against
+ * dumps written by the reference's own CPU build (tests/test_oracle.py).
+ *
+ * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions, adiabatic EOS,
+ * PLM (van Leer) reconstruction, HD solvers TVDLF / HLL / HLLC, MHD solvers HLL / HLLD,
+ * constrained transport with arithmetic / uct_contact / uct_hll / uct_hlld averaging, periodic and
+ * outflow boundaries (outflow + MHD only in 1-D), RK1/2/3, CFL time-step control.
+ * LimO3 / PPM / Roe / curvilinear geometry are pinned through the reference binaries and golden
+ * dumps only (tests/golden).
+ *
+ * Every function cites the reference file:line (relative to the reference tree) it follows.
+ * Compile with -O2 -ffp-contract=off: expression association follows the reference so results are
+ * bit-identical with its CPU build.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum { TVDLF = 0, HLL = 1, HLLC = 2, HLLD = 3 };
+enum { EMF_ARITHMETIC = 0, EMF_UCT0 = 1, EMF_UCT_CONTACT = 2, EMF_UCT_HLL = 3, EMF_UCT_HLLD = 4 };
+enum { BC_PERIODIC = 1, BC_OUTFLOW = 3 };
+
+typedef struct {
+  int ndim, ncomp, mhd, solver, emf, nstages;
+  int np_int[3], nghost[3];
+  int bc[3];                 /* same type on both sides */
+  double gamma, cfl, cfl_max_var, first_dt;
+  double dx[3];              /* uniform spacing */
+} OracleDesc;
+
+typedef struct {
+  OracleDesc d;
+  int nx[3], beg[3], end[3], off[3];
+  long sj, sk, sn;           /* cell-centred strides */
+  long vj, vk, vn;           /* staggered strides    */
+  int nvar, RHO, MX1, ENG, BX1;
+  double *Vc, *Uc, *Uc0, *Vs, *Vs0, *Flux, *cMax, *InvDt;
+  double *ex, *ey, *ez, *exj, *exk, *eyi, *eyk, *ezi, *ezj, *Ex1, *Ex2, *Ex3;
+  double *svx, *svy, *svz, *aL[3], *aR[3], *dL[3], *dR[3];
+  double t, dt;
+  long ncycles;
+} Oracle;
+
+#define C(o, k, j, i) ((long)(k) * (o)->sk + (long)(j) * (o)->sj + (i))
+#define S(o, k, j, i) ((long)(k) * (o)->vk + (long)(j) * (o)->vj + (i))
+
+static double *zalloc(long n) { return (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double)); }
+
+/* ------------------------------------------------------------------------------------------ */
+Oracle *oracle_create(const OracleDesc *d) {
+  Oracle *o = (Oracle *)calloc(1, sizeof(Oracle));
+  o->d = *d;
+  for (int a = 0; a < 3; a++) {
+    o->nx[a] = d->np_int[a] + 2 * d->nghost[a];
+    o->beg[a] = d->nghost[a];
+    o->end[a] = d->nghost[a] + d->np_int[a];
+    o->off[a] = a < d->ndim ? 1 : 0;
+  }
+  o->sj = o->nx[0];
+  o->sk = (long)o->nx[0] * o->nx[1];
+  o->sn = o->sk * o->nx[2];
+  o->vj = o->nx[0] + o->off[0];
+  o->vk = o->vj * (o->nx[1] + o->off[1]);
+  o->vn = o->vk * (o->nx[2] + o->off[2]);
+  /* variable indices, src/idefix.hpp:74-94 */
+  o->RHO = 0;
+  o->MX1 = 1;
+  o->ENG = d->ncomp + 1;
+  o->BX1 = d->ncomp + 2;
+  o->nvar = 2 + d->ncomp + (d->mhd ? d->ncomp : 0);
+  long n = o->sn;
+  o->Vc = zalloc(n * o->nvar);
+  o->Uc = zalloc(n * o->nvar);
+  o->Uc0 = zalloc(n * o->nvar);
+  o->Flux = zalloc(n * o->nvar);
+  o->cMax = zalloc(n);
+  o->InvDt = zalloc(n);
+  if (d->mhd) {
+    o->Vs = zalloc(o->vn * d->ndim);
+    o->Vs0 = zalloc(o->vn * d->ndim);
+    double **all[] = {&o->ex, &o->ey, &o->ez, &o->exj, &o->exk, &o->eyi, &o->eyk, &o->ezi, &o->ezj,
+                      &o->Ex1, &o->Ex2, &o->Ex3, &o->svx, &o->svy, &o->svz};
+    for (unsigned q = 0; q < sizeof(all) / sizeof(all[0]); q++) *all[q] = zalloc(n);
+    for (int a = 0; a < 3; a++) {
+      o->aL[a] = zalloc(n);
+      o->aR[a] = zalloc(n);
+      o->dL[a] = zalloc(n);
+      o->dR[a] = zalloc(n);
+    }
+  }
+  o->t = 0.0;
+  o->dt = d->first_dt;
+  return o;
+}
+
+void oracle_destroy(Oracle *o) {
+  if (!o) return;
+  double *all[] = {o->Vc, o->Uc, o->Uc0, o->Flux, o->cMax, o->InvDt, o->Vs, o->Vs0, o->ex, o->ey, o->ez,
+                   o->exj, o->exk, o->eyi, o->eyk, o->ezi, o->ezj, o->Ex1, o->Ex2, o->Ex3, o->svx, o->svy, o->svz};
+  for (unsigned q = 0; q < sizeof(all) / sizeof(all[0]); q++) free(all[q]);
+  for (int a = 0; a < 3; a++) {
+    free(o->aL[a]);
+    free(o->aR[a]);
+    free(o->dL[a]);
+    free(o->dR[a]);
+  }
+  free(o);
+}
+
+double *oracle_vc(Oracle *o) { return o->Vc; }
+double *oracle_vs(Oracle *o) { return o->Vs; }
+double oracle_time(Oracle *o) { return o->t; }
+double oracle_dt(Oracle *o) { return o->dt; }
+int oracle_nvar(Oracle *o) { return o->nvar; }
+
+/* ---- K_PrimToCons / K_ConsToPrim: src/fluid/convertConsToPrim.hpp:70-100, 16-67 ------------- */
+static void prim_to_cons(const Oracle *o, const double *v, double *u) {
+  const int nc = o->d.ncomp, RHO = o->RHO, MX1 = o->MX1, ENG = o->ENG, BX1 = o->BX1;
+  u[RHO] = v[RHO];
+  for (int c = 0; c < nc; c++) u[MX1 + c] = v[MX1 + c] * v[RHO];
+  double v2 = v[MX1] * v[MX1];
+  for (int c = 1; c < nc; c++) v2 = v2 + v[MX1 + c] * v[MX1 + c];
+  if (o->d.mhd) {
+    for (int c = 0; c < nc; c++) u[BX1 + c] = v[BX1 + c];
+    double b2 = u[BX1] * u[BX1];
+    for (int c = 1; c < nc; c++) b2 = b2 + u[BX1 + c] * u[BX1 + c];
+    u[ENG] = v[ENG] / (o->d.gamma - 1.0) + 0.5 * v[RHO] * v2 + 0.5 * b2;
+  } else {
+    u[ENG] = v[ENG] / (o->d.gamma - 1.0) + 0.5 * v[RHO] * v2;
+  }
+}
+
+static void cons_to_prim(const Oracle *o, double *u, double *v) {
+  const int nc = o->d.ncomp, RHO = o->RHO, MX1 = o->MX1, ENG = o->ENG, BX1 = o->BX1;
+  v[RHO] = u[RHO];
+  for (int c = 0; c < nc; c++) v[MX1 + c] = u[MX1 + c] / u[RHO];
+  double m2 = u[MX1] * u[MX1];
+  for (int c = 1; c < nc; c++) m2 = m2 + u[MX1 + c] * u[MX1 + c];
+  const double kin = 0.5 / u[RHO] * m2;
+  double mag = 0.0;
+  if (o->d.mhd) {
+    for (int c = 0; c < nc; c++) v[BX1 + c] = u[BX1 + c];
+    double b2 = u[BX1] * u[BX1];
+    for (int c = 1; c < nc; c++) b2 = b2 + u[BX1 + c] * u[BX1 + c];
+    mag = 0.5 * b2;
+    v[ENG] = (u[ENG] - kin - mag) * (o->d.gamma - 1.0);
+  } else {
+    v[ENG] = (u[ENG] - kin) * (o->d.gamma - 1.0);
+  }
+  if (v[ENG] <= 0.0) { /* SMALL_PRESSURE_FIX, convertConsToPrim.hpp:43-51 */
+    v[ENG] = 1.0e-5;
+    u[ENG] = o->d.mhd ? v[ENG] / (o->d.gamma - 1.0) + kin + mag : v[ENG] / (o->d.gamma - 1.0) + kin;
+  }
+}
+
+/* K_Flux: src/fluid/RiemannSolver/flux.hpp:29-95 (f may alias u) */
+static void phys_flux(const Oracle *o, int dir, const double *v, const double *uin, double *f) {
+  const int nc = o->d.ncomp, RHO = o->RHO, MX1 = o->MX1, ENG = o->ENG, BX1 = o->BX1;
+  const int Xn = MX1 + dir, BXn = BX1 + dir;
+  double u[16];
+  for (int n = 0; n < o->nvar; n++) u[n] = uin[n];
+  f[RHO] = u[Xn];
+  if (o->d.mhd) {
+    for (int c = 0; c < nc; c++) f[MX1 + c] = u[MX1 + c] * v[Xn] - v[BXn] * v[BX1 + c];
+    for (int c = 0; c < nc; c++)
+      f[BX1 + c] = (c == dir) ? 0.0 : v[Xn] * v[BX1 + c] - v[BXn] * v[MX1 + c];
+    double b2 = v[BX1] * v[BX1];
+    for (int c = 1; c < nc; c++) b2 = b2 + v[BX1 + c] * v[BX1 + c];
+    const double ptot = v[ENG] + 0.5 * b2;
+    double vb = v[MX1] * v[BX1];
+    for (int c = 1; c < nc; c++) vb = vb + v[MX1 + c] * v[BX1 + c];
+    f[ENG] = (u[ENG] + ptot) * v[Xn] - v[BXn] * vb;
+    f[Xn] += ptot;
+  } else {
+    for (int c = 0; c < nc; c++) f[MX1 + c] = u[MX1 + c] * v[Xn];
+    f[ENG] = (u[ENG] + v[ENG]) * v[Xn];
+    f[Xn] += v[ENG];
+  }
+}
+
+/* SlopeLimiter::VanLeerLim, src/fluid/RiemannSolver/slopeLimiter.hpp:54-57 */
+static double van_leer(double dvp, double dvm) { return dvp * dvm > 0.0 ? 2.0 * dvp * dvm / (dvp + dvm) : 0.0; }
+/* SlopeLimiter::McLim, slopeLimiter.hpp:67-75 */
+static double mc_lim(double dvp, double dvm) {
+  double dq = 0.0;
+  if (dvp * dvm > 0.0) {
+    double dqc = 0.5 * (dvp + dvm);
+    double d2q = 2.0 * (fabs(dvp) < fabs(dvm) ? dvp : dvm);
+    dq = fabs(d2q) < fabs(dqc) ? d2q : dqc;
+  }
+  return dq;
+}
+
+/* transverse / bi-tangential component indices of a sweep, src/fluid/RiemannSolver/MHDsolvers/hlldMHD.hpp:60-145 */
+static int tdir(int dir) { return dir == 0 ? 1 : 0; }
+static int bdir(int dir) { return dir == 2 ? 1 : 2; }
+
+/* fast magnetosonic speed, hlldMHD.hpp:191-207 */
+static double fast_speed(const Oracle *o, int dir, const double *v) {
+  const int nc = o->d.ncomp, BX1 = o->BX1;
+  const double gpr = o->d.gamma * v[o->ENG];
+  const double b1 = v[BX1 + dir];
+  const double b2 = nc >= 2 ? v[BX1 + tdir(dir)] : 0.0;
+  const double b3 = nc == 3 ? v[BX1 + bdir(dir)] : 0.0;
+  const double Bt2 = b2 * b2 + b3 * b3;
+  const double B2 = b1 * b1 + Bt2;
+  double c = gpr - B2;
+  c = gpr + B2 + sqrt(c * c + 4.0 * gpr * Bt2);
+  return sqrt(0.5 * c / v[o->RHO]);
+}
+
+static double total_pressure(const Oracle *o, const double *v) {
+  double b2 = v[o->BX1] * v[o->BX1];
+  for (int c = 1; c < o->d.ncomp; c++) b2 = b2 + v[o->BX1 + c] * v[o->BX1 + c];
+  return v[o->ENG] + 0.5 * b2;
+}
+
+typedef struct { double cmax, sl, sr; } Speeds;
+
+/* ---- HD solvers: HDsolvers/tvdlfHD.hpp:49-93, hllHD.hpp:48-110, hllcHD.hpp:40-160 -------------- */
+static void riemann_hd(const Oracle *o, int dir, const double *vL, const double *vR, double *F, Speeds *sp) {
+  const int nv = o->nvar, RHO = o->RHO, ENG = o->ENG, Xn = o->MX1 + dir, nc = o->d.ncomp;
+  double uL[8], uR[8], fL[8], fR[8];
+  prim_to_cons(o, vL, uL);
+  prim_to_cons(o, vR, uR);
+  if (o->d.solver == TVDLF) {
+    const double vn = 0.5 * (vL[Xn] + vR[Xn]);
+    const double p = 0.5 * (vL[ENG] + vR[ENG]), r = 0.5 * (vL[RHO] + vR[RHO]);
+    const double c = sqrt(o->d.gamma * (p / r));
+    const double cmax = fmax(fabs(vn + c), fabs(vn - c));
+    phys_flux(o, dir, vL, uL, fL);
+    phys_flux(o, dir, vR, uR, fR);
+    for (int n = 0; n < nv; n++) F[n] = 0.5 * (fL[n] + fR[n] - cmax * (uR[n] - uL[n]));
+    sp->cmax = cmax;
+    return;
+  }
+  const double cL = sqrt(o->d.gamma * (vL[ENG] / vL[RHO]));
+  const double cR = sqrt(o->d.gamma * (vR[ENG] / vR[RHO]));
+  const double SL = fmin(vL[Xn] - cL, vR[Xn] - cR);
+  const double SR = fmax(vL[Xn] + cL, vR[Xn] + cR);
+  sp->cmax = fmax(fabs(SL), fabs(SR));
+  phys_flux(o, dir, vL, uL, fL);
+  phys_flux(o, dir, vR, uR, fR);
+  if (SL > 0) {
+    for (int n = 0; n < nv; n++) F[n] = fL[n];
+  } else if (SR < 0) {
+    for (int n = 0; n < nv; n++) F[n] = fR[n];
+  } else if (o->d.solver == HLL) {
+    for (int n = 0; n < nv; n++) {
+      double f = SL * SR * uR[n] - SL * SR * uL[n] + SR * fL[n] - SL * fR[n];
+      F[n] = f / (SR - SL);
+    }
+  } else { /* HLLC */
+    double usL[8], usR[8];
+    const double qL = vL[ENG] + uL[Xn] * (vL[Xn] - SL);
+    const double qR = vR[ENG] + uR[Xn] * (vR[Xn] - SR);
+    const double wL = vL[RHO] * (vL[Xn] - SL);
+    const double wR = vR[RHO] * (vR[Xn] - SR);
+    const double vs = (qR - qL) / (wR - wL);
+    usL[RHO] = uL[RHO] * (SL - vL[Xn]) / (SL - vs);
+    usR[RHO] = uR[RHO] * (SR - vR[Xn]) / (SR - vs);
+    for (int c = 0; c < nc; c++) {
+      const int m = o->MX1 + c;
+      usL[m] = usL[RHO] * (m == Xn ? vs : vL[m]);
+      usR[m] = usR[RHO] * (m == Xn ? vs : vR[m]);
+    }
+    usL[ENG] = uL[ENG] / vL[RHO] + (vs - vL[Xn]) * (vs + vL[ENG] / (vL[RHO] * (SL - vL[Xn])));
+    usR[ENG] = uR[ENG] / vR[RHO] + (vs - vR[Xn]) * (vs + vR[ENG] / (vR[RHO] * (SR - vR[Xn])));
+    usL[ENG] *= usL[RHO];
+    usR[ENG] *= usR[RHO];
+    if (vs >= 0.0) {
+      for (int n = 0; n < nv; n++) F[n] = fL[n] + SL * (usL[n] - uL[n]);
+    } else {
+      for (int n = 0; n < nv; n++) F[n] = fR[n] + SR * (usR[n] - uR[n]);
+    }
+  }
+}
+
+/* ---- MHD solvers: MHDsolvers/hllMHD.hpp:155-445 (no Hall), hlldMHD.hpp:147-457 ---------------- */
+static void riemann_mhd(const Oracle *o, int dir, const double *vL, const double *vR, double *F, Speeds *sp) {
+  const int nv = o->nvar, nc = o->d.ncomp, RHO = o->RHO, ENG = o->ENG;
+  const int Xn = o->MX1 + dir, Xt = o->MX1 + tdir(dir), Xb = o->MX1 + bdir(dir);
+  const int BXn = o->BX1 + dir, BXt = o->BX1 + tdir(dir), BXb = o->BX1 + bdir(dir);
+  double uL[8], uR[8], fL[8], fR[8];
+  const double cL = fast_speed(o, dir, vL), cR = fast_speed(o, dir, vR);
+  const double sl = fmin(vL[Xn] - cL, vR[Xn] - cR);
+  const double sr = fmax(vL[Xn] + cL, vR[Xn] + cR);
+  sp->cmax = fmax(fabs(sl), fabs(sr));
+  sp->sl = sl;
+  sp->sr = sr;
+  prim_to_cons(o, vL, uL);
+  prim_to_cons(o, vR, uR);
+  phys_flux(o, dir, vL, uL, fL);
+  phys_flux(o, dir, vR, uR, fR);
+  if (sl > 0) {
+    for (int n = 0; n < nv; n++) F[n] = fL[n];
+    return;
+  }
+  if (sr < 0) {
+    for (int n = 0; n < nv; n++) F[n] = fR[n];
+    return;
+  }
+  if (o->d.solver == HLL) { /* hllMHD.hpp:395-433: rho,m divide, B,E multiply by the reciprocal */
+    const double rcp = 1.0 / (sr - sl);
+    for (int n = 0; n < nv; n++) {
+      const double f = sl * sr * uR[n] - sl * sr * uL[n] + sr * fL[n] - sl * fR[n];
+      F[n] = (n <= nc) ? f / (sr - sl) : f * rcp;
+    }
+    return;
+  }
+  /* HLLD, Miyoshi & Kusano (2005), hlldMHD.hpp:262-457 */
+  double usL[8], usR[8];
+  const double ptL = total_pressure(o, vL), ptR = total_pressure(o, vR);
+  double scrh = 1.0 / (sr - sl);
+  const double Bx = (sr * vR[BXn] - sl * vL[BXn]) * scrh;
+  const double sBx = Bx > 0.0 ? 1.0 : -1.0;
+  const double duL = sl - vL[Xn], duR = sr - vR[Xn];
+  scrh = 1.0 / (duR * uR[RHO] - duL * uL[RHO]);
+  const double SM = (duR * uR[Xn] - duL * uL[Xn] - ptR + ptL) * scrh;
+  double pts = duR * uR[RHO] * ptL - duL * uL[RHO] * ptR + vL[RHO] * vR[RHO] * duR * duL * (vR[Xn] - vL[Xn]);
+  pts *= scrh;
+  usL[RHO] = uL[RHO] * duL / (sl - SM);
+  usR[RHO] = uR[RHO] * duR / (sr - SM);
+  const double sqrL = sqrt(usL[RHO]), sqrR = sqrt(usR[RHO]);
+  double S1L = SM - fabs(Bx) / sqrL, S1R = SM + fabs(Bx) / sqrR;
+  int revert = 0;
+  if ((S1L - sl) < 1.e-4 * (SM - sl)) revert = 1;
+  if ((S1R - sr) > -1.e-4 * (sr - SM)) revert = 1;
+  double scrhL, scrhR;
+  if (revert) { /* hlldMHD.hpp:323-340 */
+    scrh = 1.0 / (sr - sl);
+    for (int c = 0; c < nc; c++) {
+      const int b = o->BX1 + c;
+      double h = sr * uR[b] - sl * uL[b] + fL[b] - fR[b];
+      h *= scrh;
+      usL[b] = usR[b] = h;
+    }
+    S1L = S1R = SM;
+  } else {
+    scrhL = (uL[RHO] * duL * duL - Bx * Bx) / (uL[RHO] * duL * (sl - SM) - Bx * Bx);
+    scrhR = (uR[RHO] * duR * duR - Bx * Bx) / (uR[RHO] * duR * (sr - SM) - Bx * Bx);
+    usL[BXn] = usR[BXn] = Bx;
+    if (nc >= 2) { usL[BXt] = uL[BXt] * scrhL; usR[BXt] = uR[BXt] * scrhR; }
+    if (nc == 3) { usL[BXb] = uL[BXb] * scrhL; usR[BXb] = uR[BXb] * scrhR; }
+  }
+  scrhL = Bx / (uL[RHO] * duL);
+  scrhR = Bx / (uR[RHO] * duR);
+  double vsL = 0, vsR = 0, wsL = 0, wsR = 0;
+  if (nc >= 2) { vsL = vL[Xt] - scrhL * (usL[BXt] - uL[BXt]); vsR = vR[Xt] - scrhR * (usR[BXt] - uR[BXt]); }
+  if (nc == 3) { wsL = vL[Xb] - scrhL * (usL[BXb] - uL[BXb]); wsR = vR[Xb] - scrhR * (usR[BXb] - uR[BXb]); }
+  usL[Xn] = usL[RHO] * SM;
+  usR[Xn] = usR[RHO] * SM;
+  if (nc >= 2) { usL[Xt] = usL[RHO] * vsL; usR[Xt] = usR[RHO] * vsR; }
+  if (nc == 3) { usL[Xb] = usL[RHO] * wsL; usR[Xb] = usR[RHO] * wsR; }
+  scrhL = vL[Xn] * Bx;
+  if (nc >= 2) scrhL = scrhL + vL[Xt] * uL[BXt];
+  if (nc == 3) scrhL = scrhL + vL[Xb] * uL[BXb];
+  {
+    double s = SM * Bx;
+    if (nc >= 2) s = s + vsL * usL[BXt];
+    if (nc == 3) s = s + wsL * usL[BXb];
+    scrhL -= s;
+  }
+  usL[ENG] = duL * uL[ENG] - ptL * vL[Xn] + pts * SM + Bx * scrhL;
+  usL[ENG] /= sl - SM;
+  scrhR = vR[Xn] * Bx;
+  if (nc >= 2) scrhR = scrhR + vR[Xt] * uR[BXt];
+  if (nc == 3) scrhR = scrhR + vR[Xb] * uR[BXb];
+  {
+    double s = SM * Bx;
+    if (nc >= 2) s = s + vsR * usR[BXt];
+    if (nc == 3) s = s + wsR * usR[BXb];
+    scrhR -= s;
+  }
+  usR[ENG] = duR * uR[ENG] - ptR * vR[Xn] + pts * SM + Bx * scrhR;
+  usR[ENG] /= sr - SM;
+
+  if (S1L >= 0.0) {
+    for (int n = 0; n < nv; n++) F[n] = fL[n] + sl * (usL[n] - uL[n]);
+  } else if (S1R <= 0.0) {
+    for (int n = 0; n < nv; n++) F[n] = fR[n] + sr * (usR[n] - uR[n]);
+  } else { /* double-star states, hlldMHD.hpp:401-455 */
+    double ussl[8], ussr[8], vss = 0, wss = 0;
+    ussl[RHO] = usL[RHO];
+    ussr[RHO] = usR[RHO];
+    if (nc >= 2) { vss = sqrL * vsL + sqrR * vsR + (usR[BXt] - usL[BXt]) * sBx; vss /= sqrL + sqrR; }
+    if (nc == 3) { wss = sqrL * wsL + sqrR * wsR + (usR[BXb] - usL[BXb]) * sBx; wss /= sqrL + sqrR; }
+    ussl[Xn] = ussl[RHO] * SM;
+    ussr[Xn] = ussr[RHO] * SM;
+    if (nc >= 2) { ussl[Xt] = ussl[RHO] * vss; ussr[Xt] = ussr[RHO] * vss; }
+    if (nc == 3) { ussl[Xb] = ussl[RHO] * wss; ussr[Xb] = ussr[RHO] * wss; }
+    ussl[BXn] = ussr[BXn] = Bx;
+    if (nc >= 2) {
+      ussl[BXt] = sqrL * usR[BXt] + sqrR * usL[BXt] + sqrL * sqrR * (vsR - vsL) * sBx;
+      ussl[BXt] /= sqrL + sqrR;
+      ussr[BXt] = ussl[BXt];
+    }
+    if (nc == 3) {
+      ussl[BXb] = sqrL * usR[BXb] + sqrR * usL[BXb] + sqrL * sqrR * (wsR - wsL) * sBx;
+      ussl[BXb] /= sqrL + sqrR;
+      ussr[BXb] = ussl[BXb];
+    }
+    scrhL = SM * Bx;
+    if (nc >= 2) scrhL = scrhL + vsL * usL[BXt];
+    if (nc == 3) scrhL = scrhL + wsL * usL[BXb];
+    {
+      double s = SM * Bx;
+      if (nc >= 2) s = s + vss * ussl[BXt];
+      if (nc == 3) s = s + wss * ussl[BXb];
+      scrhL -= s;
+    }
+    scrhR = SM * Bx;
+    if (nc >= 2) scrhR = scrhR + vsR * usR[BXt];
+    if (nc == 3) scrhR = scrhR + wsR * usR[BXb];
+    {
+      double s = SM * Bx;
+      if (nc >= 2) s = s + vss * ussr[BXt];
+      if (nc == 3) s = s + wss * ussr[BXb];
+      scrhR -= s;
+    }
+    ussl[ENG] = usL[ENG] - sqrL * scrhL * sBx;
+    ussr[ENG] = usR[ENG] + sqrR * scrhR * sBx;
+    if (SM >= 0.0) {
+      for (int n = 0; n < nv; n++) F[n] = fL[n] + S1L * (ussl[n] - usL[n]) + sl * (usL[n] - uL[n]);
+    } else {
+      for (int n = 0; n < nv; n++) F[n] = fR[n] + S1R * (ussr[n] - usR[n]) + sr * (usR[n] - uR[n]);
+    }
+  }
+}
+
+/* ---- EMF storage: MHDsolvers/storeFlux.hpp:15-208 ----------------------------------------------- */
+static void store_emf(Oracle *o, int dir, long c, const double *F, const Speeds *sp, const double *vL,
+                      const double *vR) {
+  const int nc = o->d.ncomp, nd = o->d.ndim, RHO = o->RHO;
+  const int Xn = o->MX1 + dir, Xt = o->MX1 + tdir(dir), Xb = o->MX1 + bdir(dir);
+  const int BXn = o->BX1 + dir, BXt = o->BX1 + tdir(dir), BXb = o->BX1 + bdir(dir);
+  /* per-direction arrays and signs, hlldMHD.hpp:78-145 */
+  double *Et, *Eb, *SV, st, sb;
+  if (dir == 0) { Et = o->ezi; Eb = o->eyi; SV = o->svx; st = -1.0; sb = +1.0; }
+  else if (dir == 1) { Et = o->ezj; Eb = o->exj; SV = o->svy; st = +1.0; sb = -1.0; }
+  else { Et = o->eyk; Eb = o->exk; SV = o->svz; st = -1.0; sb = +1.0; }
+  if (nd < 3) sb = 1.0;
+  const int mode = o->d.emf;
+  if (mode == EMF_ARITHMETIC || mode == EMF_UCT0 || mode == EMF_UCT_CONTACT) {
+    if (nc > 1) {
+      Et[c] = st * F[BXt];
+      if (nd == 3) Eb[c] = sb * F[BXb];
+    }
+    if (mode == EMF_UCT_CONTACT) {
+      double s = 0.5;
+      if (F[RHO] > 1.0e-6) s = 1.0;
+      if (F[RHO] < -1.0e-6) s = 0.0;
+      SV[c] = s;
+    }
+    return;
+  }
+  const double sl = sp->sl, sr = sp->sr;
+  const double ar = fmax(0.0, sr), al = fmin(0.0, sl);
+  double scrh = 1.0 / (ar - al);
+  if (nc > 1) {
+    Et[c] = -st * (ar * vL[Xt] - al * vR[Xt]) * scrh;
+    if (nc == 3) Eb[c] = -sb * (ar * vL[Xb] - al * vR[Xb]) * scrh;
+  }
+  if (mode == EMF_UCT_HLL) { /* storeFlux.hpp:46-75 */
+    o->aL[dir][c] = ar * scrh;
+    o->aR[dir][c] = -al * scrh;
+    o->dR[dir][c] = -al * ar * scrh;
+    o->dL[dir][c] = o->dR[dir][c];
+    return;
+  }
+  /* uct_hlld, storeFlux.hpp:77-208 */
+  const double ptL = total_pressure(o, vL), ptR = total_pressure(o, vR);
+  const double uLr = vL[RHO], uRr = vR[RHO], uLm = vL[Xn] * vL[RHO], uRm = vR[Xn] * vR[RHO];
+  const double Bn = (sr * vR[BXn] - sl * vL[BXn]) / (sr - sl);
+  const double duL = sl - vL[Xn], duR = sr - vR[Xn];
+  double s2 = 1.0 / (duR * uRr - duL * uLr);
+  const double Sc = (duR * uRm - duL * uLm - ptR + ptL) * s2;
+  const double sqrL = sqrt(uLr * duL / (sl - Sc)), sqrR = sqrt(uRr * duR / (sr - Sc));
+  const double SaL = Sc - fabs(Bn) / sqrL, SaR = Sc + fabs(Bn) / sqrR;
+  int revert = 0;
+  if ((SaL - sl) < 1e-4 * (Sc - sl)) revert = 1;
+  if ((SaR - sr) > -1e-4 * (sr - Sc)) revert = 1;
+  const double chiL = (vL[Xn] - Sc) * (sl - Sc) / (SaL + sl - 2.0 * Sc);
+  const double chiR = (vR[Xn] - Sc) * (sr - Sc) / (SaR + sr - 2.0 * Sc);
+  const double nuL = (SaL + sl) / (fabs(SaL) + fabs(sl));
+  const double nuR = (SaR + sr) / (fabs(SaR) + fabs(sr));
+  const double nuLR = (SaL + SaR) / (fabs(SaL) + fabs(SaR));
+  double oaL, oaR, odL, odR;
+  if (fabs(SaR - SaL) > 1.e-9 * fabs(sr - sl)) {
+    odL = 0.5 * (chiL * nuL - chiL * nuLR) + 0.5 * (fabs(SaL) - nuLR * SaL);
+    odR = 0.5 * (chiR * nuR - chiR * nuLR) + 0.5 * (fabs(SaR) - nuLR * SaR);
+    oaL = 0.5 * (1.0 + nuLR);
+    oaR = 0.5 * (1.0 - nuLR);
+  } else {
+    odL = 0.5 * chiL * nuL + 0.5 * fabs(SaL);
+    odR = 0.5 * chiR * nuR + 0.5 * fabs(SaR);
+    oaL = 0.5;
+    oaR = 0.5;
+  }
+  if (revert) {
+    oaL = ar * scrh;
+    oaR = -al * scrh;
+    odR = -al * ar * scrh;
+    odL = odR;
+  }
+  o->aL[dir][c] = oaL;
+  o->aR[dir][c] = oaR;
+  o->dL[dir][c] = odL;
+  o->dR[dir][c] = odR;
+}
+
+/* ---- RiemannSolver::CalcFlux<dir>: reconstruct (extrapolateToFaces.hpp:89-124), solve, store ------ */
+static void calc_flux(Oracle *o, int dir) {
+  const OracleDesc *d = &o->d;
+  const int nv = o->nvar;
+  /* perpendicular extension of the face box: 0 for HD; 1 or nghost for MHD (hlldMHD.hpp:32-49) */
+  int ext = 0;
+  if (d->mhd) ext = (d->emf == EMF_UCT_HLL || d->emf == EMF_UCT_HLLD) ? d->nghost[dir] : 1;
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; a++) {
+    const int e = (a < d->ndim && a != dir) ? ext : 0;
+    lo[a] = o->beg[a] - e;
+    hi[a] = o->end[a] + e + (a == dir ? 1 : 0);
+  }
+  const long s = dir == 0 ? 1 : (dir == 1 ? o->sj : o->sk);
+  for (int k = lo[2]; k < hi[2]; k++)
+    for (int j = lo[1]; j < hi[1]; j++)
+      for (int i = lo[0]; i < hi[0]; i++) {
+        const long c = C(o, k, j, i);
+        double vL[8], vR[8], F[8];
+        for (int n = 0; n < nv; n++) {
+          const double *q = o->Vc + n * o->sn + c;
+          double dvm = q[-s] - q[-2 * s];
+          double dvp = q[0] - q[-s];
+          double dv = van_leer(dvp, dvm);
+          vL[n] = q[-s] + 0.5 * dv;
+          dvm = dvp;
+          dvp = q[s] - q[0];
+          dv = van_leer(dvp, dvm);
+          vR[n] = q[0] - 0.5 * dv;
+        }
+        Speeds sp = {0, 0, 0};
+        if (d->mhd) {
+          vL[o->BX1 + dir] = vR[o->BX1 + dir] = o->Vs[dir * o->vn + S(o, k, j, i)];
+          riemann_mhd(o, dir, vL, vR, F, &sp);
+          store_emf(o, dir, c, F, &sp, vL, vR);
+        } else {
+          riemann_hd(o, dir, vL, vR, F, &sp);
+        }
+        for (int n = 0; n < nv; n++) o->Flux[n * o->sn + c] = F[n];
+        o->cMax[c] = sp.cmax;
+      }
+}
+
+/* ---- Fluid_CorrectFluxFunctor + Fluid_CalcRHSFunctor, cartesian: calcRightHandSide.hpp:152-195, 201-551 */
+static void calc_rhs(Oracle *o, int dir) {
+  const OracleDesc *d = &o->d;
+  const int nv = o->nvar;
+  const long s = dir == 0 ? 1 : (dir == 1 ? o->sj : o->sk);
+  /* face area A = product of the other spacings in D_EXPAND order (makeGeometry.cpp:139-211) */
+  double A = 1.0, dV = d->dx[0];
+  if (dir == 0) { if (d->ndim >= 2) A = A * d->dx[1]; if (d->ndim == 3) A = A * d->dx[2]; }
+  if (dir == 1) { A = d->dx[0]; if (d->ndim == 3) A = A * d->dx[2]; }
+  if (dir == 2) { A = d->dx[0] * d->dx[1]; }
+  if (d->ndim >= 2) dV = dV * d->dx[1];
+  if (d->ndim == 3) dV = dV * d->dx[2];
+  int hi[3];
+  for (int a = 0; a < 3; a++) hi[a] = o->end[a] + (a == dir ? 1 : 0);
+  for (int n = 0; n < nv; n++)
+    for (int k = o->beg[2]; k < hi[2]; k++)
+      for (int j = o->beg[1]; j < hi[1]; j++)
+        for (int i = o->beg[0]; i < hi[0]; i++) o->Flux[n * o->sn + C(o, k, j, i)] *= A;
+  const double dtdV = o->dt / dV;
+  for (int k = o->beg[2]; k < o->end[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0]; i++) {
+        const long c = C(o, k, j, i);
+        o->InvDt[c] = o->InvDt[c] + 0.5 * (o->cMax[c + s] + o->cMax[c]) / (d->dx[dir]);
+        for (int n = 0; n < nv; n++) {
+          /* the CT-evolved field components are not updated here (calcRightHandSide.hpp:541-549) */
+          if (d->mhd && n >= o->BX1 && n < o->BX1 + d->ndim) continue;
+          const double rhs = -dtdV * (o->Flux[n * o->sn + c + s] - o->Flux[n * o->sn + c]);
+          o->Uc[n * o->sn + c] += rhs;
+        }
+      }
+}
+
+/* ---- constrained transport ------------------------------------------------------------------------ */
+/* CalcCellCenteredEMF, calcCornerEmf.hpp:85-126 */
+static void cell_centered_emf(Oracle *o) {
+  const int nc = o->d.ncomp, nd = o->d.ndim, VX1 = o->MX1, BX1 = o->BX1;
+  for (long c = 0; c < o->sn; c++) {
+    const double v1 = o->Vc[VX1 * o->sn + c], B1 = o->Vc[BX1 * o->sn + c];
+    const double v2 = nc >= 2 ? o->Vc[(VX1 + 1) * o->sn + c] : 0.0, B2 = nc >= 2 ? o->Vc[(BX1 + 1) * o->sn + c] : 0.0;
+    const double v3 = nc == 3 ? o->Vc[(VX1 + 2) * o->sn + c] : 0.0, B3 = nc == 3 ? o->Vc[(BX1 + 2) * o->sn + c] : 0.0;
+    if (nd == 3) {
+      o->Ex1[c] = (v3 * B2 - v2 * B3);
+      o->Ex2[c] = (v1 * B3 - v3 * B1);
+    }
+    o->Ex3[c] = (v2 * B1 - v1 * B2);
+  }
+}
+
+/* transverse MC reconstruction towards a corner, calcRiemannEmf.hpp:95-126 */
+static void corner_states(const double *q, long p, long s, double *qL, double *qR) {
+  const long pm = p - s;
+  double dq = mc_lim(q[pm + s] - q[pm], q[pm] - q[pm - s]);
+  *qL = q[pm] + 0.5 * dq;
+  dq = mc_lim(q[p + s] - q[p], q[p] - q[p - s]);
+  *qR = q[p] - 0.5 * dq;
+}
+
+static double riemann_contribution(const Oracle *o, int a, long c, long sa, const double *B, long cB, long sB,
+                                   const double *E, long sE, double sign) {
+  const double aL = 0.5 * (o->aL[a][c - sa] + o->aL[a][c]);
+  const double aR = 0.5 * (o->aR[a][c - sa] + o->aR[a][c]);
+  const double dL = 0.5 * (o->dL[a][c - sa] + o->dL[a][c]);
+  const double dR = 0.5 * (o->dR[a][c - sa] + o->dR[a][c]);
+  double bL, bR, vL, vR;
+  corner_states(B, cB, sB, &bL, &bR);
+  corner_states(E, c, sE, &vL, &vR);
+  const double phi = dR * bR - dL * bL;
+  return (aL * vL * bL + aR * vR * bR) + sign * phi;
+}
+
+/* CalcCornerEMF dispatcher, calcCornerEmf.hpp:15-38 */
+static void corner_emf(Oracle *o) {
+  const int nd = o->d.ndim, mode = o->d.emf;
+  const long sj = o->sj, sk = o->sk;
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; a++) {
+    lo[a] = o->beg[a];
+    hi[a] = o->end[a] + o->off[a];
+  }
+  if (mode == EMF_UCT0 || mode == EMF_UCT_CONTACT) cell_centered_emf(o);
+  if (mode == EMF_UCT0) { /* calcCornerEmf.hpp:150-172: face EMFs modified in place on a +-1 box */
+    for (int k = lo[2] - o->off[2]; k < hi[2]; k++)
+      for (int j = lo[1] - o->off[1]; j < hi[1]; j++)
+        for (int i = lo[0] - o->off[0]; i < hi[0]; i++) {
+          const long c = C(o, k, j, i);
+          if (nd == 3) {
+            o->exj[c] = o->exj[c] * 2.0 - 0.5 * (o->Ex1[c - sj] + o->Ex1[c]);
+            o->exk[c] = o->exk[c] * 2.0 - 0.5 * (o->Ex1[c - sk] + o->Ex1[c]);
+            o->eyi[c] = o->eyi[c] * 2.0 - 0.5 * (o->Ex2[c - 1] + o->Ex2[c]);
+            o->eyk[c] = o->eyk[c] * 2.0 - 0.5 * (o->Ex2[c - sk] + o->Ex2[c]);
+          }
+          o->ezi[c] = o->ezi[c] * 2.0 - 0.5 * (o->Ex3[c - 1] + o->Ex3[c]);
+          o->ezj[c] = o->ezj[c] * 2.0 - 0.5 * (o->Ex3[c - sj] + o->Ex3[c]);
+        }
+  }
+  for (int k = lo[2]; k < hi[2]; k++)
+    for (int j = lo[1]; j < hi[1]; j++)
+      for (int i = lo[0]; i < hi[0]; i++) {
+        const long c = C(o, k, j, i);
+        if (mode == EMF_ARITHMETIC || mode == EMF_UCT0) { /* calcCornerEmf.hpp:44-82 */
+          if (nd == 3) {
+            o->ex[c] = 0.25 * (o->exj[c] + o->exj[c - sk] + o->exk[c] + o->exk[c - sj]);
+            o->ey[c] = 0.25 * (o->eyi[c] + o->eyi[c - sk] + o->eyk[c] + o->eyk[c - 1]);
+          }
+          o->ez[c] = 0.25 * (o->ezi[c] + o->ezi[c - sj] + o->ezj[c] + o->ezj[c - 1]);
+        } else if (mode == EMF_UCT_CONTACT) { /* calcCornerEmf.hpp:197-282 */
+          const double *wx = o->svx, *wy = o->svy, *wz = o->svz;
+          {
+            const double *ezi = o->ezi, *ezj = o->ezj, *E3 = o->Ex3;
+            const double l2 = (1 - wx[c - sj]) * (ezj[c] - E3[c - sj]) + (wx[c - sj]) * (ezj[c - 1] - E3[c - sj - 1]);
+            const double r2 = (1 - wx[c]) * (ezj[c] - E3[c]) + (wx[c]) * (ezj[c - 1] - E3[c - 1]);
+            const double l1 = (1 - wy[c - 1]) * (ezi[c] - E3[c - 1]) + (wy[c - 1]) * (ezi[c - sj] - E3[c - sj - 1]);
+            const double r1 = (1 - wy[c]) * (ezi[c] - E3[c]) + (wy[c]) * (ezi[c - sj] - E3[c - sj]);
+            o->ez[c] = 0.25 * (l2 + r2 + l1 + r1 + ezi[c] + ezi[c - sj] + ezj[c] + ezj[c - 1]);
+          }
+          if (nd == 3) {
+            const double *exj = o->exj, *exk = o->exk, *eyi = o->eyi, *eyk = o->eyk, *E1 = o->Ex1, *E2 = o->Ex2;
+            double l3 = (1 - wy[c - sk]) * (exk[c] - E1[c - sk]) + (wy[c - sk]) * (exk[c - sj] - E1[c - sk - sj]);
+            double r3 = (1 - wy[c]) * (exk[c] - E1[c]) + (wy[c]) * (exk[c - sj] - E1[c - sj]);
+            double l2 = (1 - wz[c - sj]) * (exj[c] - E1[c - sj]) + (wz[c - sj]) * (exj[c - sk] - E1[c - sk - sj]);
+            double r2 = (1 - wz[c]) * (exj[c] - E1[c]) + (wz[c]) * (exj[c - sk] - E1[c - sk]);
+            o->ex[c] = 0.25 * (l3 + r3 + l2 + r2 + exj[c] + exj[c - sk] + exk[c] + exk[c - sj]);
+            l3 = (1 - wx[c - sk]) * (eyk[c] - E2[c - sk]) + (wx[c - sk]) * (eyk[c - 1] - E2[c - sk - 1]);
+            r3 = (1 - wx[c]) * (eyk[c] - E2[c]) + (wx[c]) * (eyk[c - 1] - E2[c - 1]);
+            const double l1 = (1 - wz[c - 1]) * (eyi[c] - E2[c - 1]) + (wz[c - 1]) * (eyi[c - sk] - E2[c - sk - 1]);
+            const double r1 = (1 - wz[c]) * (eyi[c] - E2[c]) + (wz[c]) * (eyi[c - sk] - E2[c - sk]);
+            o->ey[c] = 0.25 * (l3 + r3 + l1 + r1 + eyi[c] + eyi[c - sk] + eyk[c] + eyk[c - 1]);
+          }
+        } else { /* uct_hll / uct_hlld: CalcRiemannAverage, calcRiemannEmf.hpp:62-428 */
+          const long s = S(o, k, j, i);
+          const double *B1 = o->Vs, *B2 = o->Vs + o->vn, *B3 = o->Vs + 2 * o->vn;
+          double ez = riemann_contribution(o, 0, c, sj, B2, s, 1, o->ezj, 1, +1.0);
+          double ex = 0.0, ey = 0.0;
+          if (nd == 3) {
+            ey = riemann_contribution(o, 0, c, sk, B3, s, 1, o->eyk, 1, -1.0);
+            ex = riemann_contribution(o, 1, c, sk, B3, s, o->vj, o->exk, sj, +1.0);
+          }
+          ez += riemann_contribution(o, 1, c, 1, B1, s, o->vj, o->ezi, sj, -1.0);
+          if (nd == 3) {
+            ey += riemann_contribution(o, 2, c, 1, B1, s, o->vk, o->eyi, sk, +1.0);
+            ex += riemann_contribution(o, 2, c, sj, B2, s, o->vk, o->exj, sk, -1.0);
+            o->ex[c] = ex;
+            o->ey[c] = ey;
+          }
+          o->ez[c] = ez;
+        }
+      }
+}
+
+/* EvolveMagField, cartesian: evolveMagField.hpp:61-74 */
+static void evolve_mag_field(Oracle *o) {
+  const int nd = o->d.ndim;
+  const long sj = o->sj, sk = o->sk;
+  const double dt = o->dt, *dx = o->d.dx;
+  for (int k = o->beg[2]; k < o->end[2] + o->off[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1] + o->off[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0] + o->off[0]; i++) {
+        const long c = C(o, k, j, i), s = S(o, k, j, i);
+        double r1 = 0.0, r2 = 0.0, r3 = 0.0;
+        if (nd >= 2) r1 = r1 - dt / dx[1] * (o->ez[c + sj] - o->ez[c]);
+        if (nd == 3) r1 = r1 + dt / dx[2] * (o->ey[c + sk] - o->ey[c]);
+        if (nd >= 2) {
+          r2 = dt / dx[0] * (o->ez[c + 1] - o->ez[c]);
+          if (nd == 3) r2 = r2 - dt / dx[2] * (o->ex[c + sk] - o->ex[c]);
+        }
+        if (nd == 3) r3 = -dt / dx[0] * (o->ey[c + 1] - o->ey[c]) + dt / dx[1] * (o->ex[c + sj] - o->ex[c]);
+        o->Vs[s] += r1;
+        if (nd >= 2) o->Vs[o->vn + s] += r2;
+        if (nd == 3) o->Vs[2 * o->vn + s] += r3;
+      }
+}
+
+/* Boundary::ReconstructVcField, boundary.hpp:389-404 */
+static void reconstruct_vc_field(Oracle *o, double *V) {
+  for (int k = 0; k < o->nx[2]; k++)
+    for (int j = 0; j < o->nx[1]; j++)
+      for (int i = 0; i < o->nx[0]; i++) {
+        const long c = C(o, k, j, i), s = S(o, k, j, i);
+        V[o->BX1 * o->sn + c] = 0.5 * (o->Vs[s] + o->Vs[s + 1]);
+        if (o->d.ndim >= 2) V[(o->BX1 + 1) * o->sn + c] = 0.5 * (o->Vs[o->vn + s] + o->Vs[o->vn + s + o->vj]);
+        if (o->d.ndim == 3) V[(o->BX1 + 2) * o->sn + c] = 0.5 * (o->Vs[2 * o->vn + s] + o->Vs[2 * o->vn + s + o->vk]);
+      }
+}
+
+/* ---- boundaries: boundary.hpp:240-282 (SetBoundaries), :577-673 (periodic), :740-809 (outflow) ------ */
+static void fill_ghosts(Oracle *o, double *q, long qj, long qk, int dir, int side, int type, const int *n_int,
+                        const int *n_tot, int is_normal_velocity) {
+  /* loop bounds of BoundaryForAll / BoundaryForX{1,2,3}s, boundary.hpp:1000-1098 */
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; a++) {
+    const int g = o->d.nghost[a];
+    lo[a] = (a == dir) ? side * (g + n_int[a]) : 0;
+    hi[a] = (a == dir) ? g + side * (g + n_int[a]) : n_tot[a];
+  }
+  for (int k = lo[2]; k < hi[2]; k++)
+    for (int j = lo[1]; j < hi[1]; j++)
+      for (int i = lo[0]; i < hi[0]; i++) {
+        int r[3] = {i, j, k};
+        const int g = o->d.nghost[dir], nn = o->d.np_int[dir];
+        const int x = r[dir];
+        if (type == BC_PERIODIC) r[dir] = g + (x + g * (nn - 1)) % nn;      /* boundary.hpp:591-603 */
+        else r[dir] = g + side * (nn - 1);                                   /* boundary.hpp:756-758 */
+        const double ref = q[(long)r[2] * qk + (long)r[1] * qj + r[0]];
+        double val = ref;
+        if (type == BC_OUTFLOW && is_normal_velocity) {
+          const int sign = 1 - 2 * side;
+          if (sign * ref >= 0.0) val = 0.0;                                  /* boundary.hpp:763-767 */
+        }
+        q[(long)k * qk + (long)j * qj + i] = val;
+      }
+}
+
+static void set_boundaries(Oracle *o) {
+  const OracleDesc *d = &o->d;
+  for (int dir = 0; dir < d->ndim; dir++) {
+    for (int side = 0; side < 2; side++) {
+      for (int n = 0; n < o->nvar; n++)
+        fill_ghosts(o, o->Vc + n * o->sn, o->sj, o->sk, dir, side, d->bc[dir], d->np_int, o->nx, n == o->MX1 + dir);
+      if (d->mhd) {
+        for (int comp = 0; comp < d->ndim; comp++) {
+          if (d->bc[dir] != BC_PERIODIC && comp == dir) continue; /* normal component: ReconstructNormalField */
+          int n_int[3], n_tot[3];
+          for (int a = 0; a < 3; a++) {
+            n_int[a] = d->np_int[a] + (a == comp ? 1 : 0);
+            n_tot[a] = o->nx[a] + (a == comp ? 1 : 0);
+          }
+          fill_ghosts(o, o->Vs + comp * o->vn, o->vj, o->vk, dir, side, d->bc[dir], n_int, n_tot, 0);
+        }
+      }
+    }
+    if (d->mhd && d->bc[dir] != BC_PERIODIC && d->ndim == 1) {
+      /* ReconstructNormalField in 1-D cartesian (boundary.hpp:444-466): A = 1, no transverse terms */
+      for (int i = o->beg[0] - 1; i >= 0; i--) o->Vs[i] = 1.0 / 1.0 * (1.0 * o->Vs[i + 1] + (0.0));
+      for (int i = o->end[0]; i < o->nx[0]; i++) o->Vs[i + 1] = 1.0 / 1.0 * (1.0 * o->Vs[i] - (0.0));
+    }
+  }
+  if (d->mhd) reconstruct_vc_field(o, o->Vc);
+}
+
+void oracle_set_boundaries(Oracle *o) { set_boundaries(o); }
+
+/* ---- TimeIntegrator::Cycle, timeIntegrator.cpp:246-414 ------------------------------------------------ */
+static double compute_timestep(const Oracle *o) { /* dataBlock.cpp:333-364 */
+  double m = INFINITY;
+  for (int k = o->beg[2]; k < o->end[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0]; i++) m = fmin(1.0 / o->InvDt[C(o, k, j, i)], m);
+  return m;
+}
+
+int oracle_cycle(Oracle *o) {
+  const OracleDesc *d = &o->d;
+  const long ncell = o->sn * o->nvar, nface = d->mhd ? o->vn * d->ndim : 0;
+  double wc[2] = {0, 0}, w0[2] = {0, 0};
+  if (d->nstages == 2) { wc[0] = 0.5; w0[0] = 0.5; }
+  if (d->nstages == 3) { wc[0] = 0.25; w0[0] = 0.75; wc[1] = 2.0 / 3.0; w0[1] = 1.0 / 3.0; }
+  const double t0 = o->t;
+  double newdt = 0.0;
+  memset(o->InvDt, 0, sizeof(double) * o->sn); /* ResetStage, enroll.hpp:116-129 */
+  for (int stage = 0; stage < d->nstages; stage++) {
+    set_boundaries(o);
+    for (long c = 0; c < o->sn; c++) { /* ConvertPrimToCons, convertConsToPrim.hpp:153-189 */
+      double v[8], u[8];
+      for (int n = 0; n < o->nvar; n++) v[n] = o->Vc[n * o->sn + c];
+      prim_to_cons(o, v, u);
+      for (int n = 0; n < o->nvar; n++) o->Uc[n * o->sn + c] = u[n];
+    }
+    if (d->nstages > 1 && stage == 0) { /* StateContainer::CopyFrom */
+      memcpy(o->Uc0, o->Uc, sizeof(double) * ncell);
+      if (nface) memcpy(o->Vs0, o->Vs, sizeof(double) * nface);
+    }
+    for (int dir = 0; dir < d->ndim; dir++) { /* EvolveStage, evolveStage.hpp:41-90 */
+      calc_flux(o, dir);
+      calc_rhs(o, dir);
+    }
+    if (d->mhd && d->ndim >= 2) {
+      corner_emf(o);
+      evolve_mag_field(o);
+      reconstruct_vc_field(o, o->Uc);
+    }
+    o->t += o->dt;
+    if (stage == 0) newdt = d->cfl * compute_timestep(o);
+    if (stage > 0) { /* AddAndStore: wl*Vout + wr*Vin over whole arrays, stateContainer.cpp:91-98 */
+      const double a = wc[stage - 1], b = w0[stage - 1];
+      for (long c = 0; c < ncell; c++) o->Uc[c] = a * o->Uc[c] + b * o->Uc0[c];
+      for (long c = 0; c < nface; c++) o->Vs[c] = a * o->Vs[c] + b * o->Vs0[c];
+      o->t = a * o->t + b * t0;
+    }
+    if (d->mhd) reconstruct_vc_field(o, o->Uc); /* ConvertConsToPrim starts with it, convertConsToPrim.hpp:120 */
+    for (long c = 0; c < o->sn; c++) {
+      double v[8], u[8];
+      for (int n = 0; n < o->nvar; n++) u[n] = o->Uc[n * o->sn + c];
+      cons_to_prim(o, u, v);
+      for (int n = 0; n < o->nvar; n++) o->Vc[n * o->sn + c] = v[n];
+      o->Uc[o->ENG * o->sn + c] = u[o->ENG];
+    }
+  }
+  o->t = t0 + o->dt;
+  if (newdt > d->cfl_max_var * o->dt) {
+    o->dt = d->cfl_max_var * o->dt;
+  } else {
+    if (o->ncycles == 0 && newdt < 0.5 * o->dt) return 2; /* first_dt too large */
+    o->dt = newdt;
+  }
+  if (o->dt < 1e-15) return 1;
+  o->ncycles++;
+  return 0;
+}
+
+/* main loop, main.cpp:188-225: last step clipped to land on tstop */
+int oracle_run(Oracle *o, double tstop, long maxcycles) {
+  while (o->t < tstop) {
+    if (tstop - o->t < o->dt) o->dt = tstop - o->t;
+    int rc = oracle_cycle(o);
+    if (rc) return rc;
+    if (maxcycles >= 0 && o->ncycles >= maxcycles) break;
+  }
+  return 0;
+}

@@ -1,0 +1,156 @@
+"""CPU tests of the host-side mirror: ini grammar, grid generation, dump format, set-up initial
+conditions (against the reference's own dump.0000), and the C-ABI surface."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import SHORT
+from idefix_b200 import _abi
+from idefix_b200.dump import readDump, vc_names, writeDump
+from idefix_b200.grid import Definitions, Grid
+from idefix_b200.input import Input
+from idefix_b200.setups import REGISTRY
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_input_grammar():
+    inp = Input.from_string("""
+# comment
+[Grid]            # trailing comment
+X1-grid    1  0.0  500  u  1.0
+[Empty]
+[Hydro]
+solver  hllc   # the solver
+flag    yes
+""")
+    assert inp.Get(int, "Grid", "X1-grid", 2) == 500
+    assert inp.Get(float, "Grid", "X1-grid", 4) == 1.0
+    assert inp.Get(str, "Hydro", "solver", 0) == "hllc"
+    assert inp.Get(bool, "Hydro", "flag", 0) is True
+    assert inp.CheckEntry("Hydro", "solver") == 1 and inp.CheckEntry("Hydro", "nope") == -1
+    assert inp.CheckBlock("Empty") and not inp.CheckBlock("Nope")
+    with pytest.raises(_abi.IdefixError):
+        inp.Get(str, "Hydro", "missing", 0)
+    with pytest.raises(_abi.IdefixError):
+        Input.from_string("solver hllc\n")
+
+
+def test_getorset_round_trips_through_six_digits():
+    """src/input.hpp:147-170 stores the default through an ostream: gamma 5/3 -> 1.66667"""
+    inp = Input.from_string("[Hydro]\nsolver hll\n")
+    assert inp.GetOrSet(float, "Hydro", "gamma", 0, 5.0 / 3.0) == 1.66667
+    assert inp.Get(float, "Hydro", "gamma", 0) == 1.66667
+    assert inp.GetOrSet(float, "TimeIntegrator", "CFL_max_var", 0, 1.1) == 1.1
+
+
+def _grid(text, defs):
+    return Grid(Input.from_string(text), defs)
+
+
+def test_uniform_grid_expressions():
+    g = _grid("[Grid]\nX1-grid 1 0.0 10 u 1.0\n[Boundary]\nX1-beg outflow\nX1-end outflow\n", Definitions(1, 1))
+    assert g.np_tot == [14, 1, 1] and g.nghost == [2, 0, 0] and g.isRegularCartesian
+    dx = (1.0 - 0.0) / 10
+    assert g.x[0][2] == 0.0 + 0.5 * dx and g.xl[0][0] == 0.0 + (-2) * dx and g.xr[0][13] == 0.0 + 12 * dx
+    assert g.x[1][0] == 0.0 and g.dx[1][0] == 1.0          # unused dimension: [-0.5, 0.5]
+
+
+def test_log_and_stretched_patches():
+    txt = ("[Grid]\nX1-grid 3 1.0 8 l 2.0 16 u 4.0 8 s- 8.0\n"
+           "[Boundary]\nX1-beg outflow\nX1-end outflow\n")
+    g = _grid(txt, Definitions(1, 1))
+    assert not g.isRegularCartesian and g.np_int[0] == 32
+    xl, xr, dx = g.xl[0], g.xr[0], g.dx[0]
+    assert np.allclose(xl[1:], xr[:-1], rtol=0, atol=1e-12)          # contiguous cells
+    assert abs(xl[2] - 1.0) < 1e-14 and abs(xr[2 + 31] - 8.0) < 1e-9  # patch ends
+    ratio = dx[3:9] / dx[2:8]
+    assert np.allclose(ratio, ratio[0])                               # logarithmic: constant ratio
+    assert np.all(np.diff(dx[2 + 24:2 + 32]) > 0)                     # stretched: growing cells
+    # PPM needs 3 ghost cells (grid.cpp:61-65)
+    g4 = _grid(txt, Definitions(1, 1, order=4))
+    assert g4.nghost[0] == 3
+
+
+def test_decomposition_boundaries():
+    txt = ("[Grid]\nX1-grid 1 0.0 16 u 1.0\nX2-grid 1 0.0 8 u 1.0\n"
+           "[Boundary]\nX1-beg periodic\nX1-end periodic\nX2-beg outflow\nX2-end reflective\n")
+    g = Grid(Input.from_string(txt), Definitions(2, 2), nproc=(2, 2, 1), xproc=(1, 0, 0))
+    sub = g.subdomain()
+    assert sub["np_int"][:2] == [8, 4]
+    assert sub["lbound"][0] == _abi.BC_INTERNAL and sub["rbound"][0] == _abi.BC_PERIODIC
+    assert sub["lbound"][1] == _abi.BC_OUTFLOW and sub["rbound"][1] == _abi.BC_INTERNAL
+    assert sub["x"][0][2] == g.x[0][2 + 8]
+    with pytest.raises(_abi.IdefixError):
+        Grid(Input.from_string(txt), Definitions(2, 2), nproc=(3, 1, 1))
+
+
+@pytest.mark.parametrize("case", SHORT, ids=[c.name for c in SHORT])
+def test_initial_conditions_match_reference_dump(case):
+    """InitFlow of every set-up is bit-identical with the reference's dump.0000"""
+    s = REGISTRY[case.setup](order=case.order, overrides=case.overrides, device=None)
+    s.InitFlow(s.data)
+    h, d = s.data.host_mirror, s.data
+    ref = readDump(os.path.join(GOLD, "short", f"{case.name}.c0000.dmp"))
+    kb, ke, jb, je, ib, ie = d.beg[2], d.end[2], d.beg[1], d.end[1], d.beg[0], d.end[0]
+    for n, name in enumerate(vc_names(s.definitions)):
+        if name is not None:
+            assert np.array_equal(h.Vc[n, kb:ke, jb:je, ib:ie].transpose(2, 1, 0), ref.data["Vc-" + name]), name
+    if h.Vs is not None:
+        for dd in range(s.definitions.dimensions):
+            o = [1 if e == dd else 0 for e in range(3)]
+            a = h.Vs[dd, kb:ke + o[2], jb:je + o[1], ib:ie + o[0]].transpose(2, 1, 0)
+            assert np.array_equal(a, ref.data[f"Vs-BX{dd + 1}s"])
+    for dd in range(3):
+        g = s.grid.nghost[dd]
+        assert np.array_equal(s.grid.x[dd][g:g + s.grid.np_int[dd]], getattr(ref, f"x{dd + 1}"))
+
+
+def test_dump_round_trip(tmp_path):
+    case = [c for c in SHORT if c.name == "ot2d_hlld_ucthlld_plm"][0]
+    s = REGISTRY[case.setup](order=case.order, overrides=case.overrides, device=None)
+    s.InitFlow(s.data)
+    h = s.data.host_mirror
+    path = tmp_path / "dump.0000.dmp"
+    writeDump(str(path), s.data, vc_names(s.definitions), h.Vc, h.Vs, t=0.0, dt=1e-4)
+    mine = readDump(str(path))
+    ref = readDump(os.path.join(GOLD, "short", f"{case.name}.c0000.dmp"))
+    for name, arr in ref.data.items():
+        if name.startswith(("Vc-", "Vs-")):
+            assert np.array_equal(mine.data[name], arr), name
+    assert mine.data["dt"][0] == 1e-4 and int(mine.data["geometry"][0]) == 1
+    assert [int(v) for v in mine.data["periodicity"]] == [1, 1, 0]
+    # and the reference's own reader accepts the header
+    assert mine.header.startswith("Idefix ") and "Dump Data" in mine.header
+
+
+def test_host_only_block_has_no_device_path():
+    s = REGISTRY["sod"](device=None)
+    with pytest.raises(_abi.IdefixError):
+        s.data.SetBoundaries()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """every function include/idefix_b200.h declares is exported by the library and bound"""
+    header = open(os.path.join(ROOT, "include", "idefix_b200.h")).read()
+    declared = set(re.findall(r"\b(idfx_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (idfx_[a-z0-9_]+)", out))
+    assert declared <= exported, f"missing from the library: {sorted(declared - exported)}"
+    assert declared == set(_abi.SYMBOLS), f"binding/header mismatch: {sorted(declared ^ set(_abi.SYMBOLS))}"
+    _abi.lib()
+
+
+def test_block_create_fails_loudly_without_gpu():
+    import ctypes as C
+    n = C.c_int(0)
+    _abi.lib().idfx_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_abi.IdefixError, match="no CPU fallback"):
+        REGISTRY["sod"]()
