@@ -8,6 +8,7 @@
 // 3-D dV / A arrays bit for bit.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,6 +71,7 @@ struct IdfxBlock {
   std::vector<std::vector<double>> hostCoords;  // owned copies of the descriptor's coordinate arrays
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
+  int sweepVariant = 1;
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
   bool timing = false;
   std::vector<cudaEvent_t> evPool;      // pairs: [2n] start, [2n+1] stop
@@ -354,6 +356,7 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
       a.perpExt = -1;  // resolved per direction: nghost[dir]
   }
   a.doInvDt = 1;
+  a.variant = b->sweepVariant;
   return a;
 }
 
@@ -729,6 +732,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   for (int dir = 0; dir < desc->ndim; dir++)
     if (desc->lbound[dir] == IDFX_BC_USERDEF || desc->rbound[dir] == IDFX_BC_USERDEF) b->haveUserdef = true;
   b->fused = !b->haveUserdef;
+  if (const char *v = std::getenv("IDFX_SWEEP_VARIANT")) b->sweepVariant = std::atoi(v);
   if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
     idfx_block_destroy(b);
     return fail("device initialisation failed");

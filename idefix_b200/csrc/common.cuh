@@ -85,6 +85,7 @@ struct SweepArgs {
   int doSource;       // add geometrical source terms after this sweep (last sweep only)
   int fusedP2C;       // Uc is rebuilt from Vc in this sweep instead of read (first sweep of the fused path)
   int invDtInit;      // InvDt accumulator starts from zero in this sweep (first sweep after ResetStage)
+  int variant;        // 0: tile kernel in every direction; 1: marching kernel for the x2 / x3 sweeps
   double *Uc0;        // fused path, first stage: also save the rebuilt Uc as the "begin" state (may be null)
 };
 

@@ -118,16 +118,17 @@ struct PlmWeights {
   const double *wp, *wm, *cp, *cm, *dp, *dm;
 };
 
+// Face reconstruction from a register stencil.  st[k] holds cell (index - 3 + k) along the sweep,
+// k = 0..5; orders 1-3 read st[1..4] only (cells index-2 .. index+1), PPM reads all six.
 // positive = variable for which the face value must stay positive (RHO, PRS)
 template <int ORDER>
-IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool positive, bool regular,
-                           const PlmWeights &w, const double *__restrict__ dx, int index,
-                           double &vL, double &vR) {
+IDFX_D void reconstructStencil(const double (&st)[6], bool positive, bool regular, const PlmWeights &w,
+                               const double *__restrict__ dx, int index, double &vL, double &vR) {
   if constexpr (ORDER == 1) {
-    vL = q[-s];
-    vR = q[0];
+    vL = st[2];
+    vR = st[3];
   } else if constexpr (ORDER == 2) {
-    const double qm2 = q[-2 * s], qm1 = q[-s], q0 = q[0], qp1 = q[s];
+    const double qm2 = st[1], qm1 = st[2], q0 = st[3], qp1 = st[4];
     if (regular) {
       // extrapolateToFaces.hpp:89-124
       double dvm = qm1 - qm2;
@@ -155,7 +156,7 @@ IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool posit
     }
   } else if constexpr (ORDER == 3) {
     // extrapolateToFaces.hpp:173-246
-    const double qm2 = q[-2 * s], qm1 = q[-s], q0 = q[0], qp1 = q[s];
+    const double qm2 = st[1], qm1 = st[2], q0 = st[3], qp1 = st[4];
     double dvm = qm1 - qm2;
     double dvp = q0 - qm1;
     double dv = dvp * lim::limO3(dvp, dvm, dx[index - 1]);
@@ -174,11 +175,11 @@ IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool posit
     }
   } else {
     // extrapolateToFaces.hpp:247-307
-    double vm2 = q[-3 * s];
-    double vm1 = q[-2 * s];
-    double v0 = q[-s];
-    double vp1 = q[0];
-    double vp2 = q[s];
+    double vm2 = st[0];
+    double vm1 = st[1];
+    double v0 = st[2];
+    double vp1 = st[3];
+    double vp2 = st[4];
     double vl, vr;
     lim::ppmStates(vm2, vm1, v0, vp1, vp2, vl, vr);
     if (positive && vr <= 0.0) {
@@ -190,7 +191,7 @@ IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool posit
     vm1 = v0;
     v0 = vp1;
     vp1 = vp2;
-    vp2 = q[2 * s];
+    vp2 = st[5];
     lim::ppmStates(vm2, vm1, v0, vp1, vp2, vl, vr);
     if (positive && vl <= 0.0) {
       double dv = lim::vanLeer(vp1 - v0, v0 - vm1);
@@ -198,6 +199,26 @@ IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool posit
     }
     vR = vl;
   }
+}
+
+// The same, reading the stencil from memory: `q` points at cell `index` of the variable, `s` is the
+// element stride along the sweep.
+template <int ORDER>
+IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool positive, bool regular,
+                           const PlmWeights &w, const double *__restrict__ dx, int index,
+                           double &vL, double &vR) {
+  double st[6];
+  st[0] = 0.0;
+  st[5] = 0.0;
+  if constexpr (ORDER == 4) {
+    st[0] = q[-3 * s];
+    st[5] = q[2 * s];
+  }
+  st[1] = q[-2 * s];
+  st[2] = q[-s];
+  st[3] = q[0];
+  st[4] = q[s];
+  reconstructStencil<ORDER>(st, positive, regular, w, dx, index, vL, vR);
 }
 
 #endif  // IDFX_RECON_CUH_

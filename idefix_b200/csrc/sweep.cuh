@@ -141,6 +141,121 @@ IDFX_D void geometricSource(const DevGrid &g, const double *v, const Eos &eos, d
   }
 }
 
+// K9: area weighting and curvilinear factors of the interface flux (calcRightHandSide.hpp:152-195)
+template <class P, int DIR>
+IDFX_D void areaWeightFlux(const DevGrid &g, int geo, int k, int j, int i, double *F) {
+  constexpr int NV = P::nvar;
+  const double A0 = faceArea<DIR>(g, k, j, i);
+  const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    double Ax = A0;
+    if (geo != GEO_CARTESIAN) {
+      if constexpr (DIR == IDIR) {
+        if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
+          if (nv == mphi) Ax *= fabs(g.xl[0][i]);
+          if (nv == bphi) Ax = 1.0;
+        } else if (geo == GEO_SPHERICAL) {
+          if (nv == mphi) Ax *= fabs(g.xl[0][i]);
+          if (nv == bth || nv == bphi) Ax = g.xl[0][i];
+        }
+      } else if constexpr (DIR == JDIR) {
+        if (geo == GEO_SPHERICAL && P::ncomp == 3) {
+          if (nv == mphi) Ax *= fabs(g.sinx2m[j]);
+          if (nv == bphi) Ax = 1.0;
+        }
+      }
+    }
+    F[nv] = F[nv] * Ax;
+  }
+}
+
+// K10 (+K11): flux divergence, time-step estimate, geometrical sources and conservative update of
+// one cell from the area-weighted fluxes of its two interfaces along DIR
+// (calcRightHandSide.hpp:201-551, addSourceTerms.hpp:16-195).  idir = index of the cell along DIR.
+// vcAt(nv) / ucAt(nv) / invDtPrev() fetch the cell's primitives, conservatives and InvDt accumulator
+// from wherever the calling kernel keeps them; they are only called when the value is needed.
+template <class P, int DIR, class VcF, class UcF, class DtF>
+IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double dt, int k, int j, int i,
+                       int idir, long long cell, const double *Fm, const double *Fp, double cmaxm, double cmaxp,
+                       VcF vcAt, UcF ucAt, DtF invDtPrev) {
+  constexpr int NV = P::nvar;
+  const double dtdV = dt / cellVolume(g, k, j, i);
+  double rhs[NV];
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (Fp[nv] - Fm[nv]);
+
+  if (geo != GEO_CARTESIAN) {
+    const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
+    if constexpr (DIR == IDIR) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        if (nv == mphi) rhs[nv] = rhs[nv] / g.x[0][i];
+        if constexpr (P::mhd) {
+          if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
+            if (nv == bphi) rhs[nv] = -dt / g.dx[0][i] * (Fp[nv] - Fm[nv]);
+          } else if (geo == GEO_SPHERICAL) {
+            if (nv == bth || nv == bphi) {
+              const double q = dt / (g.x[0][i] * g.dx[0][i]);
+              rhs[nv] = -q * ((Fp[nv] - Fm[nv]));
+            }
+          }
+        }
+      }
+    } else if constexpr (DIR == JDIR) {
+      if (geo == GEO_SPHERICAL && P::ncomp == 3) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) {
+          if (nv == mphi) rhs[nv] /= fabs(g.sinx2[j]);
+          if constexpr (P::mhd) {
+            if (nv == bphi) rhs[nv] = -dt / (g.rt[i] * g.dx[1][j]) * (Fp[nv] - Fm[nv]);
+          }
+        }
+      }
+    }
+  }
+
+  // time-step control (calcRightHandSide.hpp:426-531)
+  if (a.doInvDt) {
+    double dl = g.dx[DIR][idir];
+    if (geo == GEO_POLAR) {
+      if constexpr (DIR == JDIR) dl = dl * g.x[0][i];
+    } else if (geo == GEO_SPHERICAL) {
+      if constexpr (DIR == JDIR) dl = dl * g.rt[i];
+      if constexpr (DIR == KDIR) dl = dl * g.rt[i] * g.dmu[j] / g.dx[1][j];
+    }
+    // invDtInit: first sweep after ResetStage, the accumulator is known to be zero
+    const double prev = a.invDtInit ? 0.0 : invDtPrev();
+    a.invDt[cell] = prev + 0.5 * (cmaxp + cmaxm) / (dl);
+  }
+
+  // conservative update; CT-evolved field components are skipped (calcRightHandSide.hpp:541-549)
+  double s1 = 0.0, s2 = 0.0;
+  double ucell[NV];
+  if (a.doSource || a.fusedP2C) {
+    double v[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) v[nv] = vcAt(nv);
+    if (a.doSource) geometricSource<P>(g, v, eos, dt, j, i, s1, s2);
+    // fused path: the conservative state of the cell is rebuilt from the primitives
+    // (Fluid::ConvertPrimToCons) instead of being read back, and optionally saved as the
+    // "begin" state of the Runge-Kutta cycle (StateContainer::CopyFrom)
+    if (a.fusedP2C) primToCons<P>(ucell, v, eos);
+  }
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) {
+    if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
+    double u0 = a.fusedP2C ? ucell[nv] : ucAt(nv);
+    if (a.fusedP2C && a.Uc0 != nullptr) a.Uc0[nv * g.sn + cell] = u0;
+    double u = u0 + rhs[nv];
+    if (a.doSource) {
+      if (nv == P::MX1) u += s1;
+      if (P::ncomp >= 2 && nv == P::MX2) u += s2;
+    }
+    a.Uc[nv * g.sn + cell] = u;
+  }
+}
+
 template <class P, int SOLVER, int ORDER, int DIR, int BX, int BY>
 __global__ void __launch_bounds__(BX *BY) sweepKernel(const SweepArgs a) {
   constexpr int NV = P::nvar;
@@ -208,31 +323,9 @@ __global__ void __launch_bounds__(BX *BY) sweepKernel(const SweepArgs a) {
       storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
     }
 
-    // area weighting and curvilinear factors (calcRightHandSide.hpp:152-195)
-    const double A0 = faceArea<DIR>(g, k, j, i);
-    const int geo = g.geometry;
-    const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
+    areaWeightFlux<P, DIR>(g, g.geometry, k, j, i, F);
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) {
-      double Ax = A0;
-      if (geo != GEO_CARTESIAN) {
-        if constexpr (DIR == IDIR) {
-          if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
-            if (nv == mphi) Ax *= fabs(g.xl[0][i]);
-            if (nv == bphi) Ax = 1.0;
-          } else if (geo == GEO_SPHERICAL) {
-            if (nv == mphi) Ax *= fabs(g.xl[0][i]);
-            if (nv == bth || nv == bphi) Ax = g.xl[0][i];
-          }
-        } else if constexpr (DIR == JDIR) {
-          if (geo == GEO_SPHERICAL && P::ncomp == 3) {
-            if (nv == mphi) Ax *= fabs(g.sinx2m[j]);
-            if (nv == bphi) Ax = 1.0;
-          }
-        }
-      }
-      sF[nv][ty][tx] = F[nv] * Ax;
-    }
+    for (int nv = 0; nv < NV; nv++) sF[nv][ty][tx] = F[nv];
     sF[NV][ty][tx] = aux.cmax;
   }
   __syncthreads();
@@ -245,81 +338,15 @@ __global__ void __launch_bounds__(BX *BY) sweepKernel(const SweepArgs a) {
   const int txr = (DIR == IDIR) ? tx + 1 : tx;
   const int tyr = (DIR == IDIR) ? ty : ty + 1;
 
-  const double dtdV = dt / cellVolume(g, k, j, i);
-  double rhs[NV];
-#pragma unroll
-  for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (sF[nv][tyr][txr] - sF[nv][ty][tx]);
-
-  const int geo = g.geometry;
-  if (geo != GEO_CARTESIAN) {
-    const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
-    if constexpr (DIR == IDIR) {
-#pragma unroll
-      for (int nv = 0; nv < NV; nv++) {
-        if (nv == mphi) rhs[nv] = rhs[nv] / g.x[0][i];
-        if constexpr (P::mhd) {
-          if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
-            if (nv == bphi) rhs[nv] = -dt / g.dx[0][i] * (sF[nv][tyr][txr] - sF[nv][ty][tx]);
-          } else if (geo == GEO_SPHERICAL) {
-            if (nv == bth || nv == bphi) {
-              const double q = dt / (g.x[0][i] * g.dx[0][i]);
-              rhs[nv] = -q * ((sF[nv][tyr][txr] - sF[nv][ty][tx]));
-            }
-          }
-        }
-      }
-    } else if constexpr (DIR == JDIR) {
-      if (geo == GEO_SPHERICAL && P::ncomp == 3) {
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) {
-          if (nv == mphi) rhs[nv] /= fabs(g.sinx2[j]);
-          if constexpr (P::mhd) {
-            if (nv == bphi) rhs[nv] = -dt / (g.rt[i] * g.dx[1][j]) * (sF[nv][tyr][txr] - sF[nv][ty][tx]);
-          }
-        }
-      }
-    }
-  }
-
-  // time-step control (calcRightHandSide.hpp:426-531)
-  if (a.doInvDt) {
-    double dl = g.dx[DIR][idir];
-    if (geo == GEO_POLAR) {
-      if constexpr (DIR == JDIR) dl = dl * g.x[0][i];
-    } else if (geo == GEO_SPHERICAL) {
-      if constexpr (DIR == JDIR) dl = dl * g.rt[i];
-      if constexpr (DIR == KDIR) dl = dl * g.rt[i] * g.dmu[j] / g.dx[1][j];
-    }
-    // invDtInit: first sweep after ResetStage, the accumulator is known to be zero
-    const double prev = a.invDtInit ? 0.0 : a.invDt[cell];
-    a.invDt[cell] = prev + 0.5 * (sF[NV][tyr][txr] + sF[NV][ty][tx]) / (dl);
-  }
-
-  // conservative update; CT-evolved field components are skipped (calcRightHandSide.hpp:541-549)
-  double s1 = 0.0, s2 = 0.0;
-  double ucell[NV];
-  if (a.doSource || a.fusedP2C) {
-    double v[NV];
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) v[nv] = a.Vc[nv * g.sn + cell];
-    if (a.doSource) geometricSource<P>(g, v, eos, dt, j, i, s1, s2);
-    // fused path: the conservative state of the cell is rebuilt from the primitives
-    // (Fluid::ConvertPrimToCons) instead of being read back, and optionally saved as the
-    // "begin" state of the Runge-Kutta cycle (StateContainer::CopyFrom)
-    if (a.fusedP2C) primToCons<P>(ucell, v, eos);
-  }
+  double Fm[NV], Fp[NV];
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
-    if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
-    double u0 = a.fusedP2C ? ucell[nv] : a.Uc[nv * g.sn + cell];
-    if (a.fusedP2C && a.Uc0 != nullptr) a.Uc0[nv * g.sn + cell] = u0;
-    double u = u0 + rhs[nv];
-    if (a.doSource) {
-      if (nv == P::MX1) u += s1;
-      if (P::ncomp >= 2 && nv == P::MX2) u += s2;
-    }
-    a.Uc[nv * g.sn + cell] = u;
+    Fm[nv] = sF[nv][ty][tx];
+    Fp[nv] = sF[nv][tyr][txr];
   }
+  updateCell<P, DIR>(a, g, g.geometry, eos, dt, k, j, i, idir, cell, Fm, Fp, sF[NV][ty][tx], sF[NV][tyr][txr],
+                     [&](int nv) { return a.Vc[nv * g.sn + cell]; }, [&](int nv) { return a.Uc[nv * g.sn + cell]; },
+                     [&]() { return a.invDt[cell]; });
 }
 
 // ---- host-side launcher ------------------------------------------------------

@@ -5,15 +5,17 @@
 
 #include "kernels.h"
 #include "sweep.cuh"
+#include "sweep_march.cuh"
 
 template <class P, int SOLVER, int ORDER>
 inline int sweepDir(int dir, const SweepArgs &a, cudaStream_t st) {
   if (dir == 0) return (int)launchSweep<P, SOLVER, ORDER, 0>(a, st);
+  // x2 / x3: marching kernel (sweep_march.cuh) unless the tile kernel is asked for (a.variant == 0)
   if constexpr (P::ndim >= 2) {
-    if (dir == 1) return (int)launchSweep<P, SOLVER, ORDER, 1>(a, st);
+    if (dir == 1) return a.variant ? (int)launchSweepMarch<P, SOLVER, ORDER, 1>(a, st) : (int)launchSweep<P, SOLVER, ORDER, 1>(a, st);
   }
   if constexpr (P::ndim == 3) {
-    if (dir == 2) return (int)launchSweep<P, SOLVER, ORDER, 2>(a, st);
+    if (dir == 2) return a.variant ? (int)launchSweepMarch<P, SOLVER, ORDER, 2>(a, st) : (int)launchSweep<P, SOLVER, ORDER, 2>(a, st);
   }
   return -1;
 }
