@@ -71,7 +71,7 @@ struct IdfxBlock {
   std::vector<std::vector<double>> hostCoords;  // owned copies of the descriptor's coordinate arrays
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
-  int sweepVariant = 1;
+  int sweepVariant = 2;
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
   bool timing = false;
   std::vector<cudaEvent_t> evPool;      // pairs: [2n] start, [2n+1] stop

@@ -201,6 +201,60 @@ IDFX_D void reconstructStencil(const double (&st)[6], bool positive, bool regula
   }
 }
 
+// Per-CELL form of the same reconstruction: st[k] holds cell (c - 2 + k), k = 0..4 (orders 1-3 read
+// st[1..3] only).  vl / vr are the values of cell c on its left / right face, i.e. the right state
+// vR of interface c and the left state vL of interface c+1.  A kernel that walks along the sweep
+// direction evaluates this once per cell and re-uses vr at the next interface; the expressions (and
+// therefore the bits) are those the reference evaluates twice (extrapolateToFaces.hpp:89-307).
+template <int ORDER>
+IDFX_D void reconstructCell(const double (&st)[5], bool positive, bool regular, const double (&wc)[6], double dxc,
+                            double &vl, double &vr) {
+  const double qm = st[1], q0 = st[2], qp = st[3];
+  if constexpr (ORDER == 1) {
+    vl = q0;
+    vr = q0;
+  } else if constexpr (ORDER == 2) {
+    if (regular) {
+      const double dvm = q0 - qm;
+      const double dvp = qp - q0;
+      const double dv = lim::vanLeer(dvp, dvm);
+      vr = q0 + 0.5 * dv;
+      vl = q0 - 0.5 * dv;
+    } else {
+      // wc = {wp, wm, cp, cm, dp, dm} of cell c (extrapolateToFaces.hpp:43-71)
+      double dvm = q0 - qm;
+      double dvp = qp - q0;
+      dvm *= wc[1];
+      dvp *= wc[0];
+      const double dv = lim::vanLeer(dvp, dvm, wc[2], wc[3]);
+      vr = q0 + wc[4] * dv;
+      vl = q0 - wc[5] * dv;
+    }
+  } else if constexpr (ORDER == 3) {
+    const double dvm = q0 - qm;
+    const double dvp = qp - q0;
+    double dv = dvp * lim::limO3(dvp, dvm, dxc);
+    vr = q0 + 0.5 * dv;
+    if (positive && vr <= 0.0) {
+      dv = lim::minmodRef(dvp, dvm);
+      vr = q0 + 0.5 * dv;
+    }
+    dv = dvm * lim::limO3(dvm, dvp, dxc);
+    vl = q0 - 0.5 * dv;
+    if (positive && vl <= 0.0) {
+      dv = lim::minmodRef(dvp, dvm);
+      vl = q0 - 0.5 * dv;
+    }
+  } else {
+    lim::ppmStates(st[0], qm, q0, qp, st[4], vl, vr);
+    if (positive && (vr <= 0.0 || vl <= 0.0)) {
+      const double dv = lim::vanLeer(qp - q0, q0 - qm);
+      if (vr <= 0.0) vr = q0 + 0.5 * dv;
+      if (vl <= 0.0) vl = q0 - 0.5 * dv;
+    }
+  }
+}
+
 // The same, reading the stencil from memory: `q` points at cell `index` of the variable, `s` is the
 // element stride along the sweep.
 template <int ORDER>

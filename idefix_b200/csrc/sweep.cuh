@@ -143,9 +143,8 @@ IDFX_D void geometricSource(const DevGrid &g, const double *v, const Eos &eos, d
 
 // K9: area weighting and curvilinear factors of the interface flux (calcRightHandSide.hpp:152-195)
 template <class P, int DIR>
-IDFX_D void areaWeightFlux(const DevGrid &g, int geo, int k, int j, int i, double *F) {
+IDFX_D void areaWeightFlux(const DevGrid &g, int geo, double A0, int k, int j, int i, double *F) {
   constexpr int NV = P::nvar;
-  const double A0 = faceArea<DIR>(g, k, j, i);
   const int mphi = CurvIdx<P>::mphi(geo), bphi = CurvIdx<P>::bphi(geo), bth = CurvIdx<P>::bth(geo);
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
@@ -169,18 +168,23 @@ IDFX_D void areaWeightFlux(const DevGrid &g, int geo, int k, int j, int i, doubl
     F[nv] = F[nv] * Ax;
   }
 }
+template <class P, int DIR>
+IDFX_D void areaWeightFlux(const DevGrid &g, int geo, int k, int j, int i, double *F) {
+  areaWeightFlux<P, DIR>(g, geo, faceArea<DIR>(g, k, j, i), k, j, i, F);
+}
 
 // K10 (+K11): flux divergence, time-step estimate, geometrical sources and conservative update of
 // one cell from the area-weighted fluxes of its two interfaces along DIR
 // (calcRightHandSide.hpp:201-551, addSourceTerms.hpp:16-195).  idir = index of the cell along DIR.
 // vcAt(nv) / ucAt(nv) / invDtPrev() fetch the cell's primitives, conservatives and InvDt accumulator
 // from wherever the calling kernel keeps them; they are only called when the value is needed.
+// dV = volume of the cell, dxc = its width along DIR (both as the reference stores them).
 template <class P, int DIR, class VcF, class UcF, class DtF>
-IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double dt, int k, int j, int i,
-                       int idir, long long cell, const double *Fm, const double *Fp, double cmaxm, double cmaxp,
-                       VcF vcAt, UcF ucAt, DtF invDtPrev) {
+IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double dt, double dV, double dxc,
+                       int k, int j, int i, long long cell, const double *Fm, const double *Fp, double cmaxm,
+                       double cmaxp, VcF vcAt, UcF ucAt, DtF invDtPrev) {
   constexpr int NV = P::nvar;
-  const double dtdV = dt / cellVolume(g, k, j, i);
+  const double dtdV = dt / dV;
   double rhs[NV];
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (Fp[nv] - Fm[nv]);
@@ -217,7 +221,7 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
 
   // time-step control (calcRightHandSide.hpp:426-531)
   if (a.doInvDt) {
-    double dl = g.dx[DIR][idir];
+    double dl = dxc;
     if (geo == GEO_POLAR) {
       if constexpr (DIR == JDIR) dl = dl * g.x[0][i];
     } else if (geo == GEO_SPHERICAL) {
@@ -254,6 +258,14 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
     }
     a.Uc[nv * g.sn + cell] = u;
   }
+}
+
+template <class P, int DIR, class VcF, class UcF, class DtF>
+IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double dt, int k, int j, int i,
+                       int idir, long long cell, const double *Fm, const double *Fp, double cmaxm, double cmaxp,
+                       VcF vcAt, UcF ucAt, DtF invDtPrev) {
+  updateCell<P, DIR>(a, g, geo, eos, dt, cellVolume(g, k, j, i), g.dx[DIR][idir], k, j, i, cell, Fm, Fp, cmaxm, cmaxp,
+                     vcAt, ucAt, invDtPrev);
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, int BX, int BY>

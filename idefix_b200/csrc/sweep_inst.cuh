@@ -6,9 +6,26 @@
 #include "kernels.h"
 #include "sweep.cuh"
 #include "sweep_march.cuh"
+#include "sweep_pencil.cuh"
+
+template <class P, int SOLVER, int ORDER, bool CART>
+inline int sweepPencil(int dir, const SweepArgs &a, cudaStream_t st) {
+  if (dir == 0) return (int)launchPencilRow<P, SOLVER, ORDER, CART>(a, st);
+  if constexpr (P::ndim >= 2) {
+    if (dir == 1) return (int)launchPencilMarch<P, SOLVER, ORDER, 1, CART>(a, st);
+  }
+  if constexpr (P::ndim == 3) {
+    if (dir == 2) return (int)launchPencilMarch<P, SOLVER, ORDER, 2, CART>(a, st);
+  }
+  return -1;
+}
 
 template <class P, int SOLVER, int ORDER>
 inline int sweepDir(int dir, const SweepArgs &a, cudaStream_t st) {
+  if (a.variant >= 2) {
+    if (a.g.geometry == GEO_CARTESIAN && a.g.regular) return sweepPencil<P, SOLVER, ORDER, true>(dir, a, st);
+    return sweepPencil<P, SOLVER, ORDER, false>(dir, a, st);
+  }
   if (dir == 0) return (int)launchSweep<P, SOLVER, ORDER, 0>(a, st);
   // x2 / x3: marching kernel (sweep_march.cuh) unless the tile kernel is asked for (a.variant == 0)
   if constexpr (P::ndim >= 2) {

@@ -1,0 +1,514 @@
+// sweep_pencil.cuh -- the directional sweep of the Godunov update, one kernel per direction.
+//
+// Fuses what the reference runs as three kernels per direction with two DRAM round trips of the
+// 8-variable flux array (K8 reconstruct + Riemann + EMF storage, e.g. hlldMHD.hpp:147; K9 flux
+// correction, calcRightHandSide.hpp:16-196; K10 right-hand side, calcRightHandSide.hpp:201-551;
+// K11 geometrical source terms, addSourceTerms.hpp:16-195).  Design points, each taken from an
+// ncu capture of the previous kernels (profiles/r1a_*, profiles/r1b_*):
+//   * threads always run along x1 (unit stride), so every global access is coalesced;
+//   * the reconstruction is evaluated once per CELL (reconstructCell): the right-face value of a
+//     cell is the left state of the next interface, so the slope limiter (one FP64 division per
+//     variable) is paid once instead of twice per interface;
+//   * every interface is solved once; the previous interface's flux stays on chip and the flux
+//     array never exists in HBM;
+//   * primitives arrive through cp.async into shared memory one step ahead of their use (x2 / x3:
+//     a per-thread ring along the sweep; x1: a per-warp row buffer), each primitive is read from
+//     HBM once per sweep and no __syncthreads is needed in the marching loop;
+//   * the separable geometry factors a step needs are staged in shared memory / registers before
+//     the loop instead of being fetched with dependent global loads at every interface;
+//   * CART = true specialises cartesian uniform grids at compile time (no curvilinear branches).
+#ifndef IDFX_SWEEP_PENCIL_CUH_
+#define IDFX_SWEEP_PENCIL_CUH_
+
+#include "sweep.cuh"
+
+namespace pencil {
+
+IDFX_D unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+IDFX_D void cpAsync8(double *dstShared, const double *srcGlobal) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstShared)), "l"(srcGlobal) : "memory");
+}
+IDFX_D void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+IDFX_D void cpAsyncWait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int ORDER>
+struct Halo {
+  static constexpr int H = (ORDER == 4) ? 2 : 1;   // cells needed on each side of a cell to reconstruct it
+  static constexpr int W = 2 * H + 2;              // ring slots: stencil of one cell + one cell in flight
+};
+
+// rows of the per-CTA geometry table along the marching direction
+enum : int { T_DX = 0, T_VOL = 1, T_AREA = 2, T_W = 3 /* wp wm cp cm dp dm */, T_ROWS_CART = 3, T_ROWS_GEN = 9 };
+
+template <class P, int SOLVER, int DIR>
+IDFX_D void solveInterface(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double A0, int k, int j, int i,
+                           long long cell, const double *vL, const double *vR, double *F, RiemannAux &aux) {
+  riemannDispatch<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+  if constexpr (P::mhd) {
+    const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
+    storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
+  }
+  areaWeightFlux<P, DIR>(g, geo, A0, k, j, i, F);
+}
+
+}  // namespace pencil
+
+// =================================================================================================
+// x2 / x3 sweeps: a thread owns one (i, perpendicular) column and marches along the sweep direction.
+// =================================================================================================
+template <class P, int ORDER, bool CART>
+constexpr size_t pencilMarchSmem(int TX, int chunk) {
+  return sizeof(double) * ((size_t)TX * (pencil::Halo<ORDER>::W * P::nvar   // stencil ring
+                                         + P::nvar                          // left state of the next interface
+                                         + 2 * (P::nvar + 1)                // Uc + InvDt of the cell to update (x2)
+                                         + (P::nvar + 1)                    // previous interface: flux + signal speed
+                                         + 2                                // normal field at the interface (x2)
+                                         + 4)                               // per-column geometry factors
+                           + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * (chunk + 2));
+}
+
+template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART>
+__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(const SweepArgs a, const int chunk) {
+  static_assert(DIR == JDIR || DIR == KDIR, "the marching kernel sweeps along x2 or x3");
+  constexpr int NV = P::nvar;
+  using D = Dirs<P, DIR>;
+  constexpr int H = pencil::Halo<ORDER>::H, W = pencil::Halo<ORDER>::W;
+  constexpr int PDIR = (DIR == JDIR) ? KDIR : JDIR;  // the other perpendicular direction
+
+  extern __shared__ double smem[];
+  const int tx = threadIdx.x;
+  double *ring = smem + tx;                         // ring[(slot * NV + nv) * TX]
+  double *vls = smem + W * NV * TX + tx;            // vls[nv * TX]
+  double *ucb = vls + NV * TX;                      // ucb[(buf * (NV+1) + nv) * TX]
+  double *fprev = ucb + 2 * (NV + 1) * TX;          // fprev[nv * TX]
+  double *vsb = fprev + (NV + 1) * TX;              // vsb[buf * TX]
+  double *inv = vsb + 2 * TX;                       // inv[n * TX], n = 0..3
+  double *tab = smem + (size_t)TX * (W * NV + NV + 2 * (NV + 1) + (NV + 1) + 2 + 4);   // tab[row * (chunk+2) + r]
+  const int tlen = chunk + 2;
+
+  const DevGrid &g = a.g;
+  const int ext = a.perpExt;
+  const int mb = g.beg[DIR] + blockIdx.y * chunk;                      // first interface of the chunk
+  const int me = min(mb + chunk, g.end[DIR]);                          // last interface (cells mb..me-1)
+
+  // ---- geometry along the march, entries for cells / faces mb-1 .. me -------------------------------
+  for (int r = tx; r <= me - mb + 1; r += TX) {
+    const int c = mb - 1 + r;
+    tab[pencil::T_DX * tlen + r] = g.dx[DIR][c];
+    tab[pencil::T_VOL * tlen + r] = g.vol[DIR][c];
+    tab[pencil::T_AREA * tlen + r] = g.area[DIR][DIR][c];
+    if constexpr (!CART) {
+      tab[(pencil::T_W + 0) * tlen + r] = g.wp[DIR][c];
+      tab[(pencil::T_W + 1) * tlen + r] = g.wm[DIR][c];
+      tab[(pencil::T_W + 2) * tlen + r] = g.cp[DIR][c];
+      tab[(pencil::T_W + 3) * tlen + r] = g.cm[DIR][c];
+      tab[(pencil::T_W + 4) * tlen + r] = g.dp[DIR][c];
+      tab[(pencil::T_W + 5) * tlen + r] = g.dm[DIR][c];
+    }
+  }
+  __syncthreads();
+
+  // ---- column owned by this thread ------------------------------------------------------------------
+  const int ilo = g.beg[0] - ext, ni = g.end[0] - g.beg[0] + 2 * ext;
+  const int pext = (P::ndim > PDIR) ? ext : 0;
+  const int plo = g.beg[PDIR] - pext, np = g.end[PDIR] - g.beg[PDIR] + 2 * pext;
+  const long long lin = (long long)blockIdx.x * TX + tx;
+  if (lin >= (long long)ni * np) return;
+  const int i = ilo + (int)(lin % ni);
+  const int p = plo + (int)(lin / ni);
+  const long long stride = (DIR == JDIR) ? g.sj : g.sk;
+  const long long vstride = (DIR == JDIR) ? g.vsj : g.vsk;
+  const long long cell0 = (DIR == JDIR) ? cidx(g, p, 0, i) : cidx(g, 0, p, i);
+  const long long face0 = DIR * g.vsn + ((DIR == JDIR) ? sidx(g, p, 0, i) : sidx(g, 0, p, i));
+  const bool columnInterior = (i >= g.beg[0]) && (i < g.end[0]) && (p >= g.beg[PDIR]) && (p < g.end[PDIR]);
+
+  const Eos eos{a.gamma, a.csiso};
+  const double dt = *a.dt;
+  const int geo = CART ? (int)GEO_CARTESIAN : g.geometry;
+  const bool regular = CART ? true : (g.regular != 0);
+  const bool needUc = columnInterior && !a.fusedP2C;
+  const bool needInvDt = columnInterior && a.doInvDt && !a.invDtInit;
+  // separable geometry factors of this column, multiplied at every step in the reference's order
+  // dV = (vol0[i]*vol1[j])*vol2[k], A = (area[D][0][i]*area[D][1][j])*area[D][2][k] (makeGeometry.cpp:66-84,139-211)
+  if constexpr (DIR == JDIR) {
+    inv[0 * TX] = g.vol[0][i];
+    inv[1 * TX] = g.vol[2][p];
+    inv[2 * TX] = g.area[DIR][0][i];
+    inv[3 * TX] = g.area[DIR][2][p];
+  } else {
+    inv[0 * TX] = g.vol[0][i] * g.vol[1][p];
+    inv[2 * TX] = g.area[DIR][0][i] * g.area[DIR][1][p];
+  }
+
+  // ---- prologue: cells mb-1-H .. mb+H, the normal field of the first interface ---------------------------
+  {
+    const double *src = a.Vc + cell0 + (long long)(mb - 1 - H) * stride;
+#pragma unroll
+    for (int c = 0; c < W; c++) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8(ring + (c * NV + nv) * TX, src + nv * g.sn);
+      src += stride;
+    }
+  }
+  if constexpr (P::mhd) pencil::cpAsync8(vsb, a.Vs + face0 + (long long)mb * vstride);
+  pencil::cpAsyncCommit();
+  pencil::cpAsyncWait<0>();
+  // right-face values of cell mb-1 = left state of the first interface
+  {
+    const double dxc = tab[pencil::T_DX * tlen];
+    double wc[6] = {0, 0, 0, 0, 0, 0};
+    if constexpr (!CART) {
+#pragma unroll
+      for (int n = 0; n < 6; n++) wc[n] = tab[(pencil::T_W + n) * tlen];
+    }
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      if (P::mhd && nv == D::BXn) continue;
+      double st[5];
+      st[0] = st[4] = 0.0;
+#pragma unroll
+      for (int d = -H; d <= H; d++) st[2 + d] = ring[((H + d) * NV + nv) * TX];
+      const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
+      double vl, vr;
+      reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
+      vls[nv * TX] = vr;
+    }
+  }
+
+  int q = 0;  // ring slot of cell m-H-1: free, receives cell m+H+1
+  const double *pre = a.Vc + cell0 + (long long)(mb + H + 1) * stride;
+  long long cellm = cell0 + (long long)mb * stride;
+  for (int m = mb; m <= me; m++) {
+    const int r = m - mb;
+    // ---- prefetch what the next interface needs ------------------------------------------------------
+    if (m < me) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8(ring + (q * NV + nv) * TX, pre + nv * g.sn);
+      if constexpr (P::mhd) pencil::cpAsync8(vsb + ((r + 1) & 1) * TX, a.Vs + face0 + (long long)(m + 1) * vstride);
+      double *ub = ucb + ((r + 1) & 1) * (NV + 1) * TX;   // cell m is updated at the next interface
+      if (needUc) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) {
+          if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
+          pencil::cpAsync8(ub + nv * TX, a.Uc + nv * g.sn + cellm);
+        }
+      }
+      if (needInvDt) pencil::cpAsync8(ub + NV * TX, a.invDt + cellm);
+    }
+    pencil::cpAsyncCommit();
+    pencil::cpAsyncWait<1>();   // everything but the group just committed has landed
+
+    // ---- cell m: face values; interface m: left state from cell m-1, right state from cell m -----------
+    int sc = q + 1 + H;         // slot of cell m
+    if (sc >= W) sc -= W;
+    double vL[NV], vR[NV];
+    {
+      const double dxc = tab[pencil::T_DX * tlen + r + 1];
+      double wc[6] = {0, 0, 0, 0, 0, 0};
+      if constexpr (!CART) {
+#pragma unroll
+        for (int n = 0; n < 6; n++) wc[n] = tab[(pencil::T_W + n) * tlen + r + 1];
+      }
+      int so[2 * H + 1];
+#pragma unroll
+      for (int d = -H; d <= H; d++) {
+        int s = q + 1 + H + d;
+        if (s >= W) s -= W;
+        so[d + H] = s * NV * TX;
+      }
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        if (P::mhd && nv == D::BXn) continue;
+        double st[5];
+        st[0] = st[4] = 0.0;
+#pragma unroll
+        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * TX];
+        const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
+        double vr;
+        reconstructCell<ORDER>(st, positive, regular, wc, dxc, vR[nv], vr);
+        vL[nv] = vls[nv * TX];
+        vls[nv * TX] = vr;
+      }
+    }
+    if constexpr (P::mhd) {
+      const double bn = vsb[(r & 1) * TX];
+      vL[D::BXn] = bn;
+      vR[D::BXn] = bn;
+    }
+    const int j = (DIR == JDIR) ? m : p;
+    const int k = (DIR == JDIR) ? p : m;
+    double A0;
+    if constexpr (DIR == JDIR) A0 = inv[2 * TX] * tab[pencil::T_AREA * tlen + r + 1] * inv[3 * TX];
+    else A0 = inv[2 * TX] * tab[pencil::T_AREA * tlen + r + 1];
+
+    double F[NV];
+    RiemannAux aux;
+    pencil::solveInterface<P, SOLVER, DIR>(a, g, geo, eos, A0, k, j, i, cellm, vL, vR, F, aux);
+
+    // ---- cell m-1: flux difference, time-step estimate, conservative update ---------------------------
+    if (r > 0 && columnInterior) {
+      const int jc = (DIR == JDIR) ? m - 1 : p;
+      const int kc = (DIR == JDIR) ? p : m - 1;
+      double dV;
+      if constexpr (DIR == JDIR) dV = inv[0 * TX] * tab[pencil::T_VOL * tlen + r] * inv[1 * TX];
+      else dV = inv[0 * TX] * tab[pencil::T_VOL * tlen + r];
+      double Fm[NV];
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * TX];
+      const double *ub = ucb + (r & 1) * (NV + 1) * TX;
+      int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring)
+      if (sp < 0) sp += W;
+      const double *vprev = ring + sp * NV * TX;
+      updateCell<P, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
+                         fprev[NV * TX], aux.cmax, [&](int nv) { return vprev[nv * TX]; },
+                         [&](int nv) { return ub[nv * TX]; }, [&]() { return ub[NV * TX]; });
+    }
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) fprev[nv * TX] = F[nv];
+    fprev[NV * TX] = aux.cmax;
+    q = (q + 1 == W) ? 0 : q + 1;
+    pre += stride;
+    cellm += stride;
+  }
+}
+
+template <class P, int SOLVER, int ORDER, int DIR, bool CART>
+inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
+  constexpr int TX = 128;
+  const DevGrid &g = a.g;
+  constexpr int PDIR = (DIR == JDIR) ? KDIR : JDIR;
+  const int ext = a.perpExt;
+  const long long ni = g.end[0] - g.beg[0] + 2 * ext;
+  const long long np = g.end[PDIR] - g.beg[PDIR] + 2 * ((P::ndim > PDIR) ? ext : 0);
+  const int nsweep = g.end[DIR] - g.beg[DIR];
+  const long long ctasPerLayer = (ni * np + TX - 1) / TX;
+  // chunk length: long enough to amortise the extra cell per chunk, short enough to fill the GPU
+  int chunk = 64;
+  while (chunk > 8 && ctasPerLayer * ((nsweep + chunk - 1) / chunk) < 4 * 148 * 3) chunk >>= 1;
+  if (chunk > nsweep) chunk = nsweep;
+  const dim3 grid((unsigned)ctasPerLayer, (unsigned)((nsweep + chunk - 1) / chunk), 1);
+  const size_t smem = pencilMarchSmem<P, ORDER, CART>(TX, 64);
+  static bool configured = false;
+  auto kern = pencilMarchKernel<P, SOLVER, ORDER, DIR, TX, CART>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(a, chunk);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// x1 sweep: a warp owns a strip of 32 consecutive cells of one x1 row (30 of them updated, the two
+// outer lanes provide the neighbouring face value / flux) and marches over the rows of an x2 chunk.
+// Lane l holds cell c = cs - 1 + l; it reconstructs cell c, solves the interface on the LEFT face of
+// c with the right-face value of lane l-1, and updates cell c with the flux of lane l+1.
+// =================================================================================================
+template <class P, int ORDER>
+constexpr int pencilRowDoublesPerWarp() {
+  constexpr int H = pencil::Halo<ORDER>::H;
+  return 2 * P::nvar * (32 + 2 * H)   // two row buffers of primitives (current row, next row in flight)
+         + P::nvar * 32               // right-face values
+         + (P::nvar + 1) * 32         // fluxes + signal speed
+         + 2 * (P::nvar + 1) * 32     // Uc + InvDt, double buffered
+         + 2 * 32;                    // normal field, double buffered
+}
+
+template <class P, int ORDER, bool CART>
+constexpr size_t pencilRowSmem(int warps, int chunk) {
+  return sizeof(double) * ((size_t)warps * pencilRowDoublesPerWarp<P, ORDER>() + 2 * (size_t)chunk);
+}
+
+template <class P, int SOLVER, int ORDER, int WARPS, bool CART>
+__global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : 3)) pencilRowKernel(const SweepArgs a, const int chunk,
+                                                                                   const int nstrips) {
+  constexpr int DIR = IDIR;
+  constexpr int NV = P::nvar;
+  using D = Dirs<P, DIR>;
+  constexpr int H = pencil::Halo<ORDER>::H;
+  constexpr int RW = 32 + 2 * H;                      // cells per row buffer
+  constexpr int STRIP = 30;                           // cells updated per warp and row
+
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *wbase = smem + (size_t)warp * pencilRowDoublesPerWarp<P, ORDER>();
+  double *rows = wbase;                               // rows[(buf * NV + nv) * RW + x], x = cell - (cs-1-H)
+  double *vrs = rows + 2 * NV * RW;                   // vrs[nv * 32 + lane]
+  double *fls = vrs + NV * 32;                        // fls[nv * 32 + lane]
+  double *ucb = fls + (NV + 1) * 32;                  // ucb[(buf * (NV+1) + nv) * 32 + lane]
+  double *vsb = ucb + 2 * (NV + 1) * 32;              // vsb[buf * 32 + lane]
+  double *tab = smem + (size_t)WARPS * pencilRowDoublesPerWarp<P, ORDER>();   // tab[row * chunk + r]
+
+  const DevGrid &g = a.g;
+  const int ext = a.perpExt;
+  const int jext = (P::ndim > 1) ? ext : 0, kext = (P::ndim > 2) ? ext : 0;
+  const int jlo = g.beg[1] - jext, jhi = g.end[1] + jext;
+  const int jb = jlo + blockIdx.y * chunk;            // first row of the chunk
+  const int je = min(jb + chunk, jhi);                // one past the last row
+
+  // ---- geometry along the march (x2) -----------------------------------------------------------------
+  for (int r = threadIdx.x; r < je - jb; r += WARPS * 32) {
+    tab[r] = g.vol[1][jb + r];
+    tab[chunk + r] = g.area[DIR][1][jb + r];
+  }
+  __syncthreads();
+
+  // ---- strip owned by this warp ----------------------------------------------------------------------
+  const long long wlin = (long long)blockIdx.x * WARPS + warp;
+  const int nk = g.end[2] - g.beg[2] + 2 * kext;
+  if (wlin >= (long long)nstrips * nk) return;
+  const int s = (int)(wlin % nstrips);
+  const int k = g.beg[2] - kext + (int)(wlin / nstrips);
+  const int cs = g.beg[0] + s * STRIP;                // first cell this warp updates
+  const int c = cs - 1 + lane;                        // cell (and left-face interface) of this lane
+  const int nx0 = g.nx[0];
+  const bool cellLoad = (c < nx0);                    // c >= 0 always (beg[0] >= H + 1 when ORDER > 1)
+  const bool faceLane = (lane >= 1) && (c <= g.end[0]);           // solves interface c
+  const bool cellLane = (lane >= 1) && (lane <= STRIP) && (c < g.end[0]);   // updates cell c
+  const bool kInterior = (k >= g.beg[2]) && (k < g.end[2]);
+
+  const Eos eos{a.gamma, a.csiso};
+  const double dt = *a.dt;
+  const int geo = CART ? (int)GEO_CARTESIAN : g.geometry;
+  const bool regular = CART ? true : (g.regular != 0);
+  // lane-invariant geometry (same association as the reference: (f0[i]*f1[j])*f2[k])
+  const int cg = cellLoad ? c : nx0 - 1;
+  const double vol0 = g.vol[0][cg], vol2 = g.vol[2][k];
+  const double ar0 = g.area[DIR][0][cg], ar2 = g.area[DIR][2][k];
+  const double dxc = g.dx[0][cg];
+  double wc[6] = {0, 0, 0, 0, 0, 0};
+  if constexpr (!CART) {
+    wc[0] = g.wp[0][cg]; wc[1] = g.wm[0][cg]; wc[2] = g.cp[0][cg];
+    wc[3] = g.cm[0][cg]; wc[4] = g.dp[0][cg]; wc[5] = g.dm[0][cg];
+  }
+
+  // x offsets of the row-buffer entries this lane copies: cell cs-1-H+lane, and (lanes < 2H) cell cs+31-H+lane
+  const int x0 = cs - 1 - H;                          // cell index of row-buffer entry 0
+  const bool ld0 = (x0 + lane >= 0) && (x0 + lane < nx0);
+  const bool ld1 = (lane < 2 * H) && (x0 + 32 + lane < nx0);
+
+  auto issueRow = [&](int j, int buf, bool withUc) {
+    const long long rowBase = cidx(g, k, j, 0);
+    double *dst = rows + buf * NV * RW;
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {   // all of them: the update rebuilds Uc from the cell's primitives
+      const double *src = a.Vc + nv * g.sn + rowBase + x0;
+      if (ld0) pencil::cpAsync8(dst + nv * RW + lane, src + lane);
+      if (ld1) pencil::cpAsync8(dst + nv * RW + 32 + lane, src + 32 + lane);
+    }
+    if constexpr (P::mhd) {
+      if (faceLane) pencil::cpAsync8(vsb + buf * 32 + lane, a.Vs + DIR * g.vsn + sidx(g, k, j, c));
+    }
+    if (withUc && cellLane) {
+      double *ub = ucb + buf * (NV + 1) * 32 + lane;
+      const long long cell = rowBase + c;
+      if (!a.fusedP2C) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) {
+          if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
+          pencil::cpAsync8(ub + nv * 32, a.Uc + nv * g.sn + cell);
+        }
+      }
+      if (a.doInvDt && !a.invDtInit) pencil::cpAsync8(ub + NV * 32, a.invDt + cell);
+    }
+  };
+  auto rowInterior = [&](int j) { return kInterior && (j >= g.beg[1]) && (j < g.end[1]); };
+
+  issueRow(jb, 0, rowInterior(jb));
+  pencil::cpAsyncCommit();
+
+  for (int j = jb; j < je; j++) {
+    const int r = j - jb;
+    const int buf = r & 1;
+    if (j + 1 < je) issueRow(j + 1, buf ^ 1, rowInterior(j + 1));
+    pencil::cpAsyncCommit();
+    pencil::cpAsyncWait<1>();
+    __syncwarp();   // the row buffer was filled by all lanes of the warp
+
+    // ---- cell c: face values --------------------------------------------------------------------------
+    const double *row = rows + buf * NV * RW + H + lane;   // row[nv*RW + d] = cell c + d
+    double vL[NV], vR[NV];
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) {
+      if (P::mhd && nv == D::BXn) continue;
+      double st[5];
+      st[0] = st[4] = 0.0;
+#pragma unroll
+      for (int d = -H; d <= H; d++) st[2 + d] = row[nv * RW + d];
+      const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
+      double vr;
+      reconstructCell<ORDER>(st, positive, regular, wc, dxc, vR[nv], vr);
+      vrs[nv * 32 + lane] = vr;
+    }
+    __syncwarp();
+
+    // ---- interface c (left face of cell c) -----------------------------------------------------------------
+    double F[NV];
+    RiemannAux aux;
+    aux.cmax = 0.0;
+    const long long cell = cidx(g, k, j, c);
+    if (faceLane) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        if (P::mhd && nv == D::BXn) continue;
+        vL[nv] = vrs[nv * 32 + lane - 1];
+      }
+      if constexpr (P::mhd) {
+        const double bn = vsb[buf * 32 + lane];
+        vL[D::BXn] = bn;
+        vR[D::BXn] = bn;
+      }
+      const double A0 = ar0 * tab[chunk + r] * ar2;
+      pencil::solveInterface<P, SOLVER, DIR>(a, g, geo, eos, A0, k, j, c, cell, vL, vR, F, aux);
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) fls[nv * 32 + lane] = F[nv];
+      fls[NV * 32 + lane] = aux.cmax;
+    }
+    __syncwarp();
+
+    // ---- cell c: flux difference, time-step estimate, conservative update ---------------------------------
+    if (cellLane && rowInterior(j)) {
+      double Fp[NV];
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) Fp[nv] = fls[nv * 32 + lane + 1];
+      const double dV = vol0 * tab[r] * vol2;
+      const double *ub = ucb + buf * (NV + 1) * 32 + lane;
+      updateCell<P, DIR>(a, g, geo, eos, dt, dV, dxc, k, j, c, cell, F, Fp, aux.cmax, fls[NV * 32 + lane + 1],
+                         [&](int nv) { return row[nv * RW]; }, [&](int nv) { return ub[nv * 32]; },
+                         [&]() { return ub[NV * 32]; });
+    }
+    __syncwarp();   // vrs / fls are rewritten by the next row
+  }
+}
+
+template <class P, int SOLVER, int ORDER, bool CART>
+inline cudaError_t launchPencilRow(const SweepArgs &a, cudaStream_t stream) {
+  constexpr int WARPS = 4;
+  const DevGrid &g = a.g;
+  const int ext = a.perpExt;
+  const int n0 = g.end[0] - g.beg[0];
+  const int nstrips = (n0 + 29) / 30;
+  const int nj = g.end[1] - g.beg[1] + 2 * ((P::ndim > 1) ? ext : 0);
+  const int nk = g.end[2] - g.beg[2] + 2 * ((P::ndim > 2) ? ext : 0);
+  const long long ctasPerChunk = ((long long)nstrips * nk + WARPS - 1) / WARPS;
+  int chunk = 64;
+  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * 148 * 3) chunk >>= 1;
+  if (chunk > nj) chunk = nj;
+  const dim3 grid((unsigned)ctasPerChunk, (unsigned)((nj + chunk - 1) / chunk), 1);
+  static bool configured = false;
+  auto kern = pencilRowKernel<P, SOLVER, ORDER, WARPS, CART>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pencilRowSmem<P, ORDER, CART>(WARPS, 64));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, WARPS * 32, pencilRowSmem<P, ORDER, CART>(WARPS, chunk), stream>>>(a, chunk, nstrips);
+  return cudaGetLastError();
+}
+
+#endif  // IDFX_SWEEP_PENCIL_CUH_
