@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidefix_b200.so")
+# IDEFIX_B200_LIB selects another build of the same library (e.g. the DEV experiment build)
+LIB_PATH = os.environ.get("IDEFIX_B200_LIB") or os.path.join(_HERE, "libidefix_b200.so")
 
 
 class IdefixError(RuntimeError):

@@ -7,12 +7,8 @@
 //   K10 CalcRightHandSide(calcRightHandSide.hpp:201-551)  flux divergence, InvDt, Uc update
 // (+ K11 AddSourceTerms, addSourceTerms.hpp:16-195, after the last direction).
 //
-// Work decomposition: a CTA owns a BX x BY tile of interfaces.  Each thread
-// reconstructs and solves ONE interface, publishes the area-weighted flux and the
-// signal speed in shared memory, and after one barrier updates the cell to the right
-// of its interface with the flux difference.  Tiles overlap by one interface along the
-// sweep direction, so the flux array never exists in HBM.  Threads run along i (unit
-// stride) in every direction, which keeps all global accesses coalesced.
+// This header holds the per-interface / per-cell building blocks; the kernels that use them
+// are in sweep_pencil.cuh.
 #ifndef IDFX_SWEEP_CUH_
 #define IDFX_SWEEP_CUH_
 
@@ -179,10 +175,10 @@ IDFX_D void areaWeightFlux(const DevGrid &g, int geo, int k, int j, int i, doubl
 // vcAt(nv) / ucAt(nv) / invDtPrev() fetch the cell's primitives, conservatives and InvDt accumulator
 // from wherever the calling kernel keeps them; they are only called when the value is needed.
 // dV = volume of the cell, dxc = its width along DIR (both as the reference stores them).
-template <class P, int DIR, class VcF, class UcF, class DtF>
+template <class P, int DIR, class VcF>
 IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double dt, double dV, double dxc,
                        int k, int j, int i, long long cell, const double *Fm, const double *Fp, double cmaxm,
-                       double cmaxp, VcF vcAt, UcF ucAt, DtF invDtPrev) {
+                       double cmaxp, VcF vcAt) {
   constexpr int NV = P::nvar;
   const double dtdV = dt / dV;
   double rhs[NV];
@@ -228,9 +224,12 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
       if constexpr (DIR == JDIR) dl = dl * g.rt[i];
       if constexpr (DIR == KDIR) dl = dl * g.rt[i] * g.dmu[j] / g.dx[1][j];
     }
-    // invDtInit: first sweep after ResetStage, the accumulator is known to be zero
-    const double prev = a.invDtInit ? 0.0 : invDtPrev();
-    a.invDt[cell] = prev + 0.5 * (cmaxp + cmaxm) / (dl);
+    // invDtInit: first sweep after ResetStage, the accumulator is known to be zero.  Otherwise the
+    // accumulation InvDt += term is a fire-and-forget RED.ADD.F64 resolved in L2 (same IEEE addition as
+    // load-add-store, but no load latency and no register / shared-memory staging of the old value)
+    const double term = 0.5 * (cmaxp + cmaxm) / (dl);
+    if (a.invDtInit) a.invDt[cell] = 0.0 + term;
+    else atomicAdd(a.invDt + cell, term);
   }
 
   // conservative update; CT-evolved field components are skipped (calcRightHandSide.hpp:541-549)
@@ -249,142 +248,22 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) {
     if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
-    double u0 = a.fusedP2C ? ucell[nv] : ucAt(nv);
-    if (a.fusedP2C && a.Uc0 != nullptr) a.Uc0[nv * g.sn + cell] = u0;
-    double u = u0 + rhs[nv];
-    if (a.doSource) {
-      if (nv == P::MX1) u += s1;
-      if (P::ncomp >= 2 && nv == P::MX2) u += s2;
-    }
-    a.Uc[nv * g.sn + cell] = u;
-  }
-}
-
-template <class P, int DIR, class VcF, class UcF, class DtF>
-IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double dt, int k, int j, int i,
-                       int idir, long long cell, const double *Fm, const double *Fp, double cmaxm, double cmaxp,
-                       VcF vcAt, UcF ucAt, DtF invDtPrev) {
-  updateCell<P, DIR>(a, g, geo, eos, dt, cellVolume(g, k, j, i), g.dx[DIR][idir], k, j, i, cell, Fm, Fp, cmaxm, cmaxp,
-                     vcAt, ucAt, invDtPrev);
-}
-
-template <class P, int SOLVER, int ORDER, int DIR, int BX, int BY>
-__global__ void __launch_bounds__(BX *BY) sweepKernel(const SweepArgs a) {
-  constexpr int NV = P::nvar;
-  using D = Dirs<P, DIR>;
-  __shared__ double sF[NV + 1][BY][BX];
-
-  const DevGrid &g = a.g;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int ext = a.perpExt;
-
-  // ---- index mapping -------------------------------------------------------
-  int i, j, k;
-  {
-    const int ilo = (DIR == IDIR) ? g.beg[0] : g.beg[0] - ((P::ndim > 0) ? ext : 0);
-    const int jlo = (DIR == JDIR) ? g.beg[1] : g.beg[1] - ((P::ndim > 1) ? ext : 0);
-    const int klo = (DIR == KDIR) ? g.beg[2] : g.beg[2] - ((P::ndim > 2) ? ext : 0);
-    if constexpr (DIR == IDIR) {
-      i = ilo + blockIdx.x * (BX - 1) + tx;
-      j = jlo + blockIdx.y * BY + ty;
-      k = klo + blockIdx.z;
-    } else if constexpr (DIR == JDIR) {
-      i = ilo + blockIdx.x * BX + tx;
-      j = jlo + blockIdx.y * (BY - 1) + ty;
-      k = klo + blockIdx.z;
+    double *up = a.Uc + nv * g.sn + cell;
+    if (a.fusedP2C || a.doSource) {
+      const double u0 = a.fusedP2C ? ucell[nv] : *up;
+      if (a.fusedP2C && a.Uc0 != nullptr) a.Uc0[nv * g.sn + cell] = u0;
+      double u = u0 + rhs[nv];
+      if (a.doSource) {
+        if (nv == P::MX1) u += s1;
+        if (P::ncomp >= 2 && nv == P::MX2) u += s2;
+      }
+      *up = u;
     } else {
-      i = ilo + blockIdx.x * BX + tx;
-      k = klo + blockIdx.y * (BY - 1) + ty;
-      j = jlo + blockIdx.z;
+      // Uc += rhs: reduction in L2 (RED.ADD.F64), bit-identical to load-add-store since no other thread
+      // touches this cell during the sweep
+      atomicAdd(up, rhs[nv]);
     }
   }
-  const int ihi = (DIR == IDIR) ? g.end[0] + 1 : g.end[0] + ((P::ndim > 0) ? ext : 0);
-  const int jhi = (DIR == JDIR) ? g.end[1] + 1 : g.end[1] + ((P::ndim > 1) ? ext : 0);
-  const int khi = (DIR == KDIR) ? g.end[2] + 1 : g.end[2] + ((P::ndim > 2) ? ext : 0);
-  const bool faceValid = (i < ihi) && (j < jhi) && (k < khi);
-
-  const long long cell = cidx(g, k, j, i);
-  const long long stride = (DIR == IDIR) ? 1 : (DIR == JDIR ? g.sj : g.sk);
-  const int idir = (DIR == IDIR) ? i : (DIR == JDIR ? j : k);  // 1-D index along the sweep
-  const Eos eos{a.gamma, a.csiso};
-  const double dt = *a.dt;
-
-  // ---- interface phase -----------------------------------------------------
-  if (faceValid) {
-    double vL[NV], vR[NV];
-    PlmWeights w{g.wp[DIR], g.wm[DIR], g.cp[DIR], g.cm[DIR], g.dp[DIR], g.dm[DIR]};
-    const bool regular = (g.regular != 0);
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) {
-      if (P::mhd && nv == D::BXn) continue;  // replaced by the face-centred field below
-      const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
-      reconstructVar<ORDER>(a.Vc + nv * g.sn + cell, stride, positive, regular, w, g.dx[DIR], idir, vL[nv], vR[nv]);
-    }
-    if constexpr (P::mhd) {
-      const double bn = a.Vs[DIR * g.vsn + sidx(g, k, j, i)];
-      vL[D::BXn] = bn;
-      vR[D::BXn] = bn;
-    }
-
-    double F[NV];
-    RiemannAux aux;
-    riemannDispatch<P, SOLVER, DIR>(vL, vR, eos, F, aux);
-
-    if constexpr (P::mhd) {
-      const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
-      storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
-    }
-
-    areaWeightFlux<P, DIR>(g, g.geometry, k, j, i, F);
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) sF[nv][ty][tx] = F[nv];
-    sF[NV][ty][tx] = aux.cmax;
-  }
-  __syncthreads();
-
-  // ---- cell phase ------------------------------------------------------------
-  const bool neighbour = (DIR == IDIR) ? (tx < BX - 1) : (ty < BY - 1);
-  const bool cellValid = neighbour && (i >= g.beg[0]) && (i < g.end[0]) && (j >= g.beg[1]) && (j < g.end[1]) &&
-                         (k >= g.beg[2]) && (k < g.end[2]);
-  if (!cellValid) return;
-  const int txr = (DIR == IDIR) ? tx + 1 : tx;
-  const int tyr = (DIR == IDIR) ? ty : ty + 1;
-
-  double Fm[NV], Fp[NV];
-#pragma unroll
-  for (int nv = 0; nv < NV; nv++) {
-    Fm[nv] = sF[nv][ty][tx];
-    Fp[nv] = sF[nv][tyr][txr];
-  }
-  updateCell<P, DIR>(a, g, g.geometry, eos, dt, k, j, i, idir, cell, Fm, Fp, sF[NV][ty][tx], sF[NV][tyr][txr],
-                     [&](int nv) { return a.Vc[nv * g.sn + cell]; }, [&](int nv) { return a.Uc[nv * g.sn + cell]; },
-                     [&]() { return a.invDt[cell]; });
-}
-
-// ---- host-side launcher ------------------------------------------------------
-template <class P, int SOLVER, int ORDER, int DIR>
-inline cudaError_t launchSweep(const SweepArgs &a, cudaStream_t stream) {
-  constexpr int BX = (DIR == IDIR) ? 64 : 32;
-  constexpr int BY = (DIR == IDIR) ? 4 : 8;
-  const DevGrid &g = a.g;
-  const int ext = a.perpExt;
-  int n[3];
-  for (int d = 0; d < 3; d++) {
-    const int e = (d < P::ndim && d != DIR) ? ext : 0;
-    n[d] = g.end[d] - g.beg[d] + 2 * e + (d == DIR ? 1 : 0);
-  }
-  dim3 block(BX, BY, 1), grid;
-  if (DIR == IDIR) {
-    grid = dim3((n[0] - 1 + BX - 2) / (BX - 1), (n[1] + BY - 1) / BY, n[2]);
-  } else if (DIR == JDIR) {
-    grid = dim3((n[0] + BX - 1) / BX, (n[1] - 1 + BY - 2) / (BY - 1), n[2]);
-  } else {
-    grid = dim3((n[0] + BX - 1) / BX, (n[2] - 1 + BY - 2) / (BY - 1), n[1]);
-  }
-  if (grid.x == 0) grid.x = 1;
-  if (grid.y == 0) grid.y = 1;
-  sweepKernel<P, SOLVER, ORDER, DIR, BX, BY><<<grid, block, 0, stream>>>(a);
-  return cudaGetLastError();
 }
 
 #endif  // IDFX_SWEEP_CUH_

@@ -22,11 +22,23 @@
 
 #include "sweep.cuh"
 
+// resident CTAs per SM the sweep kernels are compiled for (register cap = 65536 / (threads * MINB))
+#ifndef IDFX_MARCH_MINB
+#define IDFX_MARCH_MINB 4
+#endif
+#ifndef IDFX_ROW_MINB
+#define IDFX_ROW_MINB 4
+#endif
+
 namespace pencil {
 
 IDFX_D unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 IDFX_D void cpAsync8(double *dstShared, const double *srcGlobal) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(dstShared)), "l"(srcGlobal) : "memory");
+}
+// same with a precomputed 32-bit shared-memory address (saves the generic->shared conversion per copy)
+IDFX_D void cpAsync8s(unsigned dstShared, const double *srcGlobal) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dstShared), "l"(srcGlobal) : "memory");
 }
 IDFX_D void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -63,15 +75,13 @@ template <class P, int ORDER, bool CART>
 constexpr size_t pencilMarchSmem(int TX, int chunk) {
   return sizeof(double) * ((size_t)TX * (pencil::Halo<ORDER>::W * P::nvar   // stencil ring
                                          + P::nvar                          // left state of the next interface
-                                         + 2 * (P::nvar + 1)                // Uc + InvDt of the cell to update (x2)
                                          + (P::nvar + 1)                    // previous interface: flux + signal speed
-                                         + 2                                // normal field at the interface (x2)
-                                         + 4)                               // per-column geometry factors
+                                         + 2)                               // normal field at the interface (x2)
                            + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * (chunk + 2));
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART>
-__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(const SweepArgs a, const int chunk) {
+__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencilMarchKernel(const SweepArgs a, const int chunk) {
   static_assert(DIR == JDIR || DIR == KDIR, "the marching kernel sweeps along x2 or x3");
   constexpr int NV = P::nvar;
   using D = Dirs<P, DIR>;
@@ -82,12 +92,11 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(co
   const int tx = threadIdx.x;
   double *ring = smem + tx;                         // ring[(slot * NV + nv) * TX]
   double *vls = smem + W * NV * TX + tx;            // vls[nv * TX]
-  double *ucb = vls + NV * TX;                      // ucb[(buf * (NV+1) + nv) * TX]
-  double *fprev = ucb + 2 * (NV + 1) * TX;          // fprev[nv * TX]
+  double *fprev = vls + NV * TX;                    // fprev[nv * TX]
   double *vsb = fprev + (NV + 1) * TX;              // vsb[buf * TX]
-  double *inv = vsb + 2 * TX;                       // inv[n * TX], n = 0..3
-  double *tab = smem + (size_t)TX * (W * NV + NV + 2 * (NV + 1) + (NV + 1) + 2 + 4);   // tab[row * (chunk+2) + r]
+  double *tab = smem + (size_t)TX * (W * NV + NV + (NV + 1) + 2);   // tab[row * (chunk+2) + r]
   const int tlen = chunk + 2;
+  const unsigned ringS = pencil::smemAddr(ring), vsbS = pencil::smemAddr(vsb);
 
   const DevGrid &g = a.g;
   const int ext = a.perpExt;
@@ -129,18 +138,17 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(co
   const double dt = *a.dt;
   const int geo = CART ? (int)GEO_CARTESIAN : g.geometry;
   const bool regular = CART ? true : (g.regular != 0);
-  const bool needUc = columnInterior && !a.fusedP2C;
-  const bool needInvDt = columnInterior && a.doInvDt && !a.invDtInit;
   // separable geometry factors of this column, multiplied at every step in the reference's order
   // dV = (vol0[i]*vol1[j])*vol2[k], A = (area[D][0][i]*area[D][1][j])*area[D][2][k] (makeGeometry.cpp:66-84,139-211)
+  double inv0, inv1 = 1.0, inv2, inv3 = 1.0;
   if constexpr (DIR == JDIR) {
-    inv[0 * TX] = g.vol[0][i];
-    inv[1 * TX] = g.vol[2][p];
-    inv[2 * TX] = g.area[DIR][0][i];
-    inv[3 * TX] = g.area[DIR][2][p];
+    inv0 = g.vol[0][i];
+    inv1 = g.vol[2][p];
+    inv2 = g.area[DIR][0][i];
+    inv3 = g.area[DIR][2][p];
   } else {
-    inv[0 * TX] = g.vol[0][i] * g.vol[1][p];
-    inv[2 * TX] = g.area[DIR][0][i] * g.area[DIR][1][p];
+    inv0 = g.vol[0][i] * g.vol[1][p];
+    inv2 = g.area[DIR][0][i] * g.area[DIR][1][p];
   }
 
   // ---- prologue: cells mb-1-H .. mb+H, the normal field of the first interface ---------------------------
@@ -149,11 +157,11 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(co
 #pragma unroll
     for (int c = 0; c < W; c++) {
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8(ring + (c * NV + nv) * TX, src + nv * g.sn);
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (c * NV + nv) * TX * 8, src + nv * g.sn);
       src += stride;
     }
   }
-  if constexpr (P::mhd) pencil::cpAsync8(vsb, a.Vs + face0 + (long long)mb * vstride);
+  if constexpr (P::mhd) pencil::cpAsync8s(vsbS, a.Vs + face0 + (long long)mb * vstride);
   pencil::cpAsyncCommit();
   pencil::cpAsyncWait<0>();
   // right-face values of cell mb-1 = left state of the first interface
@@ -186,17 +194,8 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(co
     // ---- prefetch what the next interface needs ------------------------------------------------------
     if (m < me) {
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8(ring + (q * NV + nv) * TX, pre + nv * g.sn);
-      if constexpr (P::mhd) pencil::cpAsync8(vsb + ((r + 1) & 1) * TX, a.Vs + face0 + (long long)(m + 1) * vstride);
-      double *ub = ucb + ((r + 1) & 1) * (NV + 1) * TX;   // cell m is updated at the next interface
-      if (needUc) {
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) {
-          if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
-          pencil::cpAsync8(ub + nv * TX, a.Uc + nv * g.sn + cellm);
-        }
-      }
-      if (needInvDt) pencil::cpAsync8(ub + NV * TX, a.invDt + cellm);
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
+      if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
     }
     pencil::cpAsyncCommit();
     pencil::cpAsyncWait<1>();   // everything but the group just committed has landed
@@ -241,8 +240,8 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(co
     const int j = (DIR == JDIR) ? m : p;
     const int k = (DIR == JDIR) ? p : m;
     double A0;
-    if constexpr (DIR == JDIR) A0 = inv[2 * TX] * tab[pencil::T_AREA * tlen + r + 1] * inv[3 * TX];
-    else A0 = inv[2 * TX] * tab[pencil::T_AREA * tlen + r + 1];
+    if constexpr (DIR == JDIR) A0 = inv2 * tab[pencil::T_AREA * tlen + r + 1] * inv3;
+    else A0 = inv2 * tab[pencil::T_AREA * tlen + r + 1];
 
     double F[NV];
     RiemannAux aux;
@@ -253,18 +252,16 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : 3)) pencilMarchKernel(co
       const int jc = (DIR == JDIR) ? m - 1 : p;
       const int kc = (DIR == JDIR) ? p : m - 1;
       double dV;
-      if constexpr (DIR == JDIR) dV = inv[0 * TX] * tab[pencil::T_VOL * tlen + r] * inv[1 * TX];
-      else dV = inv[0 * TX] * tab[pencil::T_VOL * tlen + r];
+      if constexpr (DIR == JDIR) dV = inv0 * tab[pencil::T_VOL * tlen + r] * inv1;
+      else dV = inv0 * tab[pencil::T_VOL * tlen + r];
       double Fm[NV];
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * TX];
-      const double *ub = ucb + (r & 1) * (NV + 1) * TX;
       int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring)
       if (sp < 0) sp += W;
       const double *vprev = ring + sp * NV * TX;
       updateCell<P, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
-                         fprev[NV * TX], aux.cmax, [&](int nv) { return vprev[nv * TX]; },
-                         [&](int nv) { return ub[nv * TX]; }, [&]() { return ub[NV * TX]; });
+                         fprev[NV * TX], aux.cmax, [&](int nv) { return vprev[nv * TX]; });
     }
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) fprev[nv * TX] = F[nv];
@@ -287,7 +284,7 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
   const long long ctasPerLayer = (ni * np + TX - 1) / TX;
   // chunk length: long enough to amortise the extra cell per chunk, short enough to fill the GPU
   int chunk = 64;
-  while (chunk > 8 && ctasPerLayer * ((nsweep + chunk - 1) / chunk) < 4 * 148 * 3) chunk >>= 1;
+  while (chunk > 8 && ctasPerLayer * ((nsweep + chunk - 1) / chunk) < 4 * 148 * 4) chunk >>= 1;
   if (chunk > nsweep) chunk = nsweep;
   const dim3 grid((unsigned)ctasPerLayer, (unsigned)((nsweep + chunk - 1) / chunk), 1);
   const size_t smem = pencilMarchSmem<P, ORDER, CART>(TX, 64);
@@ -314,7 +311,6 @@ constexpr int pencilRowDoublesPerWarp() {
   return 2 * P::nvar * (32 + 2 * H)   // two row buffers of primitives (current row, next row in flight)
          + P::nvar * 32               // right-face values
          + (P::nvar + 1) * 32         // fluxes + signal speed
-         + 2 * (P::nvar + 1) * 32     // Uc + InvDt, double buffered
          + 2 * 32;                    // normal field, double buffered
 }
 
@@ -324,7 +320,7 @@ constexpr size_t pencilRowSmem(int warps, int chunk) {
 }
 
 template <class P, int SOLVER, int ORDER, int WARPS, bool CART>
-__global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : 3)) pencilRowKernel(const SweepArgs a, const int chunk,
+__global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) pencilRowKernel(const SweepArgs a, const int chunk,
                                                                                    const int nstrips) {
   constexpr int DIR = IDIR;
   constexpr int NV = P::nvar;
@@ -339,8 +335,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : 3)) pencilRowKer
   double *rows = wbase;                               // rows[(buf * NV + nv) * RW + x], x = cell - (cs-1-H)
   double *vrs = rows + 2 * NV * RW;                   // vrs[nv * 32 + lane]
   double *fls = vrs + NV * 32;                        // fls[nv * 32 + lane]
-  double *ucb = fls + (NV + 1) * 32;                  // ucb[(buf * (NV+1) + nv) * 32 + lane]
-  double *vsb = ucb + 2 * (NV + 1) * 32;              // vsb[buf * 32 + lane]
+  double *vsb = fls + (NV + 1) * 32;                  // vsb[buf * 32 + lane]
   double *tab = smem + (size_t)WARPS * pencilRowDoublesPerWarp<P, ORDER>();   // tab[row * chunk + r]
 
   const DevGrid &g = a.g;
@@ -391,40 +386,29 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : 3)) pencilRowKer
   const bool ld0 = (x0 + lane >= 0) && (x0 + lane < nx0);
   const bool ld1 = (lane < 2 * H) && (x0 + 32 + lane < nx0);
 
-  auto issueRow = [&](int j, int buf, bool withUc) {
+  const unsigned rowsS = pencil::smemAddr(rows), vsbS = pencil::smemAddr(vsb);
+  auto issueRow = [&](int j, int buf) {
     const long long rowBase = cidx(g, k, j, 0);
-    double *dst = rows + buf * NV * RW;
+    const unsigned dst = rowsS + (buf * NV * RW + lane) * 8;
+    const double *src = a.Vc + rowBase + x0 + lane;
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) {   // all of them: the update rebuilds Uc from the cell's primitives
-      const double *src = a.Vc + nv * g.sn + rowBase + x0;
-      if (ld0) pencil::cpAsync8(dst + nv * RW + lane, src + lane);
-      if (ld1) pencil::cpAsync8(dst + nv * RW + 32 + lane, src + 32 + lane);
+      if (ld0) pencil::cpAsync8s(dst + nv * RW * 8, src + nv * g.sn);
+      if (ld1) pencil::cpAsync8s(dst + (nv * RW + 32) * 8, src + nv * g.sn + 32);
     }
     if constexpr (P::mhd) {
-      if (faceLane) pencil::cpAsync8(vsb + buf * 32 + lane, a.Vs + DIR * g.vsn + sidx(g, k, j, c));
-    }
-    if (withUc && cellLane) {
-      double *ub = ucb + buf * (NV + 1) * 32 + lane;
-      const long long cell = rowBase + c;
-      if (!a.fusedP2C) {
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) {
-          if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
-          pencil::cpAsync8(ub + nv * 32, a.Uc + nv * g.sn + cell);
-        }
-      }
-      if (a.doInvDt && !a.invDtInit) pencil::cpAsync8(ub + NV * 32, a.invDt + cell);
+      if (faceLane) pencil::cpAsync8s(vsbS + (buf * 32 + lane) * 8, a.Vs + DIR * g.vsn + sidx(g, k, j, c));
     }
   };
   auto rowInterior = [&](int j) { return kInterior && (j >= g.beg[1]) && (j < g.end[1]); };
 
-  issueRow(jb, 0, rowInterior(jb));
+  issueRow(jb, 0);
   pencil::cpAsyncCommit();
 
   for (int j = jb; j < je; j++) {
     const int r = j - jb;
     const int buf = r & 1;
-    if (j + 1 < je) issueRow(j + 1, buf ^ 1, rowInterior(j + 1));
+    if (j + 1 < je) issueRow(j + 1, buf ^ 1);
     pencil::cpAsyncCommit();
     pencil::cpAsyncWait<1>();
     __syncwarp();   // the row buffer was filled by all lanes of the warp
@@ -476,10 +460,8 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : 3)) pencilRowKer
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) Fp[nv] = fls[nv * 32 + lane + 1];
       const double dV = vol0 * tab[r] * vol2;
-      const double *ub = ucb + buf * (NV + 1) * 32 + lane;
       updateCell<P, DIR>(a, g, geo, eos, dt, dV, dxc, k, j, c, cell, F, Fp, aux.cmax, fls[NV * 32 + lane + 1],
-                         [&](int nv) { return row[nv * RW]; }, [&](int nv) { return ub[nv * 32]; },
-                         [&]() { return ub[NV * 32]; });
+                         [&](int nv) { return row[nv * RW]; });
     }
     __syncwarp();   // vrs / fls are rewritten by the next row
   }
@@ -496,7 +478,7 @@ inline cudaError_t launchPencilRow(const SweepArgs &a, cudaStream_t stream) {
   const int nk = g.end[2] - g.beg[2] + 2 * ((P::ndim > 2) ? ext : 0);
   const long long ctasPerChunk = ((long long)nstrips * nk + WARPS - 1) / WARPS;
   int chunk = 64;
-  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * 148 * 3) chunk >>= 1;
+  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * 148 * 4) chunk >>= 1;
   if (chunk > nj) chunk = nj;
   const dim3 grid((unsigned)ctasPerChunk, (unsigned)((nj + chunk - 1) / chunk), 1);
   static bool configured = false;

@@ -1,0 +1,346 @@
+// dataBlock.hpp -- DataBlock and Fluid<Phys> / Hydro on top of the C ABI
+// (reference: src/dataBlock/dataBlock.hpp:54-183, src/fluid/fluid.hpp:53-247,
+// src/fluid/enroll.hpp:13-129, src/fluid/boundary/boundary.hpp:28-35).
+//
+// The public data members user set-ups touch are kept (data.x, data.beg/end/np_tot/nghost,
+// data.t/dt, data.hydro->Vc/Vs/Uc/InvDt ...).  The field arrays are non-owning views of the
+// device memory owned by the IdfxBlock, so a user's idefix_for kernel, the DataBlockHost mirror
+// and the library's kernels all work on the same (n,k,j,i) arrays.  Every method that launched
+// Kokkos kernels in the reference forwards to one idfx_* entry point.
+#ifndef IDEFIX_B200_HOST_DATABLOCK_HPP_
+#define IDEFIX_B200_HOST_DATABLOCK_HPP_
+
+class DataBlock;
+struct DefaultPhysics {};
+template <typename Phys> class Fluid;
+using Hydro = Fluid<DefaultPhysics>;
+
+template <typename Phys>
+using UserDefBoundaryFunc = void (*)(Fluid<Phys> *, int dir, BoundarySide side, const real t);
+using UserDefBoundaryFuncOld = void (*)(DataBlock &, int dir, BoundarySide side, const real t);
+template <typename Phys>
+using InternalBoundaryFunc = void (*)(Fluid<Phys> *, const real t);
+using StepFunc = void (*)(DataBlock &, const real t, const real dt);
+
+enum Solver { TVDLF = IDFX_TVDLF, HLL = IDFX_HLL, HLLC = IDFX_HLLC, HLLD = IDFX_HLLD, ROE = IDFX_ROE };
+
+// Stand-in for Fluid::boundary (the reference exposes SetBoundaries / EnforceBoundaryDir there)
+template <typename Phys>
+class Boundary {
+ public:
+  explicit Boundary(Fluid<Phys> *f) : fluid(f) {}
+  void SetBoundaries(real t);
+  void EnforceBoundaryDir(real t, int dir);
+  void ReconstructVcField(IdefixArray4D<real> &);
+
+ private:
+  Fluid<Phys> *fluid;
+};
+
+template <typename Phys>
+class Fluid {
+ public:
+  IdefixArray4D<real> Vc;      // primitive variables (nvar,k,j,i)
+  IdefixArray4D<real> Vs;      // staggered field (ndim,k+1,j+1,i+1)
+  IdefixArray4D<real> Uc;      // conservative variables
+  IdefixArray3D<real> InvDt;   // inverse time step accumulator
+  std::vector<std::string> VcName, VsName;
+  DataBlock *data{nullptr};
+  std::unique_ptr<Boundary<Phys>> boundary;
+  Solver mySolver{HLL};
+  int emf{IDFX_EMF_UCT_CONTACT};
+  real gamma{5.0 / 3.0};
+  real csiso{0.0};
+  bool haveTracer{false};
+  int nTracer{0};
+  bool haveSourceTerms{GEOMETRY != CARTESIAN};
+  bool haveUserSourceTerm{false};
+  std::string prefix{"Hydro"};
+  UserDefBoundaryFunc<Phys> userDefBoundaryFunc{nullptr};
+  UserDefBoundaryFuncOld userDefBoundaryFuncOld{nullptr};
+
+  Fluid(Input &input, DataBlock *d) : data(d) {
+    boundary = std::make_unique<Boundary<Phys>>(this);
+    const std::string s = input.Get<std::string>("Hydro", "solver", 0);
+    if (s == "tvdlf") mySolver = TVDLF;
+    else if (s == "hll") mySolver = HLL;
+#if MHD == YES
+    else if (s == "hlld") mySolver = HLLD;
+#else
+    else if (s == "hllc") mySolver = HLLC;
+#endif
+    else if (s == "roe") mySolver = ROE;
+    else IDEFIX_ERROR(std::string("Unknown ") + (MHD == YES ? "MHD" : "HD") + " solver type " + s);
+#if MHD == NO
+    if (mySolver == ROE) IDEFIX_ERROR("the HD Roe solver is outside the scope of this build");
+#endif
+#if MHD == YES
+    if (input.CheckEntry("Hydro", "emf") >= 0) {
+      const std::string e = input.Get<std::string>("Hydro", "emf", 0);
+      if (e == "arithmetic") emf = IDFX_EMF_ARITHMETIC;
+      else if (e == "uct0") emf = IDFX_EMF_UCT0;
+      else if (e == "uct_contact") emf = IDFX_EMF_UCT_CONTACT;
+      else if (e == "uct_hll") emf = IDFX_EMF_UCT_HLL;
+      else if (e == "uct_hlld") emf = IDFX_EMF_UCT_HLLD;
+      else IDEFIX_ERROR("Unknown EMF averaging scheme " + e);
+      // constrainedTransport.hpp:254-259
+      if (emf == IDFX_EMF_UCT_HLLD && mySolver != HLLD)
+        IDEFIX_ERROR("uct_hlld averaging is only compatible with the HLLD Riemann solver");
+    }
+#endif
+#ifdef ISOTHERMAL
+    if (input.Get<std::string>("Hydro", "csiso", 0) != "constant")
+      IDEFIX_ERROR("csiso admits only constant entries in this build");
+    csiso = input.Get<real>("Hydro", "csiso", 1);
+#else
+    gamma = input.GetOrSet<real>("Hydro", "gamma", 0, 5.0 / 3.0);
+#endif
+    const char *unsupported[] = {"shockFlattening", "tracer", "viscosity", "resistivity", "ambipolar", "hall",
+                                 "rotation", "gravity", "fargo", "TDiffusion", "bragViscosity", "bragTDiffusion",
+                                 "drag"};
+    for (const char *opt : unsupported)
+      if (input.CheckEntry("Hydro", opt) >= 0)
+        IDEFIX_ERROR(std::string("[Hydro] ") + opt + " is outside the scope of this build (explicit Godunov path only)");
+    VcName.push_back("RHO");
+    for (int c = 0; c < COMPONENTS; c++) VcName.push_back("VX" + std::to_string(c + 1));
+#if HAVE_ENERGY
+    VcName.push_back("PRS");
+#endif
+#if MHD == YES
+    for (int c = 0; c < COMPONENTS; c++) VcName.push_back("BX" + std::to_string(c + 1));
+    for (int c = 0; c < DIMENSIONS; c++) VsName.push_back("BX" + std::to_string(c + 1) + "s");
+#endif
+  }
+
+  real GetGamma() const { return gamma; }
+
+  // ---- enrolment (enroll.hpp:13-113) ------------------------------------------------------------
+  void EnrollUserDefBoundary(UserDefBoundaryFunc<Phys> f);
+  void EnrollUserDefBoundary(UserDefBoundaryFuncOld f);
+  template <typename F>
+  void EnrollInternalBoundary(F) { IDEFIX_ERROR("internal boundary functions are outside the scope of this build"); }
+  template <typename F>
+  void EnrollUserSourceTerm(F) { IDEFIX_ERROR("user source terms are outside the scope of this build"); }
+  template <typename F>
+  void EnrollEmfBoundary(F) { IDEFIX_ERROR("user EMF boundaries are outside the scope of this build"); }
+  template <typename F>
+  void EnrollIsoSoundSpeed(F) { IDEFIX_ERROR("user-defined sound speeds are outside the scope of this build"); }
+
+  // ---- forwards to the C ABI ------------------------------------------------------------------------
+  void ConvertConsToPrim();
+  void ConvertPrimToCons();
+  void ResetStage();
+  void EvolveStage(const real t, const real dt);
+  real CheckDivB();
+  int CheckNan();
+  void ShowConfig();
+};
+
+class DataBlock {
+ public:
+  std::array<IdefixArray1D<real>, 3> x, xr, xl, dx;   // device copies of the block coordinates
+  std::array<real, 3> xbeg{}, xend{};
+  std::array<int, 3> np_tot{}, np_int{}, nghost{}, beg{}, end{}, gbeg{}, gend{};
+  std::array<BoundaryType, 3> lbound{}, rbound{};
+  real t{0.0}, dt{0.0};
+  Grid *mygrid{nullptr};
+  std::unique_ptr<Hydro> hydro;
+  bool haveUserStepFirst{false}, haveUserStepLast{false};
+  StepFunc userStepFirst{nullptr}, userStepLast{nullptr};
+  IdfxBlock *handle{nullptr};   // the C-ABI block behind this DataBlock
+  // time-integrator options the device-side dt control needs
+  int nstages{1};
+  real cfl{0.0}, cflMaxVar{1.1}, firstDt{1e-10}, fixedDt{-1.0};
+
+  DataBlock(Grid &grid, Input &input) : mygrid(&grid) {
+    for (int dir = 0; dir < 3; dir++) {
+      np_int[dir] = grid.np_int[dir];
+      nghost[dir] = grid.nghost[dir];
+      np_tot[dir] = grid.np_tot[dir];
+      beg[dir] = nghost[dir];
+      end[dir] = nghost[dir] + np_int[dir];
+      gbeg[dir] = nghost[dir];
+      gend[dir] = nghost[dir] + np_int[dir];
+      lbound[dir] = grid.lbound[dir];
+      rbound[dir] = grid.rbound[dir];
+      xbeg[dir] = grid.xbeg[dir];
+      xend[dir] = grid.xend[dir];
+    }
+    hydro = std::make_unique<Hydro>(input, this);
+    nstages = input.Get<int>("TimeIntegrator", "nstages", 0);
+    if (input.CheckEntry("TimeIntegrator", "fixed_dt") > 0) {
+      fixedDt = input.Get<real>("TimeIntegrator", "fixed_dt", 0);
+    } else {
+      cfl = input.Get<real>("TimeIntegrator", "CFL", 0);
+      cflMaxVar = input.GetOrSet<real>("TimeIntegrator", "CFL_max_var", 0, 1.1);
+      firstDt = input.GetOrSet<real>("TimeIntegrator", "first_dt", 0, 1.0e-10);
+    }
+
+    IdfxBlockDesc d{};
+    d.ndim = DIMENSIONS;
+    d.ncomp = COMPONENTS;
+    d.mhd = (MHD == YES);
+    d.isothermal = !HAVE_ENERGY;
+    d.geometry = GEOMETRY;
+    d.order = ORDER;
+    d.solver = hydro->mySolver;
+    d.emf = hydro->emf;
+    d.nstages = nstages;
+    for (int dir = 0; dir < 3; dir++) {
+      d.np_int[dir] = np_int[dir];
+      d.nghost[dir] = nghost[dir];
+      d.lbound[dir] = lbound[dir];   // BoundaryType values == enum IdfxBoundary (idefix.hpp:220)
+      d.rbound[dir] = rbound[dir];
+      d.x[dir] = grid.x[dir].data();
+      d.xl[dir] = grid.xl[dir].data();
+      d.xr[dir] = grid.xr[dir].data();
+      d.dx[dir] = grid.dx[dir].data();
+    }
+    d.regular_grid = grid.isRegularCartesian;
+    d.device = input.device;
+    d.gamma = hydro->gamma;
+    d.csiso = hydro->csiso;
+    d.cfl = cfl;
+    d.cfl_max_var = cflMaxVar;
+    d.first_dt = firstDt;
+    d.fixed_dt = fixedDt;
+    IDFX_CUDA(cudaSetDevice(input.device));
+    IDFX_ABI(idfx_block_create(&d, &handle));
+    // user kernels (idefix_for) run on the legacy default stream: put the library there too so that
+    // everything is ordered without explicit fences, like the reference's single execution space
+    IDFX_ABI(idfx_set_stream(handle, nullptr));
+    dt = firstDt;
+    if (fixedDt > 0) dt = fixedDt;
+
+    // views of the block's state arrays
+    double *p = nullptr;
+    int n[4];
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_VC, &p, n));
+    hydro->Vc = IdefixArray4D<real>(p, n[0], n[1], n[2], n[3]);
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_UC, &p, n));
+    hydro->Uc = IdefixArray4D<real>(p, n[0], n[1], n[2], n[3]);
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_INVDT, &p, n));
+    hydro->InvDt = IdefixArray3D<real>(p, n[1], n[2], n[3]);
+#if MHD == YES
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_VS, &p, n));
+    hydro->Vs = IdefixArray4D<real>(p, n[0], n[1], n[2], n[3]);
+#endif
+    for (int dir = 0; dir < 3; dir++) {
+      x[dir] = IdefixArray1D<real>("DataBlock_x", np_tot[dir]);
+      xl[dir] = IdefixArray1D<real>("DataBlock_xl", np_tot[dir]);
+      xr[dir] = IdefixArray1D<real>("DataBlock_xr", np_tot[dir]);
+      dx[dir] = IdefixArray1D<real>("DataBlock_dx", np_tot[dir]);
+      Kokkos::deep_copy(x[dir], grid.x[dir]);
+      Kokkos::deep_copy(xl[dir], grid.xl[dir]);
+      Kokkos::deep_copy(xr[dir], grid.xr[dir]);
+      Kokkos::deep_copy(dx[dir], grid.dx[dir]);
+    }
+  }
+  ~DataBlock() {
+    if (handle) idfx_block_destroy(handle);
+  }
+  DataBlock(const DataBlock &) = delete;
+  DataBlock &operator=(const DataBlock &) = delete;
+
+  // ---- forwards (dataBlock.hpp:120-160) ----------------------------------------------------------
+  void PushTime() { IDFX_ABI(idfx_set_time(handle, t, dt)); }
+  void PullTime() { IDFX_ABI(idfx_get_time(handle, &t, &dt)); }
+  void SetBoundaries() { IDFX_ABI(idfx_set_boundaries(handle, t)); }
+  void ResetStage() { hydro->ResetStage(); }
+  void ConsToPrim() { hydro->ConvertConsToPrim(); }
+  void PrimToCons() { hydro->ConvertPrimToCons(); }
+  void EvolveStage() { hydro->EvolveStage(t, dt); }
+  void DeriveVectorPotential() {}
+  void Validate() {
+    if (CheckNan() > 0) IDEFIX_ERROR("DataBlock::Validate: the initial state contains NaNs");
+  }
+  real ComputeTimestep() {
+    real v;
+    IDFX_ABI(idfx_compute_timestep(handle, &v));
+    return v;
+  }
+  int CheckNan() { return hydro->CheckNan(); }
+  void EnrollUserStepFirst(StepFunc f) {
+    userStepFirst = f;
+    haveUserStepFirst = true;
+  }
+  void EnrollUserStepLast(StepFunc f) {
+    userStepLast = f;
+    haveUserStepLast = true;
+  }
+  void LaunchUserStepFirst() {
+    if (haveUserStepFirst) userStepFirst(*this, t, dt);
+  }
+  void LaunchUserStepLast() {
+    if (haveUserStepLast) userStepLast(*this, t, dt);
+  }
+  void ShowConfig() { hydro->ShowConfig(); }
+};
+
+// ---- Fluid / Boundary members that need the complete DataBlock -----------------------------------------
+template <typename Phys> void Fluid<Phys>::ConvertConsToPrim() { IDFX_ABI(idfx_cons_to_prim(data->handle)); }
+template <typename Phys> void Fluid<Phys>::ConvertPrimToCons() { IDFX_ABI(idfx_prim_to_cons(data->handle)); }
+template <typename Phys> void Fluid<Phys>::ResetStage() { IDFX_ABI(idfx_reset_stage(data->handle)); }
+template <typename Phys> void Fluid<Phys>::EvolveStage(const real t, const real dt) {
+  IDFX_ABI(idfx_evolve_stage(data->handle, t, dt));
+}
+template <typename Phys> real Fluid<Phys>::CheckDivB() {
+  real v = 0.0;
+  IDFX_ABI(idfx_check_divb(data->handle, &v));
+  return v;
+}
+template <typename Phys> int Fluid<Phys>::CheckNan() {
+  int n = 0;
+  IDFX_ABI(idfx_check_nan(data->handle, &n));
+  return n;
+}
+template <typename Phys> void Boundary<Phys>::SetBoundaries(real t) {
+  IDFX_ABI(idfx_set_boundaries(fluid->data->handle, t));
+}
+template <typename Phys> void Boundary<Phys>::EnforceBoundaryDir(real t, int dir) {
+  IDFX_ABI(idfx_enforce_boundary_dir(fluid->data->handle, t, dir));
+}
+template <typename Phys> void Boundary<Phys>::ReconstructVcField(IdefixArray4D<real> &V) {
+  IDFX_ABI(idfx_reconstruct_vc_field(fluid->data->handle, V.data() == fluid->Uc.data() ? IDFX_FIELD_UC : IDFX_FIELD_VC));
+}
+
+namespace idfxhost {
+template <typename Phys>
+inline void userBoundaryTrampoline(IdfxBlock *, int dir, int side, double t, void *user) {
+  auto *f = static_cast<Fluid<Phys> *>(user);
+  if (f->userDefBoundaryFunc) f->userDefBoundaryFunc(f, dir, side == 0 ? left : right, t);
+  else if (f->userDefBoundaryFuncOld) f->userDefBoundaryFuncOld(*f->data, dir, side == 0 ? left : right, t);
+}
+}  // namespace idfxhost
+
+template <typename Phys> void Fluid<Phys>::EnrollUserDefBoundary(UserDefBoundaryFunc<Phys> f) {
+  userDefBoundaryFunc = f;
+  IDFX_ABI(idfx_enroll_userdef_boundary(data->handle, &idfxhost::userBoundaryTrampoline<Phys>, this));
+}
+template <typename Phys> void Fluid<Phys>::EnrollUserDefBoundary(UserDefBoundaryFuncOld f) {
+  userDefBoundaryFuncOld = f;
+  IDFX_ABI(idfx_enroll_userdef_boundary(data->handle, &idfxhost::userBoundaryTrampoline<Phys>, this));
+}
+
+template <typename Phys> void Fluid<Phys>::ShowConfig() {
+  // src/fluid/showConfig.hpp:20-120 (the lines the reference's test harness greps are kept verbatim)
+  idfx::cout << "Fluid: solving " << (MHD == YES ? "MHD" : "HD") << " equations." << std::endl;
+  idfx::cout << "Fluid: Reconstruction: ";
+  if (ORDER == 1) idfx::cout << "1st order (donor cell)" << std::endl;
+  if (ORDER == 2) idfx::cout << "2nd order (PLM Van Leer)" << std::endl;
+  if (ORDER == 3) idfx::cout << "3rd order (LimO3)" << std::endl;
+  if (ORDER == 4) idfx::cout << "4th order (PPM)" << std::endl;
+#if HAVE_ENERGY
+  idfx::cout << "Fluid: EOS: ideal with gamma=" << gamma << std::endl;
+#else
+  idfx::cout << "Fluid: EOS: isothermal with cs=" << csiso << "." << std::endl;
+#endif
+  const char *names[] = {"tvdlf (Lax-Friedrich)", "HLL", "HLLC", "HLLD", "ROE"};
+  idfx::cout << "Fluid: Riemann solver: " << names[mySolver] << "." << std::endl;
+#if MHD == YES
+  const char *emfs[] = {"Arithmetic", "UCT0", "UCT_CONTACT", "UCT_HLL", "UCT_HLLD"};
+  idfx::cout << "Fluid: EMF averaging: " << emfs[emf] << "." << std::endl;
+#endif
+}
+
+#endif  // IDEFIX_B200_HOST_DATABLOCK_HPP_
