@@ -5,6 +5,7 @@
 // data(), size(); zero-initialised on allocation.  A handle can also wrap memory it does not own
 // (the state arrays of the IdfxBlock, obtained through idfx_field_info), so user kernels, host
 // mirrors and the library all see the same memory.
+#include "idefix.hpp"
 #ifndef IDEFIX_B200_HOST_ARRAYS_HPP_
 #define IDEFIX_B200_HOST_ARRAYS_HPP_
 

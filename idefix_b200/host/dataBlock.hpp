@@ -7,6 +7,7 @@
 // device memory owned by the IdfxBlock, so a user's idefix_for kernel, the DataBlockHost mirror
 // and the library's kernels all work on the same (n,k,j,i) arrays.  Every method that launched
 // Kokkos kernels in the reference forwards to one idfx_* entry point.
+#include "idefix.hpp"
 #ifndef IDEFIX_B200_HOST_DATABLOCK_HPP_
 #define IDEFIX_B200_HOST_DATABLOCK_HPP_
 

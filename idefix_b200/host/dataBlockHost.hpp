@@ -1,5 +1,6 @@
 // dataBlockHost.hpp -- DataBlockHost: the host mirror a set-up's InitFlow fills
 // (reference: src/dataBlock/dataBlockHost.hpp:25-102, dataBlockHost.cpp:108-262).
+#include "idefix.hpp"
 #ifndef IDEFIX_B200_HOST_DATABLOCKHOST_HPP_
 #define IDEFIX_B200_HOST_DATABLOCKHOST_HPP_
 

@@ -4,6 +4,7 @@
 // Coordinates are generated expression by expression like GridHost::MakeGrid (uniform "u",
 // logarithmic "l", stretched "s+" / "s-" patches with the same Newton iteration) with the same
 // libm calls, so they are bit-identical with the reference's.
+#include "idefix.hpp"
 #ifndef IDEFIX_B200_HOST_GRID_HPP_
 #define IDEFIX_B200_HOST_GRID_HPP_
 

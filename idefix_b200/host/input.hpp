@@ -1,5 +1,6 @@
 // input.hpp -- Input: idefix.ini reader + command line (reference: src/input.hpp:15-69 accessors,
 // src/input.cpp:30-110 grammar, :113-190 command line, :193-245 ShowConfig log lines).
+#include "idefix.hpp"
 #ifndef IDEFIX_B200_HOST_INPUT_HPP_
 #define IDEFIX_B200_HOST_INPUT_HPP_
 

@@ -4,6 +4,7 @@
 // of the user's extended lambda on the default stream (the same stream the library's block uses
 // unless idfx_set_stream says otherwise), threads running along the last (fastest) index.
 // Ranges are [begin, end) like the reference's.
+#include "idefix.hpp"
 #ifndef IDEFIX_B200_HOST_LOOP_HPP_
 #define IDEFIX_B200_HOST_LOOP_HPP_
 

@@ -1,0 +1,28 @@
+// 2-D Orszag-Tang vortex on [0,1]^2: uniform density and pressure, a single velocity vortex and a
+// double-periodic magnetic field given directly on the cell faces.
+#include "idefix.hpp"
+#include "setup.hpp"
+
+Setup::Setup(Input &input, Grid &grid, DataBlock &data, Output &output) {}
+
+void Setup::InitFlow(DataBlock &data) {
+  DataBlockHost host(data);
+  const real twoPi = 2.0 * M_PI;
+  const real B0 = 1.0 / sqrt(4.0 * M_PI);
+  const real rho0 = 25.0 / (36.0 * M_PI), prs0 = 5.0 / (12.0 * M_PI);
+  for (int k = 0; k < host.np_tot[KDIR]; k++) {
+    for (int j = 0; j < host.np_tot[JDIR]; j++) {
+      const real sy = sin(twoPi * host.x[JDIR](j));
+      for (int i = 0; i < host.np_tot[IDIR]; i++) {
+        const real xc = host.x[IDIR](i);
+        host.Vc(RHO, k, j, i) = rho0;
+        host.Vc(PRS, k, j, i) = prs0;
+        host.Vc(VX1, k, j, i) = -sy;
+        host.Vc(VX2, k, j, i) = sin(twoPi * xc);
+        host.Vs(BX1s, k, j, i) = -B0 * sy;
+        host.Vs(BX2s, k, j, i) = B0 * sin(4.0 * M_PI * xc);
+      }
+    }
+  }
+  host.SyncToDevice();
+}
