@@ -178,12 +178,18 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def sweep_algorithmic_bytes(nvar, ndim, emf, stage0_share):
-    """DESIGN.md 'algorithmic bytes': per interior cell and per sweep launch, in bytes.
-    read Vc (nvar) + normal Vs (1); Uc read+write of the nvar-ndim non-CT variables; face EMF
-    outputs (2 EMFs + contact weight, or 2 + 4 UCT coefficients); InvDt read+write on stage 0."""
+def sweep_algorithmic_bytes(nvar, ndim, emf, stage0_share, direction):
+    """DESIGN.md 'algorithmic bytes': per interior cell and per sweep launch (average over the RK stages).
+    Every sweep reads Vc (nvar) + the normal Vs (1) and writes the face EMF outputs (2 EMFs + contact
+    weight, or 2 + 4 UCT coefficients).  The x1 sweep rebuilds Uc from Vc: it WRITES the nvar-ndim non-CT
+    conservative variables (and their copy Uc0 on stage 0) and InvDt (stage 0); the x2/x3 sweeps
+    read-modify-write Uc and InvDt (stage 0)."""
     face = {"uct_contact": 3, None: 3, "uct0": 2, "arithmetic": 2, "uct_hll": 6, "uct_hlld": 6}[emf]
-    doubles = nvar + 1 + 2 * (nvar - ndim) + face + 2 * stage0_share
+    nu = nvar - ndim
+    if direction == 0:
+        doubles = nvar + 1 + nu + nu * stage0_share + face + 1 * stage0_share
+    else:
+        doubles = nvar + 1 + 2 * nu + face + 2 * stage0_share
     return 8.0 * doubles
 
 
@@ -270,7 +276,7 @@ def main_gpu(args):
     sweeps = [(tim[2 * i + 1] / max(tim[2 * i], 1), i) for i in range(3)]
     dur_ms, top = max(sweeps)
     nstages = 2
-    bytes_cell = sweep_algorithmic_bytes(8, 3, args.emf, 1.0 / nstages)
+    bytes_cell = sweep_algorithmic_bytes(8, 3, args.emf, 1.0 / nstages, top)
     alg_bytes = bytes_cell * b ** 3
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
@@ -284,7 +290,10 @@ def main_gpu(args):
                 traffic = tj["bytes_per_launch"][classes[top]]
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"sweepKernel<HLLD,PLM,dir={top}> ({classes[top]})",
+    kname = ["pencilRowKernel<Phys<3,3,mhd>,HLLD,PLM,CART> (x1 sweep)",
+             "pencilMarchKernel<Phys<3,3,mhd>,HLLD,PLM,JDIR,CART> (x2 sweep)",
+             "pencilMarchKernel<Phys<3,3,mhd>,HLLD,PLM,KDIR,CART> (x3 sweep)"][top]
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_per_cell": bytes_cell, "avg_launch_ms": dur_ms,

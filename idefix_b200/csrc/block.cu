@@ -72,6 +72,7 @@ struct IdfxBlock {
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
   int sweepVariant = 2;
+  bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
   bool timing = false;
   std::vector<cudaEvent_t> evPool;      // pairs: [2n] start, [2n+1] stop
@@ -438,9 +439,9 @@ int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
   return 0;
 }
 
-int reconstructVc(IdfxBlock *b, double *V) {
+int reconstructVc(IdfxBlock *b, double *V, int ghostsOnly = 0) {
   if (!b->cfg.mhd) return 0;
-  KTRY(idfxk::reconstructVcField(b->cfg, b->g, b->Vs, V, b->stream));
+  KTRY(idfxk::reconstructVcField(b->cfg, b->g, b->Vs, V, b->stream, ghostsOnly));
   b->launches++;
   return 0;
 }
@@ -546,7 +547,9 @@ int cycleFused(IdfxBlock *b) {
   b->launches++;
   for (int stage = 0; stage < d.nstages; stage++) {
     if (setBoundariesCore(b, 0.0, false)) return 1;
-    if (reconstructVc(b, b->Vc)) return 1;
+    // the active cells already hold the face average when the previous step on this block was our own
+    // stage epilogue (b->vcFieldFresh): only the ghost cells changed with the boundary conditions
+    if (reconstructVc(b, b->Vc, b->vcFieldFresh ? 1 : 0)) return 1;
     if (evolveStageImpl(b, stage)) return 1;
     const double wc = stage > 0 ? b->wc[stage - 1] : 0.0, w0 = stage > 0 ? b->w0[stage - 1] : 0.0;
     KTRY(idfxk::stageTimeAdvance(b->state, stage, wc, w0, b->stream));
@@ -561,6 +564,7 @@ int cycleFused(IdfxBlock *b) {
                                 b->stream));
     }
     b->launches++;
+    b->vcFieldFresh = !b->userBc;   // a user boundary function may write anywhere
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
                            b->stream));
@@ -967,6 +971,8 @@ int idfx_check_nan(IdfxBlock *b, int *nan_count) {
 
 // ---- fused path -------------------------------------------------------------------------------
 int idfx_cycles(IdfxBlock *b, int ncycles) {
+  // the caller holds device pointers to the state (idfx_field_info) and may have changed it since the last call
+  b->vcFieldFresh = false;
   for (int n = 0; n < ncycles; n++) {
     if (b->fused) {
       if (cycleFused(b)) return 1;

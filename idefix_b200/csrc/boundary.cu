@@ -13,12 +13,17 @@ constexpr int TBX = 64, TBY = 4;
 struct Box {
   int lo[3], hi[3];
 };
-inline dim3 boxGrid(const Box &b, int nz = 1) {
+inline dim3 boxGrid(const Box &b, int nz = 1, dim3 block = dim3(TBX, TBY, 1)) {
   int n0 = b.hi[0] - b.lo[0], n1 = b.hi[1] - b.lo[1], n2 = b.hi[2] - b.lo[2];
   if (n0 < 1) n0 = 1;
   if (n1 < 1) n1 = 1;
   if (n2 < 1) n2 = 1;
-  return dim3((n0 + TBX - 1) / TBX, (n1 + TBY - 1) / TBY, n2 * nz);
+  return dim3((n0 + block.x - 1) / block.x, (n1 + block.y - 1) / block.y, n2 * nz);
+}
+// thread block of the ghost-fill kernel: an x1 slab is only nghost cells wide along i, so the threads
+// go along j there (a 64 x 4 block would idle 60 of its 64 columns)
+inline dim3 slabBlock(const Box &b) {
+  return (b.hi[0] - b.lo[0] <= 4) ? dim3(4, 64, 1) : dim3(TBX, TBY, 1);
 }
 inline bool emptyBox(const Box &b) {
   return b.hi[0] <= b.lo[0] || b.hi[1] <= b.lo[1] || b.hi[2] <= b.lo[2];
@@ -51,8 +56,8 @@ Box ghostSlab(const DevGrid &g, int dir, int side, int stag) {
 __global__ void ghostFillKernel(double *__restrict__ q, long long sj, long long sk, Box b, int nvars,
                                 long long sn, int dir, int side, int type, int ng, int nint, int signMask,
                                 int zeroInflowVar) {
-  const int i = b.lo[0] + blockIdx.x * TBX + threadIdx.x;
-  const int j = b.lo[1] + blockIdx.y * TBY + threadIdx.y;
+  const int i = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = b.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
   const int nk = b.hi[2] - b.lo[2];
   const int k = b.lo[2] + (int)(blockIdx.z % nk);
   const int n = (int)(blockIdx.z / nk);
@@ -285,8 +290,9 @@ int idfxk::enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *V
         if (flip) signMask |= (1 << n);
       }
     }
-    ghostFillKernel<<<boxGrid(b, c.nvar), block, 0, st>>>(Vc, g.sj, g.sk, b, c.nvar, g.sn, dir, side, type, ng, nint,
-                                                          signMask, c.MX1 + dir);
+    const dim3 blk = slabBlock(b);
+    ghostFillKernel<<<boxGrid(b, c.nvar, blk), blk, 0, st>>>(Vc, g.sj, g.sk, b, c.nvar, g.sn, dir, side, type, ng, nint,
+                                                             signMask, c.MX1 + dir);
     (*launches)++;
   }
   if (c.mhd) {
@@ -295,8 +301,9 @@ int idfxk::enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *V
       if (type != BC_PERIODIC && comp == dir) continue;
       const Box b = ghostSlab(g, dir, side, comp);
       const int signMask = (type == BC_REFLECTIVE) ? 1 : 0;
-      ghostFillKernel<<<boxGrid(b, 1), block, 0, st>>>(Vs + comp * g.vsn, g.vsj, g.vsk, b, 1, 0, dir, side, type, ng,
-                                                       nint, signMask, -1);
+      const dim3 blk = slabBlock(b);
+      ghostFillKernel<<<boxGrid(b, 1, blk), blk, 0, st>>>(Vs + comp * g.vsn, g.vsj, g.vsk, b, 1, 0, dir, side, type, ng,
+                                                          nint, signMask, -1);
       (*launches)++;
     }
   }

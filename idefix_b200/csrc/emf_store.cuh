@@ -56,9 +56,9 @@ IDFX_D void storeFluxEmf(const EmfFaceArrays &A, long long idx, const double *F,
 }
 
 // storeFlux.hpp:46-75
-template <class P, int DIR>
-IDFX_D void storeHllEmf(const EmfFaceArrays &A, long long idx, double sl, double sr, const double *vL,
-                        const double *vR) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void storeHllEmf(const EmfFaceArrays &A, long long idx, double sl, double sr, const VL &vL,
+                        const VR &vR) {
   using D = Dirs<P, DIR>;
   const double ar = fmax(0.0, sr);
   const double al = fmin(0.0, sl);
@@ -75,9 +75,9 @@ IDFX_D void storeHllEmf(const EmfFaceArrays &A, long long idx, double sl, double
 }
 
 // storeFlux.hpp:77-208
-template <class P, int DIR>
+template <class P, int DIR, class VL, class VR>
 IDFX_D void storeHlldEmf(const EmfFaceArrays &A, long long idx, double c2iso, double sl, double sr,
-                         const double *vL, const double *vR) {
+                         const VL &vL, const VR &vR) {
   using D = Dirs<P, DIR>;
   constexpr int Xn = D::Xn, BXn = D::BXn, RHO = P::RHO;
   const double ptL = totalPressure<P>(vL, c2iso);
@@ -149,9 +149,9 @@ IDFX_D void storeHlldEmf(const EmfFaceArrays &A, long long idx, double c2iso, do
   }
 }
 
-template <class P, int DIR, int SOLVER>
+template <class P, int DIR, int SOLVER, class VL, class VR>
 IDFX_D void storeEmf(int mode, const EmfFaceArrays &A, long long idx, const double *F, const RiemannAux &aux,
-                     const double *vL, const double *vR) {
+                     const VL &vL, const VR &vR) {
   if (mode == EMF_ARITHMETIC || mode == EMF_UCT0) {
     storeFluxEmf<P, DIR>(A, idx, F, false);
   } else if (mode == EMF_UCT_CONTACT) {

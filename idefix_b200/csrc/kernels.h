@@ -39,7 +39,8 @@ struct Eos2 { double gamma, csiso; };
 int primToCons(const PhysCfg &c, const DevGrid &g, const double *Vc, double *Uc, double gamma, cudaStream_t st);
 int consToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, double gamma, cudaStream_t st);
 // cell-centred field from the staggered one over the whole block (boundary.hpp:389-404)
-int reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st);
+int reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st,
+                       int ghostsOnly = 0);
 int fill(double *p, long long n, double value, cudaStream_t st);
 int copy(double *dst, const double *src, long long n, cudaStream_t st);
 // dst = wl*dst + wr*src (stateContainer.cpp:91-98)

@@ -54,8 +54,8 @@ struct Eos {
 };
 
 // convertConsToPrim.hpp:70-100
-template <class P>
-IDFX_HD void primToCons(double *u, const double *v, const Eos &eos) {
+template <class P, class V>
+IDFX_HD void primToCons(double *u, const V &v, const Eos &eos) {
   u[P::RHO] = v[P::RHO];
   u[P::MX1] = v[P::MX1] * v[P::RHO];
   if constexpr (P::ncomp >= 2) u[P::MX2] = v[P::MX2] * v[P::RHO];
@@ -123,8 +123,8 @@ IDFX_HD bool consToPrim(double *v, double *u, const Eos &eos) {
 
 // flux.hpp:29-95.  f may alias u (the MHD solvers call it that way, hlldMHD.hpp:246-252):
 // every u[] entry is consumed before the corresponding f[] entry is written.
-template <class P, int DIR>
-IDFX_HD void physFlux(double *f, const double *v, const double *u, double c2iso) {
+template <class P, int DIR, class V>
+IDFX_HD void physFlux(double *f, const V &v, const double *u, double c2iso) {
   using D = Dirs<P, DIR>;
   constexpr int Xn = D::Xn;
   const double un = u[Xn];

@@ -75,14 +75,19 @@ __global__ void consToPrimKernel(DevGrid g, double *__restrict__ Vc, double *__r
   }
 }
 
-// V(BXn) = 0.5*(Vs(n,.) + Vs(n,.+1)) for the CT components, over the whole block
+// V(BXn) = 0.5*(Vs(n,.) + Vs(n,.+1)) for the CT components, over the box [lo, hi) of cells
+// (the whole block, or one ghost slab: the boundary conditions never touch a face of an active cell, so
+// after our own stage epilogue the active cells already hold exactly these values)
+struct CellBox {
+  int lo[3], hi[3];
+};
 __global__ void reconstructVcFieldKernel(DevGrid g, const double *__restrict__ Vs, double *__restrict__ V, int bx1,
-                                         long long n) {
-  const long long c = (long long)blockIdx.x * TB + threadIdx.x;
-  if (c >= n) return;
-  const int i = (int)(c % g.nx[0]);
-  const int j = (int)((c / g.nx[0]) % g.nx[1]);
-  const int k = (int)(c / ((long long)g.nx[0] * g.nx[1]));
+                                         CellBox b) {
+  const int i = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = b.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = b.lo[2] + blockIdx.z;
+  if (i >= b.hi[0] || j >= b.hi[1] || k >= b.hi[2]) return;
+  const long long c = cidx(g, k, j, i);
   const long long s = sidx(g, k, j, i);
   V[(bx1 + 0) * g.sn + c] = 0.5 * (Vs[s] + Vs[s + 1]);
   if (g.ndim >= 2) V[(bx1 + 1) * g.sn + c] = 0.5 * (Vs[g.vsn + s] + Vs[g.vsn + s + g.vsj]);
@@ -158,9 +163,38 @@ int idfxk::consToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc
   PHYS_DISPATCH((consToPrimKernel<P><<<blocksFor(n), TB, 0, st>>>(g, Vc, Uc, eos, n)))
 }
 
-int idfxk::reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st) {
-  const long long n = g.sn;
-  reconstructVcFieldKernel<<<blocksFor(n), TB, 0, st>>>(g, Vs, V, c.BX1, n);
+int idfxk::reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st,
+                              int ghostsOnly) {
+  auto launch = [&](const CellBox &b) {
+    const int n0 = b.hi[0] - b.lo[0], n1 = b.hi[1] - b.lo[1], n2 = b.hi[2] - b.lo[2];
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) return;
+    const dim3 blk = (n0 <= 4) ? dim3(4, 64, 1) : dim3(64, 4, 1);
+    const dim3 grd((n0 + blk.x - 1) / blk.x, (n1 + blk.y - 1) / blk.y, n2);
+    reconstructVcFieldKernel<<<grd, blk, 0, st>>>(g, Vs, V, c.BX1, b);
+  };
+  CellBox all;
+  for (int d = 0; d < 3; d++) {
+    all.lo[d] = 0;
+    all.hi[d] = g.nx[d];
+  }
+  if (!ghostsOnly) {
+    launch(all);
+  } else {
+    // the ghost shell as six disjoint slabs: x3 slabs span everything, x2 slabs the active k range, x1 slabs
+    // the active k and j ranges
+    for (int d = 2; d >= 0; d--) {
+      if (g.ng[d] == 0) continue;
+      CellBox lo = all, hi = all;
+      for (int e = d + 1; e < 3; e++) {
+        lo.lo[e] = hi.lo[e] = g.beg[e];
+        lo.hi[e] = hi.hi[e] = g.end[e];
+      }
+      lo.hi[d] = g.beg[d];
+      hi.lo[d] = g.end[d];
+      launch(lo);
+      launch(hi);
+    }
+  }
   return (int)cudaGetLastError();
 }
 

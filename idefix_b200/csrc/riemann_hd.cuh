@@ -14,8 +14,8 @@ struct RiemannAux {
   double c2iso;  // squared isothermal sound speed handed to the EMF storage (0 when adiabatic)
 };
 
-template <class P>
-IDFX_D void soundSpeedsHD(const double *vL, const double *vR, const Eos &eos, double &cL, double &cR) {
+template <class P, class VL, class VR>
+IDFX_D void soundSpeedsHD(const VL &vL, const VR &vR, const Eos &eos, double &cL, double &cR) {
   if constexpr (P::energy) {
     cL = sqrt(eos.gamma * (vL[P::PRS] / vL[P::RHO]));
     cR = sqrt(eos.gamma * (vR[P::PRS] / vR[P::RHO]));
@@ -26,8 +26,8 @@ IDFX_D void soundSpeedsHD(const double *vL, const double *vR, const Eos &eos, do
 }
 
 // tvdlfHD.hpp:49-93
-template <class P, int DIR>
-IDFX_D void riemannTvdlfHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannTvdlfHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   constexpr int Xn = Dirs<P, DIR>::Xn;
   double uL[P::nvar], uR[P::nvar], fL[P::nvar], fR[P::nvar];
   double cRL;
@@ -53,8 +53,8 @@ IDFX_D void riemannTvdlfHD(const double *vL, const double *vR, const Eos &eos, d
 }
 
 // hllHD.hpp:48-110
-template <class P, int DIR>
-IDFX_D void riemannHllHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannHllHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   constexpr int Xn = Dirs<P, DIR>::Xn;
   double uL[P::nvar], uR[P::nvar], fL[P::nvar], fR[P::nvar];
   double cL, cR;
@@ -85,8 +85,8 @@ IDFX_D void riemannHllHD(const double *vL, const double *vR, const Eos &eos, dou
 }
 
 // hllcHD.hpp:40-160
-template <class P, int DIR>
-IDFX_D void riemannHllcHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannHllcHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   using D = Dirs<P, DIR>;
   constexpr int Xn = D::Xn;
   double uL[P::nvar], uR[P::nvar], fL[P::nvar], fR[P::nvar];

@@ -10,8 +10,8 @@
 #include "riemann_hd.cuh"
 
 // fast magnetosonic speed of one state (hlldMHD.hpp:191-207)
-template <class P, int DIR>
-IDFX_D double fastSpeed(const double *v, double gpr) {
+template <class P, int DIR, class V>
+IDFX_D double fastSpeed(const V &v, double gpr) {
   using D = Dirs<P, DIR>;
   double b1 = v[D::BXn];
   double b2 = 0.0, b3 = 0.0;
@@ -24,8 +24,8 @@ IDFX_D double fastSpeed(const double *v, double gpr) {
   return sqrt(0.5 * c / v[P::RHO]);
 }
 
-template <class P>
-IDFX_D double totalPressure(const double *v, double c2iso) {
+template <class P, class V>
+IDFX_D double totalPressure(const V &v, double c2iso) {
   double b2 = v[P::BX1] * v[P::BX1];
   if constexpr (P::ncomp >= 2) b2 = b2 + v[P::BX2] * v[P::BX2];
   if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
@@ -37,8 +37,8 @@ IDFX_D double totalPressure(const double *v, double c2iso) {
 }
 
 // tvdlfMHD.hpp:147-210
-template <class P, int DIR>
-IDFX_D void riemannTvdlfMHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannTvdlfMHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   using D = Dirs<P, DIR>;
   constexpr int Xn = D::Xn;
   double uL[P::nvar], uR[P::nvar], fL[P::nvar], fR[P::nvar];
@@ -82,8 +82,8 @@ IDFX_D void riemannTvdlfMHD(const double *vL, const double *vR, const Eos &eos, 
 }
 
 // hllMHD.hpp:155-445 without Hall
-template <class P, int DIR>
-IDFX_D void riemannHllMHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannHllMHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   using D = Dirs<P, DIR>;
   constexpr int Xn = D::Xn;
   double uL[P::nvar], uR[P::nvar], fL[P::nvar], fR[P::nvar];
@@ -137,8 +137,8 @@ IDFX_D void riemannHllMHD(const double *vL, const double *vR, const Eos &eos, do
 }
 
 // hlldMHD.hpp:147-575
-template <class P, int DIR>
-IDFX_D void riemannHlldMHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   using D = Dirs<P, DIR>;
   constexpr int Xn = D::Xn, Xt = D::Xt, Xb = D::Xb;
   constexpr int BXn = D::BXn, BXt = D::BXt, BXb = D::BXb;

@@ -24,8 +24,8 @@ struct RoeModes {
   static constexpr int KALFVP = (P::energy ? 7 : 6);
 };
 
-template <class P, int DIR>
-IDFX_D void riemannRoeMHD(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int DIR, class VL, class VR>
+IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   using D = Dirs<P, DIR>;
   using M = RoeModes<P>;
   constexpr int Xn = D::Xn, Xt = D::Xt, Xb = D::Xb;

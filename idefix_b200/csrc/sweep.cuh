@@ -20,8 +20,8 @@
 #include "riemann_roe.cuh"
 #include "emf_store.cuh"
 
-template <class P, int SOLVER, int DIR>
-IDFX_D void riemannDispatch(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+template <class P, int SOLVER, int DIR, class VL, class VR>
+IDFX_D void riemannDispatch(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   if constexpr (P::mhd) {
     if constexpr (SOLVER == SOLVER_TVDLF) riemannTvdlfMHD<P, DIR>(vL, vR, eos, F, aux);
     if constexpr (SOLVER == SOLVER_HLL) riemannHllMHD<P, DIR>(vL, vR, eos, F, aux);
@@ -59,8 +59,8 @@ struct CurvIdx {
 };
 
 // Geometrical source terms of one cell (addSourceTerms.hpp:96-192), rotation/Fargo excluded.
-template <class P>
-IDFX_D void geometricSource(const DevGrid &g, const double *v, const Eos &eos, double dt, int j, int i,
+template <class P, class V>
+IDFX_D void geometricSource(const DevGrid &g, const V &v, const Eos &eos, double dt, int j, int i,
                             double &s1, double &s2) {
   s1 = 0.0;
   s2 = 0.0;

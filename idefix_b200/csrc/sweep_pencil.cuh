@@ -50,14 +50,17 @@ template <int ORDER>
 struct Halo {
   static constexpr int H = (ORDER == 4) ? 2 : 1;   // cells needed on each side of a cell to reconstruct it
   static constexpr int W = 2 * H + 2;              // ring slots: stencil of one cell + one cell in flight
+  // LATE variant (cartesian marches): the next cell is prefetched right AFTER the reconstruction, into the
+  // slot of the cell that just left the stencil; the Riemann solve that follows hides the latency
+  static constexpr int WL = 2 * H + 1;
 };
 
 // rows of the per-CTA geometry table along the marching direction
 enum : int { T_DX = 0, T_VOL = 1, T_AREA = 2, T_W = 3 /* wp wm cp cm dp dm */, T_ROWS_CART = 3, T_ROWS_GEN = 9 };
 
-template <class P, int SOLVER, int DIR>
+template <class P, int SOLVER, int DIR, class VL, class VR>
 IDFX_D void solveInterface(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double A0, int k, int j, int i,
-                           long long cell, const double *vL, const double *vR, double *F, RiemannAux &aux) {
+                           long long cell, const VL &vL, const VR &vR, double *F, RiemannAux &aux) {
   riemannDispatch<P, SOLVER, DIR>(vL, vR, eos, F, aux);
   if constexpr (P::mhd) {
     const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
@@ -73,7 +76,7 @@ IDFX_D void solveInterface(const SweepArgs &a, const DevGrid &g, int geo, const 
 // =================================================================================================
 template <class P, int ORDER, bool CART>
 constexpr size_t pencilMarchSmem(int TX, int chunk) {
-  return sizeof(double) * ((size_t)TX * (pencil::Halo<ORDER>::W * P::nvar   // stencil ring
+  return sizeof(double) * ((size_t)TX * ((CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * P::nvar   // stencil ring
                                          + P::nvar                          // left state of the next interface
                                          + (P::nvar + 1)                    // previous interface: flux + signal speed
                                          + 2)                               // normal field at the interface (x2)
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
   static_assert(DIR == JDIR || DIR == KDIR, "the marching kernel sweeps along x2 or x3");
   constexpr int NV = P::nvar;
   using D = Dirs<P, DIR>;
-  constexpr int H = pencil::Halo<ORDER>::H, W = pencil::Halo<ORDER>::W;
+  constexpr bool LATE = CART;   // prefetch after the reconstruction (no cell behind the stencil is needed)
+  constexpr int H = pencil::Halo<ORDER>::H, W = LATE ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W;
   constexpr int PDIR = (DIR == JDIR) ? KDIR : JDIR;  // the other perpendicular direction
 
   extern __shared__ double smem[];
@@ -186,19 +190,30 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
     }
   }
 
-  int q = 0;  // ring slot of cell m-H-1: free, receives cell m+H+1
-  const double *pre = a.Vc + cell0 + (long long)(mb + H + 1) * stride;
+  int q = 0;  // ring slot of cell m-H-1: free, receives cell m+H+1 (LATE: cell m+H, issued at the end of step m-1)
+  const double *pre = a.Vc + cell0 + (long long)(mb + H + (LATE ? 0 : 1)) * stride;
   long long cellm = cell0 + (long long)mb * stride;
+  if constexpr (LATE) {
+    // cell mb+H completes the stencil of cell mb
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
+    pencil::cpAsyncCommit();
+    pre += stride;
+  }
   for (int m = mb; m <= me; m++) {
     const int r = m - mb;
-    // ---- prefetch what the next interface needs ------------------------------------------------------
-    if (m < me) {
+    if constexpr (!LATE) {
+      // ---- prefetch what the next interface needs ----------------------------------------------------
+      if (m < me) {
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
-      if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
+        for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
+        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
+      }
+      pencil::cpAsyncCommit();
+      pencil::cpAsyncWait<1>();   // everything but the group just committed has landed
+    } else {
+      pencil::cpAsyncWait<0>();   // cell m+H and the normal field of interface m (issued one step ago)
     }
-    pencil::cpAsyncCommit();
-    pencil::cpAsyncWait<1>();   // everything but the group just committed has landed
 
     // ---- cell m: face values; interface m: left state from cell m-1, right state from cell m -----------
     int sc = q + 1 + H;         // slot of cell m
@@ -231,6 +246,17 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         vL[nv] = vls[nv * TX];
         vls[nv * TX] = vr;
       }
+    }
+    if constexpr (LATE) {
+      // cell m-H has left the stencil: its slot receives cell m+H+1 while the Riemann problem is solved
+      if (m < me) {
+        int qn = q + 1;
+        if (qn >= W) qn -= W;
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (qn * NV + nv) * TX * 8, pre + nv * g.sn);
+        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
+      }
+      pencil::cpAsyncCommit();
     }
     if constexpr (P::mhd) {
       const double bn = vsb[(r & 1) * TX];

@@ -17,4 +17,8 @@ b ot2d_ppm     test/MHD/OrszagTang        YES 4 TPX
 b mhdsod_plm   test/MHD/sod               YES 2
 b sod_limo3    test/HD/sod                NO  3
 b sod_ppm      test/HD/sod                NO  4
+P=$(cd ../../idefix_b200/host/problems && pwd)
+b sph_limo3    $P/SphericalMHD            YES 3
+b sph_plm      $P/SphericalMHD            YES 2
+b polar_plm    $P/PolarMHD                YES 2
 echo done

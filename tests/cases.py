@@ -80,6 +80,41 @@ SHORT = [
     Short("lw_slow_hlld_plm_rk3", "linearwave", 2, "lw_plm", _lw(32, 16, 16, "hlld", 3, 3), (1, 10)),
 ]
 
+# Curvilinear cases (BASELINE config 5 physics and polar geometry).  Their problem directories
+# (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
+# reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
+# fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
+PROBLEM_DIRS = {"sph": "SphericalMHD", "polar": "PolarMHD"}
+
+
+def _sph(solver, emf=None, nstages=2):
+    o = _grid(["1", "1.0", "24", "l", "4.0"], ["1", "0.785398163397448", "12", "u", "2.356194490192345"],
+              ["1", "0.0", "24", "u", "6.283185307179586"])
+    o[("Hydro", "solver")] = solver
+    o[("Hydro", "emf")] = emf
+    o[("TimeIntegrator", "nstages")] = nstages
+    return o
+
+
+def _polar(solver, emf=None, nstages=2):
+    o = _grid(["2", "1.0", "12", "u", "2.0", "4", "s-", "3.0"], ["1", "0.0", "16", "u", "6.283185307179586"],
+              ["1", "-0.5", "8", "u", "0.5"])
+    o[("Hydro", "solver")] = solver
+    o[("Hydro", "emf")] = emf
+    o[("TimeIntegrator", "nstages")] = nstages
+    return o
+
+
+HOST_SHORT = [
+    # C5 physics: spherical, log-r grid, Roe + LimO3 + uct_contact (Roe goes with uct_contact)
+    Short("sph_roe_contact_limo3", "sph", 3, "sph_limo3", _sph("roe"), (1, 10)),
+    Short("sph_hlld_ucthlld_plm_rk3", "sph", 2, "sph_plm", _sph("hlld", "uct_hlld", 3), (1, 10)),
+    Short("sph_hll_uct0_plm", "sph", 2, "sph_plm", _sph("hll", "uct0"), (1, 10)),
+    Short("sph_tvdlf_arith_limo3", "sph", 3, "sph_limo3", _sph("tvdlf", "arithmetic"), (1, 10)),
+    Short("polar_hlld_contact_plm", "polar", 2, "polar_plm", _polar("hlld"), (1, 10)),
+    Short("polar_hll_ucthll_plm_rk3", "polar", 2, "polar_plm", _polar("hll", "uct_hll", 3), (1, 10)),
+]
+
 FULL = [
     Full("sod_hllc", "sod", 2, _sod("hllc"), "HD/sod/dump.ref.double.plm.idefix-hllc.ini.dmp", 0.0),
     Full("sod_hll", "sod", 2, _sod("hll"), "HD/sod/dump.ref.double.plm.idefix-hll.ini.dmp", 0.0),
@@ -121,9 +156,16 @@ FULL = [
 
 def ini_for(case, dump_every_cycle=False):
     """ini text of a case = the set-up's default ini with the case's overrides applied"""
+    import os
     from idefix_b200.input import Input
-    from idefix_b200.setups import REGISTRY
-    inp = Input.from_string(REGISTRY[case.setup].ini)
+    if case.setup in PROBLEM_DIRS:
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        inp = Input(os.path.join(here, "idefix_b200", "host", "problems", PROBLEM_DIRS[case.setup], "idefix.ini"))
+        for name in ("dmp", "vtk"):
+            inp.remove("Output", name)
+    else:
+        from idefix_b200.setups import REGISTRY
+        inp = Input.from_string(REGISTRY[case.setup].ini)
     for (block, name), vals in case.overrides.items():
         if vals is None:
             inp.remove(block, name)

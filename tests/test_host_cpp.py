@@ -18,13 +18,13 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import SHORT, ini_for
+from cases import HOST_SHORT, SHORT, ini_for
 from idefix_b200.dump import readDump
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "idefix_b200", "host")
 PROBLEMS = {"sod": ("sod", "NO"), "ot2d": ("OrszagTang", "YES"), "ot3d": ("OrszagTang3D", "YES"),
-            "sodUserBC": ("sodUserBC", "NO")}
+            "sodUserBC": ("sodUserBC", "NO"), "sph": ("SphericalMHD", "YES"), "polar": ("PolarMHD", "YES")}
 
 
 def build(problem, order, tmp_path_factory):
@@ -56,15 +56,25 @@ def run_idefix(exe, workdir, ini_text, *args):
     return res.stdout
 
 
-@pytest.mark.parametrize("problem", ["sod", "sodUserBC", "ot2d", "ot3d"])
+@pytest.mark.parametrize("problem", ["sod", "sodUserBC", "ot2d", "ot3d", "sph", "polar"])
 def test_problem_compiles_against_host_layer(problem, tmp_path_factory):
     exe = binary(problem, 2, tmp_path_factory)
     assert os.access(exe, os.X_OK)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test"), reason="reference tree not present on this box")
+@pytest.mark.parametrize("ref_problem,mhd", [("HD/sod", "NO"), ("MHD/OrszagTang3D", "YES")])
+def test_unmodified_reference_setups_compile(ref_problem, mhd, tmp_path):
+    """drop-in check: the reference's own definitions.hpp + setup.cpp build against our headers"""
+    out = tmp_path / "idefix"
+    cmd = ["make", "-s", "-C", HOST, f"PROBLEM=/root/reference/test/{ref_problem}", f"MHD={mhd}", f"OUT={out}"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and os.access(out, os.X_OK), res.stdout[-3000:] + res.stderr[-3000:]
+
+
 HOST_CASES = [c for c in SHORT if c.name in ("sod_hllc_plm", "sod_hllc_limo3", "ot2d_hlld_ucthlld_plm",
                                              "ot2d_hlld_contact_plm", "ot3d_hlld_contact_plm",
-                                             "ot3d_hlld_ucthlld_plm")]
+                                             "ot3d_hlld_ucthlld_plm")] + HOST_SHORT
 
 
 def assert_same_fields(mine, gold):
