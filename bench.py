@@ -182,12 +182,13 @@ def sweep_algorithmic_bytes(nvar, ndim, emf, stage0_share, direction):
     """DESIGN.md 'algorithmic bytes': per interior cell and per sweep launch (average over the RK stages).
     Every sweep reads Vc (nvar) + the normal Vs (1) and writes the face EMF outputs (2 EMFs + contact
     weight, or 2 + 4 UCT coefficients).  The x1 sweep rebuilds Uc from Vc: it WRITES the nvar-ndim non-CT
-    conservative variables (and their copy Uc0 on stage 0) and InvDt (stage 0); the x2/x3 sweeps
-    read-modify-write Uc and InvDt (stage 0)."""
+    conservative variables (and their copy Uc0 on stage 0), InvDt (stage 0) and, for uct_contact, the
+    ndim cell-centred EMFs; the x2/x3 sweeps read-modify-write Uc and InvDt (stage 0)."""
     face = {"uct_contact": 3, None: 3, "uct0": 2, "arithmetic": 2, "uct_hll": 6, "uct_hlld": 6}[emf]
     nu = nvar - ndim
     if direction == 0:
-        doubles = nvar + 1 + nu + nu * stage0_share + face + 1 * stage0_share
+        centre = ndim if emf in (None, "uct_contact") else 0   # cell-centred EMFs written for the contact average
+        doubles = nvar + 1 + nu + nu * stage0_share + face + centre + 1 * stage0_share
     else:
         doubles = nvar + 1 + 2 * nu + face + 2 * stage0_share
     return 8.0 * doubles

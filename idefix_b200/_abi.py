@@ -43,6 +43,7 @@ class IdfxBlockDesc(C.Structure):
         ("gamma", C.c_double), ("csiso", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double),
         ("first_dt", C.c_double), ("fixed_dt", C.c_double),
         ("x", _pd * 3), ("xl", _pd * 3), ("xr", _pd * 3), ("dx", _pd * 3),
+        ("ntracer", C.c_int),
     ]
 
 

@@ -72,6 +72,7 @@ struct IdfxBlock {
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
   int sweepVariant = 2;
+  double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
   bool timing = false;
@@ -298,6 +299,7 @@ int setupPhys(IdfxBlock *b) {
   c.BX2 = (c.mhd && c.ncomp >= 2) ? c.BX1 + 1 : 252;
   c.BX3 = (c.mhd && c.ncomp == 3) ? c.BX1 + 2 : 251;
   c.nvar = 1 + c.ncomp + energy + (c.mhd ? c.ncomp : 0);
+  c.ntr = d.ntracer;
   return 0;
 }
 
@@ -306,6 +308,7 @@ int validate(const IdfxBlockDesc &d) {
   if (d.ncomp < d.ndim || d.ncomp > 3) return fail("ncomp must satisfy ndim <= ncomp <= 3");
   if (d.order < 1 || d.order > 4) return fail("order must be 1..4");
   if (d.nstages < 1 || d.nstages > 3) return fail("nstages must be 1..3");
+  if (d.ntracer < 0 || d.ntracer > 8) return fail("The number of passive tracers should be between 0 and 8");
   if (d.geometry < IDFX_CARTESIAN || d.geometry > IDFX_SPHERICAL) return fail("unknown geometry");
   if (d.geometry == IDFX_CYLINDRICAL && d.ndim == 3) return fail("CYLINDRICAL is 2-D only; use POLAR");
   if (d.mhd) {
@@ -357,6 +360,7 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
       a.perpExt = -1;  // resolved per direction: nghost[dir]
   }
   a.doInvDt = 1;
+  a.fluxRho = b->fluxRho;
   a.variant = b->sweepVariant;
   return a;
 }
@@ -451,6 +455,11 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
   const IdfxBlockDesc &d = b->desc;
   const bool fused = fusedStage >= 0;
   const bool multi = d.nstages > 1;
+  if (fused && b->cfg.ntr > 0) {
+    // Tracer::ConvertPrimToCons (+ the "begin" copy on the first stage); the fluid part is done by the x1 sweep
+    KTRY(idfxk::tracerPrimToCons(b->cfg, b->g, b->Vc, b->Uc, (fusedStage == 0 && multi) ? b->Uc0 : nullptr, b->stream));
+    b->launches++;
+  }
   for (int dir = 0; dir < d.ndim; dir++) {
     SweepArgs a = baseSweepArgs(b);
     a.doSource = (dir == d.ndim - 1 && d.geometry != IDFX_CARTESIAN) ? 1 : 0;
@@ -461,11 +470,16 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
       a.Uc0 = (dir == 0 && fusedStage == 0 && multi) ? b->Uc0 : nullptr;
     }
     KTRY(launchSweepDir(b, dir, a));
+    if (b->cfg.ntr > 0) {   // Tracer::CalcFlux / CalcRightHandSide (evolveStage.hpp:22-31)
+      const long long off = (long long)b->cfg.nvar * b->nCells;
+      KTRY(idfxk::tracerSweep(b->g, dir, b->Vc + off, b->Uc + off, b->fluxRho, b->state + 1, b->cfg.ntr, b->stream));
+      b->launches++;
+    }
   }
   if (b->cfg.mhd && d.ndim >= 2) {
     TimeScope ts(b, TIME_CT);
     KTRY(idfxk::calcCornerEmf(b->g, b->emf, b->Vc, b->Vs, b->cfg.emf, b->cfg.order, b->cfg.ncomp, b->cfg.MX1,
-                              b->cfg.BX1, b->stream, &b->launches));
+                              b->cfg.BX1, b->stream, &b->launches, 1));
     int mode = 0;
     double wc = 0, w0 = 0;
     if (fused && multi) {
@@ -506,8 +520,12 @@ int cycleReferenceOrder(IdfxBlock *b) {
     if (reconstructVc(b, b->Vc)) return 1;
     KTRY(idfxk::primToCons(b->cfg, b->g, b->Vc, b->Uc, d.gamma, b->stream));
     b->launches++;
+    if (b->cfg.ntr > 0) {
+      KTRY(idfxk::tracerPrimToCons(b->cfg, b->g, b->Vc, b->Uc, nullptr, b->stream));
+      b->launches++;
+    }
     if (d.nstages > 1 && stage == 0) {
-      KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * b->cfg.nvar, b->stream));
+      KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * (b->cfg.nvar + b->cfg.ntr), b->stream));
       b->launches++;
       if (b->cfg.mhd) {
         KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * d.ndim, b->stream));
@@ -523,7 +541,7 @@ int cycleReferenceOrder(IdfxBlock *b) {
       crossBlockReduce(b, (double *)b->redBits, IDFX_REDUCE_MIN);
     }
     if (stage > 0) {
-      KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * b->cfg.nvar, wc, w0, b->stream));
+      KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * (b->cfg.nvar + b->cfg.ntr), wc, w0, b->stream));
       b->launches++;
       if (b->cfg.mhd) {
         KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * d.ndim, wc, w0, b->stream));
@@ -533,6 +551,10 @@ int cycleReferenceOrder(IdfxBlock *b) {
     if (reconstructVc(b, b->Uc)) return 1;
     KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, d.gamma, b->stream));
     b->launches++;
+    if (b->cfg.ntr > 0) {
+      KTRY(idfxk::tracerConsToPrim(b->cfg, b->g, b->Vc, b->Uc, nullptr, 0, 0.0, 0.0, 0, b->stream));
+      b->launches++;
+    }
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
                            b->stream));
@@ -564,6 +586,10 @@ int cycleFused(IdfxBlock *b) {
                                 b->stream));
     }
     b->launches++;
+    if (b->cfg.ntr > 0) {   // RK combination + Tracer::ConvertConsToPrim with the final Uc(RHO)
+      KTRY(idfxk::tracerConsToPrim(b->cfg, b->g, b->Vc, b->Uc, b->Uc0, stage > 0 ? 1 : 0, wc, w0, 1, b->stream));
+      b->launches++;
+    }
     b->vcFieldFresh = !b->userBc;   // a user boundary function may write anywhere
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
@@ -579,9 +605,9 @@ int fieldPtr(IdfxBlock *b, int field, double **p, int dims[4]) {
   dims[3] = g.nx[0];
   dims[0] = 1;
   switch (field) {
-    case IDFX_FIELD_VC: *p = b->Vc; dims[0] = b->cfg.nvar; break;
-    case IDFX_FIELD_UC: *p = b->Uc; dims[0] = b->cfg.nvar; break;
-    case IDFX_FIELD_UC0: *p = b->Uc0; dims[0] = b->cfg.nvar; break;
+    case IDFX_FIELD_VC: *p = b->Vc; dims[0] = b->cfg.nvar + b->cfg.ntr; break;
+    case IDFX_FIELD_UC: *p = b->Uc; dims[0] = b->cfg.nvar + b->cfg.ntr; break;
+    case IDFX_FIELD_UC0: *p = b->Uc0; dims[0] = b->cfg.nvar + b->cfg.ntr; break;
     case IDFX_FIELD_VS:
     case IDFX_FIELD_VS0:
       *p = (field == IDFX_FIELD_VS) ? b->Vs : b->Vs0;
@@ -667,7 +693,8 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
 
   int rc = 0;
   rc |= buildGeometry(b);
-  const int nv = b->cfg.nvar;
+  const int nv = b->cfg.nvar + b->cfg.ntr;
+  if (b->cfg.ntr > 0) rc = rc || devAlloc(b, &b->fluxRho, b->nCells);
   rc = rc || devAlloc(b, &b->Vc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->Uc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->invDt, b->nCells);
@@ -888,6 +915,10 @@ int idfx_reconstruct_vc_field(IdfxBlock *b, int field) {
 int idfx_prim_to_cons(IdfxBlock *b) {
   KTRY(idfxk::primToCons(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
   b->launches++;
+  if (b->cfg.ntr > 0) {
+    KTRY(idfxk::tracerPrimToCons(b->cfg, b->g, b->Vc, b->Uc, nullptr, b->stream));
+    b->launches++;
+  }
   return 0;
 }
 
@@ -895,12 +926,16 @@ int idfx_cons_to_prim(IdfxBlock *b) {
   if (reconstructVc(b, b->Uc)) return 1;
   KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
   b->launches++;
+  if (b->cfg.ntr > 0) {
+    KTRY(idfxk::tracerConsToPrim(b->cfg, b->g, b->Vc, b->Uc, nullptr, 0, 0.0, 0.0, 0, b->stream));
+    b->launches++;
+  }
   return 0;
 }
 
 int idfx_state_copy(IdfxBlock *b) {
   if (!b->Uc0) return fail("states[\"begin\"] exists only when nstages > 1");
-  KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * b->cfg.nvar, b->stream));
+  KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * (b->cfg.nvar + b->cfg.ntr), b->stream));
   b->launches++;
   if (b->cfg.mhd) {
     KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * b->desc.ndim, b->stream));
@@ -911,7 +946,7 @@ int idfx_state_copy(IdfxBlock *b) {
 
 int idfx_state_add_and_store(IdfxBlock *b, double wc, double w0) {
   if (!b->Uc0) return fail("states[\"begin\"] exists only when nstages > 1");
-  KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * b->cfg.nvar, wc, w0, b->stream));
+  KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * (b->cfg.nvar + b->cfg.ntr), wc, w0, b->stream));
   b->launches++;
   if (b->cfg.mhd) {
     KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * b->desc.ndim, wc, w0, b->stream));

@@ -192,7 +192,7 @@ inline long long boxCount(const Box &b) {
 VarList haloVars(const PhysCfg &c) {
   VarList l;
   l.n = 0;
-  for (int n = 0; n < c.nvar; n++) {
+  for (int n = 0; n < c.nvar + c.ntr; n++) {
     if (c.mhd && n >= c.BX1 && n < c.BX1 + c.ndim) continue;
     l.v[l.n++] = n;
   }
@@ -291,8 +291,9 @@ int idfxk::enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *V
       }
     }
     const dim3 blk = slabBlock(b);
-    ghostFillKernel<<<boxGrid(b, c.nvar, blk), blk, 0, st>>>(Vc, g.sj, g.sk, b, c.nvar, g.sn, dir, side, type, ng, nint,
-                                                             signMask, c.MX1 + dir);
+    const int nall = c.nvar + c.ntr;   // tracers behave like scalars (boundary.hpp:136)
+    ghostFillKernel<<<boxGrid(b, nall, blk), blk, 0, st>>>(Vc, g.sj, g.sk, b, nall, g.sn, dir, side, type, ng, nint,
+                                                           signMask, c.MX1 + dir);
     (*launches)++;
   }
   if (c.mhd) {

@@ -183,17 +183,20 @@ __global__ void riemannAverageKernel(DevGrid g, DevEmf e, const double *__restri
 }
 
 // evolveMagField.hpp:53-131
-template <int ND>
-__global__ void evolveMagFieldKernel(DevGrid g, DevEmf e, double *__restrict__ Vs, double *__restrict__ Vs0,
-                                     const double *dtp, int haveAxis, int mode, double wc, double w0, Box b) {
+// CART: cartesian geometry fixed at compile time (drops the curvilinear branches and their registers, which
+// doubles the resident warps of this latency-bound kernel)
+template <int ND, bool CART>
+__global__ void __launch_bounds__(TBX *TBY, CART ? 6 : 4)
+    evolveMagFieldKernel(DevGrid g, DevEmf e, double *__restrict__ Vs, double *__restrict__ Vs0, const double *dtp,
+                         int haveAxis, int mode, double wc, double w0, Box b) {
   BOX_INDEX(b)
   const double dt = *dtp;
   const long long c = cidx(g, k, j, i);
   const long long sj = g.sj, sk = g.sk;
-  const double *Ex1 = e.ex, *Ex2 = e.ey, *Ex3 = e.ez;
+  const double *__restrict__ Ex1 = e.ex, *__restrict__ Ex2 = e.ey, *__restrict__ Ex3 = e.ez;
   const double *dx1 = g.dx[0], *dx2 = g.dx[1], *dx3 = g.dx[2];
   double rhsx1 = 0.0, rhsx2 = 0.0, rhsx3 = 0.0;
-  const int geo = g.geometry;
+  const int geo = CART ? (int)GEO_CARTESIAN : g.geometry;
   if (geo == GEO_CARTESIAN) {
     if (ND >= 2) rhsx1 = rhsx1 - dt / dx2[j] * (Ex3[c + sj] - Ex3[c]);
     if (ND == 3) rhsx1 = rhsx1 + dt / dx3[k] * (Ex2[c + sk] - Ex2[c]);
@@ -267,7 +270,8 @@ Box cornerBox(const DevGrid &g, int extra) {
 
 // ConstrainedTransport::CalcCornerEMF (calcCornerEmf.hpp:15-38)
 int idfxk::calcCornerEmf(const DevGrid &g, const DevEmf &e, const double *Vc, const double *Vs, int emfMode,
-                         int order, int ncomp, int vx1, int bx1, cudaStream_t st, long long *launches) {
+                         int order, int ncomp, int vx1, int bx1, cudaStream_t st, long long *launches,
+                         int emfFromSweep) {
   if (g.ndim < 2) return 0;
   const dim3 block(TBX, TBY, 1);
   Box corner = cornerBox(g, 0);
@@ -280,8 +284,13 @@ int idfxk::calcCornerEmf(const DevGrid &g, const DevEmf &e, const double *Vc, co
       all.lo[d] = 0;
       all.hi[d] = g.nx[d];
     }
-    LAUNCH_ND(g.ndim, cellCenteredEmfKernel, boxGrid(all), block, st, g, e, Vc, ncomp, vx1, bx1, all);
-    (*launches)++;
+    // uct_contact: the cell-centred EMFs of every cell the averaging reads ([beg-1, end] in each direction)
+    // were written by the x1 sweep of this stage (sweep_pencil.cuh); the stand-alone kernel remains for uct0
+    // (which also reads beg-2) and for callers that have not run a sweep (emfFromSweep == 0)
+    if (!(emfFromSweep && emfMode == EMF_UCT_CONTACT)) {
+      LAUNCH_ND(g.ndim, cellCenteredEmfKernel, boxGrid(all), block, st, g, e, Vc, ncomp, vx1, bx1, all);
+      (*launches)++;
+    }
     if (emfMode == EMF_UCT0) {
       Box fb;
       for (int d = 0; d < 3; d++) {
@@ -316,7 +325,13 @@ int idfxk::evolveMagField(const DevGrid &g, const DevEmf &e, double *Vs, double 
   if (g.ndim == 1) {
     return 0;  // EvolveStage only calls CT for DIMENSIONS >= 2 (evolveStage.hpp:70-87)
   }
-  LAUNCH_ND(g.ndim, evolveMagFieldKernel, boxGrid(b), block, st, g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
+  if (g.geometry == GEO_CARTESIAN) {
+    if (g.ndim == 2) evolveMagFieldKernel<2, true><<<boxGrid(b), block, 0, st>>>(g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
+    else evolveMagFieldKernel<3, true><<<boxGrid(b), block, 0, st>>>(g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
+  } else {
+    if (g.ndim == 2) evolveMagFieldKernel<2, false><<<boxGrid(b), block, 0, st>>>(g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
+    else evolveMagFieldKernel<3, false><<<boxGrid(b), block, 0, st>>>(g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
+  }
   (*launches)++;
   return (int)cudaGetLastError();
 }

@@ -9,6 +9,7 @@
 struct PhysCfg {
   int ndim, ncomp, mhd, iso;
   int nvar;
+  int ntr;   // passive tracers stored behind the nvar fluid variables (fluid.hpp:315-323)
   int order, solver, emf;
   // variable indices (255.. when absent)
   int RHO, MX1, MX2, MX3, ENG, BX1, BX2, BX3;
@@ -28,7 +29,7 @@ int sweepMhdRoeIso(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t s
 
 // ---- constrained transport (ct.cu) ------------------------------------------
 int calcCornerEmf(const DevGrid &g, const DevEmf &e, const double *Vc, const double *Vs, int emfMode, int order,
-                  int ncomp, int vx1, int bx1, cudaStream_t st, long long *launches);
+                  int ncomp, int vx1, int bx1, cudaStream_t st, long long *launches, int emfFromSweep = 0);
 // mode 0: Vs += rhs (reference behaviour); 1: additionally save the old Vs into Vs0 (first stage of the
 // fused path); 2: Vs <- wc*(Vs+rhs) + w0*Vs0 (later stages of the fused path)
 int evolveMagField(const DevGrid &g, const DevEmf &e, double *Vs, double *Vs0, const double *dt, int haveAxis,
@@ -48,6 +49,16 @@ int addAndStore(double *dst, const double *src, long long n, double wl, double w
 // fused stage epilogue over the interior: RK combine of Uc, Uc(B) <- Vs, Vc <- C2P(Uc)
 int stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs, const double *Uc0,
                   double gamma, int combine, double wc, double w0, int keepUc, cudaStream_t st);
+
+// ---- passive tracers (tracer.cu) ------------------------------------------------
+// Tracer::CalcFlux + CalcRightHandSide of one direction from the mass flux the sweep stored
+int tracerSweep(const DevGrid &g, int dir, const double *Vtr, double *Utr, const double *fluxRho, const double *dt,
+                int ntr, cudaStream_t st);
+// Tracer::ConvertPrimToCons over the whole block; Uc0 != null also saves the result as the "begin" state
+int tracerPrimToCons(const PhysCfg &c, const DevGrid &g, const double *Vc, double *Uc, double *Uc0, cudaStream_t st);
+// Tracer::ConvertConsToPrim; combine: u <- wc*u + w0*u0 first (fused path)
+int tracerConsToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Uc0, int combine,
+                     double wc, double w0, int interiorOnly, cudaStream_t st);
 
 // ---- boundaries (boundary.cu) -------------------------------------------------
 int enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side, int type,

@@ -62,6 +62,7 @@ template <class P, int SOLVER, int DIR, class VL, class VR>
 IDFX_D void solveInterface(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double A0, int k, int j, int i,
                            long long cell, const VL &vL, const VR &vR, double *F, RiemannAux &aux) {
   riemannDispatch<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+  if (a.fluxRho != nullptr) a.fluxRho[cell] = F[P::RHO];   // for the tracer kernels (Tracer::CalcFlux)
   if constexpr (P::mhd) {
     const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
     storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
@@ -455,6 +456,28 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
       vrs[nv * 32 + lane] = vr;
     }
     __syncwarp();
+
+    // ---- cell-centred EMFs of cell c (CalcCellCenteredEMF, calcCornerEmf.hpp:85-126) ------------------------
+    // uct_contact averages them onto the corners from the cells [beg-1, end] of every direction; the
+    // primitives are already on chip here, so the separate full-array kernel (6 reads + 3 writes per cell) is
+    // folded into this sweep.  Each cell is written by exactly one lane: the strip's own 30 cells, plus the
+    // cell in front of the first strip and the one behind the last.  (uct0 also reads beg-2: it keeps the
+    // stand-alone kernel.)
+    if constexpr (P::mhd && P::ndim >= 2) {
+      if (a.emfMode == EMF_UCT_CONTACT) {
+        const bool owner = (lane >= 1 && lane <= STRIP) || (lane == 0 && s == 0) || (lane == 31 && s == nstrips - 1);
+        if (owner && c <= g.end[0]) {
+          const long long cc = cidx(g, k, j, c);
+          const double v1 = row[P::MX1 * RW], v2 = row[P::MX2 * RW], B1 = row[P::BX1 * RW], B2 = row[P::BX2 * RW];
+          if constexpr (P::ndim == 3) {
+            const double v3 = row[P::MX3 * RW], B3 = row[P::BX3 * RW];
+            a.emf.Ex1[cc] = (v3 * B2 - v2 * B3);
+            a.emf.Ex2[cc] = (v1 * B3 - v3 * B1);
+          }
+          a.emf.Ex3[cc] = (v2 * B1 - v1 * B2);
+        }
+      }
+    }
 
     // ---- interface c (left face of cell c) -----------------------------------------------------------------
     double F[NV];

@@ -49,7 +49,14 @@ class Fluid:
             self.csiso = inp.Get(float, "Hydro", "csiso", 1)
         else:
             self.gamma = inp.GetOrSet(float, "Hydro", "gamma", 0, 5.0 / 3.0)
-        for opt in ("shockFlattening", "tracer", "viscosity", "resistivity", "ambipolar", "hall", "rotation",
+        # passive tracers (fluid.hpp:315-323): stored behind the fluid variables, first index TRG = nvar
+        self.nTracer = 0
+        if inp.CheckEntry("Hydro", "tracer") >= 0:
+            self.nTracer = inp.Get(int, "Hydro", "tracer", 0)
+            if self.nTracer < 1:
+                raise IdefixError("The number of passive tracers should be >= 1")
+        self.haveTracer = self.nTracer > 0
+        for opt in ("shockFlattening", "viscosity", "resistivity", "ambipolar", "hall", "rotation",
                     "gravity", "fargo", "TDiffusion", "bragViscosity", "bragTDiffusion", "drag"):
             if inp.CheckEntry("Hydro", opt) >= 0:
                 raise IdefixError(f"[Hydro] {opt} is outside the scope of this build (explicit Godunov path only)")
@@ -60,7 +67,7 @@ class Fluid:
         self.PRS = nc + 1 if energy else None
         self.BX1 = nc + 1 + energy if defs.mhd else None
         self.nvar = 1 + nc + energy + (nc if defs.mhd else 0)
-        self.haveTracer = False
+        self.TRG = self.nvar
 
     # ---- forwards ------------------------------------------------------------------
     def _h(self):
@@ -132,6 +139,7 @@ class DataBlock:
         d.device = device or 0
         d.gamma, d.csiso = self.hydro.gamma, self.hydro.csiso
         d.cfl, d.cfl_max_var, d.first_dt, d.fixed_dt = self.cfl, self.cfl_max_var, first_dt, self.fixed_dt
+        d.ntracer = self.hydro.nTracer
         self._desc = d
         self._callbacks = []
         self._handle = None
@@ -262,7 +270,7 @@ class DataBlockHost:
         self.beg, self.end, self.nghost = data.beg, data.end, data.nghost
         self.x, self.xl, self.xr, self.dx = data.x, data.xl, data.xr, data.dx
         n3, n2, n1 = data.np_tot[2], data.np_tot[1], data.np_tot[0]
-        self.Vc = np.zeros((data.hydro.nvar, n3, n2, n1))
+        self.Vc = np.zeros((data.hydro.nvar + data.hydro.nTracer, n3, n2, n1))
         self._Uc = None      # allocated on first access; an untouched mirror is all zeros
         self._InvDt = None
         self.Vs = None

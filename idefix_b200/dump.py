@@ -108,7 +108,7 @@ def writeDump(filename, data, vc_names, Vc, Vs=None, t=0.0, dt=0.0, number=0, ve
         _write_field(fh, "eof", np.zeros(1), 0)
 
 
-def vc_names(defs):
+def vc_names(defs, ntracer=0):
     """names of the dumped Vc entries in variable order; None for those not dumped"""
     names = ["RHO"] + [f"VX{c + 1}" for c in range(defs.components)]
     if not defs.isothermal:
@@ -116,6 +116,7 @@ def vc_names(defs):
     if defs.mhd:
         # components evolved by CT are dumped through Vs only; BX(n > DIMENSIONS) stays in Vc
         names += [None if c < defs.dimensions else f"BX{c + 1}" for c in range(defs.components)]
+    names += [f"TR{n}" for n in range(ntracer)]   # fluid.hpp:634
     return names
 
 

@@ -96,7 +96,12 @@ class Fluid {
 #else
     gamma = input.GetOrSet<real>("Hydro", "gamma", 0, 5.0 / 3.0);
 #endif
-    const char *unsupported[] = {"shockFlattening", "tracer", "viscosity", "resistivity", "ambipolar", "hall",
+    if (input.CheckEntry("Hydro", "tracer") >= 0) {   // fluid.hpp:315-323
+      haveTracer = true;
+      nTracer = input.Get<int>("Hydro", "tracer", 0);
+      if (nTracer < 1) IDEFIX_ERROR("The number of passive tracers should be >= 1");
+    }
+    const char *unsupported[] = {"shockFlattening", "viscosity", "resistivity", "ambipolar", "hall",
                                  "rotation", "gravity", "fargo", "TDiffusion", "bragViscosity", "bragTDiffusion",
                                  "drag"};
     for (const char *opt : unsupported)
@@ -111,6 +116,7 @@ class Fluid {
     for (int c = 0; c < COMPONENTS; c++) VcName.push_back("BX" + std::to_string(c + 1));
     for (int c = 0; c < DIMENSIONS; c++) VsName.push_back("BX" + std::to_string(c + 1) + "s");
 #endif
+    for (int n = 0; n < nTracer; n++) VcName.push_back("TR" + std::to_string(n));   // fluid.hpp:634
   }
 
   real GetGamma() const { return gamma; }
@@ -205,6 +211,7 @@ class DataBlock {
     d.cfl_max_var = cflMaxVar;
     d.first_dt = firstDt;
     d.fixed_dt = fixedDt;
+    d.ntracer = hydro->nTracer;
     IDFX_CUDA(cudaSetDevice(input.device));
     IDFX_ABI(idfx_block_create(&d, &handle));
     // user kernels (idefix_for) run on the legacy default stream: put the library there too so that

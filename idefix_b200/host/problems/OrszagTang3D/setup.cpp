@@ -24,6 +24,10 @@ void Setup::InitFlow(DataBlock &data) {
         host.Vc(VX1, k, j, i) = -sy;
         host.Vc(VX2, k, j, i) = sin(twoPi * xc) + cz;
         host.Vc(VX3, k, j, i) = cos(twoPi * xc);
+        if (data.hydro->haveTracer) {   // passive tracers: two step functions
+          host.Vc(TRG, k, j, i) = xc > 0.5 ? 1.0 : 0.0;
+          if (data.hydro->nTracer > 1) host.Vc(TRG + 1, k, j, i) = host.x[KDIR](k) > 0.5 ? 1.0 : 0.0;
+        }
         A(IDIR, k, j, i) = amp * cyl;
         A(JDIR, k, j, i) = amp * sin(twoPi * xf);
         A(KDIR, k, j, i) = amp * (cyl + cos(4.0 * M_PI * xf) / 2.0);

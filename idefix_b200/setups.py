@@ -200,6 +200,11 @@ X3-end    periodic
         Ve[0][:n3, :n2, :n1] = np.broadcast_to(B0 / (2.0 * math.pi) * (fcos(2.0 * math.pi * yl)), shape)
         Ve[1][:n3, :n2, :n1] = np.broadcast_to(B0 / (2.0 * math.pi) * fsin(2.0 * math.pi * xl), shape)
         Ve[2][:n3, :n2, :n1] = B0 / (2.0 * math.pi) * (fcos(2.0 * math.pi * yl) + fcos(4.0 * math.pi * xl) / 2.0)
+        if data.hydro.haveTracer:   # test/MHD/OrszagTang3D/setup.cpp:247-250: two step functions
+            trg = data.hydro.TRG
+            d.Vc[trg] = np.broadcast_to(np.where(x > 0.5, 1.0, 0.0), shape)
+            if data.hydro.nTracer > 1:
+                d.Vc[trg + 1] = np.broadcast_to(np.where(z > 0.5, 1.0, 0.0), shape)
         d.MakeVsFromAmag(Ve)
         d.SyncToDevice()
 

@@ -75,6 +75,8 @@ typedef struct IdfxBlockDesc {
   const double *xl[3];
   const double *xr[3];
   const double *dx[3];
+  int ntracer;         /* [Hydro] tracer N: passive tracers stored behind the fluid variables in
+                          Vc / Uc, index nvar .. nvar+N-1 (fluid.hpp:315-323, tracer.hpp:58-125) */
 } IdfxBlockDesc;
 
 typedef struct IdfxBlock IdfxBlock;

@@ -21,7 +21,7 @@ class OracleDesc(C.Structure):
     _fields_ = [("ndim", C.c_int), ("ncomp", C.c_int), ("mhd", C.c_int), ("solver", C.c_int), ("emf", C.c_int),
                 ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
                 ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
-                ("dx", C.c_double * 3)]
+                ("dx", C.c_double * 3), ("ntracer", C.c_int)]
 
 
 _lib = None
@@ -55,8 +55,9 @@ class Oracle:
     (n, k, j, i) like the reference's IdefixArray4D."""
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
-                 cfl_max_var=1.1):
+                 cfl_max_var=1.1, ntracer=0):
         d = OracleDesc()
+        d.ntracer = ntracer
         d.ndim, d.ncomp, d.mhd = ndim, ncomp, int(mhd)
         d.solver, d.emf, d.nstages = SOLVERS[solver], EMFS[emf or "uct_contact"], nstages
         for a in range(3):
@@ -89,7 +90,7 @@ class Oracle:
         o = cls(nd, defs.components, defs.mhd, inp.Get(str, "Hydro", "solver", 0), emf,
                 inp.Get(int, "TimeIntegrator", "nstages", 0), grid.np_int, [names[grid.lbound[a]] for a in range(nd)],
                 setup.data.hydro.gamma, inp.Get(float, "TimeIntegrator", "CFL", 0), first_dt,
-                [float(grid.dx[a][0]) for a in range(3)])
+                [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer)
         return o
 
     def set_state(self, Vc, Vs=None):

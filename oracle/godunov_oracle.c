@@ -32,6 +32,7 @@ typedef struct {
   int bc[3];                 /* same type on both sides */
   double gamma, cfl, cfl_max_var, first_dt;
   double dx[3];              /* uniform spacing */
+  int ntracer;               /* passive tracers behind the fluid variables, fluid.hpp:315-323 */
 } OracleDesc;
 
 typedef struct {
@@ -40,6 +41,7 @@ typedef struct {
   long sj, sk, sn;           /* cell-centred strides */
   long vj, vk, vn;           /* staggered strides    */
   int nvar, RHO, MX1, ENG, BX1;
+  int ntr;                   /* Vc / Uc / Flux hold nvar + ntr variables */
   double *Vc, *Uc, *Uc0, *Vs, *Vs0, *Flux, *cMax, *InvDt;
   double *ex, *ey, *ez, *exj, *exk, *eyi, *eyk, *ezi, *ezj, *Ex1, *Ex2, *Ex3;
   double *svx, *svy, *svz, *aL[3], *aR[3], *dL[3], *dR[3];
@@ -75,10 +77,11 @@ Oracle *oracle_create(const OracleDesc *d) {
   o->BX1 = d->ncomp + 2;
   o->nvar = 2 + d->ncomp + (d->mhd ? d->ncomp : 0);
   long n = o->sn;
-  o->Vc = zalloc(n * o->nvar);
-  o->Uc = zalloc(n * o->nvar);
-  o->Uc0 = zalloc(n * o->nvar);
-  o->Flux = zalloc(n * o->nvar);
+  o->ntr = d->ntracer;
+  o->Vc = zalloc(n * (o->nvar + o->ntr));
+  o->Uc = zalloc(n * (o->nvar + o->ntr));
+  o->Uc0 = zalloc(n * (o->nvar + o->ntr));
+  o->Flux = zalloc(n * (o->nvar + o->ntr));
   o->cMax = zalloc(n);
   o->InvDt = zalloc(n);
   if (d->mhd) {
@@ -117,7 +120,7 @@ double *oracle_vc(Oracle *o) { return o->Vc; }
 double *oracle_vs(Oracle *o) { return o->Vs; }
 double oracle_time(Oracle *o) { return o->t; }
 double oracle_dt(Oracle *o) { return o->dt; }
-int oracle_nvar(Oracle *o) { return o->nvar; }
+int oracle_nvar(Oracle *o) { return o->nvar + o->ntr; }
 
 /* ---- K_PrimToCons / K_ConsToPrim: src/fluid/convertConsToPrim.hpp:70-100, 16-67 ------------- */
 static void prim_to_cons(const Oracle *o, const double *v, double *u) {
@@ -591,6 +594,58 @@ static void calc_rhs(Oracle *o, int dir) {
       }
 }
 
+/* ---- passive tracers: Tracer::CalcFlux and Tracer::CalcRightHandSide, tracer/tracer.hpp:58-125 ------ */
+static double face_area(const Oracle *o, int dir) {
+  const OracleDesc *d = &o->d;
+  double A = 1.0;
+  if (dir == 0) { if (d->ndim >= 2) A = A * d->dx[1]; if (d->ndim == 3) A = A * d->dx[2]; }
+  if (dir == 1) { A = d->dx[0]; if (d->ndim == 3) A = A * d->dx[2]; }
+  if (dir == 2) { A = d->dx[0] * d->dx[1]; }
+  return A;
+}
+
+/* called between CalcRiemannFlux and CalcRightHandSide (evolveStage.hpp:22-31): uses the RAW mass flux */
+static void tracer_calc_flux(Oracle *o, int dir) {
+  const long s = dir == 0 ? 1 : (dir == 1 ? o->sj : o->sk);
+  const double A = face_area(o, dir);
+  int hi[3];
+  for (int a = 0; a < 3; a++) hi[a] = o->end[a] + (a == dir ? 1 : 0);
+  for (int n = o->nvar; n < o->nvar + o->ntr; n++)
+    for (int k = o->beg[2]; k < hi[2]; k++)
+      for (int j = o->beg[1]; j < hi[1]; j++)
+        for (int i = o->beg[0]; i < hi[0]; i++) {
+          const long c = C(o, k, j, i);
+          const double *q = o->Vc + n * o->sn + c;
+          const double frho = o->Flux[o->RHO * o->sn + c];
+          double vface;
+          if (frho > 0) { /* interpolate from the left */
+            const double dvm = q[-s] - q[-2 * s];
+            const double dvp = q[0] - q[-s];
+            vface = q[-s] + 0.5 * van_leer(dvp, dvm);
+          } else {        /* from the right */
+            const double dvm = q[0] - q[-s];
+            const double dvp = q[s] - q[0];
+            vface = q[0] - 0.5 * van_leer(dvp, dvm);
+          }
+          o->Flux[n * o->sn + c] = frho * vface * A; /* flux*Area, unlike the fluid flux */
+        }
+}
+
+static void tracer_calc_rhs(Oracle *o, int dir) {
+  const OracleDesc *d = &o->d;
+  const long s = dir == 0 ? 1 : (dir == 1 ? o->sj : o->sk);
+  double dV = d->dx[0];
+  if (d->ndim >= 2) dV = dV * d->dx[1];
+  if (d->ndim == 3) dV = dV * d->dx[2];
+  for (int n = o->nvar; n < o->nvar + o->ntr; n++)
+    for (int k = o->beg[2]; k < o->end[2]; k++)
+      for (int j = o->beg[1]; j < o->end[1]; j++)
+        for (int i = o->beg[0]; i < o->end[0]; i++) {
+          const long c = C(o, k, j, i);
+          o->Uc[n * o->sn + c] += -o->dt / dV * (o->Flux[n * o->sn + c + s] - o->Flux[n * o->sn + c]);
+        }
+}
+
 /* ---- constrained transport ------------------------------------------------------------------------ */
 /* CalcCellCenteredEMF, calcCornerEmf.hpp:85-126 */
 static void cell_centered_emf(Oracle *o) {
@@ -775,7 +830,7 @@ static void set_boundaries(Oracle *o) {
   const OracleDesc *d = &o->d;
   for (int dir = 0; dir < d->ndim; dir++) {
     for (int side = 0; side < 2; side++) {
-      for (int n = 0; n < o->nvar; n++)
+      for (int n = 0; n < o->nvar + o->ntr; n++) /* tracers are filled like scalars, boundary.hpp:136 */
         fill_ghosts(o, o->Vc + n * o->sn, o->sj, o->sk, dir, side, d->bc[dir], d->np_int, o->nx, n == o->MX1 + dir);
       if (d->mhd) {
         for (int comp = 0; comp < d->ndim; comp++) {
@@ -811,7 +866,7 @@ static double compute_timestep(const Oracle *o) { /* dataBlock.cpp:333-364 */
 
 int oracle_cycle(Oracle *o) {
   const OracleDesc *d = &o->d;
-  const long ncell = o->sn * o->nvar, nface = d->mhd ? o->vn * d->ndim : 0;
+  const long ncell = o->sn * (o->nvar + o->ntr), nface = d->mhd ? o->vn * d->ndim : 0;
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   if (d->nstages == 2) { wc[0] = 0.5; w0[0] = 0.5; }
   if (d->nstages == 3) { wc[0] = 0.25; w0[0] = 0.75; wc[1] = 2.0 / 3.0; w0[1] = 1.0 / 3.0; }
@@ -825,6 +880,8 @@ int oracle_cycle(Oracle *o) {
       for (int n = 0; n < o->nvar; n++) v[n] = o->Vc[n * o->sn + c];
       prim_to_cons(o, v, u);
       for (int n = 0; n < o->nvar; n++) o->Uc[n * o->sn + c] = u[n];
+      for (int n = o->nvar; n < o->nvar + o->ntr; n++) /* Tracer::ConvertPrimToCons, tracer.cpp:35-49 */
+        o->Uc[n * o->sn + c] = o->Vc[n * o->sn + c] * o->Vc[o->RHO * o->sn + c];
     }
     if (d->nstages > 1 && stage == 0) { /* StateContainer::CopyFrom */
       memcpy(o->Uc0, o->Uc, sizeof(double) * ncell);
@@ -832,7 +889,9 @@ int oracle_cycle(Oracle *o) {
     }
     for (int dir = 0; dir < d->ndim; dir++) { /* EvolveStage, evolveStage.hpp:41-90 */
       calc_flux(o, dir);
+      if (o->ntr > 0) tracer_calc_flux(o, dir);
       calc_rhs(o, dir);
+      if (o->ntr > 0) tracer_calc_rhs(o, dir);
     }
     if (d->mhd && d->ndim >= 2) {
       corner_emf(o);
@@ -854,6 +913,8 @@ int oracle_cycle(Oracle *o) {
       cons_to_prim(o, u, v);
       for (int n = 0; n < o->nvar; n++) o->Vc[n * o->sn + c] = v[n];
       o->Uc[o->ENG * o->sn + c] = u[o->ENG];
+      for (int n = o->nvar; n < o->nvar + o->ntr; n++) /* Tracer::ConvertConsToPrim, tracer.cpp:12-29 */
+        o->Vc[n * o->sn + c] = o->Uc[n * o->sn + c] / o->Uc[o->RHO * o->sn + c];
     }
   }
   o->t = t0 + o->dt;

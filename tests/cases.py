@@ -72,6 +72,10 @@ SHORT = [
     # C4 physics: 3-D Orszag-Tang
     Short("ot3d_hlld_contact_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16), (1, 2, 10)),
     Short("ot3d_hlld_ucthlld_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, emf="uct_hlld"), (1, 10)),
+    # passive tracers: the stock test/MHD/OrszagTang3D/idefix.ini carries two
+    Short("ot3d_hlld_contact_plm_tr2", "ot3d", 2, "ot3d_plm", {**_ot3d(16, 32, 16), ("Hydro", "tracer"): "2"}, (1, 10)),
+    Short("ot3d_hll_uct0_plm_rk3_tr2", "ot3d", 2, "ot3d_plm",
+          {**_ot3d(16, 32, 16, solver="hll", emf="uct0", nstages=3), ("Hydro", "tracer"): "2"}, (1, 10)),
     Short("ot3d_roe_contact_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, solver="roe"), (1, 10)),
     Short("ot3d_hll_uct0_plm_rk3", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, solver="hll", emf="uct0", nstages=3), (1, 10)),
     # C3 physics: linear waves, HLLD + PPM + RK3 has no shipped golden -> reference binary
@@ -145,6 +149,9 @@ FULL = [
     Full("ot2d_hlld_hlld_ppm", "ot2d", 4, _ot2d(128, "hlld", "uct_hlld"),
          "MHD/OrszagTang/dump.ref.double.ppm.idefix-hlld-hlld.ini.dmp", 1e-12),
     Full("ot3d_hlld_contact", "ot3d", 2, _ot3d(32, 64, 32), "MHD/OrszagTang3D/dump.ref.double.plm.idefix.ini.dmp", 1e-13),
+    # the same shipped golden with the two tracers of the stock ini switched on: Vc-TR0 / Vc-TR1 are compared too
+    Full("ot3d_hlld_contact_tracers", "ot3d", 2, {**_ot3d(32, 64, 32), ("Hydro", "tracer"): "2"},
+         "MHD/OrszagTang3D/dump.ref.double.plm.idefix.ini.dmp", 1e-13),
     Full("lw_fast_roe_plm", "linearwave", 2, _lw(64, 32, 32, "roe", 2, 1),
          "MHD/LinearWaveTest/dump.ref.double.plm.idefix-fast.ini.dmp", 1e-14),
     Full("lw_alfven_roe_ppm", "linearwave", 4, {**_lw(64, 32, 32, "roe", 3, 2), ("TimeIntegrator", "tstop"): "1.0"},

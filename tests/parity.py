@@ -20,7 +20,7 @@ def fields_of(setup):
     Vc = d.download(_abi.FIELD_VC)
     kb, ke, jb, je, ib, ie = d.beg[2], d.end[2], d.beg[1], d.end[1], d.beg[0], d.end[0]
     out = {}
-    for n, name in enumerate(vc_names(setup.definitions)):
+    for n, name in enumerate(vc_names(setup.definitions, setup.data.hydro.nTracer)):
         if name is not None:
             out[f"Vc-{name}"] = Vc[n, kb:ke, jb:je, ib:ie].transpose(2, 1, 0)
     if setup.definitions.mhd:

@@ -74,7 +74,7 @@ def test_unmodified_reference_setups_compile(ref_problem, mhd, tmp_path):
 
 HOST_CASES = [c for c in SHORT if c.name in ("sod_hllc_plm", "sod_hllc_limo3", "ot2d_hlld_ucthlld_plm",
                                              "ot2d_hlld_contact_plm", "ot3d_hlld_contact_plm",
-                                             "ot3d_hlld_ucthlld_plm")] + HOST_SHORT
+                                             "ot3d_hlld_ucthlld_plm", "ot3d_hlld_contact_plm_tr2")] + HOST_SHORT
 
 
 def assert_same_fields(mine, gold):

@@ -20,7 +20,7 @@ def _run(nranks, case, nproc, mode="fused", port=29611):
     assert res.returncode == 0 and "MGPU OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
-@pytest.mark.parametrize("case,nproc", [("ot3d_hlld_contact_plm", (1, 2, 1)), ("ot3d_hlld_ucthlld_plm", (2, 1, 1)),
+@pytest.mark.parametrize("case,nproc", [("ot3d_hlld_contact_plm", (1, 2, 1)), ("ot3d_hlld_contact_plm_tr2", (2, 1, 1)), ("ot3d_hlld_ucthlld_plm", (2, 1, 1)),
                                         ("ot2d_hlld_ucthlld_plm", (1, 2, 1)), ("lw_fast_hlld_ppm_rk3", (1, 1, 2))])
 def test_two_gpus(case, nproc):
     _run(2, case, nproc)

@@ -39,7 +39,7 @@ def compare(s, o, dump):
     d = s.data
     kb, ke, jb, je, ib, ie = d.beg[2], d.end[2], d.beg[1], d.end[1], d.beg[0], d.end[0]
     worst = 0.0
-    for n, name in enumerate(vc_names(s.definitions)):
+    for n, name in enumerate(vc_names(s.definitions, s.data.hydro.nTracer)):
         if name is not None:
             a = o.Vc[n, kb:ke, jb:je, ib:ie].transpose(2, 1, 0)
             worst = max(worst, float(np.abs(a - dump.data[f"Vc-{name}"]).max()))

@@ -15,7 +15,7 @@ from oracle.godunov import Oracle
 pytestmark = pytest.mark.gpu
 
 
-def make_ini(n, solver, emf, nstages, bc, mhd):
+def make_ini(n, solver, emf, nstages, bc, mhd, ntracer=0):
     lines = ["[Grid]"]
     for d, nn in enumerate(n):
         lines.append(f"X{d + 1}-grid 1 0.0 {nn} u {1.0 + 0.5 * d}")
@@ -23,6 +23,8 @@ def make_ini(n, solver, emf, nstages, bc, mhd):
               "[Hydro]", f"solver {solver}", "gamma 1.4"]
     if mhd and emf:
         lines.append(f"emf {emf}")
+    if ntracer:
+        lines.append(f"tracer {ntracer}")
     lines.append("[Boundary]")
     for d in range(len(n)):
         lines += [f"X{d + 1}-beg {bc}", f"X{d + 1}-end {bc}"]
@@ -41,6 +43,8 @@ class RandomFlow(Setup):
         for c in range(data.defs.components):
             d.Vc[h.VX1 + c] = 0.4 * (rng.random(shape) - 0.5)
         d.Vc[h.PRS] = 1.0 + 0.3 * rng.random(shape)
+        for n in range(h.nTracer):
+            d.Vc[h.TRG + n] = rng.random(shape)
         if data.defs.mhd:
             nd = data.defs.dimensions
             for c in range(nd, data.defs.components):
@@ -54,9 +58,9 @@ class RandomFlow(Setup):
         d.SyncToDevice()
 
 
-def build(ndim, ncomp, mhd, n, solver, emf, nstages, bc, seed, device=0):
+def build(ndim, ncomp, mhd, n, solver, emf, nstages, bc, seed, ntracer=0, device=0):
     cls = type("RandomFlowCase", (RandomFlow,), {"defs": Definitions(ndim, ncomp, _abi.CARTESIAN, mhd=mhd), "seed": seed})
-    return cls(order=2, ini=make_ini(n, solver, emf, nstages, bc, mhd), device=device)
+    return cls(order=2, ini=make_ini(n, solver, emf, nstages, bc, mhd, ntracer), device=device)
 
 
 CASES = [
@@ -74,14 +78,19 @@ CASES = [
     (3, 3, True, (7, 12, 5), "hlld", "uct_hlld", 3, "periodic", 11),
     (3, 3, True, (6, 5, 9), "hll", "arithmetic", 2, "periodic", 12),
     (3, 3, True, (5, 8, 6), "hlld", "uct0", 1, "periodic", 13),
+    # passive tracers (10th entry = number of tracers)
+    (3, 3, True, (9, 7, 8), "hlld", "uct_contact", 2, "periodic", 14, 2),
+    (3, 3, True, (6, 9, 5), "hll", "uct_hll", 3, "periodic", 15, 1),
+    (2, 2, False, (11, 6), "hllc", None, 2, "outflow", 16, 3),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}d{c[1]}c_{'mhd' if c[2] else 'hd'}_{c[4]}_{c[5]}_rk{c[6]}_{c[7]}" for c in CASES])
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}d{c[1]}c_{'mhd' if c[2] else 'hd'}_{c[4]}_{c[5]}_rk{c[6]}_{c[7]}" + (f"_tr{c[9]}" if len(c) > 9 else "") for c in CASES])
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "granular"])
 def test_cuda_equals_oracle_bitwise(case, fused):
-    ndim, ncomp, mhd, n, solver, emf, nstages, bc, seed = case
-    s = build(ndim, ncomp, mhd, n, solver, emf, nstages, bc, seed)
+    ndim, ncomp, mhd, n, solver, emf, nstages, bc, seed = case[:9]
+    ntracer = case[9] if len(case) > 9 else 0
+    s = build(ndim, ncomp, mhd, n, solver, emf, nstages, bc, seed, ntracer)
     s.InitFlow(s.data)
     host = s.data.host_mirror
     o = Oracle.from_setup(s)
