@@ -88,7 +88,7 @@ SHORT = [
 # (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
 # reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
 # fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
-PROBLEM_DIRS = {"sph": "SphericalMHD", "polar": "PolarMHD"}
+PROBLEM_DIRS = {"sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D"}
 
 
 def _sph(solver, emf=None, nstages=2):
@@ -117,6 +117,16 @@ HOST_SHORT = [
     Short("sph_tvdlf_arith_limo3", "sph", 3, "sph_limo3", _sph("tvdlf", "arithmetic"), (1, 10)),
     Short("polar_hlld_contact_plm", "polar", 2, "polar_plm", _polar("hlld"), (1, 10)),
     Short("polar_hll_ucthll_plm_rk3", "polar", 2, "polar_plm", _polar("hll", "uct_hll", 3), (1, 10)),
+    # isothermal EOS: HD tube, and 2.5-D MHD (COMPONENTS 3 > DIMENSIONS 2: B_z through Uc)
+    Short("sodiso_hllc_plm", "sodiso", 2, "sodiso_plm", _sod("hllc"), (1, 20)),
+    Short("sodiso_hll_plm_rk3", "sodiso", 2, "sodiso_plm", _sod("hll", 3), (1, 20)),
+    Short("sodiso_tvdlf_plm", "sodiso", 2, "sodiso_plm", _sod("tvdlf"), (1, 20)),
+    Short("iso25d_hlld_contact_plm", "iso25d", 2, "iso25d_plm", {("Hydro", "solver"): "hlld"}, (1, 10)),
+    Short("iso25d_roe_contact_limo3", "iso25d", 3, "iso25d_limo3", {("Hydro", "solver"): "roe", ("Hydro", "emf"): None}, (1, 10)),
+    Short("iso25d_hll_uct0_plm_rk3", "iso25d", 2, "iso25d_plm",
+          {("Hydro", "solver"): "hll", ("Hydro", "emf"): "uct0", ("TimeIntegrator", "nstages"): 3}, (1, 10)),
+    Short("iso25d_tvdlf_arith_limo3", "iso25d", 3, "iso25d_limo3",
+          {("Hydro", "solver"): "tvdlf", ("Hydro", "emf"): "arithmetic"}, (1, 10)),
 ]
 
 FULL = [

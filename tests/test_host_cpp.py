@@ -24,7 +24,8 @@ from idefix_b200.dump import readDump
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "idefix_b200", "host")
 PROBLEMS = {"sod": ("sod", "NO"), "ot2d": ("OrszagTang", "YES"), "ot3d": ("OrszagTang3D", "YES"),
-            "sodUserBC": ("sodUserBC", "NO"), "sph": ("SphericalMHD", "YES"), "polar": ("PolarMHD", "YES")}
+            "sodUserBC": ("sodUserBC", "NO"), "sph": ("SphericalMHD", "YES"), "polar": ("PolarMHD", "YES"),
+            "sodiso": ("sodIso", "NO"), "iso25d": ("IsoMHD25D", "YES")}
 
 
 def build(problem, order, tmp_path_factory):
@@ -56,7 +57,7 @@ def run_idefix(exe, workdir, ini_text, *args):
     return res.stdout
 
 
-@pytest.mark.parametrize("problem", ["sod", "sodUserBC", "ot2d", "ot3d", "sph", "polar"])
+@pytest.mark.parametrize("problem", ["sod", "sodUserBC", "ot2d", "ot3d", "sph", "polar", "sodiso", "iso25d"])
 def test_problem_compiles_against_host_layer(problem, tmp_path_factory):
     exe = binary(problem, 2, tmp_path_factory)
     assert os.access(exe, os.X_OK)
