@@ -268,8 +268,10 @@ def main_gpu(args):
     # sanity: the run must have produced finite data and a solenoidal field
     nan = data.CheckNan()
     divb = data.hydro.CheckDivB()
-    if nan or not divb < 1e-10:
-        raise SystemExit(f"bench.py: invalid state after the timed region (nan={nan}, divB={divb})")
+    mathexc = data.math_exceptions()
+    if nan or not divb < 1e-10 or mathexc:
+        raise SystemExit(f"bench.py: invalid state after the timed region (nan={nan}, divB={divb}, "
+                         f"fast-math range-check failures={mathexc})")
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     classes = ["sweep_x1", "sweep_x2", "sweep_x3", "constrained_transport", "stage_epilogue", "boundaries"]

@@ -84,6 +84,7 @@ SYMBOLS = {
     "idfx_set_fused": (C.c_int, [_h, C.c_int]),
     "idfx_get_ncycles": (C.c_int, [_h, C.POINTER(C.c_longlong)]),
     "idfx_launch_count": (C.c_int, [_h, C.POINTER(C.c_longlong)]),
+    "idfx_math_exceptions": (C.c_int, [_h, C.POINTER(C.c_uint)]),
     "idfx_enroll_userdef_boundary": (C.c_int, [_h, USER_BOUNDARY_FN, C.c_void_p]),
     "idfx_enroll_halo_exchange": (C.c_int, [_h, HALO_FN, C.c_void_p]),
     "idfx_enroll_reduce": (C.c_int, [_h, REDUCE_FN, C.c_void_p]),

@@ -72,6 +72,7 @@ struct IdfxBlock {
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
   int sweepVariant = 2;
+  unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
@@ -361,6 +362,8 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
   }
   a.doInvDt = 1;
   a.fluxRho = b->fluxRho;
+  a.mathFlag = b->mathFlag;
+  a.validateInputs = b->vcFieldFresh ? 0 : 1;   // our own stage epilogue already validated what it wrote
   a.variant = b->sweepVariant;
   return a;
 }
@@ -479,7 +482,11 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
   if (b->cfg.mhd && d.ndim >= 2) {
     TimeScope ts(b, TIME_CT);
     KTRY(idfxk::calcCornerEmf(b->g, b->emf, b->Vc, b->Vs, b->cfg.emf, b->cfg.order, b->cfg.ncomp, b->cfg.MX1,
+#ifdef IDFX_ROW_NOFOLD
+                              b->cfg.BX1, b->stream, &b->launches, 0));
+#else
                               b->cfg.BX1, b->stream, &b->launches, 1));
+#endif
     int mode = 0;
     double wc = 0, w0 = 0;
     if (fused && multi) {
@@ -583,7 +590,7 @@ int cycleFused(IdfxBlock *b) {
     {
       TimeScope ts(b, TIME_EPILOGUE);
       KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, 1,
-                                b->stream));
+                                b->stream, b->mathFlag));
     }
     b->launches++;
     if (b->cfg.ntr > 0) {   // RK combination + Tracer::ConvertConsToPrim with the final Uc(RHO)
@@ -694,6 +701,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   int rc = 0;
   rc |= buildGeometry(b);
   const int nv = b->cfg.nvar + b->cfg.ntr;
+  rc = rc || devAlloc(b, &b->mathFlag, 1);
   if (b->cfg.ntr > 0) rc = rc || devAlloc(b, &b->fluxRho, b->nCells);
   rc = rc || devAlloc(b, &b->Vc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->Uc, b->nCells * nv);
@@ -1028,6 +1036,14 @@ int idfx_cycle(IdfxBlock *b, double *t, double *dt, int *status_flags) {
   int s;
   std::memcpy(&s, b->hostState + 14, sizeof(int));
   if (status_flags) *status_flags = s;
+  return 0;
+}
+
+// Number of threads whose branch-free division / square root failed its range check since the block was
+// created (fastmath.cuh).  Zero = every quotient and root of the sweeps was the correctly rounded IEEE one.
+int idfx_math_exceptions(IdfxBlock *b, unsigned int *count) {
+  CUDA_TRY(cudaMemcpyAsync(count, b->mathFlag, sizeof(unsigned int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
   return 0;
 }
 

@@ -86,6 +86,8 @@ struct SweepArgs {
   int fusedP2C;       // Uc is rebuilt from Vc in this sweep instead of read (first sweep of the fused path)
   int invDtInit;      // InvDt accumulator starts from zero in this sweep (first sweep after ResetStage)
   int variant;        // 0: tile kernel in every direction; 1: marching kernel for the x2 / x3 sweeps
+  int validateInputs;       // x1 sweep: check that the primitives lie in the envelope of fastmath.cuh
+  unsigned int *mathFlag;   // incremented by threads whose branch-free division / sqrt failed a range check (fastmath.cuh)
   double *fluxRho;    // when tracers are on: raw Riemann mass flux of every interface of this sweep (else null)
   double *Uc0;        // fused path, first stage: also save the rebuilt Uc as the "begin" state (may be null)
 };

@@ -48,7 +48,8 @@ int copy(double *dst, const double *src, long long n, cudaStream_t st);
 int addAndStore(double *dst, const double *src, long long n, double wl, double wr, cudaStream_t st);
 // fused stage epilogue over the interior: RK combine of Uc, Uc(B) <- Vs, Vc <- C2P(Uc)
 int stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs, const double *Uc0,
-                  double gamma, int combine, double wc, double w0, int keepUc, cudaStream_t st);
+                  double gamma, int combine, double wc, double w0, int keepUc, cudaStream_t st,
+                  unsigned int *mathFlag = nullptr);
 
 // ---- passive tracers (tracer.cu) ------------------------------------------------
 // Tracer::CalcFlux + CalcRightHandSide of one direction from the mass flux the sweep stored

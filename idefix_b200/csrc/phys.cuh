@@ -10,12 +10,18 @@
 #define IDFX_PHYS_CUH_
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 #define SMALL_PRESSURE_FIX (1.0e-5)   // src/fluid/fluid_defs.hpp:23
 #define EPS_UCT_CONTACT (1.0e-6)      // src/fluid/fluid_defs.hpp:24
 
-template <int ND, int NC, bool MHD_, bool ISO_>
+// FAST_: divisions and square roots of the interface solve use the branch-free sequences of fastmath.cuh
+// (the sweep kernels try Phys<...,true> first and fall back on Phys<...,false> when a range check failed)
+template <int ND, int NC, bool MHD_, bool ISO_, bool FAST_ = false>
 struct Phys {
+  static constexpr bool fast = FAST_;
+  using Fast = Phys<ND, NC, MHD_, ISO_, true>;
+  using Exact = Phys<ND, NC, MHD_, ISO_, false>;
   static constexpr int ndim = ND;
   static constexpr int ncomp = NC;
   static constexpr bool mhd = MHD_;
@@ -73,9 +79,9 @@ IDFX_HD void primToCons(double *u, const V &v, const Eos &eos) {
       double b2 = u[P::BX1] * u[P::BX1];
       if constexpr (P::ncomp >= 2) b2 = b2 + u[P::BX2] * u[P::BX2];
       if constexpr (P::ncomp == 3) b2 = b2 + u[P::BX3] * u[P::BX3];
-      u[P::ENG] = eos.internalEnergy(v[P::PRS]) + 0.5 * v[P::RHO] * v2 + 0.5 * b2;
+      u[P::ENG] = idfxDiv<P::fast>(v[P::PRS], eos.gamma - 1.0) + 0.5 * v[P::RHO] * v2 + 0.5 * b2;
     } else {
-      u[P::ENG] = eos.internalEnergy(v[P::PRS]) + 0.5 * v[P::RHO] * v2;
+      u[P::ENG] = idfxDiv<P::fast>(v[P::PRS], eos.gamma - 1.0) + 0.5 * v[P::RHO] * v2;
     }
   }
 }

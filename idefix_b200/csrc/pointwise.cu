@@ -118,7 +118,7 @@ __global__ void addAndStoreKernel(double *__restrict__ d, const double *__restri
 template <class P>
 __global__ void stageEpilogueKernel(DevGrid g, double *__restrict__ Vc, double *__restrict__ Uc,
                                     const double *__restrict__ Vs, const double *__restrict__ Uc0, Eos eos,
-                                    int combine, double wc, double w0, int keepUc) {
+                                    int combine, double wc, double w0, int keepUc, unsigned int *mathFlag) {
   const int ni = g.end[0] - g.beg[0], nj = g.end[1] - g.beg[1], nk = g.end[2] - g.beg[2];
   const long long t = (long long)blockIdx.x * TB + threadIdx.x;
   if (t >= (long long)ni * nj * nk) return;
@@ -141,11 +141,16 @@ __global__ void stageEpilogueKernel(DevGrid g, double *__restrict__ Vc, double *
     u[nv] = x;
   }
   consToPrim<P>(v, u, eos);
+  // the primitives the next sweeps start from must lie in the validated envelope of the branch-free
+  // division / square root (fastmath.cuh); free here, this kernel is bandwidth-bound
+  bool bad = false;
 #pragma unroll
   for (int nv = 0; nv < P::nvar; nv++) {
     Vc[nv * g.sn + c] = v[nv];
     if (keepUc) Uc[nv * g.sn + c] = u[nv];
+    bad |= !idfxStateInRange(v[nv]);
   }
+  if (bad && mathFlag != nullptr) atomicAdd(mathFlag, 1u);
 }
 
 }  // namespace
@@ -213,9 +218,9 @@ int idfxk::addAndStore(double *dst, const double *src, long long n, double wl, d
 
 int idfxk::stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs,
                          const double *Uc0, double gamma, int combine, double wc, double w0, int keepUc,
-                         cudaStream_t st) {
+                         cudaStream_t st, unsigned int *mathFlag) {
   const long long n = (long long)(g.end[0] - g.beg[0]) * (g.end[1] - g.beg[1]) * (g.end[2] - g.beg[2]);
   const Eos eos{gamma, 0.0};
   PHYS_DISPATCH((stageEpilogueKernel<P><<<blocksFor(n), TB, 0, st>>>(g, Vc, Uc, Vs, Uc0, eos, combine, wc, w0,
-                                                                      keepUc)))
+                                                                      keepUc, mathFlag)))
 }

@@ -8,6 +8,7 @@
 #define IDFX_RECON_CUH_
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace lim {
 
@@ -18,6 +19,14 @@ IDFX_HD double minmodRef(double, double) { return 0.0; }
 // slopeLimiter.hpp:54-57
 IDFX_HD double vanLeer(double dvp, double dvm) {
   return (dvp * dvm > 0.0 ? 2.0 * dvp * dvm / (dvp + dvm) : 0.0);
+}
+// the same with the branch-free division (device only; fastmath.cuh).  The quotient is formed unconditionally
+// and selected afterwards, so the limiter stays inside one basic block; when the product is not positive the
+// operands are replaced by harmless ones so that the range check is not tripped by a value that is discarded.
+IDFX_D double vanLeerFast(double dvp, double dvm) {
+  const bool on = dvp * dvm > 0.0;
+  const double q = idfxDivFast(on ? 2.0 * dvp * dvm : 1.0, on ? dvp + dvm : 1.0);
+  return on ? q : 0.0;
 }
 // slopeLimiter.hpp:60-65 (non-uniform spacing)
 IDFX_HD double vanLeer(double dvp, double dvm, double cp, double cm) {
@@ -206,7 +215,7 @@ IDFX_D void reconstructStencil(const double (&st)[6], bool positive, bool regula
 // vR of interface c and the left state vL of interface c+1.  A kernel that walks along the sweep
 // direction evaluates this once per cell and re-uses vr at the next interface; the expressions (and
 // therefore the bits) are those the reference evaluates twice (extrapolateToFaces.hpp:89-307).
-template <int ORDER>
+template <int ORDER, bool FAST = false>
 IDFX_D void reconstructCell(const double (&st)[5], bool positive, bool regular, const double (&wc)[6], double dxc,
                             double &vl, double &vr) {
   const double qm = st[1], q0 = st[2], qp = st[3];
@@ -217,7 +226,9 @@ IDFX_D void reconstructCell(const double (&st)[5], bool positive, bool regular, 
     if (regular) {
       const double dvm = q0 - qm;
       const double dvp = qp - q0;
-      const double dv = lim::vanLeer(dvp, dvm);
+      double dv;
+      if constexpr (FAST && IDFX_FASTDIV) dv = lim::vanLeerFast(dvp, dvm);
+      else dv = lim::vanLeer(dvp, dvm);
       vr = q0 + 0.5 * dv;
       vl = q0 - 0.5 * dv;
     } else {

@@ -6,6 +6,7 @@
 #ifndef IDFX_RIEMANN_MHD_CUH_
 #define IDFX_RIEMANN_MHD_CUH_
 
+#include "fastmath.cuh"
 #include "phys.cuh"
 #include "riemann_hd.cuh"
 
@@ -20,8 +21,8 @@ IDFX_D double fastSpeed(const V &v, double gpr) {
   const double Btmag2 = b2 * b2 + b3 * b3;
   const double Bmag2 = b1 * b1 + Btmag2;
   double c = gpr - Bmag2;
-  c = gpr + Bmag2 + sqrt(c * c + 4.0 * gpr * Btmag2);
-  return sqrt(0.5 * c / v[P::RHO]);
+  c = gpr + Bmag2 + idfxSqrt<P::fast>(c * c + 4.0 * gpr * Btmag2);
+  return idfxSqrt<P::fast>(idfxDiv<P::fast>(0.5 * c, v[P::RHO]));
 }
 
 template <class P, class V>
@@ -195,34 +196,34 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
     [[maybe_unused]] double vsL = 0.0, vsR = 0.0, wsL = 0.0, wsR = 0.0;
     bool revert_to_hllc = false;
 
-    scrh = 1.0 / (sr - sl);
+    scrh = idfxDiv<P::fast>(1.0, (sr - sl));
     Bx = (sr * vR[BXn] - sl * vL[BXn]) * scrh;
     sBx = (Bx > 0.0 ? 1.0 : -1.0);
 
     duL = sl - vL[Xn];
     duR = sr - vR[Xn];
 
-    scrh = 1.0 / (duR * uR[RHO] - duL * uL[RHO]);
+    scrh = idfxDiv<P::fast>(1.0, (duR * uR[RHO] - duL * uL[RHO]));
     SM = (duR * uR[Xn] - duL * uL[Xn] - ptR + ptL) * scrh;
 
     double pts = duR * uR[RHO] * ptL - duL * uL[RHO] * ptR + vL[RHO] * vR[RHO] * duR * duL * (vR[Xn] - vL[Xn]);
     pts *= scrh;
 
-    usL[RHO] = uL[RHO] * duL / (sl - SM);
-    usR[RHO] = uR[RHO] * duR / (sr - SM);
+    usL[RHO] = idfxDiv<P::fast>(uL[RHO] * duL, (sl - SM));
+    usR[RHO] = idfxDiv<P::fast>(uR[RHO] * duR, (sr - SM));
 
-    const double sqrL = sqrt(usL[RHO]);
-    const double sqrR = sqrt(usR[RHO]);
+    const double sqrL = idfxSqrt<P::fast>(usL[RHO]);
+    const double sqrR = idfxSqrt<P::fast>(usR[RHO]);
 
-    S1L = SM - fabs(Bx) / sqrL;
-    S1R = SM + fabs(Bx) / sqrR;
+    S1L = SM - idfxDiv<P::fast>(fabs(Bx), sqrL);
+    S1R = SM + idfxDiv<P::fast>(fabs(Bx), sqrR);
 
     // degeneracy: fall back on HLLC-type star states (hlldMHD.hpp:311-340)
     if ((S1L - sl) < 1.e-4 * (SM - sl)) revert_to_hllc = true;
     if ((S1R - sr) > -1.e-4 * (sr - SM)) revert_to_hllc = true;
 
     if (revert_to_hllc) {
-      scrh = 1.0 / (sr - sl);
+      scrh = idfxDiv<P::fast>(1.0, (sr - sl));
       // only the field components of the HLL state are needed
       {
         double h = sr * uR[BXn] - sl * uL[BXn] + fL[BXn] - fR[BXn];
@@ -241,8 +242,8 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
       }
       S1L = S1R = SM;
     } else {
-      scrhL = (uL[RHO] * duL * duL - Bx * Bx) / (uL[RHO] * duL * (sl - SM) - Bx * Bx);
-      scrhR = (uR[RHO] * duR * duR - Bx * Bx) / (uR[RHO] * duR * (sr - SM) - Bx * Bx);
+      scrhL = idfxDiv<P::fast>((uL[RHO] * duL * duL - Bx * Bx), (uL[RHO] * duL * (sl - SM) - Bx * Bx));
+      scrhR = idfxDiv<P::fast>((uR[RHO] * duR * duR - Bx * Bx), (uR[RHO] * duR * (sr - SM) - Bx * Bx));
       usL[BXn] = Bx;
       usR[BXn] = Bx;
       if constexpr (P::ncomp >= 2) {
@@ -255,8 +256,8 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
       }
     }
 
-    scrhL = Bx / (uL[RHO] * duL);
-    scrhR = Bx / (uR[RHO] * duR);
+    scrhL = idfxDiv<P::fast>(Bx, (uL[RHO] * duL));
+    scrhR = idfxDiv<P::fast>(Bx, (uR[RHO] * duR));
 
     if constexpr (P::ncomp >= 2) {
       vsL = vL[Xt] - scrhL * (usL[BXt] - uL[BXt]);
@@ -289,7 +290,7 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
       scrhL -= s;
     }
     usL[ENG] = duL * uL[ENG] - ptL * vL[Xn] + pts * SM + Bx * scrhL;
-    usL[ENG] /= sl - SM;
+    usL[ENG] = idfxDiv<P::fast>(usL[ENG], sl - SM);
 
     scrhR = vR[Xn] * Bx;
     if constexpr (P::ncomp >= 2) scrhR = scrhR + vR[Xt] * uR[BXt];
@@ -301,7 +302,7 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
       scrhR -= s;
     }
     usR[ENG] = duR * uR[ENG] - ptR * vR[Xn] + pts * SM + Bx * scrhR;
-    usR[ENG] /= sr - SM;
+    usR[ENG] = idfxDiv<P::fast>(usR[ENG], sr - SM);
 
     if (S1L >= 0.0) {  // region L*
 #pragma unroll
@@ -316,11 +317,11 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
       ussr[RHO] = usR[RHO];
       if constexpr (P::ncomp >= 2) {
         vss = sqrL * vsL + sqrR * vsR + (usR[BXt] - usL[BXt]) * sBx;
-        vss /= sqrL + sqrR;
+        vss = idfxDiv<P::fast>(vss, sqrL + sqrR);
       }
       if constexpr (P::ncomp == 3) {
         wss = sqrL * wsL + sqrR * wsR + (usR[BXb] - usL[BXb]) * sBx;
-        wss /= sqrL + sqrR;
+        wss = idfxDiv<P::fast>(wss, sqrL + sqrR);
       }
       ussl[Xn] = ussl[RHO] * SM;
       ussr[Xn] = ussr[RHO] * SM;
@@ -335,12 +336,12 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
       ussl[BXn] = ussr[BXn] = Bx;
       if constexpr (P::ncomp >= 2) {
         ussl[BXt] = sqrL * usR[BXt] + sqrR * usL[BXt] + sqrL * sqrR * (vsR - vsL) * sBx;
-        ussl[BXt] /= sqrL + sqrR;
+        ussl[BXt] = idfxDiv<P::fast>(ussl[BXt], sqrL + sqrR);
         ussr[BXt] = ussl[BXt];
       }
       if constexpr (P::ncomp == 3) {
         ussl[BXb] = sqrL * usR[BXb] + sqrR * usL[BXb] + sqrL * sqrR * (wsR - wsL) * sBx;
-        ussl[BXb] /= sqrL + sqrR;
+        ussl[BXb] = idfxDiv<P::fast>(ussl[BXb], sqrL + sqrR);
         ussr[BXb] = ussl[BXb];
       }
       // energy jump across the rotational waves

@@ -27,7 +27,7 @@
 #define IDFX_MARCH_MINB 4
 #endif
 #ifndef IDFX_ROW_MINB
-#define IDFX_ROW_MINB 4
+#define IDFX_ROW_MINB 3
 #endif
 
 namespace pencil {
@@ -58,16 +58,48 @@ struct Halo {
 // rows of the per-CTA geometry table along the marching direction
 enum : int { T_DX = 0, T_VOL = 1, T_AREA = 2, T_W = 3 /* wp wm cp cm dp dm */, T_ROWS_CART = 3, T_ROWS_GEN = 9 };
 
+// Reconstruction-independent tail of an interface: tracer mass flux, face EMF storage, area weighting
 template <class P, int SOLVER, int DIR, class VL, class VR>
-IDFX_D void solveInterface(const SweepArgs &a, const DevGrid &g, int geo, const Eos &eos, double A0, int k, int j, int i,
-                           long long cell, const VL &vL, const VR &vR, double *F, RiemannAux &aux) {
-  riemannDispatch<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+IDFX_D void finishInterface(const SweepArgs &a, const DevGrid &g, int geo, double A0, int k, int j, int i,
+                            long long cell, const VL &vL, const VR &vR, double *F, const RiemannAux &aux) {
   if (a.fluxRho != nullptr) a.fluxRho[cell] = F[P::RHO];   // for the tracer kernels (Tracer::CalcFlux)
   if constexpr (P::mhd) {
     const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
     storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
   }
   areaWeightFlux<P, DIR>(g, geo, A0, k, j, i, F);
+}
+
+// Riemann problem of one interface with the branch-free divisions / square roots of fastmath.cuh
+// (Phys<...>::Fast).  A failed range check is recorded in the per-thread flag and reported through
+// SweepArgs::mathFlag at the end of the kernel (reportMathFlag below): when the flag of a run is zero --
+// which the parity tests and bench.py assert -- every quotient and root was nvcc's own correctly rounded one.
+template <class P, int SOLVER, int DIR>
+IDFX_D void solveInterface(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+  riemannDispatch<typename P::Fast, SOLVER, DIR>(vL, vR, eos, F, aux);
+}
+
+// range validation of the branch-free arithmetic (fastmath.cuh): the primitives of a cell entering the sweeps
+// and the fluxes leaving the solver
+template <int NV, class V>
+IDFX_D bool cellOutOfRange(V vcAt) {
+  bool bad = false;
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) bad |= !idfxStateInRange(vcAt(nv));
+  return bad;
+}
+template <int NV>
+IDFX_D bool fluxNotFinite(const double *F, double cmax) {
+  unsigned m = (unsigned)__double2hiint(cmax) & 0x7ff00000u;
+  bool bad = (m == 0x7ff00000u);
+#pragma unroll
+  for (int nv = 0; nv < NV; nv++) bad |= !idfxFinite(F[nv]);
+  return bad;
+}
+IDFX_D void reportMathFlag(const SweepArgs &a, bool bad) {
+#if IDFX_FASTDIV
+  if (bad) atomicAdd(a.mathFlag, 1u);
+#endif
 }
 
 }  // namespace pencil
@@ -191,6 +223,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
     }
   }
 
+  bool mathBad = false;
   int q = 0;  // ring slot of cell m-H-1: free, receives cell m+H+1 (LATE: cell m+H, issued at the end of step m-1)
   const double *pre = a.Vc + cell0 + (long long)(mb + H + (LATE ? 0 : 1)) * stride;
   long long cellm = cell0 + (long long)mb * stride;
@@ -243,7 +276,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * TX];
         const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
         double vr;
-        reconstructCell<ORDER>(st, positive, regular, wc, dxc, vR[nv], vr);
+        reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
         vL[nv] = vls[nv * TX];
         vls[nv * TX] = vr;
       }
@@ -272,7 +305,9 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
 
     double F[NV];
     RiemannAux aux;
-    pencil::solveInterface<P, SOLVER, DIR>(a, g, geo, eos, A0, k, j, i, cellm, vL, vR, F, aux);
+    pencil::solveInterface<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+    mathBad |= pencil::fluxNotFinite<NV>(F, aux.cmax);
+    pencil::finishInterface<P, SOLVER, DIR>(a, g, geo, A0, k, j, i, cellm, vL, vR, F, aux);
 
     // ---- cell m-1: flux difference, time-step estimate, conservative update ---------------------------
     if (r > 0 && columnInterior) {
@@ -297,6 +332,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
     pre += stride;
     cellm += stride;
   }
+  pencil::reportMathFlag(a, mathBad);
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, bool CART>
@@ -431,6 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
 
   issueRow(jb, 0);
   pencil::cpAsyncCommit();
+  bool mathBad = false;
 
   for (int j = jb; j < je; j++) {
     const int r = j - jb;
@@ -452,10 +489,18 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
       for (int d = -H; d <= H; d++) st[2 + d] = row[nv * RW + d];
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vr;
-      reconstructCell<ORDER>(st, positive, regular, wc, dxc, vR[nv], vr);
+      reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
       vrs[nv * 32 + lane] = vr;
     }
     __syncwarp();
+
+    // ---- every primitive of the cells this lane owns must lie in the validated envelope (fastmath.cuh) ----------
+    // (only when the state was not produced by our own stage epilogue, which validates what it writes)
+#if IDFX_FASTDIV
+    if (a.validateInputs && ((lane >= 1 && lane <= STRIP) || (lane == 0 && s == 0) || (lane == 31 && s == nstrips - 1)) &&
+        c <= g.end[0])
+      mathBad |= pencil::cellOutOfRange<NV>([&](int nv) { return row[nv * RW]; });
+#endif
 
     // ---- cell-centred EMFs of cell c (CalcCellCenteredEMF, calcCornerEmf.hpp:85-126) ------------------------
     // uct_contact averages them onto the corners from the cells [beg-1, end] of every direction; the
@@ -463,6 +508,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
     // folded into this sweep.  Each cell is written by exactly one lane: the strip's own 30 cells, plus the
     // cell in front of the first strip and the one behind the last.  (uct0 also reads beg-2: it keeps the
     // stand-alone kernel.)
+#ifndef IDFX_ROW_NOFOLD
     if constexpr (P::mhd && P::ndim >= 2) {
       if (a.emfMode == EMF_UCT_CONTACT) {
         const bool owner = (lane >= 1 && lane <= STRIP) || (lane == 0 && s == 0) || (lane == 31 && s == nstrips - 1);
@@ -478,6 +524,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
         }
       }
     }
+#endif
 
     // ---- interface c (left face of cell c) -----------------------------------------------------------------
     double F[NV];
@@ -496,7 +543,9 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
         vR[D::BXn] = bn;
       }
       const double A0 = ar0 * tab[chunk + r] * ar2;
-      pencil::solveInterface<P, SOLVER, DIR>(a, g, geo, eos, A0, k, j, c, cell, vL, vR, F, aux);
+      pencil::solveInterface<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+      mathBad |= pencil::fluxNotFinite<NV>(F, aux.cmax);
+      pencil::finishInterface<P, SOLVER, DIR>(a, g, geo, A0, k, j, c, cell, vL, vR, F, aux);
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) fls[nv * 32 + lane] = F[nv];
       fls[NV * 32 + lane] = aux.cmax;
@@ -514,6 +563,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
     }
     __syncwarp();   // vrs / fls are rewritten by the next row
   }
+  pencil::reportMathFlag(a, mathBad);
 }
 
 template <class P, int SOLVER, int ORDER, bool CART>
@@ -527,7 +577,7 @@ inline cudaError_t launchPencilRow(const SweepArgs &a, cudaStream_t stream) {
   const int nk = g.end[2] - g.beg[2] + 2 * ((P::ndim > 2) ? ext : 0);
   const long long ctasPerChunk = ((long long)nstrips * nk + WARPS - 1) / WARPS;
   int chunk = 64;
-  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * 148 * 4) chunk >>= 1;
+  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * 148 * IDFX_ROW_MINB) chunk >>= 1;
   if (chunk > nj) chunk = nj;
   const dim3 grid((unsigned)ctasPerChunk, (unsigned)((nj + chunk - 1) / chunk), 1);
   static bool configured = false;

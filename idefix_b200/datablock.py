@@ -243,6 +243,12 @@ class DataBlock:
             raise IdefixError(f"upload: array of size {a.shape} does not match field dims {dims}")
         check(lib().idfx_upload(self._handle, field, a.ctypes.data))
 
+    def math_exceptions(self):
+        """threads whose branch-free division / sqrt failed a range check (0 = IEEE-exact arithmetic)"""
+        n = C.c_uint()
+        check(lib().idfx_math_exceptions(self._handle, C.byref(n)))
+        return n.value
+
     def launch_count(self):
         n = C.c_longlong()
         check(lib().idfx_launch_count(self._handle, C.byref(n)))

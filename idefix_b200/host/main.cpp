@@ -89,6 +89,12 @@ int main(int argc, char **argv) {
     idfx::cout << "Main: Completed in " << static_cast<long long>(secs) << " seconds and " << Tint.GetNCycles()
                << " cycle" << (Tint.GetNCycles() != 1 ? "s" : "") << std::endl;
     idfx::cout << "Main: Perfs are " << std::scientific << 1 / perfs << " cell updates/second" << std::endl;
+    unsigned int mathExceptions = 0;
+    IDFX_ABI(idfx_math_exceptions(data.handle, &mathExceptions));
+    if (mathExceptions > 0)
+      IDEFIX_WARNING("the branch-free FP64 division / square root of the sweeps met " + std::to_string(mathExceptions) +
+                     " out-of-range operands (zero, subnormal, infinite or NaN); rebuild libidefix_b200.so with "
+                     "FASTDIV=0 for strictly IEEE results in that regime");
     idfx::cout << "Outputs represent " << static_cast<int>(100.0 * output.GetTimer() / secs) << "% of total run time."
                << std::endl;
   }

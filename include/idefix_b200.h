@@ -130,6 +130,12 @@ int idfx_set_tstop(IdfxBlock *blk, double tstop);
  * folds the point-wise passes into the sweeps.  Both give bit-identical Vc / Vs. */
 int idfx_set_fused(IdfxBlock *blk, int fused);
 int idfx_get_ncycles(IdfxBlock *blk, long long *ncycles);
+/* The sweeps evaluate FP64 divisions and square roots with the branch-free form of nvcc's own Newton
+ * sequences (idefix_b200/csrc/fastmath.cuh); a thread whose operands fail nvcc's range check (zero,
+ * subnormal, infinite or NaN operands or results) is counted here instead of taking nvcc's slow path.
+ * count == 0 (asserted by the parity tests and bench.py) means every quotient and root was the correctly
+ * rounded IEEE value.  Build with `make FASTDIV=0` for a library that uses the ordinary operators only. */
+int idfx_math_exceptions(IdfxBlock *blk, unsigned int *count);
 /* number of kernels launched by this block since creation (bench "gpu_launches") */
 int idfx_launch_count(IdfxBlock *blk, long long *count);
 

@@ -113,5 +113,6 @@ def test_cuda_equals_oracle_bitwise(case, fused):
         if ndim >= 2:
             assert d.hydro.CheckDivB() < 1e-12
     assert d.CheckNan() == 0
+    assert d.math_exceptions() == 0   # every FP64 quotient / root was the correctly rounded one (fastmath.cuh)
     o.close()
     d.close()
