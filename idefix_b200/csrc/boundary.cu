@@ -172,8 +172,8 @@ template <bool PACK>
 __global__ void haloCopyKernel(double *__restrict__ q, long long sj, long long sk, long long sn, VarList vars, Box b,
                                double *__restrict__ buf) {
   const int n0 = b.hi[0] - b.lo[0], n1 = b.hi[1] - b.lo[1], n2 = b.hi[2] - b.lo[2];
-  const int ii = blockIdx.x * TBX + threadIdx.x;
-  const int jj = blockIdx.y * TBY + threadIdx.y;
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jj = blockIdx.y * blockDim.y + threadIdx.y;
   const int kk = (int)(blockIdx.z % n2);
   const int n = (int)(blockIdx.z / n2);
   if (ii >= n0 || jj >= n1 || n >= vars.n) return;
@@ -235,7 +235,8 @@ int haloTransfer(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int
     const VarList vars = haloVars(c);
     const Box b = haloBox(g, dir, side, -1, PACK);
     if (!emptyBox(b) && vars.n > 0) {
-      haloCopyKernel<PACK><<<boxGrid(b, vars.n), block, 0, st>>>(Vc, g.sj, g.sk, g.sn, vars, b, buf + offset);
+      const dim3 blk = slabBlock(b);   // x1 slabs are only nghost cells wide along i
+      haloCopyKernel<PACK><<<boxGrid(b, vars.n, blk), blk, 0, st>>>(Vc, g.sj, g.sk, g.sn, vars, b, buf + offset);
       (*launches)++;
       offset += boxCount(b) * vars.n;
     }
@@ -247,7 +248,8 @@ int haloTransfer(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int
       one.v[0] = comp;
       const Box b = haloBox(g, dir, side, comp, PACK);
       if (emptyBox(b)) continue;
-      haloCopyKernel<PACK><<<boxGrid(b, 1), block, 0, st>>>(Vs, g.vsj, g.vsk, g.vsn, one, b, buf + offset);
+      const dim3 blk = slabBlock(b);
+      haloCopyKernel<PACK><<<boxGrid(b, 1, blk), blk, 0, st>>>(Vs, g.vsj, g.vsk, g.vsn, one, b, buf + offset);
       (*launches)++;
       offset += boxCount(b);
     }
