@@ -71,7 +71,6 @@ struct IdfxBlock {
   std::vector<std::vector<double>> hostCoords;  // owned copies of the descriptor's coordinate arrays
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
-  int sweepVariant = 2;
   unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
@@ -364,7 +363,6 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
   a.fluxRho = b->fluxRho;
   a.mathFlag = b->mathFlag;
   a.validateInputs = b->vcFieldFresh ? 0 : 1;   // our own stage epilogue already validated what it wrote
-  a.variant = b->sweepVariant;
   return a;
 }
 
@@ -771,7 +769,6 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   for (int dir = 0; dir < desc->ndim; dir++)
     if (desc->lbound[dir] == IDFX_BC_USERDEF || desc->rbound[dir] == IDFX_BC_USERDEF) b->haveUserdef = true;
   b->fused = !b->haveUserdef;
-  if (const char *v = std::getenv("IDFX_SWEEP_VARIANT")) b->sweepVariant = std::atoi(v);
   if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
     idfx_block_destroy(b);
     return fail("device initialisation failed");

@@ -85,7 +85,6 @@ struct SweepArgs {
   int doSource;       // add geometrical source terms after this sweep (last sweep only)
   int fusedP2C;       // Uc is rebuilt from Vc in this sweep instead of read (first sweep of the fused path)
   int invDtInit;      // InvDt accumulator starts from zero in this sweep (first sweep after ResetStage)
-  int variant;        // 0: tile kernel in every direction; 1: marching kernel for the x2 / x3 sweeps
   int validateInputs;       // x1 sweep: check that the primitives lie in the envelope of fastmath.cuh
   unsigned int *mathFlag;   // incremented by threads whose branch-free division / sqrt failed a range check (fastmath.cuh)
   double *fluxRho;    // when tracers are on: raw Riemann mass flux of every interface of this sweep (else null)

@@ -44,19 +44,20 @@ IDFX_HD double mc(double dvp, double dvm) {
   }
   return dq;
 }
-// slopeLimiter.hpp:25-52
+// slopeLimiter.hpp:25-52.  FAST: branch-free divisions (fastmath.cuh), device code of the sweeps only
+template <bool FAST = false>
 IDFX_HD double limO3(double dvp, double dvm, double dx) {
   const double r = 0.1;
   const double eps = 1.e-12;
-  double th = dvm / (dvp + 1.e-16);
-  double q = (2.0 + th) / 3.0;
+  double th = idfxDiv<FAST>(dvm, (dvp + 1.e-16));
+  double q = idfxDiv<FAST>((2.0 + th), 3.0);
   double a = fmin(1.5, 2.0 * th);
   a = fmin(q, a);
   double b = fmax(-0.5 * th, a);
   double c = fmin(q, b);
   double psi = fmax(0.0, c);
   double eta = r * dx;
-  eta = (dvm * dvm + dvp * dvp) / (eta * eta);
+  eta = idfxDiv<FAST>((dvm * dvm + dvp * dvp), (eta * eta));
   double l;
   if (eta <= 1.0 - eps) {
     l = q;
@@ -122,94 +123,6 @@ IDFX_HD void ppmStates(double vm2, double vm1, double v0, double vp1, double vp2
 }
 }  // namespace lim
 
-// Irregular-grid PLM weights of one direction, already offset to the face index
-struct PlmWeights {
-  const double *wp, *wm, *cp, *cm, *dp, *dm;
-};
-
-// Face reconstruction from a register stencil.  st[k] holds cell (index - 3 + k) along the sweep,
-// k = 0..5; orders 1-3 read st[1..4] only (cells index-2 .. index+1), PPM reads all six.
-// positive = variable for which the face value must stay positive (RHO, PRS)
-template <int ORDER>
-IDFX_D void reconstructStencil(const double (&st)[6], bool positive, bool regular, const PlmWeights &w,
-                               const double *__restrict__ dx, int index, double &vL, double &vR) {
-  if constexpr (ORDER == 1) {
-    vL = st[2];
-    vR = st[3];
-  } else if constexpr (ORDER == 2) {
-    const double qm2 = st[1], qm1 = st[2], q0 = st[3], qp1 = st[4];
-    if (regular) {
-      // extrapolateToFaces.hpp:89-124
-      double dvm = qm1 - qm2;
-      double dvp = q0 - qm1;
-      double dv = lim::vanLeer(dvp, dvm);
-      vL = qm1 + 0.5 * dv;
-      dvm = dvp;
-      dvp = qp1 - q0;
-      dv = lim::vanLeer(dvp, dvm);
-      vR = q0 - 0.5 * dv;
-    } else {
-      // extrapolateToFaces.hpp:125-171
-      double dvm = qm1 - qm2;
-      double dvp = q0 - qm1;
-      dvm *= w.wm[index - 1];
-      dvp *= w.wp[index - 1];
-      double dv = lim::vanLeer(dvp, dvm, w.cp[index - 1], w.cm[index - 1]);
-      vL = qm1 + w.dp[index - 1] * dv;
-      dvm = q0 - qm1;
-      dvp = qp1 - q0;
-      dvm *= w.wm[index];
-      dvp *= w.wp[index];
-      dv = lim::vanLeer(dvp, dvm, w.cp[index], w.cm[index]);
-      vR = q0 - w.dm[index] * dv;
-    }
-  } else if constexpr (ORDER == 3) {
-    // extrapolateToFaces.hpp:173-246
-    const double qm2 = st[1], qm1 = st[2], q0 = st[3], qp1 = st[4];
-    double dvm = qm1 - qm2;
-    double dvp = q0 - qm1;
-    double dv = dvp * lim::limO3(dvp, dvm, dx[index - 1]);
-    vL = qm1 + 0.5 * dv;
-    if (positive && vL <= 0.0) {
-      dv = lim::minmodRef(dvp, dvm);
-      vL = qm1 + 0.5 * dv;
-    }
-    dvm = dvp;
-    dvp = qp1 - q0;
-    dv = dvm * lim::limO3(dvm, dvp, dx[index]);
-    vR = q0 - 0.5 * dv;
-    if (positive && vR <= 0.0) {
-      dv = lim::minmodRef(dvp, dvm);
-      vR = q0 - 0.5 * dv;
-    }
-  } else {
-    // extrapolateToFaces.hpp:247-307
-    double vm2 = st[0];
-    double vm1 = st[1];
-    double v0 = st[2];
-    double vp1 = st[3];
-    double vp2 = st[4];
-    double vl, vr;
-    lim::ppmStates(vm2, vm1, v0, vp1, vp2, vl, vr);
-    if (positive && vr <= 0.0) {
-      double dv = lim::vanLeer(vp1 - v0, v0 - vm1);
-      vr = v0 + 0.5 * dv;
-    }
-    vL = vr;
-    vm2 = vm1;
-    vm1 = v0;
-    v0 = vp1;
-    vp1 = vp2;
-    vp2 = st[5];
-    lim::ppmStates(vm2, vm1, v0, vp1, vp2, vl, vr);
-    if (positive && vl <= 0.0) {
-      double dv = lim::vanLeer(vp1 - v0, v0 - vm1);
-      vl = v0 - 0.5 * dv;
-    }
-    vR = vl;
-  }
-}
-
 // Per-CELL form of the same reconstruction: st[k] holds cell (c - 2 + k), k = 0..4 (orders 1-3 read
 // st[1..3] only).  vl / vr are the values of cell c on its left / right face, i.e. the right state
 // vR of interface c and the left state vL of interface c+1.  A kernel that walks along the sweep
@@ -244,13 +157,13 @@ IDFX_D void reconstructCell(const double (&st)[5], bool positive, bool regular, 
   } else if constexpr (ORDER == 3) {
     const double dvm = q0 - qm;
     const double dvp = qp - q0;
-    double dv = dvp * lim::limO3(dvp, dvm, dxc);
+    double dv = dvp * lim::limO3<FAST>(dvp, dvm, dxc);
     vr = q0 + 0.5 * dv;
     if (positive && vr <= 0.0) {
       dv = lim::minmodRef(dvp, dvm);
       vr = q0 + 0.5 * dv;
     }
-    dv = dvm * lim::limO3(dvm, dvp, dxc);
+    dv = dvm * lim::limO3<FAST>(dvm, dvp, dxc);
     vl = q0 - 0.5 * dv;
     if (positive && vl <= 0.0) {
       dv = lim::minmodRef(dvp, dvm);
@@ -264,26 +177,6 @@ IDFX_D void reconstructCell(const double (&st)[5], bool positive, bool regular, 
       if (vl <= 0.0) vl = q0 - 0.5 * dv;
     }
   }
-}
-
-// The same, reading the stencil from memory: `q` points at cell `index` of the variable, `s` is the
-// element stride along the sweep.
-template <int ORDER>
-IDFX_D void reconstructVar(const double *__restrict__ q, long long s, bool positive, bool regular,
-                           const PlmWeights &w, const double *__restrict__ dx, int index,
-                           double &vL, double &vR) {
-  double st[6];
-  st[0] = 0.0;
-  st[5] = 0.0;
-  if constexpr (ORDER == 4) {
-    st[0] = q[-3 * s];
-    st[5] = q[2 * s];
-  }
-  st[1] = q[-2 * s];
-  st[2] = q[-s];
-  st[3] = q[0];
-  st[4] = q[s];
-  reconstructStencil<ORDER>(st, positive, regular, w, dx, index, vL, vR);
 }
 
 #endif  // IDFX_RECON_CUH_

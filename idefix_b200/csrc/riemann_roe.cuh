@@ -69,12 +69,12 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
   }
 
   // Roe averages (roeMHD.hpp:258-300)
-  const double sqr_rho_L = sqrt(vL[RHO]);
-  const double sqr_rho_R = sqrt(vR[RHO]);
-  double sl = sqr_rho_L / (sqr_rho_L + sqr_rho_R);
-  double sr = sqr_rho_R / (sqr_rho_L + sqr_rho_R);
+  const double sqr_rho_L = idfxSqrt<P::fast>(vL[RHO]);
+  const double sqr_rho_R = idfxSqrt<P::fast>(vR[RHO]);
+  double sl = idfxDiv<P::fast>(sqr_rho_L, (sqr_rho_L + sqr_rho_R));
+  double sr = idfxDiv<P::fast>(sqr_rho_R, (sqr_rho_L + sqr_rho_R));
   const double rho = sr * vL[RHO] + sl * vR[RHO];
-  const double sqrt_rho = sqrt(rho);
+  const double sqrt_rho = idfxSqrt<P::fast>(rho);
 
   [[maybe_unused]] double u = 0, v = 0, w = 0, Bx = 0, By = 0, Bz = 0, bx = 0, by = 0, bz = 0;
   u = sl * vL[Xn] + sr * vR[Xn];
@@ -84,19 +84,19 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
   if constexpr (P::ncomp >= 2) By = sr * vL[BXt] + sl * vR[BXt];
   if constexpr (P::ncomp == 3) Bz = sr * vL[BXb] + sl * vR[BXb];
   const double sBx = (Bx >= 0.0 ? 1.0 : -1.0);
-  bx = Bx / sqrt_rho;
-  if constexpr (P::ncomp >= 2) by = By / sqrt_rho;
-  if constexpr (P::ncomp == 3) bz = Bz / sqrt_rho;
+  bx = idfxDiv<P::fast>(Bx, sqrt_rho);
+  if constexpr (P::ncomp >= 2) by = idfxDiv<P::fast>(By, sqrt_rho);
+  if constexpr (P::ncomp == 3) bz = idfxDiv<P::fast>(Bz, sqrt_rho);
   double bt2 = 0.0;
   if constexpr (P::ncomp >= 2) bt2 = bt2 + by * by;
   if constexpr (P::ncomp == 3) bt2 = bt2 + bz * bz;
   const double b2 = bx * bx + bt2;
-  const double Btmag = sqrt(bt2 * rho);
+  const double Btmag = idfxSqrt0<P::fast>(bt2 * rho);
 
   double X = dV[BXn] * dV[BXn];
   if constexpr (P::ncomp >= 2) X = X + dV[BXt] * dV[BXt];
   if constexpr (P::ncomp == 3) X = X + dV[BXb] * dV[BXb];
-  X /= (sqr_rho_L + sqr_rho_R) * (sqr_rho_L + sqr_rho_R) * 2.0;
+  X = idfxDiv<P::fast>(X, (sqr_rho_L + sqr_rho_R) * (sqr_rho_L + sqr_rho_R) * 2.0);
 
   double Bmag2L = vL[P::BX1] * vL[P::BX1];
   double Bmag2R = vR[P::BX1] * vR[P::BX1];
@@ -122,8 +122,8 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     if constexpr (P::ncomp >= 2) vel2 = vel2 + v * v;
     if constexpr (P::ncomp == 3) vel2 = vel2 + w * w;
     dV[P::PRS] = (gamma - 1.0) * ((0.5 * vel2 - X) * dV[RHO] - vdm + dU[P::ENG] - BdB);
-    const double HL = (uL[P::ENG] + pL) / vL[RHO];
-    const double HR = (uR[P::ENG] + pR) / vR[RHO];
+    const double HL = idfxDiv<P::fast>((uL[P::ENG] + pL), vL[RHO]);
+    const double HR = idfxDiv<P::fast>((uR[P::ENG] + pR), vR[RHO]);
     const double H = sl * HL + sr * HR;
     Hgas = H - b2;
     a2 = (2.0 - gamma) * X + (gamma - 1.0) * (Hgas - 0.5 * vel2);
@@ -135,13 +135,13 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
   double scrh = a2 - b2;
   const double ca2 = bx * bx;
   scrh = scrh * scrh + 4.0 * bt2 * a2;
-  scrh = sqrt(scrh);
+  scrh = idfxSqrt0<P::fast>(scrh);
   const double cf2 = 0.5 * (a2 + b2 + scrh);
-  const double cs2 = a2 * ca2 / cf2;
-  const double cf = sqrt(cf2);
-  const double cs = sqrt(cs2);
-  const double ca = sqrt(ca2);
-  a = sqrt(a2);
+  const double cs2 = idfxDiv<P::fast>(a2 * ca2, cf2);
+  const double cf = idfxSqrt<P::fast>(cf2);
+  const double cs = idfxSqrt0<P::fast>(cs2);
+  const double ca = idfxSqrt0<P::fast>(ca2);
+  a = idfxSqrt<P::fast>(a2);
 
   double alpha_f, alpha_s;
   if (cf == cs) {
@@ -154,21 +154,21 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     alpha_f = 1.0;
     alpha_s = 0.0;
   } else {
-    scrh = 1.0 / (cf2 - cs2);
+    scrh = idfxDiv<P::fast>(1.0, (cf2 - cs2));
     alpha_f = (a2 - cs2) * scrh;
     alpha_s = (cf2 - a2) * scrh;
     alpha_f = fmax(0.0, alpha_f);
     alpha_s = fmax(0.0, alpha_s);
-    alpha_f = sqrt(alpha_f);
-    alpha_s = sqrt(alpha_s);
+    alpha_f = idfxSqrt0<P::fast>(alpha_f);
+    alpha_s = idfxSqrt0<P::fast>(alpha_s);
   }
 
   [[maybe_unused]] double beta_y = 0, beta_z = 0;
   if (Btmag > 1.e-9) {
     if constexpr (P::ncomp == 2) beta_y = (By >= 0.0 ? 1.0 : -1.0);
     if constexpr (P::ncomp == 3) {
-      beta_y = By / Btmag;
-      beta_z = Bz / Btmag;
+      beta_y = idfxDiv<P::fast>(By, Btmag);
+      beta_z = idfxDiv<P::fast>(Bz, Btmag);
     }
   } else {
     if constexpr (P::ncomp == 2) beta_y = 1.0;
@@ -194,18 +194,18 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
   Rc[Xn][kk] = alpha_f * lambda[kk];
   if constexpr (P::ncomp >= 2) Rc[Xt][kk] = alpha_f * v + scrh * beta_y;
   if constexpr (P::ncomp == 3) Rc[Xb][kk] = alpha_f * w + scrh * beta_z;
-  if constexpr (P::ncomp >= 2) Rc[BXt][kk] = alpha_s * a * beta_y / sqrt_rho;
-  if constexpr (P::ncomp == 3) Rc[BXb][kk] = alpha_s * a * beta_z / sqrt_rho;
+  if constexpr (P::ncomp >= 2) Rc[BXt][kk] = idfxDiv<P::fast>(alpha_s * a * beta_y, sqrt_rho);
+  if constexpr (P::ncomp == 3) Rc[BXb][kk] = idfxDiv<P::fast>(alpha_s * a * beta_z, sqrt_rho);
   if constexpr (P::energy) {
     if constexpr (P::ncomp >= 2) beta_v = beta_v + beta_y * v;
     if constexpr (P::ncomp == 3) beta_v = beta_v + beta_z * w;
-    Rc[P::ENG][kk] = alpha_f * (Hgas - u * cf) + scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
+    Rc[P::ENG][kk] = alpha_f * (Hgas - u * cf) + scrh * beta_v + idfxDiv<P::fast>(alpha_s * a * Btmag, sqrt_rho);
     eta[kk] = alpha_f * (X * dV[RHO] + dV[P::PRS]);
   } else {
     eta[kk] = alpha_f * a2 * dV[RHO];
   }
   eta[kk] += rho * scrh * beta_dv - rho * alpha_f * cf * dV[Xn] + sqrt_rho * alpha_s * a * beta_dB;
-  eta[kk] *= 0.5 / a2;
+  eta[kk] *= idfxDiv<P::fast>(0.5, a2);
 
   // ---- fast wave u + cf
   kk = M::KFASTP;
@@ -217,14 +217,14 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
   if constexpr (P::ncomp >= 2) Rc[BXt][kk] = Rc[BXt][M::KFASTM];
   if constexpr (P::ncomp == 3) Rc[BXb][kk] = Rc[BXb][M::KFASTM];
   if constexpr (P::energy) {
-    Rc[P::ENG][kk] = alpha_f * (Hgas + u * cf) - scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
+    Rc[P::ENG][kk] = alpha_f * (Hgas + u * cf) - scrh * beta_v + idfxDiv<P::fast>(alpha_s * a * Btmag, sqrt_rho);
     eta[kk] = alpha_f * (X * dV[RHO] + dV[P::PRS]) - rho * scrh * beta_dv + rho * alpha_f * cf * dV[Xn] +
               sqrt_rho * alpha_s * a * beta_dB;
   } else {
     eta[kk] = alpha_f * (0. * X + a2) * dV[RHO] - rho * scrh * beta_dv + rho * alpha_f * cf * dV[Xn] +
               sqrt_rho * alpha_s * a * beta_dB;
   }
-  eta[kk] *= 0.5 / a2;
+  eta[kk] *= idfxDiv<P::fast>(0.5, a2);
 
   // ---- entropy wave
   if constexpr (P::energy) {
@@ -234,8 +234,8 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     Rc[Xn][kk] = u;
     if constexpr (P::ncomp >= 2) Rc[Xt][kk] = v;
     if constexpr (P::ncomp == 3) Rc[Xb][kk] = w;
-    Rc[P::ENG][kk] = 0.5 * vel2 + (gamma - 2.0) / (gamma - 1.0) * X;
-    eta[kk] = ((a2 - X) * dV[RHO] - dV[P::PRS]) / a2;
+    Rc[P::ENG][kk] = 0.5 * vel2 + idfxDiv<P::fast>((gamma - 2.0), (gamma - 1.0)) * X;
+    eta[kk] = idfxDiv<P::fast>(((a2 - X) * dV[RHO] - dV[P::PRS]), a2);
   }
 
   // ---- div B wave: carries no jump with CT
@@ -252,17 +252,17 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     Rc[Xn][kk] = alpha_s * lambda[kk];
     if constexpr (P::ncomp >= 2) Rc[Xt][kk] = alpha_s * v - scrh * beta_y;
     if constexpr (P::ncomp == 3) Rc[Xb][kk] = alpha_s * w - scrh * beta_z;
-    if constexpr (P::ncomp >= 2) Rc[BXt][kk] = -alpha_f * a * beta_y / sqrt_rho;
-    if constexpr (P::ncomp == 3) Rc[BXb][kk] = -alpha_f * a * beta_z / sqrt_rho;
+    if constexpr (P::ncomp >= 2) Rc[BXt][kk] = idfxDiv<P::fast>(-alpha_f * a * beta_y, sqrt_rho);
+    if constexpr (P::ncomp == 3) Rc[BXb][kk] = idfxDiv<P::fast>(-alpha_f * a * beta_z, sqrt_rho);
     if constexpr (P::energy) {
-      Rc[P::ENG][kk] = alpha_s * (Hgas - u * cs) - scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
+      Rc[P::ENG][kk] = alpha_s * (Hgas - u * cs) - scrh * beta_v - idfxDiv<P::fast>(alpha_f * a * Btmag, sqrt_rho);
       eta[kk] = alpha_s * (X * dV[RHO] + dV[P::PRS]) - rho * scrh * beta_dv - rho * alpha_s * cs * dV[Xn] -
                 sqrt_rho * alpha_f * a * beta_dB;
     } else {
       eta[kk] = alpha_s * (0. * X + a2) * dV[RHO] - rho * scrh * beta_dv - rho * alpha_s * cs * dV[Xn] -
                 sqrt_rho * alpha_f * a * beta_dB;
     }
-    eta[kk] *= 0.5 / a2;
+    eta[kk] *= idfxDiv<P::fast>(0.5, a2);
 
     // ---- slow wave u + cs
     kk = M::KSLOWP;
@@ -274,14 +274,14 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     if constexpr (P::ncomp >= 2) Rc[BXt][kk] = Rc[BXt][M::KSLOWM];
     if constexpr (P::ncomp == 3) Rc[BXb][kk] = Rc[BXb][M::KSLOWM];
     if constexpr (P::energy) {
-      Rc[P::ENG][kk] = alpha_s * (Hgas + u * cs) + scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
+      Rc[P::ENG][kk] = alpha_s * (Hgas + u * cs) + scrh * beta_v - idfxDiv<P::fast>(alpha_f * a * Btmag, sqrt_rho);
       eta[kk] = alpha_s * (X * dV[RHO] + dV[P::PRS]) + rho * scrh * beta_dv + rho * alpha_s * cs * dV[Xn] -
                 sqrt_rho * alpha_f * a * beta_dB;
     } else {
       eta[kk] = alpha_s * (0. * X + a2) * dV[RHO] + rho * scrh * beta_dv + rho * alpha_s * cs * dV[Xn] -
                 sqrt_rho * alpha_f * a * beta_dB;
     }
-    eta[kk] *= 0.5 / a2;
+    eta[kk] *= idfxDiv<P::fast>(0.5, a2);
   }
 
   if constexpr (P::ncomp == 3) {
@@ -293,7 +293,7 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     Rc[BXt][kk] = -sBx * sqrt_rho * beta_z;
     Rc[BXb][kk] = sBx * sqrt_rho * beta_y;
     if constexpr (P::energy) Rc[P::ENG][kk] = -rho * (v * beta_z - w * beta_y);
-    eta[kk] = +beta_y * dV[Xb] - beta_z * dV[Xt] + sBx / sqrt_rho * (beta_y * dV[BXb] - beta_z * dV[BXt]);
+    eta[kk] = +beta_y * dV[Xb] - beta_z * dV[Xt] + idfxDiv<P::fast>(sBx, sqrt_rho) * (beta_y * dV[BXb] - beta_z * dV[BXt]);
     eta[kk] *= 0.5;
 
     // ---- Alfven wave u + ca
@@ -304,7 +304,7 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
     Rc[BXt][kk] = Rc[BXt][M::KALFVM];
     Rc[BXb][kk] = Rc[BXb][M::KALFVM];
     if constexpr (P::energy) Rc[P::ENG][kk] = -Rc[P::ENG][M::KALFVM];
-    eta[kk] = -beta_y * dV[Xb] + beta_z * dV[Xt] + sBx / sqrt_rho * (beta_y * dV[BXb] - beta_z * dV[BXt]);
+    eta[kk] = -beta_y * dV[Xb] + beta_z * dV[Xt] + idfxDiv<P::fast>(sBx, sqrt_rho) * (beta_y * dV[BXb] - beta_z * dV[BXt]);
     eta[kk] *= 0.5;
   }
 
@@ -318,14 +318,14 @@ IDFX_D void riemannRoeMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
 
   // entropy fix (roeMHD.hpp:606-623)
   if (alambda[M::KFASTM] < 0.5 * delta)
-    alambda[M::KFASTM] = lambda[M::KFASTM] * lambda[M::KFASTM] / delta + 0.25 * delta;
+    alambda[M::KFASTM] = idfxDiv<P::fast>(lambda[M::KFASTM] * lambda[M::KFASTM], delta) + 0.25 * delta;
   if (alambda[M::KFASTP] < 0.5 * delta)
-    alambda[M::KFASTP] = lambda[M::KFASTP] * lambda[M::KFASTP] / delta + 0.25 * delta;
+    alambda[M::KFASTP] = idfxDiv<P::fast>(lambda[M::KFASTP] * lambda[M::KFASTP], delta) + 0.25 * delta;
   if constexpr (P::ncomp > 1) {
     if (alambda[M::KSLOWM] < 0.5 * delta)
-      alambda[M::KSLOWM] = lambda[M::KSLOWM] * lambda[M::KSLOWM] / delta + 0.25 * delta;
+      alambda[M::KSLOWM] = idfxDiv<P::fast>(lambda[M::KSLOWM] * lambda[M::KSLOWM], delta) + 0.25 * delta;
     if (alambda[M::KSLOWP] < 0.5 * delta)
-      alambda[M::KSLOWP] = lambda[M::KSLOWP] * lambda[M::KSLOWP] / delta + 0.25 * delta;
+      alambda[M::KSLOWP] = idfxDiv<P::fast>(lambda[M::KSLOWP] * lambda[M::KSLOWP], delta) + 0.25 * delta;
   }
 
 #pragma unroll

@@ -1,14 +1,17 @@
 #!/bin/bash
 # Builds every reference (Kokkos-OpenMP CPU) binary the parity tests and bench.py use.
 # Needs /root/reference; the outputs under oracle/_ref/ travel to the GPU box via gpurun.
+# `build_all.sh core` builds only what bench.py and smoke() use; the rest are the generators of tests/golden/short.
 set -e
 cd "$(dirname "$0")"
 J=${J:-8}
 b() { [ -x ../_ref/$1/idefix ] || make -s -j$J NAME=$1 SETUP=$2 MHD=$3 ORDER=$4 LOOP=$5; }
 make -s -j$J kokkos
+# core set: the CPU baseline of bench.py (ot3d_plm) and the smoke / headline parity cases
+b ot3d_plm     test/MHD/OrszagTang3D      YES 2
 b sod_plm      test/HD/sod                NO  2
 b ot2d_plm     test/MHD/OrszagTang        YES 2 TPX
-b ot3d_plm     test/MHD/OrszagTang3D      YES 2
+if [ "$1" = core ]; then echo "done (core set; run without argument for every fixture generator)"; exit 0; fi
 b lw_ppm       test/MHD/LinearWaveTest    YES 4
 b lw_plm       test/MHD/LinearWaveTest    YES 2
 b lw_limo3     test/MHD/LinearWaveTest    YES 3
