@@ -5,6 +5,7 @@
 #ifndef IDFX_EMF_STORE_CUH_
 #define IDFX_EMF_STORE_CUH_
 
+#include "fastmath.cuh"
 #include "phys.cuh"
 #include "riemann_hd.cuh"
 #include "riemann_mhd.cuh"
@@ -62,7 +63,7 @@ IDFX_D void storeHllEmf(const EmfFaceArrays &A, long long idx, double sl, double
   using D = Dirs<P, DIR>;
   const double ar = fmax(0.0, sr);
   const double al = fmin(0.0, sl);
-  const double scrh = 1.0 / (ar - al);
+  const double scrh = idfxDiv<P::fast>(1.0, (ar - al));
   if constexpr (P::ncomp > 1) {
     A.Et[idx] = -A.st * (ar * vL[D::Xt] - al * vR[D::Xt]) * scrh;
     if constexpr (P::ncomp == 3) A.Eb[idx] = -A.sb * (ar * vL[D::Xb] - al * vR[D::Xb]) * scrh;
@@ -87,36 +88,36 @@ IDFX_D void storeHlldEmf(const EmfFaceArrays &A, long long idx, double c2iso, do
   const double uLmn = vL[Xn] * vL[RHO], uRmn = vR[Xn] * vR[RHO];
 
   bool revert_to_hll = false;
-  const double Bn = (sr * vR[BXn] - sl * vL[BXn]) / (sr - sl);
+  const double Bn = idfxDiv<P::fast>((sr * vR[BXn] - sl * vL[BXn]), (sr - sl));
   double chiL, chiR, nuLR, nuL, nuR, SaL, SaR, Sc;
   const double duL = sl - vL[Xn];
   const double duR = sr - vR[Xn];
   double scrh;
   if constexpr (P::energy) {
-    scrh = 1.0 / (duR * uRrho - duL * uLrho);
+    scrh = idfxDiv<P::fast>(1.0, (duR * uRrho - duL * uLrho));
     Sc = (duR * uRmn - duL * uLmn - ptR + ptL) * scrh;
-    const double usLRHO = uLrho * duL / (sl - Sc);
-    const double usRRHO = uRrho * duR / (sr - Sc);
-    const double sqrL = sqrt(usLRHO);
-    const double sqrR = sqrt(usRRHO);
-    SaL = Sc - fabs(Bn) / sqrL;
-    SaR = Sc + fabs(Bn) / sqrR;
+    const double usLRHO = idfxDiv<P::fast>(uLrho * duL, (sl - Sc));
+    const double usRRHO = idfxDiv<P::fast>(uRrho * duR, (sr - Sc));
+    const double sqrL = idfxSqrt<P::fast>(usLRHO);
+    const double sqrR = idfxSqrt<P::fast>(usRRHO);
+    SaL = Sc - idfxDiv<P::fast>(fabs(Bn), sqrL);
+    SaR = Sc + idfxDiv<P::fast>(fabs(Bn), sqrR);
   } else {
-    scrh = 1.0 / (sr - sl);
+    scrh = idfxDiv<P::fast>(1.0, (sr - sl));
     const double rho_h = (uRrho * duR - uLrho * duL) * scrh;
-    Sc = (sl * uRrho * duR - sr * uLrho * duL) * scrh / rho_h;
-    const double sqrho_h = sqrt(rho_h);
-    SaL = Sc - fabs(Bn) / sqrho_h;
-    SaR = Sc + fabs(Bn) / sqrho_h;
+    Sc = idfxDiv<P::fast>((sl * uRrho * duR - sr * uLrho * duL) * scrh, rho_h);
+    const double sqrho_h = idfxSqrt<P::fast>(rho_h);
+    SaL = Sc - idfxDiv<P::fast>(fabs(Bn), sqrho_h);
+    SaR = Sc + idfxDiv<P::fast>(fabs(Bn), sqrho_h);
   }
   if ((SaL - sl) < 1e-4 * (Sc - sl)) revert_to_hll = true;
   if ((SaR - sr) > -1e-4 * (sr - Sc)) revert_to_hll = true;
-  chiL = (vL[Xn] - Sc) * (sl - Sc) / (SaL + sl - 2.0 * Sc);
-  chiR = (vR[Xn] - Sc) * (sr - Sc) / (SaR + sr - 2.0 * Sc);
+  chiL = idfxDiv<P::fast>((vL[Xn] - Sc) * (sl - Sc), (SaL + sl - 2.0 * Sc));
+  chiR = idfxDiv<P::fast>((vR[Xn] - Sc) * (sr - Sc), (SaR + sr - 2.0 * Sc));
 
-  nuL = (SaL + sl) / (fabs(SaL) + fabs(sl));
-  nuR = (SaR + sr) / (fabs(SaR) + fabs(sr));
-  nuLR = (SaL + SaR) / (fabs(SaL) + fabs(SaR));
+  nuL = idfxDiv<P::fast>((SaL + sl), (fabs(SaL) + fabs(sl)));
+  nuR = idfxDiv<P::fast>((SaR + sr), (fabs(SaR) + fabs(sr)));
+  nuLR = idfxDiv<P::fast>((SaL + SaR), (fabs(SaL) + fabs(SaR)));
 
   double oaL, oaR, odL, odR;
   if (fabs(SaR - SaL) > 1.e-9 * fabs(sr - sl)) {
@@ -132,7 +133,7 @@ IDFX_D void storeHlldEmf(const EmfFaceArrays &A, long long idx, double c2iso, do
   }
   const double ar = fmax(0.0, sr);
   const double al = fmin(0.0, sl);
-  scrh = 1.0 / (ar - al);
+  scrh = idfxDiv<P::fast>(1.0, (ar - al));
   if (revert_to_hll) {
     oaL = ar * scrh;
     oaR = -al * scrh;

@@ -20,6 +20,12 @@ IDFX_HD double minmodRef(double, double) { return 0.0; }
 IDFX_HD double vanLeer(double dvp, double dvm) {
   return (dvp * dvm > 0.0 ? 2.0 * dvp * dvm / (dvp + dvm) : 0.0);
 }
+IDFX_D double vanLeerFast(double dvp, double dvm, double cp, double cm) {
+  const bool on = dvp * dvm > 0.0;
+  const double q = idfxDivFast(on ? dvp * dvm * (cp * dvm + cm * dvp) : 1.0,
+                               on ? dvp * dvp + dvm * dvm + (cp + cm - 2.0) * dvp * dvm : 1.0);
+  return on ? q : 0.0;
+}
 // the same with the branch-free division (device only; fastmath.cuh).  The quotient is formed unconditionally
 // and selected afterwards, so the limiter stays inside one basic block; when the product is not positive the
 // operands are replaced by harmless ones so that the range check is not tripped by a value that is discarded.
@@ -150,7 +156,9 @@ IDFX_D void reconstructCell(const double (&st)[5], bool positive, bool regular, 
       double dvp = qp - q0;
       dvm *= wc[1];
       dvp *= wc[0];
-      const double dv = lim::vanLeer(dvp, dvm, wc[2], wc[3]);
+      double dv;
+      if constexpr (FAST && IDFX_FASTDIV) dv = lim::vanLeerFast(dvp, dvm, wc[2], wc[3]);
+      else dv = lim::vanLeer(dvp, dvm, wc[2], wc[3]);
       vr = q0 + wc[4] * dv;
       vl = q0 - wc[5] * dv;
     }

@@ -6,6 +6,7 @@
 #ifndef IDFX_RIEMANN_HD_CUH_
 #define IDFX_RIEMANN_HD_CUH_
 
+#include "fastmath.cuh"
 #include "phys.cuh"
 
 struct RiemannAux {
@@ -17,8 +18,8 @@ struct RiemannAux {
 template <class P, class VL, class VR>
 IDFX_D void soundSpeedsHD(const VL &vL, const VR &vR, const Eos &eos, double &cL, double &cR) {
   if constexpr (P::energy) {
-    cL = sqrt(eos.gamma * (vL[P::PRS] / vL[P::RHO]));
-    cR = sqrt(eos.gamma * (vR[P::PRS] / vR[P::RHO]));
+    cL = idfxSqrt<P::fast>(eos.gamma * idfxDiv<P::fast>(vL[P::PRS], vL[P::RHO]));
+    cR = idfxSqrt<P::fast>(eos.gamma * idfxDiv<P::fast>(vR[P::PRS], vR[P::RHO]));
   } else {
     cL = 0.5 * (eos.csiso + eos.csiso);
     cR = cL;
@@ -35,7 +36,7 @@ IDFX_D void riemannTvdlfHD(const VL &vL, const VR &vR, const Eos &eos, double *F
   if constexpr (P::energy) {
     const double pRL = 0.5 * (vL[P::PRS] + vR[P::PRS]);
     const double rRL = 0.5 * (vL[P::RHO] + vR[P::RHO]);
-    cRL = sqrt(eos.gamma * (pRL / rRL));
+    cRL = idfxSqrt<P::fast>(eos.gamma * idfxDiv<P::fast>(pRL, rRL));
   } else {
     cRL = 0.5 * (eos.csiso + eos.csiso);
   }
@@ -79,7 +80,7 @@ IDFX_D void riemannHllHD(const VL &vL, const VR &vR, const Eos &eos, double *F, 
 #pragma unroll
     for (int nv = 0; nv < P::nvar; nv++) {
       double f = SL * SR * uR[nv] - SL * SR * uL[nv] + SR * fL[nv] - SL * fR[nv];
-      F[nv] = f / (SR - SL);
+      F[nv] = idfxDiv<P::fast>(f, (SR - SL));
     }
   }
 }
@@ -116,9 +117,9 @@ IDFX_D void riemannHllcHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
       const double qR = vR[P::PRS] + uR[Xn] * (vR[Xn] - SR);
       const double wL = vL[P::RHO] * (vL[Xn] - SL);
       const double wR = vR[P::RHO] * (vR[Xn] - SR);
-      vs = (qR - qL) / (wR - wL);
-      usL[P::RHO] = uL[P::RHO] * (SL - vL[Xn]) / (SL - vs);
-      usR[P::RHO] = uR[P::RHO] * (SR - vR[Xn]) / (SR - vs);
+      vs = idfxDiv<P::fast>((qR - qL), (wR - wL));
+      usL[P::RHO] = idfxDiv<P::fast>(uL[P::RHO] * (SL - vL[Xn]), (SL - vs));
+      usR[P::RHO] = idfxDiv<P::fast>(uR[P::RHO] * (SR - vR[Xn]), (SR - vs));
       usL[Xn] = usL[P::RHO] * vs;
       usR[Xn] = usR[P::RHO] * vs;
       if constexpr (P::ncomp >= 2) {
@@ -129,19 +130,19 @@ IDFX_D void riemannHllcHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
         usL[D::Xb] = usL[P::RHO] * vL[D::Xb];
         usR[D::Xb] = usR[P::RHO] * vR[D::Xb];
       }
-      usL[P::ENG] = uL[P::ENG] / vL[P::RHO] + (vs - vL[Xn]) * (vs + vL[P::PRS] / (vL[P::RHO] * (SL - vL[Xn])));
-      usR[P::ENG] = uR[P::ENG] / vR[P::RHO] + (vs - vR[Xn]) * (vs + vR[P::PRS] / (vR[P::RHO] * (SR - vR[Xn])));
+      usL[P::ENG] = idfxDiv<P::fast>(uL[P::ENG], vL[P::RHO]) + (vs - vL[Xn]) * (vs + idfxDiv<P::fast>(vL[P::PRS], (vL[P::RHO] * (SL - vL[Xn]))));
+      usR[P::ENG] = idfxDiv<P::fast>(uR[P::ENG], vR[P::RHO]) + (vs - vR[Xn]) * (vs + idfxDiv<P::fast>(vR[P::PRS], (vR[P::RHO] * (SR - vR[Xn]))));
       usL[P::ENG] *= usL[P::RHO];
       usR[P::ENG] *= usR[P::RHO];
     } else {
-      const double scrh = 1.0 / (SR - SL);
+      const double scrh = idfxDiv<P::fast>(1.0, (SR - SL));
       const double rho = (SR * uR[P::RHO] - SL * uL[P::RHO] - fR[P::RHO] + fL[P::RHO]) * scrh;
       const double mx = (SR * uR[Xn] - SL * uL[Xn] - fR[Xn] + fL[Xn]) * scrh;
       usL[P::RHO] = usR[P::RHO] = rho;
       usL[Xn] = usR[Xn] = mx;
       vs = (SR * fL[P::RHO] - SL * fR[P::RHO] + SR * SL * (uR[P::RHO] - uL[P::RHO]));
       vs *= scrh;
-      vs /= rho;
+      vs = idfxDiv<P::fast>(vs, rho);
       if constexpr (P::ncomp >= 2) {
         usL[D::Xt] = rho * vL[D::Xt];
         usR[D::Xt] = rho * vR[D::Xt];

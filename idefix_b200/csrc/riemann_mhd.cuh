@@ -67,8 +67,8 @@ IDFX_D void riemannTvdlfMHD(const VL &vL, const VR &vR, const Eos &eos, double *
   const double B2 = Bt2 + bn * bn;
   // note: the reference re-uses cRL here, which cancels the +B2 (tvdlfMHD.hpp:192-194)
   double cRL = gpr - B2;
-  cRL = cRL + B2 + sqrt(cRL * cRL + 4.0 * gpr * Bt2);
-  cRL = sqrt(0.5 * cRL / rho);
+  cRL = cRL + B2 + idfxSqrt<P::fast>(cRL * cRL + 4.0 * gpr * Bt2);
+  cRL = idfxSqrt<P::fast>(idfxDiv<P::fast>(0.5 * cRL, rho));
   const double cmax = fmax(fabs(vn + cRL), fabs(vn - cRL));
   primToCons<P>(uL, vL, eos);
   primToCons<P>(uR, vR, eos);
@@ -124,12 +124,12 @@ IDFX_D void riemannHllMHD(const VL &vL, const VR &vR, const Eos &eos, double *F,
 #pragma unroll
     for (int nv = 0; nv < P::nvar; nv++) F[nv] = fR[nv];
   } else {
-    const double rcp = 1.0 / (sr - sl);
+    const double rcp = idfxDiv<P::fast>(1.0, (sr - sl));
 #pragma unroll
     for (int nv = 0; nv < P::nvar; nv++) {
       const double f = sl * sr * uR[nv] - sl * sr * uL[nv] + sr * fL[nv] - sl * fR[nv];
       if (nv <= P::ncomp) {
-        F[nv] = f / (sr - sl);
+        F[nv] = idfxDiv<P::fast>(f, (sr - sl));
       } else {
         F[nv] = f * rcp;
       }
@@ -380,20 +380,20 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
     // isothermal HLLD (hlldMHD.hpp:459-572)
     double usc[P::nvar];
     bool revert_to_hll = false;
-    scrh = 1.0 / (sr - sl);
+    scrh = idfxDiv<P::fast>(1.0, (sr - sl));
     duL = sl - vL[Xn];
     duR = sr - vR[Xn];
     Bx = (sr * vR[BXn] - sl * vL[BXn]) * scrh;
     const double rho = (uR[RHO] * duR - uL[RHO] * duL) * scrh;
     F[RHO] = (sl * uR[RHO] * duR - sr * uL[RHO] * duL) * scrh;
-    const double sqrho = sqrt(rho);
-    SM = F[RHO] / rho;
-    S1L = SM - fabs(Bx) / sqrho;
-    S1R = SM + fabs(Bx) / sqrho;
+    const double sqrho = idfxSqrt<P::fast>(rho);
+    SM = idfxDiv<P::fast>(F[RHO], rho);
+    S1L = SM - idfxDiv<P::fast>(fabs(Bx), sqrho);
+    S1R = SM + idfxDiv<P::fast>(fabs(Bx), sqrho);
     if ((S1L - sl) < 1.e-4 * (sr - sl)) revert_to_hll = true;
     if ((S1R - sr) > -1.e-4 * (sr - sl)) revert_to_hll = true;
     if (revert_to_hll) {
-      scrh = 1.0 / (sr - sl);
+      scrh = idfxDiv<P::fast>(1.0, (sr - sl));
 #pragma unroll
       for (int nv = 0; nv < P::nvar; nv++) {
         F[nv] = sl * sr * (uR[nv] - uL[nv]) + sr * fL[nv] - sl * fR[nv];
@@ -402,8 +402,8 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
     } else {
       F[Xn] = (sr * fL[Xn] - sl * fR[Xn] + sr * sl * (uR[Xn] - uL[Xn])) * scrh;
       F[BXn] = sr * sl * (uR[BXn] - uL[BXn]) * scrh;
-      scrhL = 1.0 / ((sl - S1L) * (sl - S1R));
-      scrhR = 1.0 / ((sr - S1L) * (sr - S1R));
+      scrhL = idfxDiv<P::fast>(1.0, ((sl - S1L) * (sl - S1R)));
+      scrhR = idfxDiv<P::fast>(1.0, ((sr - S1L) * (sr - S1R)));
       if constexpr (P::ncomp >= 2) {
         usL[Xt] = rho * vL[Xt] - Bx * uL[BXt] * (SM - vL[Xn]) * scrhL;
         usR[Xt] = rho * vR[Xt] - Bx * uR[BXt] * (SM - vR[Xn]) * scrhR;
@@ -413,12 +413,12 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
         usR[Xb] = rho * vR[Xb] - Bx * uR[BXb] * (SM - vR[Xn]) * scrhR;
       }
       if constexpr (P::ncomp >= 2) {
-        usL[BXt] = uL[BXt] / rho * (uL[RHO] * duL * duL - Bx * Bx) * scrhL;
-        usR[BXt] = uR[BXt] / rho * (uR[RHO] * duR * duR - Bx * Bx) * scrhR;
+        usL[BXt] = idfxDiv<P::fast>(uL[BXt], rho) * (uL[RHO] * duL * duL - Bx * Bx) * scrhL;
+        usR[BXt] = idfxDiv<P::fast>(uR[BXt], rho) * (uR[RHO] * duR * duR - Bx * Bx) * scrhR;
       }
       if constexpr (P::ncomp == 3) {
-        usL[BXb] = uL[BXb] / rho * (uL[RHO] * duL * duL - Bx * Bx) * scrhL;
-        usR[BXb] = uR[BXb] / rho * (uR[RHO] * duR * duR - Bx * Bx) * scrhR;
+        usL[BXb] = idfxDiv<P::fast>(uL[BXb], rho) * (uL[RHO] * duL * duL - Bx * Bx) * scrhL;
+        usR[BXb] = idfxDiv<P::fast>(uR[BXb], rho) * (uR[RHO] * duR * duR - Bx * Bx) * scrhR;
       }
       if (S1L >= 0.0) {
         if constexpr (P::ncomp >= 2) {
@@ -442,15 +442,15 @@ IDFX_D void riemannHlldMHD(const VL &vL, const VR &vR, const Eos &eos, double *F
         sBx = (Bx > 0.0 ? 1.0 : -1.0);
         if constexpr (P::ncomp >= 2) {
           usc[Xt] = 0.5 * (usR[Xt] + usL[Xt] + (usR[BXt] - usL[BXt]) * sBx * sqrho);
-          usc[BXt] = 0.5 * (usR[BXt] + usL[BXt] + (usR[Xt] - usL[Xt]) * sBx / sqrho);
+          usc[BXt] = 0.5 * (usR[BXt] + usL[BXt] + idfxDiv<P::fast>((usR[Xt] - usL[Xt]) * sBx, sqrho));
           F[Xt] = usc[Xt] * SM - Bx * usc[BXt];
-          F[BXt] = usc[BXt] * SM - Bx * usc[Xt] / rho;
+          F[BXt] = usc[BXt] * SM - idfxDiv<P::fast>(Bx * usc[Xt], rho);
         }
         if constexpr (P::ncomp == 3) {
           usc[Xb] = 0.5 * (usR[Xb] + usL[Xb] + (usR[BXb] - usL[BXb]) * sBx * sqrho);
-          usc[BXb] = 0.5 * (usR[BXb] + usL[BXb] + (usR[Xb] - usL[Xb]) * sBx / sqrho);
+          usc[BXb] = 0.5 * (usR[BXb] + usL[BXb] + idfxDiv<P::fast>((usR[Xb] - usL[Xb]) * sBx, sqrho));
           F[Xb] = usc[Xb] * SM - Bx * usc[BXb];
-          F[BXb] = usc[BXb] * SM - Bx * usc[Xb] / rho;
+          F[BXb] = usc[BXb] * SM - idfxDiv<P::fast>(Bx * usc[Xb], rho);
         }
       }
     }

@@ -76,7 +76,7 @@ IDFX_D void geometricSource(const DevGrid &g, const V &v, const Eos &eos, double
         Sm -= v[P::BX3] * v[P::BX3];
         Sm += 0.5 * (v[P::BX1] * v[P::BX1] + v[P::BX2] * v[P::BX2] + v[P::BX3] * v[P::BX3]);
       }
-      s1 = dt * Sm / g.x[0][i];
+      s1 = idfxDiv<P::fast>(dt * Sm, g.x[0][i]);
     }
   } else if (geo == GEO_POLAR) {
     if constexpr (P::ncomp >= 2) {
@@ -91,7 +91,7 @@ IDFX_D void geometricSource(const DevGrid &g, const V &v, const Eos &eos, double
         if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
         Sm += 0.5 * b2;
       }
-      s1 = dt * Sm / g.x[0][i];
+      s1 = idfxDiv<P::fast>(dt * Sm, g.x[0][i]);
     }
   } else if (geo == GEO_SPHERICAL) {
     double vphi = 0.0;
@@ -113,9 +113,9 @@ IDFX_D void geometricSource(const DevGrid &g, const V &v, const Eos &eos, double
       if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
       Sm += b2;
     }
-    s1 = dt * Sm / g.rt[i];
+    s1 = idfxDiv<P::fast>(dt * Sm, g.rt[i]);
     if constexpr (P::ncomp >= 2) {
-      const double ct = 1.0 / g.tanx2[j];
+      const double ct = idfxDiv<P::fast>(1.0, g.tanx2[j]);
       double cc = 0.0;
       cc = cc - v[P::MX2] * v[P::MX1];
       if constexpr (P::ncomp == 3) cc = cc + ct * vphi * vphi;
@@ -132,7 +132,7 @@ IDFX_D void geometricSource(const DevGrid &g, const V &v, const Eos &eos, double
         if constexpr (P::ncomp == 3) b2 = b2 + v[P::BX3] * v[P::BX3];
         Sm += 0.5 * ct * b2;
       }
-      s2 = dt * Sm / g.rt[i];
+      s2 = idfxDiv<P::fast>(dt * Sm, g.rt[i]);
     }
   }
 }
@@ -180,7 +180,7 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
                        int k, int j, int i, long long cell, const double *Fm, const double *Fp, double cmaxm,
                        double cmaxp, VcF vcAt) {
   constexpr int NV = P::nvar;
-  const double dtdV = dt / dV;
+  const double dtdV = idfxDiv<P::fast>(dt, dV);
   double rhs[NV];
 #pragma unroll
   for (int nv = 0; nv < NV; nv++) rhs[nv] = -dtdV * (Fp[nv] - Fm[nv]);
@@ -190,13 +190,13 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
     if constexpr (DIR == IDIR) {
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) {
-        if (nv == mphi) rhs[nv] = rhs[nv] / g.x[0][i];
+        if (nv == mphi) rhs[nv] = idfxDiv<P::fast>(rhs[nv], g.x[0][i]);
         if constexpr (P::mhd) {
           if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
-            if (nv == bphi) rhs[nv] = -dt / g.dx[0][i] * (Fp[nv] - Fm[nv]);
+            if (nv == bphi) rhs[nv] = idfxDiv<P::fast>(-dt, g.dx[0][i]) * (Fp[nv] - Fm[nv]);
           } else if (geo == GEO_SPHERICAL) {
             if (nv == bth || nv == bphi) {
-              const double q = dt / (g.x[0][i] * g.dx[0][i]);
+              const double q = idfxDiv<P::fast>(dt, (g.x[0][i] * g.dx[0][i]));
               rhs[nv] = -q * ((Fp[nv] - Fm[nv]));
             }
           }
@@ -206,9 +206,9 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
       if (geo == GEO_SPHERICAL && P::ncomp == 3) {
 #pragma unroll
         for (int nv = 0; nv < NV; nv++) {
-          if (nv == mphi) rhs[nv] /= fabs(g.sinx2[j]);
+          if (nv == mphi) rhs[nv] = idfxDiv<P::fast>(rhs[nv], fabs(g.sinx2[j]));
           if constexpr (P::mhd) {
-            if (nv == bphi) rhs[nv] = -dt / (g.rt[i] * g.dx[1][j]) * (Fp[nv] - Fm[nv]);
+            if (nv == bphi) rhs[nv] = idfxDiv<P::fast>(-dt, (g.rt[i] * g.dx[1][j])) * (Fp[nv] - Fm[nv]);
           }
         }
       }
@@ -222,12 +222,12 @@ IDFX_D void updateCell(const SweepArgs &a, const DevGrid &g, int geo, const Eos 
       if constexpr (DIR == JDIR) dl = dl * g.x[0][i];
     } else if (geo == GEO_SPHERICAL) {
       if constexpr (DIR == JDIR) dl = dl * g.rt[i];
-      if constexpr (DIR == KDIR) dl = dl * g.rt[i] * g.dmu[j] / g.dx[1][j];
+      if constexpr (DIR == KDIR) dl = idfxDiv<P::fast>(dl * g.rt[i] * g.dmu[j], g.dx[1][j]);
     }
     // invDtInit: first sweep after ResetStage, the accumulator is known to be zero.  Otherwise the
     // accumulation InvDt += term is a fire-and-forget RED.ADD.F64 resolved in L2 (same IEEE addition as
     // load-add-store, but no load latency and no register / shared-memory staging of the old value)
-    const double term = 0.5 * (cmaxp + cmaxm) / (dl);
+    const double term = idfxDiv<P::fast>(0.5 * (cmaxp + cmaxm), (dl));
     if (a.invDtInit) a.invDt[cell] = 0.0 + term;
     else atomicAdd(a.invDt + cell, term);
   }

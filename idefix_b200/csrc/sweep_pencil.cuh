@@ -65,7 +65,7 @@ IDFX_D void finishInterface(const SweepArgs &a, const DevGrid &g, int geo, doubl
   if (a.fluxRho != nullptr) a.fluxRho[cell] = F[P::RHO];   // for the tracer kernels (Tracer::CalcFlux)
   if constexpr (P::mhd) {
     const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(a.emf);
-    storeEmf<P, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
+    storeEmf<typename P::Fast, DIR, SOLVER>(a.emfMode, A, cell, F, aux, vL, vR);
   }
   areaWeightFlux<P, DIR>(g, geo, A0, k, j, i, F);
 }
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring)
       if (sp < 0) sp += W;
       const double *vprev = ring + sp * NV * TX;
-      updateCell<P, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
+      updateCell<typename P::Fast, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
                          fprev[NV * TX], aux.cmax, [&](int nv) { return vprev[nv * TX]; });
     }
 #pragma unroll
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) Fp[nv] = fls[nv * 32 + lane + 1];
       const double dV = vol0 * tab[r] * vol2;
-      updateCell<P, DIR>(a, g, geo, eos, dt, dV, dxc, k, j, c, cell, F, Fp, aux.cmax, fls[NV * 32 + lane + 1],
+      updateCell<typename P::Fast, DIR>(a, g, geo, eos, dt, dV, dxc, k, j, c, cell, F, Fp, aux.cmax, fls[NV * 32 + lane + 1],
                          [&](int nv) { return row[nv * RW]; });
     }
     __syncwarp();   // vrs / fls are rewritten by the next row
