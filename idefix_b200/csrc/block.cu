@@ -395,11 +395,10 @@ int readState(IdfxBlock *b) {
 
 bool needsExchange(const IdfxBlock *b, int dir) { return b->nproc[dir] > 1; }
 
-// Boundary::SetBoundaries without the final ReconstructVcField (boundary.hpp:252-275)
-int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
+// Boundary::EnforceBoundaryDir (boundary.hpp:287-385) + ReconstructNormalField (:408-530) of one direction
+int enforceBoundaryDirImpl(IdfxBlock *b, int dir, double t, bool tKnown) {
   const IdfxBlockDesc &d = b->desc;
-  TimeScope ts(b, TIME_BOUNDARY);
-  for (int dir = 0; dir < d.ndim; dir++) {
+  {
     if (needsExchange(b, dir)) {
       if (!b->haloFn) return fail("nproc > 1 in a direction but no halo exchange has been enrolled");
       b->haloFn(b, dir, b->haloData);
@@ -441,6 +440,14 @@ int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
       KTRY(idfxk::reconstructNormalField(b->cfg, b->g, b->Vs, dir, left, right, b->stream, &b->launches));
     }
   }
+  return 0;
+}
+
+// Boundary::SetBoundaries without the final ReconstructVcField (boundary.hpp:252-275)
+int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
+  TimeScope ts(b, TIME_BOUNDARY);
+  for (int dir = 0; dir < b->desc.ndim; dir++)
+    if (enforceBoundaryDirImpl(b, dir, t, tKnown)) return 1;
   return 0;
 }
 
@@ -901,9 +908,10 @@ int idfx_reset_stage(IdfxBlock *b) {
 }
 
 int idfx_enforce_boundary_dir(IdfxBlock *b, double t, int dir) {
-  (void)t;
-  (void)dir;
-  return fail("idfx_enforce_boundary_dir: use idfx_set_boundaries");
+  if (dir < 0 || dir >= b->desc.ndim) return fail("idfx_enforce_boundary_dir: direction out of range");
+  b->vcFieldFresh = false;
+  TimeScope ts(b, TIME_BOUNDARY);
+  return enforceBoundaryDirImpl(b, dir, t, true);
 }
 
 int idfx_set_boundaries(IdfxBlock *b, double t) {

@@ -133,3 +133,23 @@ def test_branch_free_division_and_sqrt_are_bit_identical(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
     assert ", 0 mismatches," in out.stdout and "sqrt:" in out.stdout and out.stdout.count(" 0 mismatches") == 2, out.stdout
+
+
+def test_enforce_boundary_dir_composes_to_set_boundaries():
+    """idfx_enforce_boundary_dir (Boundary::EnforceBoundaryDir, boundary.hpp:287-385) direction by direction,
+    then ReconstructVcField, fills the ghosts exactly like idfx_set_boundaries"""
+    import ctypes as C
+    outs = []
+    for granular in (False, True):
+        s = build(3, 3, True, (7, 6, 5), "hlld", "uct_contact", 2, "outflow", seed=21)
+        s.InitFlow(s.data)
+        h = s.data._handle
+        if granular:
+            for d in range(3):
+                _abi.check(_abi.lib().idfx_enforce_boundary_dir(h, C.c_double(0.0), d))
+            _abi.check(_abi.lib().idfx_reconstruct_vc_field(h, _abi.FIELD_VC))
+        else:
+            s.data.SetBoundaries()
+        outs.append((s.data.download(_abi.FIELD_VC), s.data.download(_abi.FIELD_VS)))
+        s.data.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
