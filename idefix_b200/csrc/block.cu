@@ -575,7 +575,7 @@ int cycleReferenceOrder(IdfxBlock *b) {
 }
 
 // The same cycle with the point-wise steps folded into the sweeps / CT / one epilogue.
-int cycleFused(IdfxBlock *b) {
+int cycleFused(IdfxBlock *b, bool lastOfBatch) {
   const IdfxBlockDesc &d = b->desc;
   KTRY(idfxk::dtControlBegin(b->state, b->redBits, b->stream));
   b->launches++;
@@ -594,7 +594,11 @@ int cycleFused(IdfxBlock *b) {
     }
     {
       TimeScope ts(b, TIME_EPILOGUE);
-      KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, 1,
+      // Uc is rebuilt from Vc by the x1 sweep of the next stage, so its write-back (8 of the 24-29 doubles this
+      // kernel moves per cell) is only needed where somebody can look at it: after the last stage of the last
+      // cycle of this call, or when the tracer kernels need Uc(RHO)
+      const int keepUc = (b->cfg.ntr > 0 || (lastOfBatch && stage == d.nstages - 1)) ? 1 : 0;
+      KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, keepUc,
                                 b->stream, b->mathFlag));
     }
     b->launches++;
@@ -1023,7 +1027,7 @@ int idfx_cycles(IdfxBlock *b, int ncycles) {
   b->vcFieldFresh = false;
   for (int n = 0; n < ncycles; n++) {
     if (b->fused) {
-      if (cycleFused(b)) return 1;
+      if (cycleFused(b, n == ncycles - 1)) return 1;
     } else {
       if (cycleReferenceOrder(b)) return 1;
     }
