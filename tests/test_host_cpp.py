@@ -166,3 +166,71 @@ def test_cpp_host_vtk_layout(tmp_path_factory, tmp_path):
     assert np.all(np.isfinite(rho)) and abs(float(rho.mean()) - 25.0 / (36.0 * np.pi)) < 1e-3
     t = struct.unpack(">f", raw[raw.index(b"TIME 1 1 float\n") + 15:][:4])[0]
     assert t > 0.0
+
+
+HOST_LOGIC_INI = """
+# comment line
+[Grid]
+X1-grid    3  0.5  6  s+  1.0  8  u  3.0  5  l  9.0   # stretched | uniform | logarithmic patches
+X2-grid    1  0.3  7  u  2.8
+X3-grid    2  0.0  4  u  1.0  6  s-  4.0
+
+[TimeIntegrator]
+CFL         0.4
+tstop       1.0
+nstages     3
+
+[Hydro]
+solver    hlld      # trailing comment
+
+[Boundary]
+X1-beg    userdef
+X1-end    outflow
+X2-beg    reflective
+X2-end    reflective
+X3-beg    periodic
+X3-end    periodic
+"""
+
+
+def test_cpp_host_input_and_grid_match_python_mirror(tmp_path):
+    """CPU-only: the C++ Input / Grid (ini grammar, patch types u / l / s+ / s-, Newton solve of the stretch
+    factor, GetOrSet's ostream round trip of defaults) produce bit-identical coordinates and the same values as
+    the Python mirror, which tests/test_host.py pins against the reference's own grids"""
+    from idefix_b200 import _abi
+    from idefix_b200.grid import Definitions, Grid
+    from idefix_b200.input import Input
+    exe = tmp_path / "host_logic_check"
+    src = os.path.join(ROOT, "tests", "host_cpp")
+    cmd = ["nvcc", "-std=c++17", "-O1", "-x", "cu", "--extended-lambda", "--expt-relaxed-constexpr", "-fmad=false",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-DMHD=YES", "-DORDER=2", "-I", src, "-I", HOST,
+           "-I", os.path.join(ROOT, "include"), os.path.join(src, "host_logic_check.cpp"), "-o", str(exe),
+           "-L", os.path.join(ROOT, "idefix_b200"), "-lidefix_b200", "-Xlinker", "-rpath", "-Xlinker",
+           os.path.join(ROOT, "idefix_b200"), "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    ini = tmp_path / "check.ini"
+    ini.write_text(HOST_LOGIC_INI)
+    out = subprocess.run([str(exe), "-i", str(ini), "-nolog"], capture_output=True, text=True, timeout=120, cwd=tmp_path)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    inp = Input.from_string(HOST_LOGIC_INI)
+    g = Grid(inp, Definitions(3, 3, _abi.SPHERICAL, mhd=True, order=2))
+    lines = out.stdout.splitlines()
+    assert f"regular {int(g.isRegularCartesian)}" in lines
+    got = {}
+    for ln in lines:
+        tok = ln.split()
+        if tok[0] == "x":
+            got[(int(tok[1]), int(tok[2]))] = [float.fromhex(v) for v in tok[3:7]]
+        if tok[0] == "dir":
+            d = int(tok[1])
+            assert int(tok[3]) == g.np_int[d] and int(tok[5]) == g.np_tot[d] and int(tok[7]) == g.nghost[d]
+            assert int(tok[9]) == g.lbound[d] and int(tok[11]) == g.rbound[d]
+            assert float.fromhex(tok[13]) == g.xbeg[d] and float.fromhex(tok[15]) == g.xend[d]
+    for d in range(3):
+        for i in range(g.np_tot[d]):
+            assert got[(d, i)] == [float(g.x[d][i]), float(g.xl[d][i]), float(g.xr[d][i]), float(g.dx[d][i])], (d, i)
+    vals = {ln.split()[0]: ln.split()[1:] for ln in lines if ln.split()[0] in ("gamma", "cflmaxvar", "nstages", "solver", "check")}
+    assert float.fromhex(vals["gamma"][0]) == inp.GetOrSet(float, "Hydro", "gamma", 0, 5.0 / 3.0) == 1.66667
+    assert float.fromhex(vals["cflmaxvar"][0]) == 1.1 and vals["nstages"] == ["3"] and vals["solver"] == ["hlld"]
+    assert vals["check"] == [str(inp.CheckEntry("Hydro", "emf")), str(inp.CheckEntry("Grid", "X1-grid")), "0"] == ["-1", "11", "0"]
