@@ -153,3 +153,105 @@ def test_enforce_boundary_dir_composes_to_set_boundaries():
         outs.append((s.data.download(_abi.FIELD_VC), s.data.download(_abi.FIELD_VS)))
         s.data.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_two_blocks_on_one_gpu_peer_halo_bitwise():
+    """Block decomposition on a SINGLE GPU: two blocks (2 x 1 x 1, periodic) in one process, each bound to the
+    other's receive buffers with idfx_halo_bind_peer, so that idfx_halo_pack writes the slabs straight into the
+    neighbour (the peer-to-peer path a multi-GPU run uses over NVLink).  The two blocks are advanced in lockstep
+    through the granular entry points (the reference's TimeIntegrator::Cycle order, dt = min over blocks) and the
+    assembled state must equal the dump the reference's own build wrote for the undecomposed run, bit for bit."""
+    import ctypes as C
+    import os
+
+    from cases import SHORT
+    from idefix_b200.dump import readDump
+    from idefix_b200.setups import REGISTRY
+    lib = _abi.lib()
+    case = [c for c in SHORT if c.name == "ot3d_hlld_contact_plm_tr2"][0]
+    nproc = (2, 1, 1)
+    blocks = [REGISTRY[case.setup](order=case.order, overrides=case.overrides, nproc=nproc, xproc=(x, 0, 0)) for x in (0, 1)]
+    hs = [s.data._handle for s in blocks]
+    pd = C.POINTER(C.c_double)
+    recv = []
+    for h in hs:
+        _abi.check(lib.idfx_set_stream(h, None))          # both blocks on the legacy default stream
+        _abi.check(lib.idfx_set_fused(h, 0))
+        sides = []
+        for side in range(2):
+            ps, pr = pd(), pd()
+            _abi.check(lib.idfx_halo_buffers(h, 0, side, C.byref(ps), C.byref(pr)))
+            sides.append(pr)
+        recv.append(sides)
+    for me, other in ((0, 1), (1, 0)):
+        # our left slab fills the neighbour's RIGHT ghosts and vice versa (two blocks: both neighbours are `other`)
+        _abi.check(lib.idfx_halo_bind_peer(hs[me], 0, 0, C.cast(recv[other][1], C.c_void_p)))
+        _abi.check(lib.idfx_halo_bind_peer(hs[me], 0, 1, C.cast(recv[other][0], C.c_void_p)))
+
+    def exchange_first(data, d):      # block 0: both blocks pack (peer stores), block 0 unpacks
+        for h in hs:
+            _abi.check(lib.idfx_halo_pack(h, d))
+        _abi.check(lib.idfx_halo_unpack(hs[0], d))
+
+    def exchange_second(data, d):     # block 1: its receive buffers were filled by block 0's pack
+        _abi.check(lib.idfx_halo_unpack(hs[1], d))
+
+    blocks[0].data.enroll_halo_exchange(exchange_first)
+    blocks[1].data.enroll_halo_exchange(exchange_second)
+    for s in blocks:
+        s.InitFlow(s.data)
+    datas = [s.data for s in blocks]
+    for d in datas:
+        d.SetBoundaries()
+    tint = blocks[0].tint
+    ncyc = max(case.cycles)
+    for cyc in range(ncyc):
+        t, dt = datas[0]._time()
+        t0 = t
+        for d in datas:
+            d.ResetStage()
+        newdt = None
+        for stage in range(tint.nstages):
+            for d in datas:
+                d.SetBoundaries()
+            for d in datas:
+                d.PrimToCons()
+                if tint.nstages > 1 and stage == 0:
+                    d.state_copy()
+                d.hydro.EvolveStage(t, dt)
+            t += dt
+            if stage == 0:
+                newdt = tint.cfl * min(d.ComputeTimestep() for d in datas)
+            if stage > 0:
+                wc, w0 = tint.wc[stage - 1], tint.w0[stage - 1]
+                for d in datas:
+                    d.state_add_and_store(wc, w0)
+                t = wc * t + w0 * t0
+            for d in datas:
+                d.set_time(t, dt)
+                d.ConsToPrim()
+        t = t0 + dt
+        dt = tint.cflMaxVar * dt if newdt > tint.cflMaxVar * dt else newdt
+        for d in datas:
+            d.set_time(t, dt)
+    gold = readDump(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "short", f"{case.name}.c{ncyc:04d}.dmp"))
+    assert t == float(gold.data["time"][0])
+    parts = [parity.fields_of(s) for s in blocks]
+    checked = 0
+    for name, ref in gold.data.items():
+        if not name.startswith(("Vc-", "Vs-")):
+            continue
+        ref = np.asarray(ref)
+        n0 = parts[0][name].shape[0]
+        if name == "Vs-BX1s":       # the shared face belongs to both blocks (and must agree)
+            assert np.array_equal(parts[0][name][-1], parts[1][name][0])
+            full = np.concatenate([parts[0][name][:-1], parts[1][name]], axis=0)
+        else:
+            full = np.concatenate([parts[0][name], parts[1][name]], axis=0)
+        assert full.shape == ref.shape, (name, full.shape, ref.shape, n0)
+        assert np.array_equal(full, ref), name
+        checked += 1
+    assert checked >= 9     # 5 Vc fields + 2 tracers + 3 Vs components
+    for d in datas:
+        assert d.math_exceptions() == 0
+        d.close()
