@@ -234,3 +234,28 @@ def test_cpp_host_input_and_grid_match_python_mirror(tmp_path):
     assert float.fromhex(vals["gamma"][0]) == inp.GetOrSet(float, "Hydro", "gamma", 0, 5.0 / 3.0) == 1.66667
     assert float.fromhex(vals["cflmaxvar"][0]) == 1.1 and vals["nstages"] == ["3"] and vals["solver"] == ["hlld"]
     assert vals["check"] == [str(inp.CheckEntry("Hydro", "emf")), str(inp.CheckEntry("Grid", "X1-grid")), "0"] == ["-1", "11", "0"]
+
+
+@pytest.mark.gpu
+def test_cpp_host_api_tour(tmp_path_factory, tmp_path):
+    """problems/apiTour: user device array + idefix_for, idefix_reduce (Sum / Max), analysis function, user-defined
+    VTK variables, create_mirror_view / deep_copy and a step hook (which sends TimeIntegrator::Cycle through the
+    granular, reference-ordered ABI path)"""
+    PROBLEMS["apitour"] = ("apiTour", "NO")
+    exe = binary("apitour", 2, tmp_path_factory)
+    ini = open(os.path.join(HOST, "problems", "apiTour", "idefix.ini")).read()
+    out = run_idefix(exe, str(tmp_path), ini, "-maxcycles", "6")
+    rows = [[float(v) for v in ln.split()] for ln in open(tmp_path / "analysis.txt")]
+    assert len(rows) == 7                                  # t = 0 and one per cycle
+    assert [int(r[4]) for r in rows] == list(range(7))     # the step hook ran once per cycle
+    for t, mass, mass_host, vmax, _ in rows:
+        assert abs(mass - mass_host) <= 1e-13 * mass_host  # device reduction == host sum
+        assert abs(mass - rows[0][1]) <= 1e-13 * mass      # periodic box: mass is conserved to round-off
+        assert 0.9 < vmax < 1.2
+    assert rows[-1][0] > rows[0][0] == 0.0
+    raw = open(tmp_path / "data.0000.vtk", "rb").read()
+    names = re.findall(rb"\nSCALARS (\w+) float\nLOOKUP_TABLE default\n", raw)
+    assert names == [b"BLOB", b"MACH", b"PRS", b"RHO", b"VX1", b"VX2"]
+    off = raw.index(b"SCALARS BLOB float\nLOOKUP_TABLE default\n") + len(b"SCALARS BLOB float\nLOOKUP_TABLE default\n")
+    blob = np.frombuffer(raw[off:off + 4 * 48 * 32], dtype=">f4")
+    assert abs(float(blob.max()) - 0.5) < 0.02 and float(blob.min()) >= 0.0   # the user array made it into the file
