@@ -27,4 +27,5 @@ b polar_plm    $P/PolarMHD                YES 2
 b sodiso_plm   $P/sodIso                  NO  2
 b iso25d_plm   $P/IsoMHD25D               YES 2 TPX
 b iso25d_limo3 $P/IsoMHD25D               YES 3 TPX
+b sph25d_plm   $P/Spherical25D            YES 2 TPX
 echo done
