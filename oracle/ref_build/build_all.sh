@@ -28,4 +28,6 @@ b sodiso_plm   $P/sodIso                  NO  2
 b iso25d_plm   $P/IsoMHD25D               YES 2 TPX
 b iso25d_limo3 $P/IsoMHD25D               YES 3 TPX
 b sph25d_plm   $P/Spherical25D            YES 2 TPX
+b polarhd_ppm  $P/PolarHD2D               NO  4 TPX
+b polarhd_limo3 $P/PolarHD2D              NO  3 TPX
 echo done

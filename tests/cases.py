@@ -88,7 +88,7 @@ SHORT = [
 # (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
 # reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
 # fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
-PROBLEM_DIRS = {"sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D"}
+PROBLEM_DIRS = {"sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
 
 
 def _sph(solver, emf=None, nstages=2):
@@ -129,6 +129,10 @@ HOST_SHORT = [
     Short("sph25d_hlld_contact_plm", "sph25d", 2, "sph25d_plm", {("Hydro", "solver"): "hlld"}, (1, 10)),
     Short("sph25d_roe_uct0_plm_rk3", "sph25d", 2, "sph25d_plm",
           {("Hydro", "solver"): "roe", ("Hydro", "emf"): "uct0", ("TimeIntegrator", "nstages"): 3}, (1, 10)),
+    # hydrodynamics in 2-D polar geometry: HLLC + PPM + RK3, HLL + LimO3
+    Short("polarhd_hllc_ppm_rk3", "polarhd", 4, "polarhd_ppm", {("Hydro", "solver"): "hllc"}, (1, 10)),
+    Short("polarhd_hll_limo3", "polarhd", 3, "polarhd_limo3",
+          {("Hydro", "solver"): "hll", ("TimeIntegrator", "nstages"): 2}, (1, 10)),
     Short("iso25d_tvdlf_arith_limo3", "iso25d", 3, "iso25d_limo3",
           {("Hydro", "solver"): "tvdlf", ("Hydro", "emf"): "arithmetic"}, (1, 10)),
 ]

@@ -25,7 +25,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "idefix_b200", "host")
 PROBLEMS = {"sod": ("sod", "NO"), "ot2d": ("OrszagTang", "YES"), "ot3d": ("OrszagTang3D", "YES"),
             "sodUserBC": ("sodUserBC", "NO"), "sph": ("SphericalMHD", "YES"), "polar": ("PolarMHD", "YES"),
-            "sodiso": ("sodIso", "NO"), "iso25d": ("IsoMHD25D", "YES"), "sph25d": ("Spherical25D", "YES")}
+            "sodiso": ("sodIso", "NO"), "iso25d": ("IsoMHD25D", "YES"), "sph25d": ("Spherical25D", "YES"),
+            "polarhd": ("PolarHD2D", "NO")}
 
 
 def build(problem, order, tmp_path_factory):
