@@ -73,6 +73,10 @@ struct IdfxBlock {
   bool ownStream = true;
   unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
+  // steady-state cycle of the fused path captured as a CUDA graph (launch-bound small grids: ~40 launches per cycle)
+  cudaGraphExec_t cycleGraph = nullptr;
+  long long cycleGraphLaunches = 0;
+  bool useGraph = true;
   bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
   bool timing = false;
@@ -80,6 +84,11 @@ struct IdfxBlock {
   std::vector<int> evCat;               // category of pair n
   size_t evUsed = 0;
 };
+
+static void dropCycleGraph(IdfxBlock *b) {
+  if (b->cycleGraph) cudaGraphExecDestroy(b->cycleGraph);
+  b->cycleGraph = nullptr;
+}
 
 enum { TIME_SWEEP_X1 = 0, TIME_SWEEP_X2 = 1, TIME_SWEEP_X3 = 2, TIME_CT = 3, TIME_EPILOGUE = 4, TIME_BOUNDARY = 5,
        TIME_NCAT = 6 };
@@ -685,6 +694,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   }
   setupPhys(b);
   CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  if (std::getenv("IDFX_NO_GRAPH")) b->useGraph = false;   // A/B switch: always launch the cycle kernel by kernel
 
   DevGrid &g = b->g;
   std::memset(&g, 0, sizeof(g));
@@ -789,6 +799,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
 }
 
 int idfx_block_destroy(IdfxBlock *b) {
+  if (b) dropCycleGraph(b);
   if (!b) return 0;
   cudaSetDevice(b->desc.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
@@ -872,6 +883,7 @@ int idfx_launch_count(IdfxBlock *b, long long *count) {
 
 int idfx_set_stream(IdfxBlock *b, void *stream) {
   CUDA_TRY(cudaStreamSynchronize(b->stream));
+  dropCycleGraph(b);
   if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
   b->stream = (cudaStream_t)stream;
   b->ownStream = false;
@@ -900,6 +912,7 @@ int idfx_timing(IdfxBlock *b, int mode, double *out) {
 }
 
 int idfx_set_nproc(IdfxBlock *b, const int nproc[3]) {
+  dropCycleGraph(b);
   for (int d = 0; d < 3; d++) b->nproc[d] = nproc[d] < 1 ? 1 : nproc[d];
   return 0;
 }
@@ -1022,9 +1035,53 @@ int idfx_check_nan(IdfxBlock *b, int *nan_count) {
 }
 
 // ---- fused path -------------------------------------------------------------------------------
+namespace {
+// The steady-state cycle (every cycle of a call but the first, which re-validates the caller's state, and the
+// last, which leaves Uc behind) is identical launch for launch: it is captured once into a CUDA graph and
+// replayed, which removes the per-launch CPU cost that dominates small grids (2-D 1024^2: ~40 launches of
+// ~15 us each per 0.7 ms cycle).  Only for a single block without host callbacks on a capturable stream.
+bool graphEligible(const IdfxBlock *b, int ncycles) {
+  return b->useGraph && b->fused && ncycles >= 4 && !b->userBc && !b->haloFn && !b->timing && b->stream != nullptr &&
+         b->nproc[0] * b->nproc[1] * b->nproc[2] == 1;
+}
+}  // namespace
+
 int idfx_cycles(IdfxBlock *b, int ncycles) {
   // the caller holds device pointers to the state (idfx_field_info) and may have changed it since the last call
   b->vcFieldFresh = false;
+  if (graphEligible(b, ncycles)) {
+    if (cycleFused(b, false)) return 1;                       // first cycle: eager (full validation of the inputs)
+    int done = 1;
+    if (!b->cycleGraph) {
+      const long long l0 = b->launches;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc = cycleFused(b, false);
+        const cudaError_t ce = cudaStreamEndCapture(b->stream, &graph);
+        if (rc == 0 && ce == cudaSuccess && graph != nullptr &&
+            cudaGraphInstantiate(&b->cycleGraph, graph, 0) == cudaSuccess) {
+          b->cycleGraphLaunches = b->launches - l0;
+        } else {
+          b->cycleGraph = nullptr;
+          b->useGraph = false;                                 // never try again on this block
+        }
+        if (graph) cudaGraphDestroy(graph);
+        b->launches = l0;                                      // the capture itself launched nothing
+      } else {
+        b->useGraph = false;
+      }
+      cudaGetLastError();                                      // clear a capture failure, the eager path follows
+    }
+    if (b->cycleGraph) {
+      for (; done < ncycles - 1; done++) {
+        CUDA_TRY(cudaGraphLaunch(b->cycleGraph, b->stream));
+        b->launches += b->cycleGraphLaunches;
+      }
+    }
+    for (; done < ncycles; done++)
+      if (cycleFused(b, done == ncycles - 1)) return 1;
+    return 0;
+  }
   for (int n = 0; n < ncycles; n++) {
     if (b->fused) {
       if (cycleFused(b, n == ncycles - 1)) return 1;
@@ -1058,6 +1115,7 @@ int idfx_math_exceptions(IdfxBlock *b, unsigned int *count) {
 
 // selects the reference-ordered (un-fused) kernel sequence; used by the parity tests
 int idfx_set_fused(IdfxBlock *b, int fused) {
+  dropCycleGraph(b);
   if (fused && b->haveUserdef) return fail("the fused path is not available with user-defined boundaries");
   b->fused = fused != 0;
   return 0;
@@ -1065,16 +1123,19 @@ int idfx_set_fused(IdfxBlock *b, int fused) {
 
 // ---- callbacks -----------------------------------------------------------------------------------
 int idfx_enroll_userdef_boundary(IdfxBlock *b, IdfxUserBoundaryFn fn, void *user) {
+  dropCycleGraph(b);
   b->userBc = fn;
   b->userBcData = user;
   return 0;
 }
 int idfx_enroll_reduce(IdfxBlock *b, IdfxReduceFn fn, void *user) {
+  dropCycleGraph(b);
   b->reduceFn = fn;
   b->reduceData = user;
   return 0;
 }
 int idfx_enroll_halo_exchange(IdfxBlock *b, IdfxHaloFn fn, void *user) {
+  dropCycleGraph(b);
   b->haloFn = fn;
   b->haloData = user;
   return 0;

@@ -155,6 +155,7 @@ class DataBlock {
   bool haveUserStepFirst{false}, haveUserStepLast{false};
   StepFunc userStepFirst{nullptr}, userStepLast{nullptr};
   IdfxBlock *handle{nullptr};   // the C-ABI block behind this DataBlock
+  cudaStream_t stream{nullptr};  // the stream the library's kernels run on
   // time-integrator options the device-side dt control needs
   int nstages{1};
   real cfl{0.0}, cflMaxVar{1.1}, firstDt{1e-10}, fixedDt{-1.0};
@@ -214,9 +215,12 @@ class DataBlock {
     d.ntracer = hydro->nTracer;
     IDFX_CUDA(cudaSetDevice(input.device));
     IDFX_ABI(idfx_block_create(&d, &handle));
-    // user kernels (idefix_for) run on the legacy default stream: put the library there too so that
-    // everything is ordered without explicit fences, like the reference's single execution space
-    IDFX_ABI(idfx_set_stream(handle, nullptr));
+    // user kernels (idefix_for) run on the legacy default stream.  The library gets a BLOCKING stream of its
+    // own: blocking streams synchronise implicitly with the legacy default stream, so everything stays ordered
+    // without explicit fences (like the reference's single execution space), and -- unlike the legacy stream --
+    // it can be captured, which lets idfx_cycles replay the steady-state cycle as a CUDA graph
+    IDFX_CUDA(cudaStreamCreate(&stream));
+    IDFX_ABI(idfx_set_stream(handle, stream));
     dt = firstDt;
     if (fixedDt > 0) dt = fixedDt;
 
@@ -246,6 +250,7 @@ class DataBlock {
   }
   ~DataBlock() {
     if (handle) idfx_block_destroy(handle);
+    if (stream) cudaStreamDestroy(stream);
   }
   DataBlock(const DataBlock &) = delete;
   DataBlock &operator=(const DataBlock &) = delete;
