@@ -154,3 +154,23 @@ def test_block_create_fails_loudly_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(_abi.IdefixError, match="no CPU fallback"):
         REGISTRY["sod"]()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU build from oracle/_ref, no GPU involved) prints one
+    JSON line with the keys the driver reads; skipped where the reference binary has not been built"""
+    import json
+    import subprocess
+    import sys
+    from oracle.ref_run import have
+    if not have("ot3d_plm"):
+        pytest.skip("oracle/_ref/ot3d_plm/idefix not built on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-block", "32",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "cell-updates/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"] == {"value": line["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("test/MHD/OrszagTang3D")
