@@ -21,7 +21,7 @@ class OracleDesc(C.Structure):
     _fields_ = [("ndim", C.c_int), ("ncomp", C.c_int), ("mhd", C.c_int), ("solver", C.c_int), ("emf", C.c_int),
                 ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
                 ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
-                ("dx", C.c_double * 3), ("ntracer", C.c_int)]
+                ("dx", C.c_double * 3), ("ntracer", C.c_int), ("order", C.c_int)]
 
 
 _lib = None
@@ -55,14 +55,15 @@ class Oracle:
     (n, k, j, i) like the reference's IdefixArray4D."""
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
-                 cfl_max_var=1.1, ntracer=0):
+                 cfl_max_var=1.1, ntracer=0, order=2):
         d = OracleDesc()
         d.ntracer = ntracer
+        d.order = order
         d.ndim, d.ncomp, d.mhd = ndim, ncomp, int(mhd)
         d.solver, d.emf, d.nstages = SOLVERS[solver], EMFS[emf or "uct_contact"], nstages
         for a in range(3):
             d.np_int[a] = np_int[a] if a < ndim else 1
-            d.nghost[a] = 2 if a < ndim else 0
+            d.nghost[a] = (3 if order == 4 else 2) if a < ndim else 0
             d.bc[a] = BCS[bc[a]] if a < ndim else 0
             d.dx[a] = dx[a]
         d.gamma, d.cfl, d.cfl_max_var, d.first_dt = gamma, cfl, cfl_max_var, first_dt
@@ -81,8 +82,8 @@ class Oracle:
     def from_setup(cls, setup):
         """same configuration as an idefix_b200.setups.Setup built with device=None (host only)"""
         defs, inp, grid = setup.definitions, setup.input, setup.grid
-        if defs.order != 2 or defs.isothermal or defs.geometry != 1:
-            raise ValueError("the C oracle restates PLM / adiabatic / cartesian only")
+        if defs.order not in (2, 3, 4) or defs.isothermal or defs.geometry != 1:
+            raise ValueError("the C oracle restates PLM / LimO3 / PPM, adiabatic, cartesian only")
         names = {1: "periodic", 3: "outflow"}
         nd = defs.dimensions
         emf = inp.Get(str, "Hydro", "emf", 0) if inp.CheckEntry("Hydro", "emf") >= 0 else "uct_contact"
@@ -90,7 +91,8 @@ class Oracle:
         o = cls(nd, defs.components, defs.mhd, inp.Get(str, "Hydro", "solver", 0), emf,
                 inp.Get(int, "TimeIntegrator", "nstages", 0), grid.np_int, [names[grid.lbound[a]] for a in range(nd)],
                 setup.data.hydro.gamma, inp.Get(float, "TimeIntegrator", "CFL", 0), first_dt,
-                [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer)
+                [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer,
+                order=defs.order)
         return o
 
     def set_state(self, Vc, Vs=None):

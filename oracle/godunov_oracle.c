@@ -8,10 +8,11 @@
  * dumps written by the reference's own CPU build (tests/test_oracle.py).
  *
  * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions, adiabatic EOS,
- * PLM (van Leer) reconstruction, HD solvers TVDLF / HLL / HLLC, MHD solvers HLL / HLLD,
- * constrained transport with arithmetic / uct_contact / uct_hll / uct_hlld averaging, periodic and
- * outflow boundaries (outflow + MHD only in 1-D), RK1/2/3, CFL time-step control.
- * LimO3 / PPM / Roe / curvilinear geometry are pinned through the reference binaries and golden
+ * PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC, MHD solvers HLL / HLLD,
+ * constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld averaging (PPM corner
+ * states when ORDER is 4), passive tracers, periodic and outflow boundaries (outflow + MHD only in
+ * 1-D), RK1/2/3, CFL time-step control.
+ * Roe, isothermal EOS and curvilinear geometry are pinned through the reference binaries and golden
  * dumps only (tests/golden).
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
@@ -33,6 +34,7 @@ typedef struct {
   double gamma, cfl, cfl_max_var, first_dt;
   double dx[3];              /* uniform spacing */
   int ntracer;               /* passive tracers behind the fluid variables, fluid.hpp:315-323 */
+  int order;                 /* Idefix_RECONSTRUCTION: 2 PLM (van Leer), 3 LimO3, 4 PPM (0 is read as 2) */
 } OracleDesc;
 
 typedef struct {
@@ -201,6 +203,121 @@ static double mc_lim(double dvp, double dvm) {
 }
 
 /* transverse / bi-tangential component indices of a sweep, src/fluid/RiemannSolver/MHDsolvers/hlldMHD.hpp:60-145 */
+/* slopeLimiter.hpp:16-23 -- MinModLim shadows its result and always returns 0 */
+static double minmod_ref(double dvp, double dvm) { (void)dvp; (void)dvm; return 0.0; }
+
+/* slopeLimiter.hpp:25-52 */
+static double lim_o3(double dvp, double dvm, double dx) {
+  const double r = 0.1, eps = 1.e-12;
+  const double th = dvm / (dvp + 1.e-16);
+  const double q = (2.0 + th) / 3.0;
+  double a = fmin(1.5, 2.0 * th);
+  a = fmin(q, a);
+  const double b = fmax(-0.5 * th, a);
+  const double c = fmin(q, b);
+  double psi = fmax(0.0, c);
+  double eta = r * dx;
+  eta = (dvm * dvm + dvp * dvp) / (eta * eta);
+  if (eta <= 1.0 - eps) return q;
+  if (eta >= 1.0 + eps) return psi;
+  psi = (1.0 - (eta - 1.0) / eps) * q + (1.0 + (eta - 1.0) / eps) * psi;
+  return 0.5 * psi;
+}
+
+static int sgn_i(double v) { return (0.0 < v) - (v < 0.0); }
+
+/* slopeLimiter.hpp:121-140 */
+static void ppm_limit_face(double vm1, double v0, double vp1, double vp2, double *vph) {
+  if ((vp1 - *vph) * (*vph - v0) < 0.0) {
+    const double deltaL = (vm1 - 2 * v0 + vp1);
+    const double deltaC = 3 * (v0 - 2 * (*vph) + vp1);
+    const double deltaR = (v0 - 2 * vp1 + vp2);
+    double delta = 0.0;
+    if (sgn_i(deltaL) == sgn_i(deltaC) && sgn_i(deltaR) == sgn_i(deltaC)) {
+      const double C = 1.25;
+      delta = C * fmin(fabs(deltaL), fabs(deltaR));
+      delta = sgn_i(deltaC) * fmin(delta, fabs(deltaC));
+    }
+    *vph = 0.5 * (v0 + vp1) - delta / 6.0;
+  }
+}
+
+/* slopeLimiter.hpp:142-190: limited parabola of cell "0"; vl / vr = its left / right face values */
+static void ppm_states(double vm2, double vm1, double v0, double vp1, double vp2, double *vlo, double *vro) {
+  const int n = 2;
+  double vr = 7.0 / 12.0 * (v0 + vp1) - 1.0 / 12.0 * (vm1 + vp2);
+  double vl = 7.0 / 12.0 * (vm1 + v0) - 1.0 / 12.0 * (vm2 + vp1);
+  ppm_limit_face(vm2, vm1, v0, vp1, &vl);
+  ppm_limit_face(vm1, v0, vp1, vp2, &vr);
+  const double d2qf = 6.0 * (vl + vr - 2.0 * v0);
+  const double d2qc0 = vm1 + vp1 - 2.0 * v0;
+  const double d2qcp1 = v0 + vp2 - 2.0 * vp1;
+  const double d2qcm1 = vm2 + v0 - 2.0 * vm1;
+  double d2q = 0.0;
+  if (sgn_i(d2qf) == sgn_i(d2qc0) && sgn_i(d2qf) == sgn_i(d2qcp1) && sgn_i(d2qf) == sgn_i(d2qcm1)) {
+    const double C = 1.25;
+    d2q = fmin(fabs(d2qc0), fabs(d2qcp1));
+    d2q = C * fmin(fabs(d2qcm1), d2q);
+    d2q = sgn_i(d2qf) * fmin(fabs(d2qf), d2q);
+  }
+  const double qmax = fmax(fmax(fabs(vm1), fabs(v0)), fabs(vp1));
+  double rho = 0.0;
+  if (fabs(d2qf) > 1e-12 * qmax) rho = d2q / d2qf;
+  if (((vr - v0) * (v0 - vl) <= 0) || (vm1 - v0) * (v0 - vp1) <= 0) {
+    if (rho <= (1.0 - 1e-12)) {
+      vl = v0 - rho * (v0 - vl);
+      vr = v0 + rho * (vr - v0);
+    }
+  } else {
+    if (fabs(vr - v0) >= n * fabs(v0 - vl)) vr = v0 + n * (v0 - vl);
+    if (fabs(vl - v0) >= n * fabs(v0 - vr)) vl = v0 + n * (v0 - vr);
+  }
+  *vlo = vl;
+  *vro = vr;
+}
+
+/* ExtrapolatePrimVar on a regular grid (extrapolateToFaces.hpp:89-124 PLM, :173-246 LimO3, :247-307 PPM):
+ * q points at cell i of the variable, s = stride along the sweep; interface i-1/2 gets vL from cell i-1
+ * and vR from cell i.  positive = RHO or PRS (face values that must stay positive). */
+static void reconstruct_interface(int order, const double *q, long s, int positive, double dx, double *vL,
+                                  double *vR) {
+  if (order == 3) {
+    double dvm = q[-s] - q[-2 * s];
+    double dvp = q[0] - q[-s];
+    double dv = dvp * lim_o3(dvp, dvm, dx);
+    *vL = q[-s] + 0.5 * dv;
+    if (positive && *vL <= 0.0) {
+      dv = minmod_ref(dvp, dvm);
+      *vL = q[-s] + 0.5 * dv;
+    }
+    dvm = dvp;
+    dvp = q[s] - q[0];
+    dv = dvm * lim_o3(dvm, dvp, dx);
+    *vR = q[0] - 0.5 * dv;
+    if (positive && *vR <= 0.0) {
+      dv = minmod_ref(dvp, dvm);
+      *vR = q[0] - 0.5 * dv;
+    }
+  } else if (order == 4) {
+    double vl, vr;
+    ppm_states(q[-3 * s], q[-2 * s], q[-s], q[0], q[s], &vl, &vr); /* cell i-1 */
+    if (positive && vr <= 0.0) vr = q[-s] + 0.5 * van_leer(q[0] - q[-s], q[-s] - q[-2 * s]);
+    *vL = vr;
+    ppm_states(q[-2 * s], q[-s], q[0], q[s], q[2 * s], &vl, &vr);  /* cell i */
+    if (positive && vl <= 0.0) vl = q[0] - 0.5 * van_leer(q[s] - q[0], q[0] - q[-s]);
+    *vR = vl;
+  } else {
+    double dvm = q[-s] - q[-2 * s];
+    double dvp = q[0] - q[-s];
+    double dv = van_leer(dvp, dvm);
+    *vL = q[-s] + 0.5 * dv;
+    dvm = dvp;
+    dvp = q[s] - q[0];
+    dv = van_leer(dvp, dvm);
+    *vR = q[0] - 0.5 * dv;
+  }
+}
+
 static int tdir(int dir) { return dir == 0 ? 1 : 0; }
 static int bdir(int dir) { return dir == 2 ? 1 : 2; }
 
@@ -537,17 +654,9 @@ static void calc_flux(Oracle *o, int dir) {
       for (int i = lo[0]; i < hi[0]; i++) {
         const long c = C(o, k, j, i);
         double vL[8], vR[8], F[8];
-        for (int n = 0; n < nv; n++) {
-          const double *q = o->Vc + n * o->sn + c;
-          double dvm = q[-s] - q[-2 * s];
-          double dvp = q[0] - q[-s];
-          double dv = van_leer(dvp, dvm);
-          vL[n] = q[-s] + 0.5 * dv;
-          dvm = dvp;
-          dvp = q[s] - q[0];
-          dv = van_leer(dvp, dvm);
-          vR[n] = q[0] - 0.5 * dv;
-        }
+        for (int n = 0; n < nv; n++)
+          reconstruct_interface(d->order, o->Vc + n * o->sn + c, s, n == o->RHO || n == o->ENG, d->dx[dir], &vL[n],
+                                &vR[n]);
         Speeds sp = {0, 0, 0};
         if (d->mhd) {
           vL[o->BX1 + dir] = vR[o->BX1 + dir] = o->Vs[dir * o->vn + S(o, k, j, i)];
@@ -663,8 +772,15 @@ static void cell_centered_emf(Oracle *o) {
 }
 
 /* transverse MC reconstruction towards a corner, calcRiemannEmf.hpp:95-126 */
+static int g_corner_ppm = 0; /* ORDER == 4: the corner states use the PPM reconstruction (calcRiemannEmf.hpp:80-93) */
 static void corner_states(const double *q, long p, long s, double *qL, double *qR) {
   const long pm = p - s;
+  if (g_corner_ppm) {
+    double dummy;
+    ppm_states(q[pm - 2 * s], q[pm - s], q[pm], q[pm + s], q[pm + 2 * s], &dummy, qL);
+    ppm_states(q[p - 2 * s], q[p - s], q[p], q[p + s], q[p + 2 * s], qR, &dummy);
+    return;
+  }
   double dq = mc_lim(q[pm + s] - q[pm], q[pm] - q[pm - s]);
   *qL = q[pm] + 0.5 * dq;
   dq = mc_lim(q[p + s] - q[p], q[p] - q[p - s]);
@@ -686,6 +802,7 @@ static double riemann_contribution(const Oracle *o, int a, long c, long sa, cons
 
 /* CalcCornerEMF dispatcher, calcCornerEmf.hpp:15-38 */
 static void corner_emf(Oracle *o) {
+  g_corner_ppm = (o->d.order == 4);
   const int nd = o->d.ndim, mode = o->d.emf;
   const long sj = o->sj, sk = o->sk;
   int lo[3], hi[3];

@@ -19,7 +19,7 @@ ORACLE_SOLVERS = {"tvdlf", "hll", "hllc", "hlld"}
 def in_scope(case):
     solver = case.overrides.get(("Hydro", "solver"))
     emf = case.overrides.get(("Hydro", "emf"))
-    if case.order != 2 or solver not in ORACLE_SOLVERS:
+    if case.order not in (2, 3, 4) or solver not in ORACLE_SOLVERS:
         return False
     if case.setup in ("ot2d", "ot3d", "linearwave", "mhdsod") and solver == "tvdlf":
         return False   # TVDLF-MHD is not restated
