@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libgodunov_oracle.so")
 
-SOLVERS = {"tvdlf": 0, "hll": 1, "hllc": 2, "hlld": 3}
+SOLVERS = {"tvdlf": 0, "hll": 1, "hllc": 2, "hlld": 3, "roe": 4}
 EMFS = {"arithmetic": 0, "uct0": 1, "uct_contact": 2, "uct_hll": 3, "uct_hlld": 4}
 BCS = {"periodic": 1, "outflow": 3}
 

@@ -8,11 +8,11 @@
  * dumps written by the reference's own CPU build (tests/test_oracle.py).
  *
  * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions, adiabatic EOS,
- * PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC, MHD solvers HLL / HLLD,
+ * PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC, MHD solvers HLL / HLLD / Roe,
  * constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld averaging (PPM corner
  * states when ORDER is 4), passive tracers, periodic and outflow boundaries (outflow + MHD only in
  * 1-D), RK1/2/3, CFL time-step control.
- * Roe, isothermal EOS and curvilinear geometry are pinned through the reference binaries and golden
+ * TVDLF-MHD, the isothermal EOS and curvilinear geometry are pinned through the reference binaries and golden
  * dumps only (tests/golden).
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
@@ -23,7 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-enum { TVDLF = 0, HLL = 1, HLLC = 2, HLLD = 3 };
+enum { TVDLF = 0, HLL = 1, HLLC = 2, HLLD = 3, ROE = 4 };
 enum { EMF_ARITHMETIC = 0, EMF_UCT0 = 1, EMF_UCT_CONTACT = 2, EMF_UCT_HLL = 3, EMF_UCT_HLLD = 4 };
 enum { BC_PERIODIC = 1, BC_OUTFLOW = 3 };
 
@@ -402,6 +402,229 @@ static void riemann_hd(const Oracle *o, int dir, const double *vL, const double 
   }
 }
 
+/* ---- RoeMHD<DIR>, adiabatic: roeMHD.hpp:180-654 (Cargo & Gallice eigenvectors, entropy fix delta = 1e-6).
+ * Modes in the reference's order: fast-, fast+, divB, entropy, slow-, slow+, Alfven-, Alfven+. ------------- */
+static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const double *vR, double *F, Speeds *sp) {
+  enum { KFASTM = 0, KFASTP = 1, KDIVB = 2, KENTRP = 3, KSLOWM = 4, KSLOWP = 5, KALFVM = 6, KALFVP = 7 };
+  const int NV = o->nvar, nc = o->d.ncomp, RHO = o->RHO, ENG = o->ENG, PRS = o->ENG;
+  const int Xn = o->MX1 + dir, Xt = o->MX1 + tdir(dir), Xb = o->MX1 + bdir(dir);
+  const int BXn = o->BX1 + dir, BXt = o->BX1 + tdir(dir), BXb = o->BX1 + bdir(dir);
+  const double delta = 1.e-6, gamma = o->d.gamma;
+  double dV[8], uL[8], uR[8], dU[8], fL[8], fR[8], Rc[8][8];
+  for (int n = 0; n < NV; n++) dV[n] = vR[n] - vL[n];
+  prim_to_cons(o, vL, uL);
+  prim_to_cons(o, vR, uR);
+  for (int n = 0; n < NV; n++) dU[n] = uR[n] - uL[n];
+  phys_flux(o, dir, vL, uL, fL);
+  phys_flux(o, dir, vR, uR, fR);
+  for (int a = 0; a < 8; a++)
+    for (int b = 0; b < 8; b++) Rc[a][b] = 0;
+
+  /* Roe averages, roeMHD.hpp:258-300 */
+  const double sqr_rho_L = sqrt(vL[RHO]), sqr_rho_R = sqrt(vR[RHO]);
+  const double sl = sqr_rho_L / (sqr_rho_L + sqr_rho_R);
+  const double sr = sqr_rho_R / (sqr_rho_L + sqr_rho_R);
+  const double rho = sr * vL[RHO] + sl * vR[RHO];
+  const double sqrt_rho = sqrt(rho);
+  double u = 0, v = 0, w = 0, Bx = 0, By = 0, Bz = 0, bx = 0, by = 0, bz = 0;
+  u = sl * vL[Xn] + sr * vR[Xn];
+  if (nc >= 2) v = sl * vL[Xt] + sr * vR[Xt];
+  if (nc == 3) w = sl * vL[Xb] + sr * vR[Xb];
+  Bx = sr * vL[BXn] + sl * vR[BXn];
+  if (nc >= 2) By = sr * vL[BXt] + sl * vR[BXt];
+  if (nc == 3) Bz = sr * vL[BXb] + sl * vR[BXb];
+  const double sBx = (Bx >= 0.0 ? 1.0 : -1.0);
+  bx = Bx / sqrt_rho;
+  if (nc >= 2) by = By / sqrt_rho;
+  if (nc == 3) bz = Bz / sqrt_rho;
+  double bt2 = 0.0;
+  if (nc >= 2) bt2 = bt2 + by * by;
+  if (nc == 3) bt2 = bt2 + bz * bz;
+  const double b2 = bx * bx + bt2;
+  const double Btmag = sqrt(bt2 * rho);
+  double X = dV[BXn] * dV[BXn];
+  if (nc >= 2) X = X + dV[BXt] * dV[BXt];
+  if (nc == 3) X = X + dV[BXb] * dV[BXb];
+  X /= (sqr_rho_L + sqr_rho_R) * (sqr_rho_L + sqr_rho_R) * 2.0;
+  double Bmag2L = vL[o->BX1] * vL[o->BX1], Bmag2R = vR[o->BX1] * vR[o->BX1];
+  for (int c = 1; c < nc; c++) {
+    Bmag2L = Bmag2L + vL[o->BX1 + c] * vL[o->BX1 + c];
+    Bmag2R = Bmag2R + vR[o->BX1 + c] * vR[o->BX1 + c];
+  }
+  const double pL = vL[PRS] + 0.5 * Bmag2L, pR = vR[PRS] + 0.5 * Bmag2R;
+  double vdm = u * dU[Xn];
+  if (nc >= 2) vdm = vdm + v * dU[Xt];
+  if (nc == 3) vdm = vdm + w * dU[Xb];
+  double BdB = Bx * dU[BXn];
+  if (nc >= 2) BdB = BdB + By * dU[BXt];
+  if (nc == 3) BdB = BdB + Bz * dU[BXb];
+  double vel2 = u * u;
+  if (nc >= 2) vel2 = vel2 + v * v;
+  if (nc == 3) vel2 = vel2 + w * w;
+  dV[PRS] = (gamma - 1.0) * ((0.5 * vel2 - X) * dV[RHO] - vdm + dU[ENG] - BdB);
+  const double HL = (uL[ENG] + pL) / vL[RHO], HR = (uR[ENG] + pR) / vR[RHO];
+  const double H = sl * HL + sr * HR;
+  const double Hgas = H - b2;
+  const double a2 = (2.0 - gamma) * X + (gamma - 1.0) * (Hgas - 0.5 * vel2);
+
+  /* characteristic speeds, roeMHD.hpp:336-371 */
+  double scrh = a2 - b2;
+  const double ca2 = bx * bx;
+  scrh = scrh * scrh + 4.0 * bt2 * a2;
+  scrh = sqrt(scrh);
+  const double cf2 = 0.5 * (a2 + b2 + scrh);
+  const double cs2 = a2 * ca2 / cf2;
+  const double cf = sqrt(cf2), cs = sqrt(cs2), ca = sqrt(ca2), a = sqrt(a2);
+  double alpha_f, alpha_s;
+  if (cf == cs) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else if (a <= cs) {
+    alpha_f = 0.0;
+    alpha_s = 1.0;
+  } else if (cf <= a) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else {
+    scrh = 1.0 / (cf2 - cs2);
+    alpha_f = (a2 - cs2) * scrh;
+    alpha_s = (cf2 - a2) * scrh;
+    alpha_f = fmax(0.0, alpha_f);
+    alpha_s = fmax(0.0, alpha_s);
+    alpha_f = sqrt(alpha_f);
+    alpha_s = sqrt(alpha_s);
+  }
+  double beta_y = 0, beta_z = 0;
+  if (Btmag > 1.e-9) {
+    if (nc == 2) beta_y = (By >= 0.0 ? 1.0 : -1.0);
+    if (nc == 3) {
+      beta_y = By / Btmag;
+      beta_z = Bz / Btmag;
+    }
+  } else {
+    if (nc == 2) beta_y = 1.0;
+    if (nc == 3) beta_z = beta_y = 1.0;
+  }
+
+  double lambda[8], alambda[8], eta[8];
+  for (int n = 0; n < 8; n++) lambda[n] = eta[n] = 0.0;
+  double beta_dv = 0.0, beta_dB = 0.0, beta_v = 0.0;
+  int kk = KFASTM; /* fast wave u - cf */
+  lambda[kk] = u - cf;
+  scrh = alpha_s * cs * sBx;
+  if (nc >= 2) {
+    beta_dv = beta_dv + beta_y * dV[Xt];
+    beta_dB = beta_dB + beta_y * dV[BXt];
+  }
+  if (nc == 3) {
+    beta_dv = beta_dv + beta_z * dV[Xb];
+    beta_dB = beta_dB + beta_z * dV[BXb];
+  }
+  Rc[RHO][kk] = alpha_f;
+  Rc[Xn][kk] = alpha_f * lambda[kk];
+  if (nc >= 2) Rc[Xt][kk] = alpha_f * v + scrh * beta_y;
+  if (nc == 3) Rc[Xb][kk] = alpha_f * w + scrh * beta_z;
+  if (nc >= 2) Rc[BXt][kk] = alpha_s * a * beta_y / sqrt_rho;
+  if (nc == 3) Rc[BXb][kk] = alpha_s * a * beta_z / sqrt_rho;
+  if (nc >= 2) beta_v = beta_v + beta_y * v;
+  if (nc == 3) beta_v = beta_v + beta_z * w;
+  Rc[ENG][kk] = alpha_f * (Hgas - u * cf) + scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
+  eta[kk] = alpha_f * (X * dV[RHO] + dV[PRS]);
+  eta[kk] += rho * scrh * beta_dv - rho * alpha_f * cf * dV[Xn] + sqrt_rho * alpha_s * a * beta_dB;
+  eta[kk] *= 0.5 / a2;
+
+  kk = KFASTP; /* fast wave u + cf */
+  lambda[kk] = u + cf;
+  Rc[RHO][kk] = alpha_f;
+  Rc[Xn][kk] = alpha_f * lambda[kk];
+  if (nc >= 2) Rc[Xt][kk] = alpha_f * v - scrh * beta_y;
+  if (nc == 3) Rc[Xb][kk] = alpha_f * w - scrh * beta_z;
+  if (nc >= 2) Rc[BXt][kk] = Rc[BXt][KFASTM];
+  if (nc == 3) Rc[BXb][kk] = Rc[BXb][KFASTM];
+  Rc[ENG][kk] = alpha_f * (Hgas + u * cf) - scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
+  eta[kk] = alpha_f * (X * dV[RHO] + dV[PRS]) - rho * scrh * beta_dv + rho * alpha_f * cf * dV[Xn] +
+            sqrt_rho * alpha_s * a * beta_dB;
+  eta[kk] *= 0.5 / a2;
+
+  kk = KENTRP; /* entropy wave */
+  lambda[kk] = u;
+  Rc[RHO][kk] = 1.0;
+  Rc[Xn][kk] = u;
+  if (nc >= 2) Rc[Xt][kk] = v;
+  if (nc == 3) Rc[Xb][kk] = w;
+  Rc[ENG][kk] = 0.5 * vel2 + (gamma - 2.0) / (gamma - 1.0) * X;
+  eta[kk] = ((a2 - X) * dV[RHO] - dV[PRS]) / a2;
+
+  kk = KDIVB; /* div B wave: no jump with constrained transport */
+  lambda[kk] = u;
+  eta[kk] = 0.0;
+
+  if (nc > 1) {
+    scrh = alpha_f * cf * sBx;
+    kk = KSLOWM; /* slow wave u - cs */
+    lambda[kk] = u - cs;
+    Rc[RHO][kk] = alpha_s;
+    Rc[Xn][kk] = alpha_s * lambda[kk];
+    if (nc >= 2) Rc[Xt][kk] = alpha_s * v - scrh * beta_y;
+    if (nc == 3) Rc[Xb][kk] = alpha_s * w - scrh * beta_z;
+    if (nc >= 2) Rc[BXt][kk] = -alpha_f * a * beta_y / sqrt_rho;
+    if (nc == 3) Rc[BXb][kk] = -alpha_f * a * beta_z / sqrt_rho;
+    Rc[ENG][kk] = alpha_s * (Hgas - u * cs) - scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
+    eta[kk] = alpha_s * (X * dV[RHO] + dV[PRS]) - rho * scrh * beta_dv - rho * alpha_s * cs * dV[Xn] -
+              sqrt_rho * alpha_f * a * beta_dB;
+    eta[kk] *= 0.5 / a2;
+
+    kk = KSLOWP; /* slow wave u + cs */
+    lambda[kk] = u + cs;
+    Rc[RHO][kk] = alpha_s;
+    Rc[Xn][kk] = alpha_s * lambda[kk];
+    if (nc >= 2) Rc[Xt][kk] = alpha_s * v + scrh * beta_y;
+    if (nc == 3) Rc[Xb][kk] = alpha_s * w + scrh * beta_z;
+    if (nc >= 2) Rc[BXt][kk] = Rc[BXt][KSLOWM];
+    if (nc == 3) Rc[BXb][kk] = Rc[BXb][KSLOWM];
+    Rc[ENG][kk] = alpha_s * (Hgas + u * cs) + scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
+    eta[kk] = alpha_s * (X * dV[RHO] + dV[PRS]) + rho * scrh * beta_dv + rho * alpha_s * cs * dV[Xn] -
+              sqrt_rho * alpha_f * a * beta_dB;
+    eta[kk] *= 0.5 / a2;
+  }
+  if (nc == 3) {
+    kk = KALFVM; /* Alfven wave u - ca */
+    lambda[kk] = u - ca;
+    Rc[Xt][kk] = -rho * beta_z;
+    Rc[Xb][kk] = +rho * beta_y;
+    Rc[BXt][kk] = -sBx * sqrt_rho * beta_z;
+    Rc[BXb][kk] = sBx * sqrt_rho * beta_y;
+    Rc[ENG][kk] = -rho * (v * beta_z - w * beta_y);
+    eta[kk] = +beta_y * dV[Xb] - beta_z * dV[Xt] + sBx / sqrt_rho * (beta_y * dV[BXb] - beta_z * dV[BXt]);
+    eta[kk] *= 0.5;
+    kk = KALFVP; /* Alfven wave u + ca */
+    lambda[kk] = u + ca;
+    Rc[Xt][kk] = -Rc[Xt][KALFVM];
+    Rc[Xb][kk] = -Rc[Xb][KALFVM];
+    Rc[BXt][kk] = Rc[BXt][KALFVM];
+    Rc[BXb][kk] = Rc[BXb][KALFVM];
+    Rc[ENG][kk] = -Rc[ENG][KALFVM];
+    eta[kk] = -beta_y * dV[Xb] + beta_z * dV[Xt] + sBx / sqrt_rho * (beta_y * dV[BXb] - beta_z * dV[BXt]);
+    eta[kk] *= 0.5;
+  }
+  sp->cmax = fabs(u) + cf;
+  sp->sl = lambda[KFASTM];
+  sp->sr = lambda[KFASTP];
+  for (int n = 0; n < NV; n++) alambda[n] = fabs(lambda[n]);
+  /* entropy fix, roeMHD.hpp:606-623 */
+  if (alambda[KFASTM] < 0.5 * delta) alambda[KFASTM] = lambda[KFASTM] * lambda[KFASTM] / delta + 0.25 * delta;
+  if (alambda[KFASTP] < 0.5 * delta) alambda[KFASTP] = lambda[KFASTP] * lambda[KFASTP] / delta + 0.25 * delta;
+  if (nc > 1) {
+    if (alambda[KSLOWM] < 0.5 * delta) alambda[KSLOWM] = lambda[KSLOWM] * lambda[KSLOWM] / delta + 0.25 * delta;
+    if (alambda[KSLOWP] < 0.5 * delta) alambda[KSLOWP] = lambda[KSLOWP] * lambda[KSLOWP] / delta + 0.25 * delta;
+  }
+  for (int n1 = 0; n1 < NV; n1++) {
+    double acc = 0.0;
+    for (int n2 = 0; n2 < NV; n2++) acc += alambda[n2] * eta[n2] * Rc[n1][n2];
+    F[n1] = 0.5 * (fL[n1] + fR[n1] - acc);
+  }
+}
+
 /* ---- MHD solvers: MHDsolvers/hllMHD.hpp:155-445 (no Hall), hlldMHD.hpp:147-457 ---------------- */
 static void riemann_mhd(const Oracle *o, int dir, const double *vL, const double *vR, double *F, Speeds *sp) {
   const int nv = o->nvar, nc = o->d.ncomp, RHO = o->RHO, ENG = o->ENG;
@@ -642,6 +865,7 @@ static void calc_flux(Oracle *o, int dir) {
   /* perpendicular extension of the face box: 0 for HD; 1 or nghost for MHD (hlldMHD.hpp:32-49) */
   int ext = 0;
   if (d->mhd) ext = (d->emf == EMF_UCT_HLL || d->emf == EMF_UCT_HLLD) ? d->nghost[dir] : 1;
+  if (d->mhd && d->solver == ROE) ext = 1; /* hard-coded in roeMHD.hpp:63-73 */
   int lo[3], hi[3];
   for (int a = 0; a < 3; a++) {
     const int e = (a < d->ndim && a != dir) ? ext : 0;
@@ -660,7 +884,8 @@ static void calc_flux(Oracle *o, int dir) {
         Speeds sp = {0, 0, 0};
         if (d->mhd) {
           vL[o->BX1 + dir] = vR[o->BX1 + dir] = o->Vs[dir * o->vn + S(o, k, j, i)];
-          riemann_mhd(o, dir, vL, vR, F, &sp);
+          if (d->solver == ROE) riemann_roe_mhd(o, dir, vL, vR, F, &sp);
+          else riemann_mhd(o, dir, vL, vR, F, &sp);
           store_emf(o, dir, c, F, &sp, vL, vR);
         } else {
           riemann_hd(o, dir, vL, vR, F, &sp);

@@ -13,7 +13,7 @@ from idefix_b200.setups import REGISTRY
 from oracle.godunov import Oracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ORACLE_SOLVERS = {"tvdlf", "hll", "hllc", "hlld"}
+ORACLE_SOLVERS = {"tvdlf", "hll", "hllc", "hlld", "roe"}
 
 
 def in_scope(case):
