@@ -146,6 +146,50 @@ def test_c_abi_exports_every_declared_symbol():
     _abi.lib()
 
 
+def test_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
+    """include/idefix_b200.h compiles as C11 with gcc (no C++ / CUDA / torch types at the boundary) and the
+    layout of IdfxBlockDesc and the enum values equal what idefix_b200/_abi.py hands to the library"""
+    import ctypes as C
+    fields = [name for name, _ in _abi.IdfxBlockDesc._fields_]
+    enums = {"IDFX_CARTESIAN": _abi.CARTESIAN, "IDFX_CYLINDRICAL": _abi.CYLINDRICAL, "IDFX_POLAR": _abi.POLAR,
+             "IDFX_SPHERICAL": _abi.SPHERICAL, "IDFX_TVDLF": _abi.TVDLF, "IDFX_HLL": _abi.HLL, "IDFX_HLLC": _abi.HLLC,
+             "IDFX_HLLD": _abi.HLLD, "IDFX_ROE": _abi.ROE, "IDFX_EMF_ARITHMETIC": _abi.EMF_ARITHMETIC,
+             "IDFX_EMF_UCT0": _abi.EMF_UCT0, "IDFX_EMF_UCT_CONTACT": _abi.EMF_UCT_CONTACT,
+             "IDFX_EMF_UCT_HLL": _abi.EMF_UCT_HLL, "IDFX_EMF_UCT_HLLD": _abi.EMF_UCT_HLLD,
+             "IDFX_BC_INTERNAL": _abi.BC_INTERNAL, "IDFX_BC_PERIODIC": _abi.BC_PERIODIC,
+             "IDFX_BC_REFLECTIVE": _abi.BC_REFLECTIVE, "IDFX_BC_OUTFLOW": _abi.BC_OUTFLOW,
+             "IDFX_BC_SHEARINGBOX": _abi.BC_SHEARINGBOX, "IDFX_BC_AXIS": _abi.BC_AXIS,
+             "IDFX_BC_USERDEF": _abi.BC_USERDEF, "IDFX_BC_UNDEFINED": _abi.BC_UNDEFINED,
+             "IDFX_FIELD_VC": _abi.FIELD_VC, "IDFX_FIELD_UC": _abi.FIELD_UC, "IDFX_FIELD_VS": _abi.FIELD_VS,
+             "IDFX_FIELD_INVDT": _abi.FIELD_INVDT, "IDFX_FIELD_EX": _abi.FIELD_EX, "IDFX_FIELD_EY": _abi.FIELD_EY,
+             "IDFX_FIELD_EZ": _abi.FIELD_EZ, "IDFX_FIELD_UC0": _abi.FIELD_UC0, "IDFX_FIELD_VS0": _abi.FIELD_VS0,
+             "IDFX_REDUCE_MIN": _abi.REDUCE_MIN, "IDFX_REDUCE_MAX": _abi.REDUCE_MAX}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "idefix_b200.h"', 'int main(void) {',
+           '  printf("sizeof %zu\\n", sizeof(IdfxBlockDesc));']
+    src += [f'  printf("{f} %zu %zu\\n", offsetof(IdfxBlockDesc, {f}), sizeof(((IdfxBlockDesc *)0)->{f}));' for f in fields]
+    src += [f'  printf("{e} %d\\n", (int){e});' for e in enums]
+    src += ['  return 0;', '}']
+    cfile = tmp_path / "layout.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(cfile), "-o", str(exe)], check=True, capture_output=True, text=True)
+    got = dict((ln.split()[0], [int(v) for v in ln.split()[1:]])
+               for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert got.pop("sizeof") == [C.sizeof(_abi.IdfxBlockDesc)]
+    for f in fields:
+        fd = getattr(_abi.IdfxBlockDesc, f)
+        assert got.pop(f) == [fd.offset, fd.size], f
+    for e, v in enums.items():
+        assert got.pop(e) == [v], e
+    assert not got
+    # no field of the header's struct is missing from the mirror
+    body = re.search(r"typedef struct IdfxBlockDesc \{(.*?)\} IdfxBlockDesc;", open(os.path.join(ROOT, "include", "idefix_b200.h")).read(), re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = re.findall(r"\b\*?(\w+)(?:\[\d+\])?\s*;", body)
+    assert declared == fields
+
+
 def test_block_create_fails_loudly_without_gpu():
     import ctypes as C
     n = C.c_int(0)
