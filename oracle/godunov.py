@@ -21,7 +21,8 @@ class OracleDesc(C.Structure):
     _fields_ = [("ndim", C.c_int), ("ncomp", C.c_int), ("mhd", C.c_int), ("solver", C.c_int), ("emf", C.c_int),
                 ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
                 ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
-                ("dx", C.c_double * 3), ("ntracer", C.c_int), ("order", C.c_int)]
+                ("dx", C.c_double * 3), ("ntracer", C.c_int), ("order", C.c_int), ("isothermal", C.c_int),
+                ("csiso", C.c_double)]
 
 
 _lib = None
@@ -55,8 +56,13 @@ class Oracle:
     (n, k, j, i) like the reference's IdefixArray4D."""
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
-                 cfl_max_var=1.1, ntracer=0, order=2):
+                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None):
+        if csiso is not None and (solver == "roe" or (mhd and (solver == "tvdlf" or emf == "uct_hlld"))):
+            raise ValueError("isothermal: the oracle restates TVDLF / HLL / HLLC (HD) and HLL / HLLD (MHD) only, "
+                             "and not the uct_hlld average (no reference run pins it)")
         d = OracleDesc()
+        d.isothermal = int(csiso is not None)
+        d.csiso = csiso or 0.0
         d.ntracer = ntracer
         d.order = order
         d.ndim, d.ncomp, d.mhd = ndim, ncomp, int(mhd)
@@ -82,8 +88,8 @@ class Oracle:
     def from_setup(cls, setup):
         """same configuration as an idefix_b200.setups.Setup built with device=None (host only)"""
         defs, inp, grid = setup.definitions, setup.input, setup.grid
-        if defs.order not in (2, 3, 4) or defs.isothermal or defs.geometry != 1:
-            raise ValueError("the C oracle restates PLM / LimO3 / PPM, adiabatic, cartesian only")
+        if defs.order not in (2, 3, 4) or defs.geometry != 1:
+            raise ValueError("the C oracle restates PLM / LimO3 / PPM, cartesian only")
         names = {1: "periodic", 3: "outflow"}
         nd = defs.dimensions
         emf = inp.Get(str, "Hydro", "emf", 0) if inp.CheckEntry("Hydro", "emf") >= 0 else "uct_contact"
@@ -92,7 +98,7 @@ class Oracle:
                 inp.Get(int, "TimeIntegrator", "nstages", 0), grid.np_int, [names[grid.lbound[a]] for a in range(nd)],
                 setup.data.hydro.gamma, inp.Get(float, "TimeIntegrator", "CFL", 0), first_dt,
                 [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer,
-                order=defs.order)
+                order=defs.order, csiso=setup.data.hydro.csiso if defs.isothermal else None)
         return o
 
     def set_state(self, Vc, Vs=None):

@@ -7,13 +7,14 @@
  * structure of the CUDA kernels, and is pinned against the reference's golden dumps and against
  * dumps written by the reference's own CPU build (tests/test_oracle.py).
  *
- * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions, adiabatic EOS,
- * PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC, MHD solvers HLL / HLLD / Roe,
- * constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld averaging (PPM corner
- * states when ORDER is 4), passive tracers, periodic and outflow boundaries (outflow + MHD only in
- * 1-D), RK1/2/3, CFL time-step control.
- * TVDLF-MHD, the isothermal EOS and curvilinear geometry are pinned through the reference binaries and golden
- * dumps only (tests/golden).
+ * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions (and 2.5-D: more components
+ * than dimensions), adiabatic EOS, PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC,
+ * MHD solvers HLL / HLLD / Roe, constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld
+ * averaging (PPM corner states when ORDER is 4), passive tracers, periodic and outflow boundaries (with
+ * ReconstructNormalField on the outflow sides in MHD), RK1/2/3, CFL time-step control; and the isothermal
+ * EOS (constant sound speed) for HD TVDLF / HLL / HLLC and MHD HLL / HLLD.
+ * TVDLF-MHD, isothermal Roe and uct_hlld, and curvilinear geometry are pinned through the reference binaries
+ * and golden dumps only (tests/golden).
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
  * Compile with -O2 -ffp-contract=off: expression association follows the reference so results are
@@ -35,6 +36,8 @@ typedef struct {
   double dx[3];              /* uniform spacing */
   int ntracer;               /* passive tracers behind the fluid variables, fluid.hpp:315-323 */
   int order;                 /* Idefix_RECONSTRUCTION: 2 PLM (van Leer), 3 LimO3, 4 PPM (0 is read as 2) */
+  int isothermal;            /* ISOTHERMAL: no energy equation, p = csiso^2 rho (eos_isothermal, constant cs) */
+  double csiso;              /* [Hydro] csiso constant <value> */
 } OracleDesc;
 
 typedef struct {
@@ -42,7 +45,7 @@ typedef struct {
   int nx[3], beg[3], end[3], off[3];
   long sj, sk, sn;           /* cell-centred strides */
   long vj, vk, vn;           /* staggered strides    */
-  int nvar, RHO, MX1, ENG, BX1;
+  int nvar, RHO, MX1, ENG, BX1; /* ENG = -1 when isothermal */
   int ntr;                   /* Vc / Uc / Flux hold nvar + ntr variables */
   double *Vc, *Uc, *Uc0, *Vs, *Vs0, *Flux, *cMax, *InvDt;
   double *ex, *ey, *ez, *exj, *exk, *eyi, *eyk, *ezi, *ezj, *Ex1, *Ex2, *Ex3;
@@ -75,9 +78,9 @@ Oracle *oracle_create(const OracleDesc *d) {
   /* variable indices, src/idefix.hpp:74-94 */
   o->RHO = 0;
   o->MX1 = 1;
-  o->ENG = d->ncomp + 1;
-  o->BX1 = d->ncomp + 2;
-  o->nvar = 2 + d->ncomp + (d->mhd ? d->ncomp : 0);
+  o->ENG = d->isothermal ? -1 : d->ncomp + 1;
+  o->BX1 = d->ncomp + (d->isothermal ? 1 : 2);
+  o->nvar = (d->isothermal ? 1 : 2) + d->ncomp + (d->mhd ? d->ncomp : 0);
   long n = o->sn;
   o->ntr = d->ntracer;
   o->Vc = zalloc(n * (o->nvar + o->ntr));
@@ -133,10 +136,12 @@ static void prim_to_cons(const Oracle *o, const double *v, double *u) {
   for (int c = 1; c < nc; c++) v2 = v2 + v[MX1 + c] * v[MX1 + c];
   if (o->d.mhd) {
     for (int c = 0; c < nc; c++) u[BX1 + c] = v[BX1 + c];
+    if (o->d.isothermal) return;
     double b2 = u[BX1] * u[BX1];
     for (int c = 1; c < nc; c++) b2 = b2 + u[BX1 + c] * u[BX1 + c];
     u[ENG] = v[ENG] / (o->d.gamma - 1.0) + 0.5 * v[RHO] * v2 + 0.5 * b2;
   } else {
+    if (o->d.isothermal) return;
     u[ENG] = v[ENG] / (o->d.gamma - 1.0) + 0.5 * v[RHO] * v2;
   }
 }
@@ -145,6 +150,11 @@ static void cons_to_prim(const Oracle *o, double *u, double *v) {
   const int nc = o->d.ncomp, RHO = o->RHO, MX1 = o->MX1, ENG = o->ENG, BX1 = o->BX1;
   v[RHO] = u[RHO];
   for (int c = 0; c < nc; c++) v[MX1 + c] = u[MX1 + c] / u[RHO];
+  if (o->d.isothermal) { /* no pressure to recover, convertConsToPrim.hpp:28-66 */
+    if (o->d.mhd)
+      for (int c = 0; c < nc; c++) v[BX1 + c] = u[BX1 + c];
+    return;
+  }
   double m2 = u[MX1] * u[MX1];
   for (int c = 1; c < nc; c++) m2 = m2 + u[MX1 + c] * u[MX1 + c];
   const double kin = 0.5 / u[RHO] * m2;
@@ -165,7 +175,7 @@ static void cons_to_prim(const Oracle *o, double *u, double *v) {
 }
 
 /* K_Flux: src/fluid/RiemannSolver/flux.hpp:29-95 (f may alias u) */
-static void phys_flux(const Oracle *o, int dir, const double *v, const double *uin, double *f) {
+static void phys_flux(const Oracle *o, int dir, const double *v, const double *uin, double *f, double c2iso) {
   const int nc = o->d.ncomp, RHO = o->RHO, MX1 = o->MX1, ENG = o->ENG, BX1 = o->BX1;
   const int Xn = MX1 + dir, BXn = BX1 + dir;
   double u[16];
@@ -177,6 +187,11 @@ static void phys_flux(const Oracle *o, int dir, const double *v, const double *u
       f[BX1 + c] = (c == dir) ? 0.0 : v[Xn] * v[BX1 + c] - v[BXn] * v[MX1 + c];
     double b2 = v[BX1] * v[BX1];
     for (int c = 1; c < nc; c++) b2 = b2 + v[BX1 + c] * v[BX1 + c];
+    if (o->d.isothermal) { /* flux.hpp:80-81 */
+      const double ptot = c2iso * v[RHO] + 0.5 * b2;
+      f[Xn] += ptot;
+      return;
+    }
     const double ptot = v[ENG] + 0.5 * b2;
     double vb = v[MX1] * v[BX1];
     for (int c = 1; c < nc; c++) vb = vb + v[MX1 + c] * v[BX1 + c];
@@ -184,6 +199,11 @@ static void phys_flux(const Oracle *o, int dir, const double *v, const double *u
     f[Xn] += ptot;
   } else {
     for (int c = 0; c < nc; c++) f[MX1 + c] = u[MX1 + c] * v[Xn];
+    if (o->d.isothermal) { /* flux.hpp:90-91 */
+      const double ptot = c2iso * v[RHO];
+      f[Xn] += ptot;
+      return;
+    }
     f[ENG] = (u[ENG] + v[ENG]) * v[Xn];
     f[Xn] += v[ENG];
   }
@@ -321,10 +341,18 @@ static void reconstruct_interface(int order, const double *q, long s, int positi
 static int tdir(int dir) { return dir == 0 ? 1 : 0; }
 static int bdir(int dir) { return dir == 2 ? 1 : 2; }
 
+/* c2Iso of an interface: HALF_F*(cs(k,j,i) + cs(k,j,i-1)), squared (hlldMHD.hpp:188-190); cs is constant here */
+static double iso_c2(const Oracle *o) {
+  double c = 0.5 * (o->d.csiso + o->d.csiso);
+  c *= c;
+  return c;
+}
+
 /* fast magnetosonic speed, hlldMHD.hpp:191-207 */
 static double fast_speed(const Oracle *o, int dir, const double *v) {
   const int nc = o->d.ncomp, BX1 = o->BX1;
-  const double gpr = o->d.gamma * v[o->ENG];
+  /* isothermal: c2Iso * rho with c2Iso the squared mean sound speed (hlldMHD.hpp:188-193) */
+  const double gpr = o->d.isothermal ? iso_c2(o) * v[o->RHO] : o->d.gamma * v[o->ENG];
   const double b1 = v[BX1 + dir];
   const double b2 = nc >= 2 ? v[BX1 + tdir(dir)] : 0.0;
   const double b3 = nc == 3 ? v[BX1 + bdir(dir)] : 0.0;
@@ -338,6 +366,7 @@ static double fast_speed(const Oracle *o, int dir, const double *v) {
 static double total_pressure(const Oracle *o, const double *v) {
   double b2 = v[o->BX1] * v[o->BX1];
   for (int c = 1; c < o->d.ncomp; c++) b2 = b2 + v[o->BX1 + c] * v[o->BX1 + c];
+  if (o->d.isothermal) return iso_c2(o) * v[o->RHO] + 0.5 * b2; /* storeFlux.hpp:104-109 */
   return v[o->ENG] + 0.5 * b2;
 }
 
@@ -345,28 +374,39 @@ typedef struct { double cmax, sl, sr; } Speeds;
 
 /* ---- HD solvers: HDsolvers/tvdlfHD.hpp:49-93, hllHD.hpp:48-110, hllcHD.hpp:40-160 -------------- */
 static void riemann_hd(const Oracle *o, int dir, const double *vL, const double *vR, double *F, Speeds *sp) {
-  const int nv = o->nvar, RHO = o->RHO, ENG = o->ENG, Xn = o->MX1 + dir, nc = o->d.ncomp;
+  const int nv = o->nvar, RHO = o->RHO, ENG = o->ENG, Xn = o->MX1 + dir, nc = o->d.ncomp, iso = o->d.isothermal;
   double uL[8], uR[8], fL[8], fR[8];
   prim_to_cons(o, vL, uL);
   prim_to_cons(o, vR, uR);
   if (o->d.solver == TVDLF) {
     const double vn = 0.5 * (vL[Xn] + vR[Xn]);
-    const double p = 0.5 * (vL[ENG] + vR[ENG]), r = 0.5 * (vL[RHO] + vR[RHO]);
-    const double c = sqrt(o->d.gamma * (p / r));
+    double c;
+    if (iso) { /* tvdlfHD.hpp:73-76: mean of the (constant) sound speeds of the two cells */
+      c = 0.5 * (o->d.csiso + o->d.csiso);
+    } else {
+      const double p = 0.5 * (vL[ENG] + vR[ENG]), r = 0.5 * (vL[RHO] + vR[RHO]);
+      c = sqrt(o->d.gamma * (p / r));
+    }
     const double cmax = fmax(fabs(vn + c), fabs(vn - c));
-    phys_flux(o, dir, vL, uL, fL);
-    phys_flux(o, dir, vR, uR, fR);
+    phys_flux(o, dir, vL, uL, fL, c * c);
+    phys_flux(o, dir, vR, uR, fR, c * c);
     for (int n = 0; n < nv; n++) F[n] = 0.5 * (fL[n] + fR[n] - cmax * (uR[n] - uL[n]));
     sp->cmax = cmax;
     return;
   }
-  const double cL = sqrt(o->d.gamma * (vL[ENG] / vL[RHO]));
-  const double cR = sqrt(o->d.gamma * (vR[ENG] / vR[RHO]));
+  double cL, cR;
+  if (iso) { /* hllHD.hpp:66-70, hllcHD.hpp:67-71 */
+    cL = 0.5 * (o->d.csiso + o->d.csiso);
+    cR = cL;
+  } else {
+    cL = sqrt(o->d.gamma * (vL[ENG] / vL[RHO]));
+    cR = sqrt(o->d.gamma * (vR[ENG] / vR[RHO]));
+  }
   const double SL = fmin(vL[Xn] - cL, vR[Xn] - cR);
   const double SR = fmax(vL[Xn] + cL, vR[Xn] + cR);
   sp->cmax = fmax(fabs(SL), fabs(SR));
-  phys_flux(o, dir, vL, uL, fL);
-  phys_flux(o, dir, vR, uR, fR);
+  phys_flux(o, dir, vL, uL, fL, cL * cL);
+  phys_flux(o, dir, vR, uR, fR, cR * cR);
   if (SL > 0) {
     for (int n = 0; n < nv; n++) F[n] = fL[n];
   } else if (SR < 0) {
@@ -375,6 +415,25 @@ static void riemann_hd(const Oracle *o, int dir, const double *vL, const double 
     for (int n = 0; n < nv; n++) {
       double f = SL * SR * uR[n] - SL * SR * uL[n] + SR * fL[n] - SL * fR[n];
       F[n] = f / (SR - SL);
+    }
+  } else if (iso) { /* HLLC without energy, hllcHD.hpp:136-151 */
+    double usL[8], usR[8];
+    const double scrh = 1.0 / (SR - SL);
+    const double rho = (SR * uR[RHO] - SL * uL[RHO] - fR[RHO] + fL[RHO]) * scrh;
+    const double mx = (SR * uR[Xn] - SL * uL[Xn] - fR[Xn] + fL[Xn]) * scrh;
+    usL[RHO] = usR[RHO] = rho;
+    double vs = (SR * fL[RHO] - SL * fR[RHO] + SR * SL * (uR[RHO] - uL[RHO]));
+    vs *= scrh;
+    vs /= rho;
+    for (int c = 0; c < nc; c++) {
+      const int m = o->MX1 + c;
+      usL[m] = m == Xn ? mx : rho * vL[m];
+      usR[m] = m == Xn ? mx : rho * vR[m];
+    }
+    if (vs >= 0.0) {
+      for (int n = 0; n < nv; n++) F[n] = fL[n] + SL * (usL[n] - uL[n]);
+    } else {
+      for (int n = 0; n < nv; n++) F[n] = fR[n] + SR * (usR[n] - uR[n]);
     }
   } else { /* HLLC */
     double usL[8], usR[8];
@@ -415,8 +474,8 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
   prim_to_cons(o, vL, uL);
   prim_to_cons(o, vR, uR);
   for (int n = 0; n < NV; n++) dU[n] = uR[n] - uL[n];
-  phys_flux(o, dir, vL, uL, fL);
-  phys_flux(o, dir, vR, uR, fR);
+  phys_flux(o, dir, vL, uL, fL, 0.0);
+  phys_flux(o, dir, vR, uR, fR, 0.0);
   for (int a = 0; a < 8; a++)
     for (int b = 0; b < 8; b++) Rc[a][b] = 0;
 
@@ -639,8 +698,9 @@ static void riemann_mhd(const Oracle *o, int dir, const double *vL, const double
   sp->sr = sr;
   prim_to_cons(o, vL, uL);
   prim_to_cons(o, vR, uR);
-  phys_flux(o, dir, vL, uL, fL);
-  phys_flux(o, dir, vR, uR, fR);
+  const double c2iso = o->d.isothermal ? iso_c2(o) : 0.0;
+  phys_flux(o, dir, vL, uL, fL, c2iso);
+  phys_flux(o, dir, vR, uR, fR, c2iso);
   if (sl > 0) {
     for (int n = 0; n < nv; n++) F[n] = fL[n];
     return;
@@ -654,6 +714,60 @@ static void riemann_mhd(const Oracle *o, int dir, const double *vL, const double
     for (int n = 0; n < nv; n++) {
       const double f = sl * sr * uR[n] - sl * sr * uL[n] + sr * fL[n] - sl * fR[n];
       F[n] = (n <= nc) ? f / (sr - sl) : f * rcp;
+    }
+    return;
+  }
+  if (o->d.isothermal) { /* HLLD without energy (Mignone 2007), hlldMHD.hpp:459-571 */
+    double usL[8], usR[8], usc[8];
+    double scrh = 1.0 / (sr - sl);
+    const double duL = sl - vL[Xn], duR = sr - vR[Xn];
+    const double Bx = (sr * vR[BXn] - sl * vL[BXn]) * scrh;
+    const double rho = (uR[RHO] * duR - uL[RHO] * duL) * scrh;
+    F[RHO] = (sl * uR[RHO] * duR - sr * uL[RHO] * duL) * scrh;
+    const double sqrho = sqrt(rho);
+    const double SM = F[RHO] / rho;
+    const double S1L = SM - fabs(Bx) / sqrho, S1R = SM + fabs(Bx) / sqrho;
+    int revert = 0;
+    if ((S1L - sl) < 1.e-4 * (sr - sl)) revert = 1;
+    if ((S1R - sr) > -1.e-4 * (sr - sl)) revert = 1;
+    if (revert) {
+      scrh = 1.0 / (sr - sl);
+      for (int n = 0; n < nv; n++) {
+        F[n] = sl * sr * (uR[n] - uL[n]) + sr * fL[n] - sl * fR[n];
+        F[n] *= scrh;
+      }
+      return;
+    }
+    F[Xn] = (sr * fL[Xn] - sl * fR[Xn] + sr * sl * (uR[Xn] - uL[Xn])) * scrh;
+    F[BXn] = sr * sl * (uR[BXn] - uL[BXn]) * scrh;
+    const double scrhL = 1.0 / ((sl - S1L) * (sl - S1R)), scrhR = 1.0 / ((sr - S1L) * (sr - S1R));
+    const int T[2] = {Xt, Xb}, BT[2] = {BXt, BXb};
+    for (int q = 0; q < nc - 1; q++) {
+      usL[T[q]] = rho * vL[T[q]] - Bx * uL[BT[q]] * (SM - vL[Xn]) * scrhL;
+      usR[T[q]] = rho * vR[T[q]] - Bx * uR[BT[q]] * (SM - vR[Xn]) * scrhR;
+    }
+    for (int q = 0; q < nc - 1; q++) {
+      usL[BT[q]] = uL[BT[q]] / rho * (uL[RHO] * duL * duL - Bx * Bx) * scrhL;
+      usR[BT[q]] = uR[BT[q]] / rho * (uR[RHO] * duR * duR - Bx * Bx) * scrhR;
+    }
+    if (S1L >= 0.0) {
+      for (int q = 0; q < nc - 1; q++) {
+        F[T[q]] = fL[T[q]] + sl * (usL[T[q]] - uL[T[q]]);
+        F[BT[q]] = fL[BT[q]] + sl * (usL[BT[q]] - uL[BT[q]]);
+      }
+    } else if (S1R <= 0.0) {
+      for (int q = 0; q < nc - 1; q++) {
+        F[T[q]] = fR[T[q]] + sr * (usR[T[q]] - uR[T[q]]);
+        F[BT[q]] = fR[BT[q]] + sr * (usR[BT[q]] - uR[BT[q]]);
+      }
+    } else {
+      const double sBx = Bx > 0.0 ? 1.0 : -1.0;
+      for (int q = 0; q < nc - 1; q++) {
+        usc[T[q]] = 0.5 * (usR[T[q]] + usL[T[q]] + (usR[BT[q]] - usL[BT[q]]) * sBx * sqrho);
+        usc[BT[q]] = 0.5 * (usR[BT[q]] + usL[BT[q]] + (usR[T[q]] - usL[T[q]]) * sBx / sqrho);
+        F[T[q]] = usc[T[q]] * SM - Bx * usc[BT[q]];
+        F[BT[q]] = usc[BT[q]] * SM - Bx * usc[T[q]] / rho;
+      }
     }
     return;
   }
@@ -1168,6 +1282,59 @@ static void fill_ghosts(Oracle *o, double *q, long qj, long qk, int dir, int sid
       }
 }
 
+/* Boundary::ReconstructNormalField, boundary.hpp:408-530: the normal component in the ghost faces of a
+ * non-periodic side follows from div B = 0, marching outwards.  Cartesian uniform grid: constant areas. */
+static void reconstruct_normal_field(Oracle *o, int dir) {
+  const int nd = o->d.ndim;
+  const double A1 = face_area(o, 0), A2 = nd >= 2 ? face_area(o, 1) : 0.0, A3 = nd == 3 ? face_area(o, 2) : 0.0;
+  double *B1 = o->Vs, *B2 = nd >= 2 ? o->Vs + o->vn : NULL, *B3 = nd == 3 ? o->Vs + 2 * o->vn : NULL;
+  if (dir == 0) {
+    for (int k = 0; k < o->nx[2]; k++)
+      for (int j = 0; j < o->nx[1]; j++) {
+        for (int i = o->beg[0] - 1; i >= 0; i--) {
+          double tr = 0.0;
+          if (nd >= 2) tr = tr + A2 * B2[S(o, k, j + 1, i)] - A2 * B2[S(o, k, j, i)];
+          if (nd == 3) tr = tr + A3 * B3[S(o, k + 1, j, i)] - A3 * B3[S(o, k, j, i)];
+          B1[S(o, k, j, i)] = 1.0 / A1 * (A1 * B1[S(o, k, j, i + 1)] + (tr));
+        }
+        for (int i = o->end[0]; i < o->nx[0]; i++) {
+          double tr = 0.0;
+          if (nd >= 2) tr = tr + A2 * B2[S(o, k, j + 1, i)] - A2 * B2[S(o, k, j, i)];
+          if (nd == 3) tr = tr + A3 * B3[S(o, k + 1, j, i)] - A3 * B3[S(o, k, j, i)];
+          B1[S(o, k, j, i + 1)] = 1.0 / A1 * (A1 * B1[S(o, k, j, i)] - (tr));
+        }
+      }
+  } else if (dir == 1) {
+    for (int k = 0; k < o->nx[2]; k++)
+      for (int i = 0; i < o->nx[0]; i++) {
+        for (int j = o->beg[1] - 1; j >= 0; j--) {
+          double tr = A1 * B1[S(o, k, j, i + 1)] - A1 * B1[S(o, k, j, i)];
+          if (nd == 3) tr = tr + 1 * (A3 * B3[S(o, k + 1, j, i)] - A3 * B3[S(o, k, j, i)]);
+          B2[S(o, k, j, i)] = 1.0 / A2 * (A2 * B2[S(o, k, j + 1, i)] + (tr));
+        }
+        for (int j = o->end[1]; j < o->nx[1]; j++) {
+          double tr = A1 * B1[S(o, k, j, i + 1)] - A1 * B1[S(o, k, j, i)];
+          if (nd == 3) tr = tr + 1 * (A3 * B3[S(o, k + 1, j, i)] - A3 * B3[S(o, k, j, i)]);
+          B2[S(o, k, j + 1, i)] = 1.0 / A2 * (A2 * B2[S(o, k, j, i)] - (tr));
+        }
+      }
+  } else {
+    for (int j = 0; j < o->nx[1]; j++)
+      for (int i = 0; i < o->nx[0]; i++) {
+        for (int k = o->beg[2] - 1; k >= 0; k--) {
+          const double tr = A1 * B1[S(o, k, j, i + 1)] - A1 * B1[S(o, k, j, i)] + A2 * B2[S(o, k, j + 1, i)] -
+                            A2 * B2[S(o, k, j, i)];
+          B3[S(o, k, j, i)] = 1.0 / A3 * (A3 * B3[S(o, k + 1, j, i)] + (tr));
+        }
+        for (int k = o->end[2]; k < o->nx[2]; k++) {
+          const double tr = A1 * B1[S(o, k, j, i + 1)] - A1 * B1[S(o, k, j, i)] + A2 * B2[S(o, k, j + 1, i)] -
+                            A2 * B2[S(o, k, j, i)];
+          B3[S(o, k + 1, j, i)] = 1.0 / A3 * (A3 * B3[S(o, k, j, i)] - (tr));
+        }
+      }
+  }
+}
+
 static void set_boundaries(Oracle *o) {
   const OracleDesc *d = &o->d;
   for (int dir = 0; dir < d->ndim; dir++) {
@@ -1186,11 +1353,7 @@ static void set_boundaries(Oracle *o) {
         }
       }
     }
-    if (d->mhd && d->bc[dir] != BC_PERIODIC && d->ndim == 1) {
-      /* ReconstructNormalField in 1-D cartesian (boundary.hpp:444-466): A = 1, no transverse terms */
-      for (int i = o->beg[0] - 1; i >= 0; i--) o->Vs[i] = 1.0 / 1.0 * (1.0 * o->Vs[i + 1] + (0.0));
-      for (int i = o->end[0]; i < o->nx[0]; i++) o->Vs[i + 1] = 1.0 / 1.0 * (1.0 * o->Vs[i] - (0.0));
-    }
+    if (d->mhd && d->bc[dir] != BC_PERIODIC) reconstruct_normal_field(o, dir);
   }
   if (d->mhd) reconstruct_vc_field(o, o->Vc);
 }
@@ -1254,7 +1417,7 @@ int oracle_cycle(Oracle *o) {
       for (int n = 0; n < o->nvar; n++) u[n] = o->Uc[n * o->sn + c];
       cons_to_prim(o, u, v);
       for (int n = 0; n < o->nvar; n++) o->Vc[n * o->sn + c] = v[n];
-      o->Uc[o->ENG * o->sn + c] = u[o->ENG];
+      if (o->ENG >= 0) o->Uc[o->ENG * o->sn + c] = u[o->ENG]; /* the pressure floor rewrites the energy */
       for (int n = o->nvar; n < o->nvar + o->ntr; n++) /* Tracer::ConvertConsToPrim, tracer.cpp:12-29 */
         o->Vc[n * o->sn + c] = o->Uc[n * o->sn + c] / o->Uc[o->RHO * o->sn + c];
     }
