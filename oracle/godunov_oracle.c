@@ -9,11 +9,11 @@
  *
  * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions (and 2.5-D: more components
  * than dimensions), adiabatic EOS, PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC,
- * MHD solvers HLL / HLLD / Roe, constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld
+ * MHD solvers TVDLF / HLL / HLLD / Roe, constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld
  * averaging (PPM corner states when ORDER is 4), passive tracers, periodic and outflow boundaries (with
  * ReconstructNormalField on the outflow sides in MHD), RK1/2/3, CFL time-step control; and the isothermal
- * EOS (constant sound speed) for HD TVDLF / HLL / HLLC and MHD HLL / HLLD.
- * TVDLF-MHD, isothermal Roe and uct_hlld, and curvilinear geometry are pinned through the reference binaries
+ * EOS (constant sound speed) for HD TVDLF / HLL / HLLC and MHD TVDLF / HLL / HLLD.
+ * Isothermal Roe and uct_hlld, and curvilinear geometry are pinned through the reference binaries
  * and golden dumps only (tests/golden).
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
@@ -690,6 +690,29 @@ static void riemann_mhd(const Oracle *o, int dir, const double *vL, const double
   const int Xn = o->MX1 + dir, Xt = o->MX1 + tdir(dir), Xb = o->MX1 + bdir(dir);
   const int BXn = o->BX1 + dir, BXt = o->BX1 + tdir(dir), BXb = o->BX1 + bdir(dir);
   double uL[8], uR[8], fL[8], fR[8];
+  if (o->d.solver == TVDLF) { /* tvdlfMHD.hpp:160-217: one speed from the arithmetic mean state */
+    double v[8];
+    for (int n = 0; n < nv; n++) v[n] = 0.5 * (vL[n] + vR[n]);
+    const double c2 = o->d.isothermal ? iso_c2(o) : 0.0;
+    const double gpr = o->d.isothermal ? c2 * v[RHO] : o->d.gamma * v[ENG];
+    double Bt2 = 0.0;
+    if (nc >= 2) Bt2 = Bt2 + v[BXt] * v[BXt];
+    if (nc == 3) Bt2 = Bt2 + v[BXb] * v[BXb];
+    const double B2 = Bt2 + v[BXn] * v[BXn];
+    double cRL = gpr - B2;
+    cRL = cRL + B2 + sqrt(cRL * cRL + 4.0 * gpr * Bt2); /* sic: "cRL + B2", not "gpr + B2" (tvdlfMHD.hpp:194) */
+    cRL = sqrt(0.5 * cRL / v[RHO]);
+    const double cmax = fmax(fabs(v[Xn] + cRL), fabs(v[Xn] - cRL));
+    sp->cmax = cmax;
+    sp->sl = -cmax;
+    sp->sr = cmax;
+    prim_to_cons(o, vL, uL);
+    prim_to_cons(o, vR, uR);
+    phys_flux(o, dir, vL, uL, fL, c2);
+    phys_flux(o, dir, vR, uR, fR, c2);
+    for (int n = 0; n < nv; n++) F[n] = 0.5 * (fL[n] + fR[n] + cmax * (uL[n] - uR[n]));
+    return;
+  }
   const double cL = fast_speed(o, dir, vL), cR = fast_speed(o, dir, vR);
   const double sl = fmin(vL[Xn] - cL, vR[Xn] - cR);
   const double sr = fmax(vL[Xn] + cL, vR[Xn] + cR);
@@ -979,7 +1002,7 @@ static void calc_flux(Oracle *o, int dir) {
   /* perpendicular extension of the face box: 0 for HD; 1 or nghost for MHD (hlldMHD.hpp:32-49) */
   int ext = 0;
   if (d->mhd) ext = (d->emf == EMF_UCT_HLL || d->emf == EMF_UCT_HLLD) ? d->nghost[dir] : 1;
-  if (d->mhd && d->solver == ROE) ext = 1; /* hard-coded in roeMHD.hpp:63-73 */
+  if (d->mhd && (d->solver == ROE || d->solver == TVDLF)) ext = 1; /* hard-coded: roeMHD.hpp:63-73, tvdlfMHD.hpp:30-41 */
   int lo[3], hi[3];
   for (int a = 0; a < 3; a++) {
     const int e = (a < d->ndim && a != dir) ? ext : 0;
