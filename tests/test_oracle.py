@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import FULL, HOST_SHORT, SHORT, ini_for
+from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_SHORT, SHORT, ini_for
 from idefix_b200.dump import readDump, vc_names
 from idefix_b200.datablock import DataBlockHost
 from idefix_b200.grid import Definitions
@@ -51,8 +51,8 @@ def compare(s, o, dump):
     return worst
 
 
-SHORT_IN = [c for c in SHORT if in_scope(c)]
-FULL_IN = [c for c in FULL if in_scope(c) and c.setup in ("sod", "mhdsod", "ot2d")]
+SHORT_IN = [c for c in SHORT + ORACLE_SHORT if in_scope(c) and c.setup in REGISTRY]
+FULL_IN = [c for c in FULL + ORACLE_FULL if in_scope(c) and c.setup in ("sod", "mhdsod", "ot2d")]
 
 
 @pytest.mark.parametrize("case", SHORT_IN, ids=[c.name for c in SHORT_IN])
@@ -82,7 +82,8 @@ def test_oracle_matches_shipped_golden(case):
 # ---- isothermal EOS: the problems live in the C++ host layer (idefix_b200/host/problems); the oracle starts
 # from the reference's own cycle-0 dump of the case and must reproduce its later dumps bit for bit ---------------
 ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2, 3, 1, True, True)}
-ISO_IN = [c for c in HOST_SHORT if c.setup in ISO_DEFS and c.overrides.get(("Hydro", "solver")) != "roe"]
+ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ISO_DEFS
+          and not (ISO_DEFS[c.setup].mhd and c.overrides.get(("Hydro", "solver")) == "roe")]
 
 
 class _FromDump(Setup):
@@ -107,7 +108,7 @@ class _FromDump(Setup):
 
 @pytest.mark.parametrize("case", ISO_IN, ids=[c.name for c in ISO_IN])
 def test_isothermal_oracle_matches_reference_build_bitwise(case):
-    assert len(ISO_IN) >= 6
+    assert len(ISO_IN) >= 7
     s = _FromDump(case, readDump(os.path.join(GOLD, "short", f"{case.name}.c0000.dmp")))
     s.InitFlow(s.data)
     o = Oracle.from_setup(s)
