@@ -11,7 +11,13 @@
 #include <cstdint>
 
 #define IDFX_HD __host__ __device__ __forceinline__
+#ifdef IDFX_HOST_TEST
+// tests/host_cpp/riemann_host.cu compiles the per-interface physics for the HOST as well, to compare it with the
+// CPU oracle without a GPU (the *Fast sequences of fastmath.cuh stay device-only and are not reached there)
+#define IDFX_D __host__ __device__ __forceinline__
+#else
 #define IDFX_D __device__ __forceinline__
+#endif
 
 enum : int { IDIR = 0, JDIR = 1, KDIR = 2 };
 enum : int { GEO_CARTESIAN = 1, GEO_CYLINDRICAL = 2, GEO_POLAR = 3, GEO_SPHERICAL = 4 };

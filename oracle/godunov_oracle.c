@@ -381,7 +381,7 @@ static void riemann_hd(const Oracle *o, int dir, const double *vL, const double 
   if (o->d.solver == ROE) { /* roeHD.hpp:41-360, ROE_AVERAGE 0: arithmetic mean state */
     const int Xt = o->MX1 + tdir(dir), Xb = o->MX1 + bdir(dir);
     const int I0 = 0, I1 = 1, IE = 2, I2 = iso ? 2 : 3, I3 = iso ? 3 : 4;
-    double dv[8], um[8], Rc[8][8], lambda[8], alambda[8], eta[8];
+    double dv[8], um[8] = {0}, Rc[8][8], lambda[8], alambda[8] = {0}, eta[8];
     for (int n = 0; n < nv; n++) dv[n] = vR[n] - vL[n];
     double a2L, a2R;
     if (iso) {
@@ -1097,6 +1097,27 @@ static void store_emf(Oracle *o, int dir, long c, const double *F, const Speeds 
   o->aR[dir][c] = oaR;
   o->dL[dir][c] = odL;
   o->dR[dir][c] = odR;
+}
+
+/* One interface solve per (vL, vR) pair, states packed (n, nvar): the oracle's solvers on arbitrary states, for
+ * tests/test_riemann_host.py.  out4 receives (cmax, sl, sr, keep_flux); sl / sr are meaningful for MHD only. */
+void oracle_riemann(Oracle *o, int dir, long n, const double *vL, const double *vR, double *F, double *out4) {
+  const int nv = o->nvar;
+  for (long q = 0; q < n; q++) {
+    Speeds sp = {0, 0, 0, 0};
+    double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (o->d.mhd) {
+      if (o->d.solver == ROE) riemann_roe_mhd(o, dir, vL + q * nv, vR + q * nv, f, &sp);
+      else riemann_mhd(o, dir, vL + q * nv, vR + q * nv, f, &sp);
+    } else {
+      riemann_hd(o, dir, vL + q * nv, vR + q * nv, f, &sp);
+    }
+    for (int v = 0; v < nv; v++) F[q * nv + v] = f[v];
+    out4[4 * q + 0] = sp.cmax;
+    out4[4 * q + 1] = sp.sl;
+    out4[4 * q + 2] = sp.sr;
+    out4[4 * q + 3] = sp.keep_flux;
+  }
 }
 
 /* ---- RiemannSolver::CalcFlux<dir>: reconstruct (extrapolateToFaces.hpp:89-124), solve, store ------ */

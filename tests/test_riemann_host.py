@@ -1,0 +1,99 @@
+"""The product's Riemann solvers (idefix_b200/csrc/riemann_*.cuh -- the functions the sweep kernels inline)
+compiled for the HOST by nvcc and compared BIT FOR BIT with the oracle's restatement on random and on
+deliberately degenerate left / right states.  Runs without a GPU: it pins the solver source itself,
+including branches the golden runs rarely visit (supersonic sides, HLLD degeneracies and its HLLC-type
+fallback, the Roe entropy fix), for every solver x EOS x direction x number of components."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.godunov import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SOLVERS = {"tvdlf": 0, "hll": 1, "hllc": 2, "hlld": 3, "roe": 4}
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("riemann_host") / "libriemann_host.so"
+    cmd = ["nvcc", "-std=c++17", "-O2", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I", os.path.join(ROOT, "idefix_b200", "csrc"),
+           "-o", str(out), os.path.join(ROOT, "tests", "host_cpp", "riemann_host.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lib = C.CDLL(str(out))
+    lib.idfx_host_riemann.argtypes = [C.c_int] * 5 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 4
+    return lib
+
+
+def states(rng, n, ncomp, mhd, iso, dir):
+    """(n, nvar) left / right primitive states in the reference's variable order: a random bulk plus blocks of
+    special pairs (identical states, supersonic to either side, vanishing normal / transverse field, strong jumps)"""
+    nvar = 1 + ncomp + (0 if iso else 1) + (ncomp if mhd else 0)
+    PRS = None if iso else ncomp + 1
+    BX1 = ncomp + (1 if iso else 2)
+
+    def draw(m):
+        v = np.empty((m, nvar))
+        v[:, 0] = 10.0 ** rng.uniform(-1.5, 1.0, m)
+        v[:, 1:1 + ncomp] = rng.uniform(-1.5, 1.5, (m, ncomp))
+        if PRS is not None:
+            v[:, PRS] = 10.0 ** rng.uniform(-2.0, 1.0, m)
+        if mhd:
+            v[:, BX1:BX1 + ncomp] = rng.uniform(-1.5, 1.5, (m, ncomp))
+        return v
+
+    m = n // 8
+    vL, vR = draw(n), draw(n)
+    vR[0:m] = vL[0:m]                                            # no jump at all
+    vL[m:2 * m, 1 + dir] += 8.0; vR[m:2 * m, 1 + dir] += 8.0     # everything moves right: sl > 0
+    vL[2 * m:3 * m, 1 + dir] -= 8.0; vR[2 * m:3 * m, 1 + dir] -= 8.0   # sr < 0
+    vR[3 * m:4 * m] = vL[3 * m:4 * m] * (1.0 + 1e-9 * rng.standard_normal((m, nvar)))   # nearly equal states
+    if mhd:
+        vL[4 * m:5 * m, BX1:BX1 + ncomp] = 0.0                   # field-free left state (and zero normal field)
+        vR[4 * m:5 * m, BX1 + dir] = 0.0
+        for c in range(ncomp):
+            if c != dir:                                          # purely normal field: HLLD degeneracy
+                vL[5 * m:6 * m, BX1 + c] = 0.0
+                vR[5 * m:6 * m, BX1 + c] = 0.0
+        vL[6 * m:7 * m, BX1:BX1 + ncomp] *= 1e-7                  # weak field
+        vR[6 * m:7 * m, BX1:BX1 + ncomp] *= 1e-7
+        vR[:, BX1 + dir] = vL[:, BX1 + dir]                       # the sweeps impose the face value on both sides
+    if PRS is not None:
+        vL[7 * m:8 * m, PRS] *= 1e3                               # strong shock
+    vL[7 * m:8 * m, 1 + dir] = np.abs(vL[7 * m:8 * m, 1 + dir]) + 1.0   # converging flow
+    vR[7 * m:8 * m, 1 + dir] = -np.abs(vR[7 * m:8 * m, 1 + dir])
+    return vL, vR
+
+
+CASES = [(mhd, iso, solver, ncomp)
+         for mhd in (False, True) for iso in (False, True)
+         for solver in (("tvdlf", "hll", "hlld", "roe") if mhd else ("tvdlf", "hll", "hllc"))
+         for ncomp in (1, 2, 3) if not (mhd and iso and solver == "roe")]
+
+
+@pytest.mark.parametrize("mhd,iso,solver,ncomp", CASES,
+                         ids=[f"{'mhd' if m else 'hd'}-{'iso' if i else 'adi'}-{s}-{c}c" for m, i, s, c in CASES])
+def test_product_solver_source_equals_oracle_bitwise(host_lib, mhd, iso, solver, ncomp):
+    gamma, csiso, n = 5.0 / 3.0, 0.7, 40000
+    rng = np.random.default_rng(1234 + 17 * ncomp + SOLVERS[solver])
+    o = Oracle(ncomp, ncomp, mhd, solver, "uct_contact", 2, [4] * ncomp + [1] * (3 - ncomp), ["periodic"] * ncomp,
+               gamma, 0.5, 1e-4, [0.1, 0.1, 0.1], csiso=csiso if iso else None)
+    for dir in range(ncomp):
+        vL, vR = states(rng, n, ncomp, mhd, iso, dir)
+        Fo, auxo = o.riemann(dir, vL, vR)
+        Fp, auxp = np.zeros_like(vL), np.zeros((n, 4))
+        rc = host_lib.idfx_host_riemann(ncomp, int(mhd), int(iso), SOLVERS[solver], dir, gamma, csiso, n,
+                                        vL.ctypes.data, vR.ctypes.data, Fp.ctypes.data, auxp.ctypes.data)
+        assert rc == 0
+        assert np.isfinite(Fo).all(), "the state generator produced an unphysical pair"
+        bad = np.flatnonzero((Fo.view(np.int64) != Fp.view(np.int64)).any(axis=1))
+        assert bad.size == 0, (f"dir {dir}: {bad.size} of {n} fluxes differ, first at {bad[0]}: vL={vL[bad[0]]} "
+                               f"vR={vR[bad[0]]} oracle={Fo[bad[0]]} product={Fp[bad[0]]}")
+        assert (auxo[:, 0].view(np.int64) == auxp[:, 0].view(np.int64)).all(), "cmax differs"
+        if mhd:   # outermost speeds feed the UCT-HLL / UCT-HLLD coefficients
+            assert (auxo[:, 1:3].view(np.int64) == auxp[:, 1:3].view(np.int64)).all(), "sl / sr differ"
+    o.close()
