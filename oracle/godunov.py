@@ -46,7 +46,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_boundaries.argtypes = [C.c_void_p]
         L.oracle_cycle.argtypes = [C.c_void_p]
-        L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5
         L.oracle_riemann.restype = None
         L.oracle_run.argtypes = [C.c_void_p, C.c_double, C.c_long]
         _lib = L
@@ -112,12 +112,15 @@ class Oracle:
             self.Vs[...] = Vs
         lib().oracle_set_boundaries(self.h)
 
-    def riemann(self, dir, vL, vR):
-        """the oracle's interface solver on packed (n, nvar) left / right states -> (F, (cmax, sl, sr, keep))"""
+    def riemann(self, dir, vL, vR, emf=False):
+        """the oracle's interface solver on packed (n, nvar) left / right states -> F, (cmax, sl, sr, keep)
+        [, (Et, Eb, SV, aL, aR, dL, dR) as stored for constrained transport]"""
         vL, vR = np.ascontiguousarray(vL, float), np.ascontiguousarray(vR, float)
         F, out = np.zeros_like(vL), np.zeros((vL.shape[0], 4))
-        lib().oracle_riemann(self.h, dir, vL.shape[0], vL.ctypes.data, vR.ctypes.data, F.ctypes.data, out.ctypes.data)
-        return F, out
+        e7 = np.zeros((vL.shape[0], 7)) if emf else None
+        lib().oracle_riemann(self.h, dir, vL.shape[0], vL.ctypes.data, vR.ctypes.data, F.ctypes.data, out.ctypes.data,
+                             e7.ctypes.data if emf else None)
+        return (F, out, e7) if emf else (F, out)
 
     def cycle(self, n=1):
         for _ in range(n):

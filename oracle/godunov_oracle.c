@@ -1100,8 +1100,11 @@ static void store_emf(Oracle *o, int dir, long c, const double *F, const Speeds 
 }
 
 /* One interface solve per (vL, vR) pair, states packed (n, nvar): the oracle's solvers on arbitrary states, for
- * tests/test_riemann_host.py.  out4 receives (cmax, sl, sr, keep_flux); sl / sr are meaningful for MHD only. */
-void oracle_riemann(Oracle *o, int dir, long n, const double *vL, const double *vR, double *F, double *out4) {
+ * tests/test_riemann_host.py.  out4 receives (cmax, sl, sr, keep_flux); sl / sr are meaningful for MHD only.
+ * emf7 (MHD, dir < ndim, may be NULL) receives what store_emf leaves for constrained transport:
+ * (Et, Eb, SV, aL, aR, dL, dR) of the direction, zero where the averaging scheme stores nothing. */
+void oracle_riemann(Oracle *o, int dir, long n, const double *vL, const double *vR, double *F, double *out4,
+                    double *emf7) {
   const int nv = o->nvar;
   for (long q = 0; q < n; q++) {
     Speeds sp = {0, 0, 0, 0};
@@ -1117,6 +1120,15 @@ void oracle_riemann(Oracle *o, int dir, long n, const double *vL, const double *
     out4[4 * q + 1] = sp.sl;
     out4[4 * q + 2] = sp.sr;
     out4[4 * q + 3] = sp.keep_flux;
+    if (emf7 && o->d.mhd && dir < o->d.ndim) {
+      double *Et = dir == 0 ? o->ezi : (dir == 1 ? o->ezj : o->eyk);
+      double *Eb = dir == 0 ? o->eyi : (dir == 1 ? o->exj : o->exk);
+      double *SV = dir == 0 ? o->svx : (dir == 1 ? o->svy : o->svz);
+      double *all[7] = {Et, Eb, SV, o->aL[dir], o->aR[dir], o->dL[dir], o->dR[dir]};
+      for (int e = 0; e < 7; e++) all[e][0] = 0.0;
+      store_emf(o, dir, 0, f, &sp, vL + q * nv, vR + q * nv);
+      for (int e = 0; e < 7; e++) emf7[7 * q + e] = all[e][0];
+    }
   }
 }
 

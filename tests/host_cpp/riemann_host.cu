@@ -8,9 +8,11 @@
 #include "riemann_hd.cuh"
 #include "riemann_mhd.cuh"
 #include "riemann_roe.cuh"
+#include "emf_store.cuh"
 
 template <class P, int SOLVER, int DIR>
-static void solveAll(const Eos &eos, long n, const double *vL, const double *vR, double *F, double *aux4) {
+static void solveAll(const Eos &eos, long n, const double *vL, const double *vR, double *F, double *aux4,
+                     int emfMode, double *emf7) {
   for (long q = 0; q < n; q++) {
     RiemannAux aux{0.0, 0.0, 0.0, 0.0};
     double f[P::nvar];
@@ -31,49 +33,73 @@ static void solveAll(const Eos &eos, long n, const double *vL, const double *vR,
     aux4[4 * q + 1] = aux.sl;
     aux4[4 * q + 2] = aux.sr;
     aux4[4 * q + 3] = aux.c2iso;
+    if constexpr (P::mhd && DIR < P::ndim) {
+      if (emf7 != nullptr) {   // what the interface hands to constrained transport (emf_store.cuh)
+        double *e = emf7 + 7 * q;
+        DevEmf dev{};
+        dev.ezi = dev.ezj = dev.eyk = e + 0;   // Et of the direction
+        dev.eyi = dev.exj = dev.exk = e + 1;   // Eb
+        dev.svx = dev.svy = dev.svz = e + 2;
+        dev.axL = dev.ayL = dev.azL = e + 3;
+        dev.axR = dev.ayR = dev.azR = e + 4;
+        dev.dxL = dev.dyL = dev.dzL = e + 5;
+        dev.dxR = dev.dyR = dev.dzR = e + 6;
+        const EmfFaceArrays A = emfFaceArrays<P::ndim, DIR>(dev);
+        storeEmf<P, DIR, SOLVER>(emfMode, A, 0, f, aux, l, r);
+      }
+    }
   }
 }
 
 template <class P, int SOLVER>
-static int byDir(int dir, const Eos &eos, long n, const double *vL, const double *vR, double *F, double *aux4) {
-  if (dir == 0) { solveAll<P, SOLVER, 0>(eos, n, vL, vR, F, aux4); return 0; }
-  if constexpr (P::ncomp >= 2) if (dir == 1) { solveAll<P, SOLVER, 1>(eos, n, vL, vR, F, aux4); return 0; }
-  if constexpr (P::ncomp == 3) if (dir == 2) { solveAll<P, SOLVER, 2>(eos, n, vL, vR, F, aux4); return 0; }
+static int byDir(int dir, const Eos &eos, long n, const double *vL, const double *vR, double *F, double *aux4,
+                 int emfMode, double *emf7) {
+  if (dir == 0) { solveAll<P, SOLVER, 0>(eos, n, vL, vR, F, aux4, emfMode, emf7); return 0; }
+  if constexpr (P::ncomp >= 2) if (dir == 1) { solveAll<P, SOLVER, 1>(eos, n, vL, vR, F, aux4, emfMode, emf7); return 0; }
+  if constexpr (P::ncomp == 3) if (dir == 2) { solveAll<P, SOLVER, 2>(eos, n, vL, vR, F, aux4, emfMode, emf7); return 0; }
   return 1;
 }
 
 template <class P>
 static int bySolver(int solver, int dir, const Eos &eos, long n, const double *vL, const double *vR, double *F,
-                    double *aux4) {
-  if (solver == SOLVER_TVDLF) return byDir<P, SOLVER_TVDLF>(dir, eos, n, vL, vR, F, aux4);
-  if (solver == SOLVER_HLL) return byDir<P, SOLVER_HLL>(dir, eos, n, vL, vR, F, aux4);
+                    double *aux4, int emfMode, double *emf7) {
+  if (solver == SOLVER_TVDLF) return byDir<P, SOLVER_TVDLF>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+  if (solver == SOLVER_HLL) return byDir<P, SOLVER_HLL>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   if constexpr (P::mhd) {
-    if (solver == SOLVER_HLLD) return byDir<P, SOLVER_HLLD>(dir, eos, n, vL, vR, F, aux4);
-    if constexpr (!P::iso) if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4);
+    if (solver == SOLVER_HLLD) return byDir<P, SOLVER_HLLD>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+    if constexpr (!P::iso) if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   } else {
-    if (solver == SOLVER_HLLC) return byDir<P, SOLVER_HLLC>(dir, eos, n, vL, vR, F, aux4);
+    if (solver == SOLVER_HLLC) return byDir<P, SOLVER_HLLC>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   }
   return 2;
 }
 
-template <int NC>
+template <int ND, int NC>
 static int byPhysics(int mhd, int iso, int solver, int dir, const Eos &eos, long n, const double *vL,
-                     const double *vR, double *F, double *aux4) {
-  if (mhd && iso) return bySolver<Phys<NC, NC, true, true>>(solver, dir, eos, n, vL, vR, F, aux4);
-  if (mhd) return bySolver<Phys<NC, NC, true, false>>(solver, dir, eos, n, vL, vR, F, aux4);
-  if (iso) return bySolver<Phys<NC, NC, false, true>>(solver, dir, eos, n, vL, vR, F, aux4);
-  return bySolver<Phys<NC, NC, false, false>>(solver, dir, eos, n, vL, vR, F, aux4);
+                     const double *vR, double *F, double *aux4, int emfMode, double *emf7) {
+  if (mhd && iso) return bySolver<Phys<ND, NC, true, true>>(solver, dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+  if (mhd) return bySolver<Phys<ND, NC, true, false>>(solver, dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+  if (iso) return bySolver<Phys<ND, NC, false, true>>(solver, dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+  return bySolver<Phys<ND, NC, false, false>>(solver, dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
 }
 
-// states are packed (n, nvar) in the reference's variable order; aux4 receives (cmax, sl, sr, c2iso) per state.
+// states are packed (n, nvar) in the reference's variable order; aux4 receives (cmax, sl, sr, c2iso) per state and,
+// for MHD with dir < ndim and emf7 != NULL, emf7 receives (Et, Eb, SV, aL, aR, dL, dR) as stored for emfMode.
 // returns 0, or non-zero for a combination the product does not implement
-extern "C" int idfx_host_riemann(int ncomp, int mhd, int iso, int solver, int dir, double gamma, double csiso,
-                                 long n, const double *vL, const double *vR, double *F, double *aux4) {
+extern "C" int idfx_host_riemann(int ndim, int ncomp, int mhd, int iso, int solver, int dir, double gamma,
+                                 double csiso, long n, const double *vL, const double *vR, double *F, double *aux4,
+                                 int emfMode, double *emf7) {
   Eos eos;
   eos.gamma = gamma;
   eos.csiso = csiso;
-  if (ncomp == 1) return byPhysics<1>(mhd, iso, solver, dir, eos, n, vL, vR, F, aux4);
-  if (ncomp == 2) return byPhysics<2>(mhd, iso, solver, dir, eos, n, vL, vR, F, aux4);
-  if (ncomp == 3) return byPhysics<3>(mhd, iso, solver, dir, eos, n, vL, vR, F, aux4);
+#define IDFX_CASE(ND, NC) \
+  if (ndim == ND && ncomp == NC) \
+    return byPhysics<ND, NC>(mhd, iso, solver, dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+  IDFX_CASE(1, 1)
+  IDFX_CASE(2, 2)
+  IDFX_CASE(3, 3)
+  IDFX_CASE(2, 3)
+  IDFX_CASE(1, 3)
+#undef IDFX_CASE
   return 3;
 }

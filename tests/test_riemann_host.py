@@ -25,7 +25,8 @@ def host_lib(tmp_path_factory):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-3000:]
     lib = C.CDLL(str(out))
-    lib.idfx_host_riemann.argtypes = [C.c_int] * 5 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 4
+    lib.idfx_host_riemann.argtypes = ([C.c_int] * 6 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 4
+                                      + [C.c_int, C.c_void_p])
     return lib
 
 
@@ -86,8 +87,8 @@ def test_product_solver_source_equals_oracle_bitwise(host_lib, mhd, iso, solver,
         vL, vR = states(rng, n, ncomp, mhd, iso, dir)
         Fo, auxo = o.riemann(dir, vL, vR)
         Fp, auxp = np.zeros_like(vL), np.zeros((n, 4))
-        rc = host_lib.idfx_host_riemann(ncomp, int(mhd), int(iso), SOLVERS[solver], dir, gamma, csiso, n,
-                                        vL.ctypes.data, vR.ctypes.data, Fp.ctypes.data, auxp.ctypes.data)
+        rc = host_lib.idfx_host_riemann(ncomp, ncomp, int(mhd), int(iso), SOLVERS[solver], dir, gamma, csiso, n,
+                                        vL.ctypes.data, vR.ctypes.data, Fp.ctypes.data, auxp.ctypes.data, 0, None)
         assert rc == 0
         assert np.isfinite(Fo).all(), "the state generator produced an unphysical pair"
         bad = np.flatnonzero((Fo.view(np.int64) != Fp.view(np.int64)).any(axis=1))
@@ -96,4 +97,39 @@ def test_product_solver_source_equals_oracle_bitwise(host_lib, mhd, iso, solver,
         assert (auxo[:, 0].view(np.int64) == auxp[:, 0].view(np.int64)).all(), "cmax differs"
         if mhd:   # outermost speeds feed the UCT-HLL / UCT-HLLD coefficients
             assert (auxo[:, 1:3].view(np.int64) == auxp[:, 1:3].view(np.int64)).all(), "sl / sr differ"
+    o.close()
+
+
+EMFS = {"arithmetic": 0, "uct0": 1, "uct_contact": 2, "uct_hll": 3, "uct_hlld": 4}
+EMF_CASES = [(nd, nc, iso, solver, emf)
+             for nd, nc in ((2, 2), (3, 3), (2, 3)) for iso in (False, True)
+             for solver, emfs in (("hlld", ("arithmetic", "uct_contact", "uct_hll", "uct_hlld")),
+                                  ("roe", ("uct0", "uct_contact", "uct_hlld")), ("hll", ("uct0", "uct_hll")),
+                                  ("tvdlf", ("arithmetic", "uct_contact")))
+             for emf in emfs if not (iso and (solver == "roe" or emf == "uct_hlld"))]
+
+
+@pytest.mark.parametrize("nd,nc,iso,solver,emf", EMF_CASES,
+                         ids=[f"{d}d{c}c-{'iso' if i else 'adi'}-{s}-{e}" for d, c, i, s, e in EMF_CASES])
+def test_emf_storage_source_equals_oracle_bitwise(host_lib, nd, nc, iso, solver, emf):
+    """what each interface hands to constrained transport (face EMFs, contact weights, UCT-HLL / UCT-HLLD
+    coefficients; emf_store.cuh) for 2-D, 3-D and 2.5-D"""
+    gamma, csiso, n = 1.4, 0.9, 20000
+    rng = np.random.default_rng(99 + 7 * nd + nc + SOLVERS[solver] + 31 * EMFS[emf])
+    o = Oracle(nd, nc, True, solver, emf, 2, [4] * nd + [1] * (3 - nd), ["periodic"] * nd, gamma, 0.5, 1e-4,
+               [0.1, 0.1, 0.1], csiso=csiso if iso else None)
+    for dir in range(nd):
+        vL, vR = states(rng, n, nc, True, iso, dir)
+        Fo, auxo, eo = o.riemann(dir, vL, vR, emf=True)
+        Fp, auxp, ep = np.zeros_like(vL), np.zeros((n, 4)), np.zeros((n, 7))
+        rc = host_lib.idfx_host_riemann(nd, nc, 1, int(iso), SOLVERS[solver], dir, gamma, csiso, n, vL.ctypes.data,
+                                        vR.ctypes.data, Fp.ctypes.data, auxp.ctypes.data, EMFS[emf], ep.ctypes.data)
+        assert rc == 0
+        assert (Fo.view(np.int64) == Fp.view(np.int64)).all()
+        # NaN coefficients (0/0 for two identical states at rest) must be NaN on both sides; everything else bitwise
+        same = (eo.view(np.int64) == ep.view(np.int64)) | (np.isnan(eo) & np.isnan(ep))
+        bad = np.flatnonzero(~same.all(axis=1))
+        assert bad.size == 0, (f"dir {dir}: {bad.size} of {n} differ, first at {bad[0]}: vL={vL[bad[0]]} vR={vR[bad[0]]} "
+                               f"oracle={eo[bad[0]]} product={ep[bad[0]]}")
+        assert np.nansum(np.abs(eo)) > 0
     o.close()
