@@ -20,7 +20,7 @@ IDFX_HD double minmodRef(double, double) { return 0.0; }
 IDFX_HD double vanLeer(double dvp, double dvm) {
   return (dvp * dvm > 0.0 ? 2.0 * dvp * dvm / (dvp + dvm) : 0.0);
 }
-IDFX_D double vanLeerFast(double dvp, double dvm, double cp, double cm) {
+IDFX_DEV double vanLeerFast(double dvp, double dvm, double cp, double cm) {
   const bool on = dvp * dvm > 0.0;
   const double q = idfxDivFast(on ? dvp * dvm * (cp * dvm + cm * dvp) : 1.0,
                                on ? dvp * dvp + dvm * dvm + (cp + cm - 2.0) * dvp * dvm : 1.0);
@@ -29,7 +29,7 @@ IDFX_D double vanLeerFast(double dvp, double dvm, double cp, double cm) {
 // the same with the branch-free division (device only; fastmath.cuh).  The quotient is formed unconditionally
 // and selected afterwards, so the limiter stays inside one basic block; when the product is not positive the
 // operands are replaced by harmless ones so that the range check is not tripped by a value that is discarded.
-IDFX_D double vanLeerFast(double dvp, double dvm) {
+IDFX_DEV double vanLeerFast(double dvp, double dvm) {
   const bool on = dvp * dvm > 0.0;
   const double q = idfxDivFast(on ? 2.0 * dvp * dvm : 1.0, on ? dvp + dvm : 1.0);
   return on ? q : 0.0;

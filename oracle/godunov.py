@@ -48,6 +48,10 @@ def lib():
         L.oracle_cycle.argtypes = [C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5
         L.oracle_riemann.restype = None
+        L.oracle_reconstruct.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.oracle_reconstruct.restype = None
+        L.oracle_convert.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_convert.restype = None
         L.oracle_run.argtypes = [C.c_void_p, C.c_double, C.c_long]
         _lib = L
     return _lib

@@ -1132,6 +1132,17 @@ void oracle_riemann(Oracle *o, int dir, long n, const double *vL, const double *
   }
 }
 
+/* reconstruction along a 1-D array (interfaces 3 .. n-3) and the two conversions, for tests/test_riemann_host.py */
+void oracle_reconstruct(int order, long n, const double *q, int positive, double dx, double *vL, double *vR) {
+  for (long i = 3; i < n - 2; i++) reconstruct_interface(order, q + i, 1, positive, dx, &vL[i], &vR[i]);
+}
+void oracle_convert(Oracle *o, long n, double *u, double *v, double *u2) {
+  for (long q = 0; q < n; q++) {
+    cons_to_prim(o, u + q * o->nvar, v + q * o->nvar);
+    prim_to_cons(o, v + q * o->nvar, u2 + q * o->nvar);
+  }
+}
+
 /* ---- RiemannSolver::CalcFlux<dir>: reconstruct (extrapolateToFaces.hpp:89-124), solve, store ------ */
 static void calc_flux(Oracle *o, int dir) {
   const OracleDesc *d = &o->d;

@@ -103,3 +103,53 @@ extern "C" int idfx_host_riemann(int ndim, int ncomp, int mhd, int iso, int solv
 #undef IDFX_CASE
   return 3;
 }
+
+// ---- reconstruction (recon.cuh): the per-CELL form used by the pencil sweeps, evaluated along a 1-D array and
+// re-assembled per interface: vL[i] = right face value of cell i-1, vR[i] = left face value of cell i ----------
+#include "recon.cuh"
+
+template <int ORDER>
+static void reconstructAll(long n, const double *q, int positive, double dx, double *vL, double *vR) {
+  const double wc[6] = {0, 0, 0, 0, 0, 0};
+  for (long i = 3; i < n - 2; i++) {
+    double lo[2], hi[2];
+    for (int side = 0; side < 2; side++) {
+      const long c = i - 1 + side;
+      const double st[5] = {q[c - 2], q[c - 1], q[c], q[c + 1], q[c + 2]};
+      reconstructCell<ORDER, false>(st, positive != 0, true, wc, dx, lo[side], hi[side]);
+    }
+    vL[i] = hi[0];
+    vR[i] = lo[1];
+  }
+}
+
+extern "C" int idfx_host_reconstruct(int order, long n, const double *q, int positive, double dx, double *vL,
+                                     double *vR) {
+  if (order == 2) reconstructAll<2>(n, q, positive, dx, vL, vR);
+  else if (order == 3) reconstructAll<3>(n, q, positive, dx, vL, vR);
+  else if (order == 4) reconstructAll<4>(n, q, positive, dx, vL, vR);
+  else return 1;
+  return 0;
+}
+
+// ---- conservative <-> primitive conversion with the pressure floor (phys.cuh) -----------------------------------
+template <class P>
+static void convertAll(const Eos &eos, long n, double *u, double *v, double *u2) {
+  for (long q = 0; q < n; q++) {
+    consToPrim<P>(v + q * P::nvar, u + q * P::nvar, eos);       // may rewrite the energy
+    primToCons<P>(u2 + q * P::nvar, v + q * P::nvar, eos);
+  }
+}
+
+extern "C" int idfx_host_convert(int ncomp, int mhd, int iso, double gamma, double csiso, long n, double *u, double *v,
+                                 double *u2) {
+  Eos eos;
+  eos.gamma = gamma;
+  eos.csiso = csiso;
+#define IDFX_CASE(NC, M, I) \
+  if (ncomp == NC && mhd == M && iso == I) { convertAll<Phys<NC, NC, M != 0, I != 0>>(eos, n, u, v, u2); return 0; }
+  IDFX_CASE(1, 0, 0) IDFX_CASE(2, 0, 0) IDFX_CASE(3, 0, 0) IDFX_CASE(1, 0, 1) IDFX_CASE(3, 0, 1)
+  IDFX_CASE(1, 1, 0) IDFX_CASE(2, 1, 0) IDFX_CASE(3, 1, 0) IDFX_CASE(2, 1, 1) IDFX_CASE(3, 1, 1)
+#undef IDFX_CASE
+  return 1;
+}

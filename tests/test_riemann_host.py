@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from oracle.godunov import Oracle
+from oracle.godunov import Oracle, lib as oracle_lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SOLVERS = {"tvdlf": 0, "hll": 1, "hllc": 2, "hlld": 3, "roe": 4}
@@ -27,6 +27,8 @@ def host_lib(tmp_path_factory):
     lib = C.CDLL(str(out))
     lib.idfx_host_riemann.argtypes = ([C.c_int] * 6 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 4
                                       + [C.c_int, C.c_void_p])
+    lib.idfx_host_reconstruct.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    lib.idfx_host_convert.argtypes = [C.c_int] * 3 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 3
     return lib
 
 
@@ -132,4 +134,52 @@ def test_emf_storage_source_equals_oracle_bitwise(host_lib, nd, nc, iso, solver,
         assert bad.size == 0, (f"dir {dir}: {bad.size} of {n} differ, first at {bad[0]}: vL={vL[bad[0]]} vR={vR[bad[0]]} "
                                f"oracle={eo[bad[0]]} product={ep[bad[0]]}")
         assert np.nansum(np.abs(eo)) > 0
+    o.close()
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+@pytest.mark.parametrize("positive", [0, 1])
+def test_reconstruction_source_equals_oracle_bitwise(host_lib, order, positive):
+    """recon.cuh evaluates the limited profile once per CELL (the pencil sweeps reuse it for both faces); the
+    reference and the oracle evaluate it per INTERFACE -- same bits on smooth data, extrema, jumps, plateaus
+    and (positive = 1: density / pressure) on profiles that would reconstruct to negative values"""
+    rng = np.random.default_rng(5 + order)
+    n = 200000
+    q = np.cumsum(rng.standard_normal(n)) * 0.1 + np.sin(np.arange(n) * 0.05)
+    q[n // 4:n // 4 + 2000] = 1.0                                        # plateau
+    q[n // 2:n // 2 + 5000] = 10.0 ** rng.uniform(-6, 2, 5000)           # wild positive jumps
+    q[3 * n // 4:3 * n // 4 + 5000] = np.abs(q[3 * n // 4:3 * n // 4 + 5000]) * rng.choice([1e-8, 1.0], 5000)
+    if positive:
+        q = np.abs(q) + 1e-12
+    q = np.ascontiguousarray(q)
+    out = [np.zeros(n) for _ in range(4)]
+    oracle_lib().oracle_reconstruct(order, n, q.ctypes.data, positive, 0.01, out[0].ctypes.data, out[1].ctypes.data)
+    assert host_lib.idfx_host_reconstruct(order, n, q.ctypes.data, positive, 0.01, out[2].ctypes.data,
+                                          out[3].ctypes.data) == 0
+    assert np.abs(out[0]).sum() > 0
+    assert (out[0].view(np.int64) == out[2].view(np.int64)).all(), "left states differ"
+    assert (out[1].view(np.int64) == out[3].view(np.int64)).all(), "right states differ"
+
+
+@pytest.mark.parametrize("ncomp,mhd,iso", [(1, 0, 0), (2, 0, 0), (3, 0, 0), (1, 0, 1), (3, 0, 1), (1, 1, 0), (2, 1, 0),
+                                           (3, 1, 0), (2, 1, 1), (3, 1, 1)])
+def test_conversion_source_equals_oracle_bitwise(host_lib, ncomp, mhd, iso):
+    """K_ConsToPrim (with the pressure floor rewriting the energy) followed by K_PrimToCons (phys.cuh)"""
+    rng = np.random.default_rng(77 + ncomp + 2 * mhd + 4 * iso)
+    n = 100000
+    nvar = 1 + ncomp + (0 if iso else 1) + (ncomp if mhd else 0)
+    u = rng.uniform(-2.0, 2.0, (n, nvar))
+    u[:, 0] = 10.0 ** rng.uniform(-3, 2, n)
+    if not iso:
+        u[:, ncomp + 1] = rng.uniform(-0.5, 20.0, n)      # some energies below kinetic + magnetic: the floor fires
+    o = Oracle(ncomp, ncomp, bool(mhd), "hll", "uct_contact", 2, [4] * ncomp + [1] * (3 - ncomp), ["periodic"] * ncomp,
+               1.4, 0.5, 1e-4, [0.1, 0.1, 0.1], csiso=0.8 if iso else None)
+    uo, vo, u2o = u.copy(), np.zeros_like(u), np.zeros_like(u)
+    up, vp, u2p = u.copy(), np.zeros_like(u), np.zeros_like(u)
+    oracle_lib().oracle_convert(o.h, n, uo.ctypes.data, vo.ctypes.data, u2o.ctypes.data)
+    assert host_lib.idfx_host_convert(ncomp, mhd, iso, 1.4, 0.8, n, up.ctypes.data, vp.ctypes.data, u2p.ctypes.data) == 0
+    if not iso:
+        assert (uo != u).any(), "the pressure floor never fired"
+    for a, b in ((uo, up), (vo, vp), (u2o, u2p)):
+        assert (a.view(np.int64) == b.view(np.int64)).all()
     o.close()
