@@ -8,6 +8,7 @@
 #include "riemann_hd.cuh"
 #include "riemann_mhd.cuh"
 #include "riemann_roe.cuh"
+#include "riemann_roe_hd.cuh"
 #include "emf_store.cuh"
 
 template <class P, int SOLVER, int DIR>
@@ -27,6 +28,7 @@ static void solveAll(const Eos &eos, long n, const double *vL, const double *vR,
       if constexpr (SOLVER == SOLVER_TVDLF) riemannTvdlfHD<P, DIR>(l, r, eos, f, aux);
       if constexpr (SOLVER == SOLVER_HLL) riemannHllHD<P, DIR>(l, r, eos, f, aux);
       if constexpr (SOLVER == SOLVER_HLLC) riemannHllcHD<P, DIR>(l, r, eos, f, aux);
+      if constexpr (SOLVER == SOLVER_ROE) aux.c2iso = riemannRoeHD<P, DIR>(l, r, eos, f, aux) ? 1.0 : 0.0;   // keep-flux flag
     }
     for (int v = 0; v < P::nvar; v++) F[q * P::nvar + v] = f[v];
     aux4[4 * q + 0] = aux.cmax;
@@ -70,6 +72,7 @@ static int bySolver(int solver, int dir, const Eos &eos, long n, const double *v
     if constexpr (!P::iso) if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   } else {
     if (solver == SOLVER_HLLC) return byDir<P, SOLVER_HLLC>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+    if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   }
   return 2;
 }
