@@ -328,7 +328,6 @@ int validate(const IdfxBlockDesc &d) {
       return fail("HLLD EMF reconstruction is only compatible with HLLD or ROE Riemann solvers");
   } else {
     if (d.solver == IDFX_HLLD) return fail("hlld Riemann solver requires a MHD fluid");
-    if (d.solver == IDFX_ROE) return fail("roe HD solver is not available in this build");
   }
   for (int dir = 0; dir < d.ndim; dir++) {
     const int need = (d.order == 4) ? 3 : 2;
@@ -381,7 +380,7 @@ int launchSweepDir(IdfxBlock *b, int dir, SweepArgs a) {
   int rc;
   const PhysCfg &c = b->cfg;
   if (!c.mhd) {
-    rc = idfxk::sweepHD(c, dir, a, b->stream);
+    rc = (c.solver == SOLVER_ROE) ? idfxk::sweepHDRoe(c, dir, a, b->stream) : idfxk::sweepHD(c, dir, a, b->stream);
   } else {
     switch (c.solver) {
       case SOLVER_TVDLF: rc = idfxk::sweepMhdTvdlf(c, dir, a, b->stream); break;

@@ -20,6 +20,7 @@ namespace idfxk {
 // ---- sweeps (sweep_*.cu) ----------------------------------------------------
 // returns cudaError_t as int; -1 when the (physics, solver, order) combination is not instantiated
 int sweepHD(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
+int sweepHDRoe(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
 int sweepMhdTvdlf(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
 int sweepMhdHll(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
 int sweepMhdHlld(const PhysCfg &c, int dir, const SweepArgs &a, cudaStream_t st);
