@@ -63,9 +63,8 @@ class Oracle:
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
                  cfl_max_var=1.1, ntracer=0, order=2, csiso=None):
-        if csiso is not None and mhd and (solver == "roe" or emf == "uct_hlld"):
-            raise ValueError("isothermal: the oracle restates TVDLF / HLL / HLLC / Roe (HD) and TVDLF / HLL / HLLD (MHD) "
-                             "only, and not the uct_hlld average (no reference run pins it)")
+        if csiso is not None and mhd and solver == "roe":
+            raise ValueError("isothermal: the oracle restates TVDLF / HLL / HLLC / Roe (HD) and TVDLF / HLL / HLLD (MHD)")
         if mhd and solver == "tvdlf" and emf in ("uct_hll", "uct_hlld"):
             raise ValueError("TVDLF-MHD stores no upwind coefficients for uct_hlld and extends its sweeps by one "
                              "cell only (tvdlfMHD.hpp:30-41, 226-229): not pinned by any reference run")
@@ -102,6 +101,9 @@ class Oracle:
         names = {1: "periodic", 3: "outflow"}
         nd = defs.dimensions
         emf = inp.Get(str, "Hydro", "emf", 0) if inp.CheckEntry("Hydro", "emf") >= 0 else "uct_contact"
+        if defs.isothermal and defs.mhd and emf == "uct_hlld":
+            raise ValueError("isothermal uct_hlld is restated but pinned by no reference run (the reference crashes "
+                             "on it in 2.5-D): usable for solver-level cross-checks only, not as a cycle-level checker")
         first_dt = inp.GetOrSet(float, "TimeIntegrator", "first_dt", 0, 1e-10)
         o = cls(nd, defs.components, defs.mhd, inp.Get(str, "Hydro", "solver", 0), emf,
                 inp.Get(int, "TimeIntegrator", "nstages", 0), grid.np_int, [names[grid.lbound[a]] for a in range(nd)],

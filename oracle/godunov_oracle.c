@@ -13,8 +13,9 @@
  * averaging (PPM corner states when ORDER is 4), passive tracers, periodic and outflow boundaries (with
  * ReconstructNormalField on the outflow sides in MHD), RK1/2/3, CFL time-step control; and the isothermal
  * EOS (constant sound speed) for HD TVDLF / HLL / HLLC / Roe and MHD TVDLF / HLL / HLLD.
- * Isothermal Roe and uct_hlld, and curvilinear geometry are pinned through the reference binaries
- * and golden dumps only (tests/golden).
+ * Isothermal Roe-MHD and curvilinear geometry are pinned through the reference binaries and golden dumps only
+ * (tests/golden); the isothermal uct_hlld coefficients are restated for solver-level cross-checks but pinned by no
+ * reference run.
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
  * Compile with -O2 -ffp-contract=off: expression association follows the reference so results are
@@ -1063,10 +1064,23 @@ static void store_emf(Oracle *o, int dir, long c, const double *F, const Speeds 
   const double uLr = vL[RHO], uRr = vR[RHO], uLm = vL[Xn] * vL[RHO], uRm = vR[Xn] * vR[RHO];
   const double Bn = (sr * vR[BXn] - sl * vL[BXn]) / (sr - sl);
   const double duL = sl - vL[Xn], duR = sr - vR[Xn];
-  double s2 = 1.0 / (duR * uRr - duL * uLr);
-  const double Sc = (duR * uRm - duL * uLm - ptR + ptL) * s2;
-  const double sqrL = sqrt(uLr * duL / (sl - Sc)), sqrR = sqrt(uRr * duR / (sr - Sc));
-  const double SaL = Sc - fabs(Bn) / sqrL, SaR = Sc + fabs(Bn) / sqrR;
+  double Sc, SaL, SaR;
+  if (o->d.isothermal) { /* storeFlux.hpp:147-155: one density, one Alfven speed for both sides.  Cross-checked
+                          * against the product's source only (tests/test_riemann_host.py): no reference run pins
+                          * it, the reference crashes with uct_hlld in the 2.5-D isothermal set-up */
+    const double sc0 = 1.0 / (sr - sl);
+    const double rho_h = (uRr * duR - uLr * duL) * sc0;
+    Sc = (sl * uRr * duR - sr * uLr * duL) * sc0 / rho_h;
+    const double sqrho_h = sqrt(rho_h);
+    SaL = Sc - fabs(Bn) / sqrho_h;
+    SaR = Sc + fabs(Bn) / sqrho_h;
+  } else {
+    double s2 = 1.0 / (duR * uRr - duL * uLr);
+    Sc = (duR * uRm - duL * uLm - ptR + ptL) * s2;
+    const double sqrL = sqrt(uLr * duL / (sl - Sc)), sqrR = sqrt(uRr * duR / (sr - Sc));
+    SaL = Sc - fabs(Bn) / sqrL;
+    SaR = Sc + fabs(Bn) / sqrR;
+  }
   int revert = 0;
   if ((SaL - sl) < 1e-4 * (Sc - sl)) revert = 1;
   if ((SaR - sr) > -1e-4 * (sr - Sc)) revert = 1;

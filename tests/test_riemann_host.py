@@ -113,7 +113,7 @@ EMF_CASES = [(nd, nc, iso, solver, emf)
              for solver, emfs in (("hlld", ("arithmetic", "uct_contact", "uct_hll", "uct_hlld")),
                                   ("roe", ("uct0", "uct_contact", "uct_hlld")), ("hll", ("uct0", "uct_hll")),
                                   ("tvdlf", ("arithmetic", "uct_contact")))
-             for emf in emfs if not (iso and (solver == "roe" or emf == "uct_hlld"))]
+             for emf in emfs if not (iso and solver == "roe")]
 
 
 @pytest.mark.parametrize("nd,nc,iso,solver,emf", EMF_CASES,
