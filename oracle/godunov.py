@@ -63,8 +63,6 @@ class Oracle:
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
                  cfl_max_var=1.1, ntracer=0, order=2, csiso=None):
-        if csiso is not None and mhd and solver == "roe":
-            raise ValueError("isothermal: the oracle restates TVDLF / HLL / HLLC / Roe (HD) and TVDLF / HLL / HLLD (MHD)")
         if mhd and solver == "tvdlf" and emf in ("uct_hll", "uct_hlld"):
             raise ValueError("TVDLF-MHD stores no upwind coefficients for uct_hlld and extends its sweeps by one "
                              "cell only (tvdlfMHD.hpp:30-41, 226-229): not pinned by any reference run")

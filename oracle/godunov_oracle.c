@@ -12,9 +12,9 @@
  * MHD solvers TVDLF / HLL / HLLD / Roe, constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld
  * averaging (PPM corner states when ORDER is 4), passive tracers, periodic and outflow boundaries (with
  * ReconstructNormalField on the outflow sides in MHD), RK1/2/3, CFL time-step control; and the isothermal
- * EOS (constant sound speed) for HD TVDLF / HLL / HLLC / Roe and MHD TVDLF / HLL / HLLD.
- * Isothermal Roe-MHD and curvilinear geometry are pinned through the reference binaries and golden dumps only
- * (tests/golden); the isothermal uct_hlld coefficients are restated for solver-level cross-checks but pinned by no
+ * EOS (constant sound speed) for the same solvers.
+ * Curvilinear geometry is pinned through the reference binaries and golden dumps only (tests/golden); the
+ * isothermal uct_hlld coefficients are restated for solver-level cross-checks but pinned by no
  * reference run.
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
@@ -566,11 +566,14 @@ static void riemann_hd(const Oracle *o, int dir, const double *vL, const double 
   }
 }
 
-/* ---- RoeMHD<DIR>, adiabatic: roeMHD.hpp:180-654 (Cargo & Gallice eigenvectors, entropy fix delta = 1e-6).
+/* ---- RoeMHD<DIR> (adiabatic and isothermal): roeMHD.hpp:180-654 (Cargo & Gallice eigenvectors, entropy fix delta = 1e-6).
  * Modes in the reference's order: fast-, fast+, divB, entropy, slow-, slow+, Alfven-, Alfven+. ------------- */
 static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const double *vR, double *F, Speeds *sp) {
-  enum { KFASTM = 0, KFASTP = 1, KDIVB = 2, KENTRP = 3, KSLOWM = 4, KSLOWP = 5, KALFVM = 6, KALFVP = 7 };
-  const int NV = o->nvar, nc = o->d.ncomp, RHO = o->RHO, ENG = o->ENG, PRS = o->ENG;
+  /* mode numbering, roeMHD.hpp:20-44: no entropy mode without an energy equation */
+  const int iso = o->d.isothermal;
+  const int KFASTM = 0, KFASTP = 1, KDIVB = 2, KENTRP = 3, KSLOWM = iso ? 3 : 4, KSLOWP = iso ? 4 : 5,
+            KALFVM = iso ? 5 : 6, KALFVP = iso ? 6 : 7;
+  const int NV = o->nvar, nc = o->d.ncomp, RHO = o->RHO, ENG = iso ? 7 : o->ENG, PRS = ENG; /* iso: scratch slot 7 */
   const int Xn = o->MX1 + dir, Xt = o->MX1 + tdir(dir), Xb = o->MX1 + bdir(dir);
   const int BXn = o->BX1 + dir, BXt = o->BX1 + tdir(dir), BXb = o->BX1 + bdir(dir);
   const double delta = 1.e-6, gamma = o->d.gamma;
@@ -579,8 +582,14 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
   prim_to_cons(o, vL, uL);
   prim_to_cons(o, vR, uR);
   for (int n = 0; n < NV; n++) dU[n] = uR[n] - uL[n];
-  phys_flux(o, dir, vL, uL, fL, 0.0);
-  phys_flux(o, dir, vR, uR, fR, 0.0);
+  double a2L = 1.0, a2R = 1.0;
+  if (iso) { /* roeMHD.hpp:228-232 */
+    a2L = 0.5 * (o->d.csiso + o->d.csiso);
+    a2L = a2L * a2L;
+    a2R = a2L;
+  }
+  phys_flux(o, dir, vL, uL, fL, a2L);
+  phys_flux(o, dir, vR, uR, fR, a2R);
   for (int a = 0; a < 8; a++)
     for (int b = 0; b < 8; b++) Rc[a][b] = 0;
 
@@ -615,7 +624,7 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
     Bmag2L = Bmag2L + vL[o->BX1 + c] * vL[o->BX1 + c];
     Bmag2R = Bmag2R + vR[o->BX1 + c] * vR[o->BX1 + c];
   }
-  const double pL = vL[PRS] + 0.5 * Bmag2L, pR = vR[PRS] + 0.5 * Bmag2R;
+  const double pL = (iso ? a2L * vL[RHO] : vL[PRS]) + 0.5 * Bmag2L, pR = (iso ? a2R * vR[RHO] : vR[PRS]) + 0.5 * Bmag2R;
   double vdm = u * dU[Xn];
   if (nc >= 2) vdm = vdm + v * dU[Xt];
   if (nc == 3) vdm = vdm + w * dU[Xb];
@@ -625,11 +634,16 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
   double vel2 = u * u;
   if (nc >= 2) vel2 = vel2 + v * v;
   if (nc == 3) vel2 = vel2 + w * w;
-  dV[PRS] = (gamma - 1.0) * ((0.5 * vel2 - X) * dV[RHO] - vdm + dU[ENG] - BdB);
-  const double HL = (uL[ENG] + pL) / vL[RHO], HR = (uR[ENG] + pR) / vR[RHO];
-  const double H = sl * HL + sr * HR;
-  const double Hgas = H - b2;
-  const double a2 = (2.0 - gamma) * X + (gamma - 1.0) * (Hgas - 0.5 * vel2);
+  double Hgas = 0.0, a2;
+  if (!iso) {
+    dV[PRS] = (gamma - 1.0) * ((0.5 * vel2 - X) * dV[RHO] - vdm + dU[ENG] - BdB);
+    const double HL = (uL[ENG] + pL) / vL[RHO], HR = (uR[ENG] + pR) / vR[RHO];
+    const double H = sl * HL + sr * HR;
+    Hgas = H - b2;
+    a2 = (2.0 - gamma) * X + (gamma - 1.0) * (Hgas - 0.5 * vel2);
+  } else {
+    a2 = 0.5 * (a2L + a2R) + X; /* roeMHD.hpp:326-327 */
+  }
 
   /* characteristic speeds, roeMHD.hpp:336-371 */
   double scrh = a2 - b2;
@@ -692,8 +706,12 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
   if (nc == 3) Rc[BXb][kk] = alpha_s * a * beta_z / sqrt_rho;
   if (nc >= 2) beta_v = beta_v + beta_y * v;
   if (nc == 3) beta_v = beta_v + beta_z * w;
-  Rc[ENG][kk] = alpha_f * (Hgas - u * cf) + scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
-  eta[kk] = alpha_f * (X * dV[RHO] + dV[PRS]);
+  if (!iso) {
+    Rc[ENG][kk] = alpha_f * (Hgas - u * cf) + scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
+    eta[kk] = alpha_f * (X * dV[RHO] + dV[PRS]);
+  } else {
+    eta[kk] = alpha_f * a2 * dV[RHO];
+  }
   eta[kk] += rho * scrh * beta_dv - rho * alpha_f * cf * dV[Xn] + sqrt_rho * alpha_s * a * beta_dB;
   eta[kk] *= 0.5 / a2;
 
@@ -705,19 +723,26 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
   if (nc == 3) Rc[Xb][kk] = alpha_f * w - scrh * beta_z;
   if (nc >= 2) Rc[BXt][kk] = Rc[BXt][KFASTM];
   if (nc == 3) Rc[BXb][kk] = Rc[BXb][KFASTM];
-  Rc[ENG][kk] = alpha_f * (Hgas + u * cf) - scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
-  eta[kk] = alpha_f * (X * dV[RHO] + dV[PRS]) - rho * scrh * beta_dv + rho * alpha_f * cf * dV[Xn] +
-            sqrt_rho * alpha_s * a * beta_dB;
+  if (!iso) {
+    Rc[ENG][kk] = alpha_f * (Hgas + u * cf) - scrh * beta_v + alpha_s * a * Btmag / sqrt_rho;
+    eta[kk] = alpha_f * (X * dV[RHO] + dV[PRS]) - rho * scrh * beta_dv + rho * alpha_f * cf * dV[Xn] +
+              sqrt_rho * alpha_s * a * beta_dB;
+  } else {
+    eta[kk] = alpha_f * (0. * X + a2) * dV[RHO] - rho * scrh * beta_dv + rho * alpha_f * cf * dV[Xn] +
+              sqrt_rho * alpha_s * a * beta_dB;
+  }
   eta[kk] *= 0.5 / a2;
 
-  kk = KENTRP; /* entropy wave */
-  lambda[kk] = u;
-  Rc[RHO][kk] = 1.0;
-  Rc[Xn][kk] = u;
-  if (nc >= 2) Rc[Xt][kk] = v;
-  if (nc == 3) Rc[Xb][kk] = w;
-  Rc[ENG][kk] = 0.5 * vel2 + (gamma - 2.0) / (gamma - 1.0) * X;
-  eta[kk] = ((a2 - X) * dV[RHO] - dV[PRS]) / a2;
+  if (!iso) {
+    kk = KENTRP; /* entropy wave */
+    lambda[kk] = u;
+    Rc[RHO][kk] = 1.0;
+    Rc[Xn][kk] = u;
+    if (nc >= 2) Rc[Xt][kk] = v;
+    if (nc == 3) Rc[Xb][kk] = w;
+    Rc[ENG][kk] = 0.5 * vel2 + (gamma - 2.0) / (gamma - 1.0) * X;
+    eta[kk] = ((a2 - X) * dV[RHO] - dV[PRS]) / a2;
+  }
 
   kk = KDIVB; /* div B wave: no jump with constrained transport */
   lambda[kk] = u;
@@ -733,9 +758,14 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
     if (nc == 3) Rc[Xb][kk] = alpha_s * w - scrh * beta_z;
     if (nc >= 2) Rc[BXt][kk] = -alpha_f * a * beta_y / sqrt_rho;
     if (nc == 3) Rc[BXb][kk] = -alpha_f * a * beta_z / sqrt_rho;
-    Rc[ENG][kk] = alpha_s * (Hgas - u * cs) - scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
-    eta[kk] = alpha_s * (X * dV[RHO] + dV[PRS]) - rho * scrh * beta_dv - rho * alpha_s * cs * dV[Xn] -
-              sqrt_rho * alpha_f * a * beta_dB;
+    if (!iso) {
+      Rc[ENG][kk] = alpha_s * (Hgas - u * cs) - scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
+      eta[kk] = alpha_s * (X * dV[RHO] + dV[PRS]) - rho * scrh * beta_dv - rho * alpha_s * cs * dV[Xn] -
+                sqrt_rho * alpha_f * a * beta_dB;
+    } else {
+      eta[kk] = alpha_s * (0. * X + a2) * dV[RHO] - rho * scrh * beta_dv - rho * alpha_s * cs * dV[Xn] -
+                sqrt_rho * alpha_f * a * beta_dB;
+    }
     eta[kk] *= 0.5 / a2;
 
     kk = KSLOWP; /* slow wave u + cs */
@@ -746,9 +776,14 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
     if (nc == 3) Rc[Xb][kk] = alpha_s * w + scrh * beta_z;
     if (nc >= 2) Rc[BXt][kk] = Rc[BXt][KSLOWM];
     if (nc == 3) Rc[BXb][kk] = Rc[BXb][KSLOWM];
-    Rc[ENG][kk] = alpha_s * (Hgas + u * cs) + scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
-    eta[kk] = alpha_s * (X * dV[RHO] + dV[PRS]) + rho * scrh * beta_dv + rho * alpha_s * cs * dV[Xn] -
-              sqrt_rho * alpha_f * a * beta_dB;
+    if (!iso) {
+      Rc[ENG][kk] = alpha_s * (Hgas + u * cs) + scrh * beta_v - alpha_f * a * Btmag / sqrt_rho;
+      eta[kk] = alpha_s * (X * dV[RHO] + dV[PRS]) + rho * scrh * beta_dv + rho * alpha_s * cs * dV[Xn] -
+                sqrt_rho * alpha_f * a * beta_dB;
+    } else {
+      eta[kk] = alpha_s * (0. * X + a2) * dV[RHO] + rho * scrh * beta_dv + rho * alpha_s * cs * dV[Xn] -
+                sqrt_rho * alpha_f * a * beta_dB;
+    }
     eta[kk] *= 0.5 / a2;
   }
   if (nc == 3) {
@@ -758,7 +793,7 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
     Rc[Xb][kk] = +rho * beta_y;
     Rc[BXt][kk] = -sBx * sqrt_rho * beta_z;
     Rc[BXb][kk] = sBx * sqrt_rho * beta_y;
-    Rc[ENG][kk] = -rho * (v * beta_z - w * beta_y);
+    if (!iso) Rc[ENG][kk] = -rho * (v * beta_z - w * beta_y);
     eta[kk] = +beta_y * dV[Xb] - beta_z * dV[Xt] + sBx / sqrt_rho * (beta_y * dV[BXb] - beta_z * dV[BXt]);
     eta[kk] *= 0.5;
     kk = KALFVP; /* Alfven wave u + ca */
@@ -767,7 +802,7 @@ static void riemann_roe_mhd(const Oracle *o, int dir, const double *vL, const do
     Rc[Xb][kk] = -Rc[Xb][KALFVM];
     Rc[BXt][kk] = Rc[BXt][KALFVM];
     Rc[BXb][kk] = Rc[BXb][KALFVM];
-    Rc[ENG][kk] = -Rc[ENG][KALFVM];
+    if (!iso) Rc[ENG][kk] = -Rc[ENG][KALFVM];
     eta[kk] = -beta_y * dV[Xb] + beta_z * dV[Xt] + sBx / sqrt_rho * (beta_y * dV[BXb] - beta_z * dV[BXt]);
     eta[kk] *= 0.5;
   }

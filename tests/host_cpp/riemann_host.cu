@@ -69,7 +69,7 @@ static int bySolver(int solver, int dir, const Eos &eos, long n, const double *v
   if (solver == SOLVER_HLL) return byDir<P, SOLVER_HLL>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   if constexpr (P::mhd) {
     if (solver == SOLVER_HLLD) return byDir<P, SOLVER_HLLD>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
-    if constexpr (!P::iso) if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
+    if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
   } else {
     if (solver == SOLVER_HLLC) return byDir<P, SOLVER_HLLC>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);
     if (solver == SOLVER_ROE) return byDir<P, SOLVER_ROE>(dir, eos, n, vL, vR, F, aux4, emfMode, emf7);

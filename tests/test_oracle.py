@@ -82,8 +82,7 @@ def test_oracle_matches_shipped_golden(case):
 # ---- isothermal EOS: the problems live in the C++ host layer (idefix_b200/host/problems); the oracle starts
 # from the reference's own cycle-0 dump of the case and must reproduce its later dumps bit for bit ---------------
 ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2, 3, 1, True, True)}
-ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ISO_DEFS
-          and not (ISO_DEFS[c.setup].mhd and c.overrides.get(("Hydro", "solver")) == "roe")]
+ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ISO_DEFS]
 
 
 class _FromDump(Setup):
@@ -108,7 +107,7 @@ class _FromDump(Setup):
 
 @pytest.mark.parametrize("case", ISO_IN, ids=[c.name for c in ISO_IN])
 def test_isothermal_oracle_matches_reference_build_bitwise(case):
-    assert len(ISO_IN) >= 7
+    assert len(ISO_IN) >= 8
     s = _FromDump(case, readDump(os.path.join(GOLD, "short", f"{case.name}.c0000.dmp")))
     s.InitFlow(s.data)
     o = Oracle.from_setup(s)
