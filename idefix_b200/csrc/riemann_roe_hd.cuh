@@ -5,7 +5,7 @@
 // (|dp|/min(p) > 1/2 in a compression; isothermal: |drho|/min(rho) * a^2).
 //
 // STATUS: verified bit for bit against the oracle on the host (tests/test_riemann_host.py) and dispatched by the
-// sweep kernels (sweep.cuh::riemannDispatch, sweep_hd_roe.cu); GPU parity tests: tests/test_zz_roe_hd_gpu.py (first-run).
+// sweep kernels (sweep.cuh::riemannDispatch, sweep_hd_roe.cu); GPU parity tests: tests/test_zz_first_run_gpu.py (first-run).
 // Trap: with DIMENSIONS == 1 the reference compiles the HLL branch out (roeHD.hpp:314) and leaves
 // Flux(nv,k,j,i) as the previous call wrote it; this function then returns true and leaves F untouched.
 #ifndef IDFX_RIEMANN_ROE_HD_CUH_
