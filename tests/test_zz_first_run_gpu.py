@@ -144,3 +144,19 @@ def test_isothermal_cuda_equals_oracle_bitwise(case, fused):
     assert d.CheckNan() == 0 and d.math_exceptions() == 0
     o.close()
     d.close()
+
+
+def test_roe_hd_isothermal_through_cpp_host(tmp_path_factory, tmp_path):
+    """isothermal HD Roe through the C++ host layer (./idefix built from idefix_b200/host/problems/sodIso): the dumps
+    equal those of the reference's own build for the same ini"""
+    import test_host_cpp as thc
+    from cases import ini_for
+    case = [c for c in ORACLE_SHORT if c.name == "sodiso_roe_plm"][0]
+    exe = thc.binary(case.setup, case.order, tmp_path_factory)
+    ncyc = max(case.cycles)
+    thc.run_idefix(exe, str(tmp_path), ini_for(case, dump_every_cycle=True), "-maxcycles", str(ncyc))
+    for n in (0,) + tuple(case.cycles):
+        mine = readDump(os.path.join(tmp_path, f"dump.{n:04d}.dmp"))
+        gold = readDump(os.path.join(GOLD, "short", f"{case.name}.c{n:04d}.dmp"))
+        thc.assert_same_fields(mine, gold)
+        assert float(mine.data["time"][0]) == float(gold.data["time"][0])
