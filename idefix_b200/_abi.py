@@ -98,6 +98,7 @@ SYMBOLS = {
     "idfx_set_nproc": (C.c_int, [_h, C.c_int * 3]),
     "idfx_set_stream": (C.c_int, [_h, C.c_void_p]),
     "idfx_timing": (C.c_int, [_h, C.c_int, _pd]),
+    "idfx_selftest_tmem": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

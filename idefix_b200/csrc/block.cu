@@ -73,6 +73,7 @@ struct IdfxBlock {
   bool ownStream = true;
   unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
+  double *staleFlux = nullptr; // 1-D HD Roe: area-weighted flux of the previous call (roeHD.hpp:312-328)
   // steady-state cycle of the fused path captured as a CUDA graph (launch-bound small grids: ~40 launches per cycle)
   cudaGraphExec_t cycleGraph = nullptr;
   long long cycleGraphLaunches = 0;
@@ -369,6 +370,7 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
   }
   a.doInvDt = 1;
   a.fluxRho = b->fluxRho;
+  a.staleFlux = b->staleFlux;
   a.mathFlag = b->mathFlag;
   a.validateInputs = b->vcFieldFresh ? 0 : 1;   // our own stage epilogue already validated what it wrote
   return a;
@@ -721,6 +723,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   const int nv = b->cfg.nvar + b->cfg.ntr;
   rc = rc || devAlloc(b, &b->mathFlag, 1);
   if (b->cfg.ntr > 0) rc = rc || devAlloc(b, &b->fluxRho, b->nCells);
+  if (!b->cfg.mhd && b->cfg.ndim == 1 && b->cfg.solver == SOLVER_ROE) rc = rc || devAlloc(b, &b->staleFlux, b->nCells * b->cfg.nvar);
   rc = rc || devAlloc(b, &b->Vc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->Uc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->invDt, b->nCells);
@@ -811,11 +814,13 @@ int idfx_block_destroy(IdfxBlock *b) {
 }
 
 int idfx_sync(IdfxBlock *b) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   return 0;
 }
 
 int idfx_field_info(IdfxBlock *b, int field, double **dev, int dims[4]) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   double *p = nullptr;
   if (fieldPtr(b, field, &p, dims)) return 1;
   if (dev) *dev = p;
@@ -823,6 +828,7 @@ int idfx_field_info(IdfxBlock *b, int field, double **dev, int dims[4]) {
 }
 
 int idfx_upload(IdfxBlock *b, int field, const double *host) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   double *p = nullptr;
   int dims[4];
   if (fieldPtr(b, field, &p, dims)) return 1;
@@ -834,6 +840,7 @@ int idfx_upload(IdfxBlock *b, int field, const double *host) {
 }
 
 int idfx_download(IdfxBlock *b, int field, double *host) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   double *p = nullptr;
   int dims[4];
   if (fieldPtr(b, field, &p, dims)) return 1;
@@ -845,6 +852,7 @@ int idfx_download(IdfxBlock *b, int field, double *host) {
 }
 
 int idfx_set_time(IdfxBlock *b, double t, double dt) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   b->hostState[8] = t;
   b->hostState[9] = dt;
@@ -854,6 +862,7 @@ int idfx_set_time(IdfxBlock *b, double t, double dt) {
 }
 
 int idfx_get_time(IdfxBlock *b, double *t, double *dt) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (readState(b)) return 1;
   if (t) *t = b->hostState[0];
   if (dt) *dt = b->hostState[1];
@@ -861,6 +870,7 @@ int idfx_get_time(IdfxBlock *b, double *t, double *dt) {
 }
 
 int idfx_set_tstop(IdfxBlock *b, double tstop) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   b->hostState[10] = tstop;
   CUDA_TRY(cudaMemcpyAsync(b->state + 3, b->hostState + 10, sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -869,6 +879,7 @@ int idfx_set_tstop(IdfxBlock *b, double tstop) {
 }
 
 int idfx_get_ncycles(IdfxBlock *b, long long *n) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaMemcpyAsync(b->hostState + 12, b->ncyclesDev, sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   std::memcpy(n, b->hostState + 12, sizeof(long long));
@@ -876,11 +887,13 @@ int idfx_get_ncycles(IdfxBlock *b, long long *n) {
 }
 
 int idfx_launch_count(IdfxBlock *b, long long *count) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   *count = b->launches;
   return 0;
 }
 
 int idfx_set_stream(IdfxBlock *b, void *stream) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   dropCycleGraph(b);
   if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
@@ -892,6 +905,7 @@ int idfx_set_stream(IdfxBlock *b, void *stream) {
 // mode 1: start sampling, 0: stop, 2: collect into out[2*TIME_NCAT] = {launch brackets, total ms} per class
 // (X1, X2, X3 sweeps, constrained transport, stage epilogue, boundaries) and reset the samples.
 int idfx_timing(IdfxBlock *b, int mode, double *out) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (mode == 0 || mode == 1) {
     b->timing = (mode == 1);
     if (mode == 1) b->evUsed = 0;
@@ -911,6 +925,7 @@ int idfx_timing(IdfxBlock *b, int mode, double *out) {
 }
 
 int idfx_set_nproc(IdfxBlock *b, const int nproc[3]) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   dropCycleGraph(b);
   for (int d = 0; d < 3; d++) b->nproc[d] = nproc[d] < 1 ? 1 : nproc[d];
   return 0;
@@ -918,12 +933,14 @@ int idfx_set_nproc(IdfxBlock *b, const int nproc[3]) {
 
 // ---- granular entry points -----------------------------------------------------------------
 int idfx_reset_stage(IdfxBlock *b) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   KTRY(idfxk::fill(b->invDt, b->nCells, 0.0, b->stream));
   b->launches++;
   return 0;
 }
 
 int idfx_enforce_boundary_dir(IdfxBlock *b, double t, int dir) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim) return fail("idfx_enforce_boundary_dir: direction out of range");
   b->vcFieldFresh = false;
   TimeScope ts(b, TIME_BOUNDARY);
@@ -931,17 +948,20 @@ int idfx_enforce_boundary_dir(IdfxBlock *b, double t, int dir) {
 }
 
 int idfx_set_boundaries(IdfxBlock *b, double t) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (setBoundariesCore(b, t, true)) return 1;
   return reconstructVc(b, b->Vc);
 }
 
 int idfx_reconstruct_vc_field(IdfxBlock *b, int field) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (field == IDFX_FIELD_VC) return reconstructVc(b, b->Vc);
   if (field == IDFX_FIELD_UC) return reconstructVc(b, b->Uc);
   return fail("idfx_reconstruct_vc_field: field must be VC or UC");
 }
 
 int idfx_prim_to_cons(IdfxBlock *b) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   KTRY(idfxk::primToCons(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
   b->launches++;
   if (b->cfg.ntr > 0) {
@@ -952,6 +972,7 @@ int idfx_prim_to_cons(IdfxBlock *b) {
 }
 
 int idfx_cons_to_prim(IdfxBlock *b) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (reconstructVc(b, b->Uc)) return 1;
   KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
   b->launches++;
@@ -963,6 +984,7 @@ int idfx_cons_to_prim(IdfxBlock *b) {
 }
 
 int idfx_state_copy(IdfxBlock *b) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (!b->Uc0) return fail("states[\"begin\"] exists only when nstages > 1");
   KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * (b->cfg.nvar + b->cfg.ntr), b->stream));
   b->launches++;
@@ -974,6 +996,7 @@ int idfx_state_copy(IdfxBlock *b) {
 }
 
 int idfx_state_add_and_store(IdfxBlock *b, double wc, double w0) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (!b->Uc0) return fail("states[\"begin\"] exists only when nstages > 1");
   KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * (b->cfg.nvar + b->cfg.ntr), wc, w0, b->stream));
   b->launches++;
@@ -985,6 +1008,7 @@ int idfx_state_add_and_store(IdfxBlock *b, double wc, double w0) {
 }
 
 int idfx_evolve_stage(IdfxBlock *b, double t, double dt) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   (void)t;
   // dt lives on the device; only touch it when the caller's value differs from the mirror
   if (readState(b)) return 1;
@@ -996,6 +1020,7 @@ int idfx_evolve_stage(IdfxBlock *b, double t, double dt) {
 }
 
 int idfx_compute_timestep(IdfxBlock *b, double *dt_min) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   b->hostState[11] = INFINITY;
   CUDA_TRY(cudaMemcpyAsync(b->redBits, b->hostState + 11, sizeof(double), cudaMemcpyHostToDevice, b->stream));
   if (timestepReduceImpl(b)) return 1;
@@ -1007,6 +1032,7 @@ int idfx_compute_timestep(IdfxBlock *b, double *dt_min) {
 }
 
 int idfx_check_divb(IdfxBlock *b, double *divb_max) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (!b->cfg.mhd) {
     *divb_max = 0.0;
     return 0;
@@ -1022,6 +1048,7 @@ int idfx_check_divb(IdfxBlock *b, double *divb_max) {
 }
 
 int idfx_check_nan(IdfxBlock *b, int *nan_count) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaMemsetAsync(b->nanDev, 0, sizeof(int), b->stream));
   KTRY(idfxk::checkNan(b->cfg, b->g, b->Vc, b->Vs, b->nanDev, b->stream));
   b->launches += b->cfg.mhd ? 2 : 1;
@@ -1046,6 +1073,7 @@ bool graphEligible(const IdfxBlock *b, int ncycles) {
 }  // namespace
 
 int idfx_cycles(IdfxBlock *b, int ncycles) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   // the caller holds device pointers to the state (idfx_field_info) and may have changed it since the last call
   b->vcFieldFresh = false;
   if (graphEligible(b, ncycles)) {
@@ -1092,6 +1120,7 @@ int idfx_cycles(IdfxBlock *b, int ncycles) {
 }
 
 int idfx_cycle(IdfxBlock *b, double *t, double *dt, int *status_flags) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (idfx_cycles(b, 1)) return 1;
   CUDA_TRY(cudaMemcpyAsync(b->hostState, b->state, 4 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaMemcpyAsync(b->hostState + 14, b->statusDev, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
@@ -1107,6 +1136,7 @@ int idfx_cycle(IdfxBlock *b, double *t, double *dt, int *status_flags) {
 // Number of threads whose branch-free division / square root failed its range check since the block was
 // created (fastmath.cuh).  Zero = every quotient and root of the sweeps was the correctly rounded IEEE one.
 int idfx_math_exceptions(IdfxBlock *b, unsigned int *count) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   CUDA_TRY(cudaMemcpyAsync(count, b->mathFlag, sizeof(unsigned int), cudaMemcpyDeviceToHost, b->stream));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   return 0;
@@ -1114,6 +1144,7 @@ int idfx_math_exceptions(IdfxBlock *b, unsigned int *count) {
 
 // selects the reference-ordered (un-fused) kernel sequence; used by the parity tests
 int idfx_set_fused(IdfxBlock *b, int fused) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   dropCycleGraph(b);
   if (fused && b->haveUserdef) return fail("the fused path is not available with user-defined boundaries");
   b->fused = fused != 0;
@@ -1122,18 +1153,21 @@ int idfx_set_fused(IdfxBlock *b, int fused) {
 
 // ---- callbacks -----------------------------------------------------------------------------------
 int idfx_enroll_userdef_boundary(IdfxBlock *b, IdfxUserBoundaryFn fn, void *user) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   dropCycleGraph(b);
   b->userBc = fn;
   b->userBcData = user;
   return 0;
 }
 int idfx_enroll_reduce(IdfxBlock *b, IdfxReduceFn fn, void *user) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   dropCycleGraph(b);
   b->reduceFn = fn;
   b->reduceData = user;
   return 0;
 }
 int idfx_enroll_halo_exchange(IdfxBlock *b, IdfxHaloFn fn, void *user) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   dropCycleGraph(b);
   b->haloFn = fn;
   b->haloData = user;
@@ -1142,6 +1176,7 @@ int idfx_enroll_halo_exchange(IdfxBlock *b, IdfxHaloFn fn, void *user) {
 
 // ---- halo exchange building blocks ------------------------------------------------------------------
 int idfx_halo_buffer_size(IdfxBlock *b, int dir, size_t *ndoubles) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
   *ndoubles = (size_t)idfxk::haloBufferSize(b->cfg, b->g, dir);
   return 0;
@@ -1166,6 +1201,7 @@ static int ensureHaloBuffers(IdfxBlock *b, int dir) {
 }
 
 int idfx_halo_buffers(IdfxBlock *b, int dir, int side, double **send, double **recv) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim || side < 0 || side > 1) return fail("invalid direction / side");
   if (ensureHaloBuffers(b, dir)) return 1;
   if (send) *send = b->haloSend[dir][side];
@@ -1174,6 +1210,7 @@ int idfx_halo_buffers(IdfxBlock *b, int dir, int side, double **send, double **r
 }
 
 int idfx_halo_pack(IdfxBlock *b, int dir) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
   if (ensureHaloBuffers(b, dir)) return 1;
   for (int side = 0; side < 2; side++) {
@@ -1186,6 +1223,7 @@ int idfx_halo_pack(IdfxBlock *b, int dir) {
 }
 
 int idfx_halo_unpack(IdfxBlock *b, int dir) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim) return fail("invalid direction");
   if (ensureHaloBuffers(b, dir)) return 1;
   for (int side = 0; side < 2; side++) {
@@ -1196,12 +1234,14 @@ int idfx_halo_unpack(IdfxBlock *b, int dir) {
 }
 
 int idfx_halo_bind_peer(IdfxBlock *b, int dir, int side, double *peer_recv) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim || side < 0 || side > 1) return fail("invalid direction / side");
   b->haloPeer[dir][side] = peer_recv;
   return 0;
 }
 
 int idfx_halo_ipc_handle(IdfxBlock *b, int dir, int side, void *handle64) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   if (dir < 0 || dir >= b->desc.ndim || side < 0 || side > 1) return fail("invalid direction / side");
   if (ensureHaloBuffers(b, dir)) return 1;
   cudaIpcMemHandle_t h;
@@ -1212,6 +1252,7 @@ int idfx_halo_ipc_handle(IdfxBlock *b, int dir, int side, void *handle64) {
 }
 
 int idfx_halo_open_ipc(IdfxBlock *b, const void *handle64, double **ptr) {
+  cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   (void)b;
   cudaIpcMemHandle_t h;
   std::memcpy(&h, handle64, 64);

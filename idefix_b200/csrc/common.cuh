@@ -95,6 +95,7 @@ struct SweepArgs {
   unsigned int *mathFlag;   // incremented by threads whose branch-free division / sqrt failed a range check (fastmath.cuh)
   double *fluxRho;    // when tracers are on: raw Riemann mass flux of every interface of this sweep (else null)
   double *Uc0;        // fused path, first stage: also save the rebuilt Uc as the "begin" state (may be null)
+  double *staleFlux;  // 1-D HD Roe only: (nvar, nx0) area-weighted flux of the previous call (roeHD.hpp:312-328), else null
 };
 
 #endif  // IDFX_COMMON_CUH_

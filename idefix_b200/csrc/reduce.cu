@@ -151,14 +151,16 @@ __global__ void dtEndKernel(double *state, const unsigned long long *dtMinBits, 
 }
 
 int persistentBlocks() {
-  static int nb = 0;
-  if (nb == 0) {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
+  static int nb[64] = {};   // per device: a process may drive blocks on several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (nb[dev] == 0) {
+    int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    nb = sms > 0 ? sms * 8 : 1184;
+    nb[dev] = sms > 0 ? sms * 8 : 1184;
   }
-  return nb;
+  return nb[dev];
 }
 
 }  // namespace

@@ -4,10 +4,11 @@
 // roeHD.hpp:17), entropy fix delta = 1e-7 on the two acoustic modes, HLL flux across strong shocks
 // (|dp|/min(p) > 1/2 in a compression; isothermal: |drho|/min(rho) * a^2).
 //
-// STATUS: verified bit for bit against the oracle on the host (tests/test_riemann_host.py) and dispatched by the
-// sweep kernels (sweep.cuh::riemannDispatch, sweep_hd_roe.cu); GPU parity tests: tests/test_zz_first_run_gpu.py (first-run).
+// Verified bit for bit against the oracle on the host (tests/test_riemann_host.py); dispatched by the sweep kernels
+// (sweep.cuh::riemannDispatch, sweep_hd_roe.cu); GPU parity: tests/test_roe_hd_iso_gpu.py.
 // Trap: with DIMENSIONS == 1 the reference compiles the HLL branch out (roeHD.hpp:314) and leaves
-// Flux(nv,k,j,i) as the previous call wrote it; this function then returns true and leaves F untouched.
+// Flux(nv,k,j,i) as the previous call wrote it; this function then returns true and leaves F untouched, and the
+// x1 sweep substitutes the flux it kept from its previous call (SweepArgs::staleFlux, sweep_pencil.cuh).
 #ifndef IDFX_RIEMANN_ROE_HD_CUH_
 #define IDFX_RIEMANN_ROE_HD_CUH_
 

@@ -21,8 +21,12 @@
 #include "emf_store.cuh"
 #include "riemann_roe_hd.cuh"
 
+// Returns true when the solver asks the caller to keep the flux of the PREVIOUS call at this interface: only the
+// HD Roe solver in one dimension, across a strong shock (roeHD.hpp:312-328, the HLL branch is compiled out there and
+// Flux(nv,k,j,i) is left as the last CalcRightHandSide wrote it, i.e. area-weighted).  The x1 sweep then substitutes
+// SweepArgs::staleFlux.
 template <class P, int SOLVER, int DIR, class VL, class VR>
-IDFX_D void riemannDispatch(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
+IDFX_D bool riemannDispatch(const VL &vL, const VR &vR, const Eos &eos, double *F, RiemannAux &aux) {
   if constexpr (P::mhd) {
     if constexpr (SOLVER == SOLVER_TVDLF) riemannTvdlfMHD<P, DIR>(vL, vR, eos, F, aux);
     if constexpr (SOLVER == SOLVER_HLL) riemannHllMHD<P, DIR>(vL, vR, eos, F, aux);
@@ -32,16 +36,9 @@ IDFX_D void riemannDispatch(const VL &vL, const VR &vR, const Eos &eos, double *
     if constexpr (SOLVER == SOLVER_TVDLF) riemannTvdlfHD<P, DIR>(vL, vR, eos, F, aux);
     if constexpr (SOLVER == SOLVER_HLL) riemannHllHD<P, DIR>(vL, vR, eos, F, aux);
     if constexpr (SOLVER == SOLVER_HLLC) riemannHllcHD<P, DIR>(vL, vR, eos, F, aux);
-    if constexpr (SOLVER == SOLVER_ROE) {
-      // 1-D: across a strong shock the reference keeps the flux of the previous call (roeHD.hpp:314, compiled-out
-      // HLL branch).  That is not reproduced: the interface is poisoned, which the sweeps count as a math
-      // exception (idfx_math_exceptions) and which surfaces as NaN in the state.
-      if (riemannRoeHD<P, DIR>(vL, vR, eos, F, aux)) {
-#pragma unroll
-        for (int nv = 0; nv < P::nvar; nv++) F[nv] = aux.cmax * __longlong_as_double(0x7ff8000000000000LL);
-      }
-    }
+    if constexpr (SOLVER == SOLVER_ROE) return riemannRoeHD<P, DIR>(vL, vR, eos, F, aux);
   }
+  return false;
 }
 
 // Index of the azimuthal momentum / field for the curvilinear corrections (idefix.hpp:129-187)

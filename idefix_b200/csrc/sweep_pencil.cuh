@@ -21,6 +21,14 @@
 #define IDFX_SWEEP_PENCIL_CUH_
 
 #include "sweep.cuh"
+#include "tmem.cuh"
+
+// IDFX_TMEM = 1: the x2 / x3 marches keep their per-thread carry-over (left state of the next interface, flux and
+// signal speed of the previous one: 17 doubles) in tensor memory instead of shared memory (tmem.cuh).  That takes
+// 17 KB of the 45 KB of shared memory a CTA needs, which the SM turns into L1 for the register spills.
+#ifndef IDFX_TMEM
+#define IDFX_TMEM 1
+#endif
 
 // resident CTAs per SM the sweep kernels are compiled for (register cap = 65536 / (threads * MINB))
 #ifndef IDFX_MARCH_MINB
@@ -31,6 +39,32 @@
 #endif
 
 namespace pencil {
+
+// Host-side per-DEVICE caches: one process may drive blocks on several GPUs (IdfxBlockDesc::device), and both the
+// opt-in dynamic shared-memory size of a kernel and the SM count belong to the device that is current at the launch.
+inline int currentDevice() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+inline int smCount() {
+  static int sms[64] = {};
+  const int dev = currentDevice() & 63;
+  if (sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
+  }
+  return sms[dev];
+}
+template <class K>
+inline cudaError_t ensureDynamicSmem(K kern, size_t bytes, unsigned long long &doneMask) {
+  const int dev = currentDevice();
+  if (dev < 64 && ((doneMask >> dev) & 1ull)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev < 64) doneMask |= (1ull << dev);
+  return e;
+}
 
 IDFX_D unsigned smemAddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 IDFX_D void cpAsync8(double *dstShared, const double *srcGlobal) {
@@ -75,8 +109,8 @@ IDFX_D void finishInterface(const SweepArgs &a, const DevGrid &g, int geo, doubl
 // SweepArgs::mathFlag at the end of the kernel (reportMathFlag below): when the flag of a run is zero --
 // which the parity tests and bench.py assert -- every quotient and root was nvcc's own correctly rounded one.
 template <class P, int SOLVER, int DIR>
-IDFX_D void solveInterface(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
-  riemannDispatch<typename P::Fast, SOLVER, DIR>(vL, vR, eos, F, aux);
+IDFX_D bool solveInterface(const double *vL, const double *vR, const Eos &eos, double *F, RiemannAux &aux) {
+  return riemannDispatch<typename P::Fast, SOLVER, DIR>(vL, vR, eos, F, aux);
 }
 
 // range validation of the branch-free arithmetic (fastmath.cuh): the primitives of a cell entering the sweeps
@@ -110,10 +144,11 @@ IDFX_D void reportMathFlag(const SweepArgs &a, bool bad) {
 template <class P, int ORDER, bool CART>
 constexpr size_t pencilMarchSmem(int TX, int chunk) {
   return sizeof(double) * ((size_t)TX * ((CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * P::nvar   // stencil ring
-                                         + P::nvar                          // left state of the next interface
-                                         + (P::nvar + 1)                    // previous interface: flux + signal speed
+                                         + (IDFX_TMEM ? 0 : P::nvar)        // left state of the next interface
+                                         + (IDFX_TMEM ? 0 : (P::nvar + 1))  // previous interface: flux + signal speed
                                          + 2)                               // normal field at the interface (x2)
-                           + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * (chunk + 2));
+                           + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * (chunk + 2)
+                           + (IDFX_TMEM ? 2 : 0));                          // TMEM base address slot
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART>
@@ -128,10 +163,19 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
   extern __shared__ double smem[];
   const int tx = threadIdx.x;
   double *ring = smem + tx;                         // ring[(slot * NV + nv) * TX]
+#if IDFX_TMEM
+  // carry-over in tensor memory: columns [2 nv, 2 nv + 1] = left state nv, [2 NV + 2 nv, ..] = previous flux nv,
+  // [4 NV, 4 NV + 1] = previous signal speed
+  constexpr int TCOLS = (4 * NV + 2 <= 32) ? 32 : 64;
+  constexpr unsigned T_VLS = 0, T_FPREV = 2 * NV, T_CMAX = 4 * NV;
+  double *vsb = smem + W * NV * TX + tx;            // vsb[buf * TX]
+  double *tab = smem + (size_t)TX * (W * NV + 2);   // tab[row * (chunk+2) + r]
+#else
   double *vls = smem + W * NV * TX + tx;            // vls[nv * TX]
   double *fprev = vls + NV * TX;                    // fprev[nv * TX]
   double *vsb = fprev + (NV + 1) * TX;              // vsb[buf * TX]
   double *tab = smem + (size_t)TX * (W * NV + NV + (NV + 1) + 2);   // tab[row * (chunk+2) + r]
+#endif
   const int tlen = chunk + 2;
   const unsigned ringS = pencil::smemAddr(ring), vsbS = pencil::smemAddr(vsb);
 
@@ -155,21 +199,34 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       tab[(pencil::T_W + 5) * tlen + r] = g.dm[DIR][c];
     }
   }
+#if IDFX_TMEM
+  unsigned *tslot = reinterpret_cast<unsigned *>(tab + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * tlen);
+  const unsigned tbase = tmem::allocate<TCOLS>(tslot);   // contains the __syncthreads that publishes tab
+#else
   __syncthreads();
+#endif
 
   // ---- column owned by this thread ------------------------------------------------------------------
   const int ilo = g.beg[0] - ext, ni = g.end[0] - g.beg[0] + 2 * ext;
   const int pext = (P::ndim > PDIR) ? ext : 0;
   const int plo = g.beg[PDIR] - pext, np = g.end[PDIR] - g.beg[PDIR] + 2 * pext;
-  const long long lin = (long long)blockIdx.x * TX + tx;
+  long long lin = (long long)blockIdx.x * TX + tx;
+#if IDFX_TMEM
+  // tcgen05.ld / st are warp-collective: threads past the last column stay in the march as copies of the last
+  // column (same loads, same face-EMF values to the same addresses) and only skip the cell update
+  const bool columnValid = lin < (long long)ni * np;
+  if (!columnValid) lin = (long long)ni * np - 1;
+#else
+  constexpr bool columnValid = true;
   if (lin >= (long long)ni * np) return;
+#endif
   const int i = ilo + (int)(lin % ni);
   const int p = plo + (int)(lin / ni);
   const long long stride = (DIR == JDIR) ? g.sj : g.sk;
   const long long vstride = (DIR == JDIR) ? g.vsj : g.vsk;
   const long long cell0 = (DIR == JDIR) ? cidx(g, p, 0, i) : cidx(g, 0, p, i);
   const long long face0 = DIR * g.vsn + ((DIR == JDIR) ? sidx(g, p, 0, i) : sidx(g, 0, p, i));
-  const bool columnInterior = (i >= g.beg[0]) && (i < g.end[0]) && (p >= g.beg[PDIR]) && (p < g.end[PDIR]);
+  const bool columnInterior = columnValid && (i >= g.beg[0]) && (i < g.end[0]) && (p >= g.beg[PDIR]) && (p < g.end[PDIR]);
 
   const Eos eos{a.gamma, a.csiso};
   const double dt = *a.dt;
@@ -219,7 +276,12 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vl, vr;
       reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
+#if IDFX_TMEM
+      __syncwarp();
+      tmem::store1(tbase + T_VLS + 2 * nv, vr);
+#else
       vls[nv * TX] = vr;
+#endif
     }
   }
 
@@ -267,6 +329,23 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         if (s >= W) s -= W;
         so[d + H] = s * NV * TX;
       }
+#if IDFX_TMEM
+      // left state = right-face values of cell m-1, parked in tensor memory one step ago
+      tmem::Pending1 vlp[NV];
+      __syncwarp();
+      tmem::waitStores();
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        if (P::mhd && nv == D::BXn) continue;
+        vlp[nv] = tmem::load1(tbase + T_VLS + 2 * nv);
+      }
+      tmem::waitLoads();
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) {
+        if (P::mhd && nv == D::BXn) continue;
+        vL[nv] = vlp[nv].value();
+      }
+#endif
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) {
         if (P::mhd && nv == D::BXn) continue;
@@ -277,8 +356,13 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
         double vr;
         reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
+#if IDFX_TMEM
+        __syncwarp();
+        tmem::store1(tbase + T_VLS + 2 * nv, vr);
+#else
         vL[nv] = vls[nv * TX];
         vls[nv * TX] = vr;
+#endif
       }
     }
     if constexpr (LATE) {
@@ -310,29 +394,57 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
     pencil::finishInterface<P, SOLVER, DIR>(a, g, geo, A0, k, j, i, cellm, vL, vR, F, aux);
 
     // ---- cell m-1: flux difference, time-step estimate, conservative update ---------------------------
+#if IDFX_TMEM
+    // flux and signal speed of interface m-1 come back from tensor memory (collective: outside the branch)
+    double Fm[NV], cmaxm;
+    {
+      __syncwarp();
+      tmem::Pending1 fp[NV + 1];
+#pragma unroll
+      for (int nv = 0; nv <= NV; nv++) fp[nv] = tmem::load1(tbase + T_FPREV + 2 * nv);
+      tmem::waitLoads();
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) Fm[nv] = fp[nv].value();
+      cmaxm = fp[NV].value();
+    }
+#endif
     if (r > 0 && columnInterior) {
       const int jc = (DIR == JDIR) ? m - 1 : p;
       const int kc = (DIR == JDIR) ? p : m - 1;
       double dV;
       if constexpr (DIR == JDIR) dV = inv0 * tab[pencil::T_VOL * tlen + r] * inv1;
       else dV = inv0 * tab[pencil::T_VOL * tlen + r];
+#if !IDFX_TMEM
       double Fm[NV];
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * TX];
+      const double cmaxm = fprev[NV * TX];
+#endif
       int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring)
       if (sp < 0) sp += W;
       const double *vprev = ring + sp * NV * TX;
       updateCell<typename P::Fast, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
-                         fprev[NV * TX], aux.cmax, [&](int nv) { return vprev[nv * TX]; });
+                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * TX]; });
     }
+#if IDFX_TMEM
+    __syncwarp();
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) tmem::store1(tbase + T_FPREV + 2 * nv, F[nv]);
+    tmem::store1(tbase + T_CMAX, aux.cmax);
+#else
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) fprev[nv * TX] = F[nv];
     fprev[NV * TX] = aux.cmax;
+#endif
     q = (q + 1 == W) ? 0 : q + 1;
     pre += stride;
     cellm += stride;
   }
-  pencil::reportMathFlag(a, mathBad);
+  pencil::reportMathFlag(a, mathBad && columnValid);
+#if IDFX_TMEM
+  tmem::waitStores();
+  tmem::release<TCOLS>(tslot);
+#endif
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, bool CART>
@@ -347,17 +459,13 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
   const long long ctasPerLayer = (ni * np + TX - 1) / TX;
   // chunk length: long enough to amortise the extra cell per chunk, short enough to fill the GPU
   int chunk = 64;
-  while (chunk > 8 && ctasPerLayer * ((nsweep + chunk - 1) / chunk) < 4 * 148 * 4) chunk >>= 1;
+  while (chunk > 8 && ctasPerLayer * ((nsweep + chunk - 1) / chunk) < 4 * pencil::smCount() * 4) chunk >>= 1;
   if (chunk > nsweep) chunk = nsweep;
   const dim3 grid((unsigned)ctasPerLayer, (unsigned)((nsweep + chunk - 1) / chunk), 1);
   const size_t smem = pencilMarchSmem<P, ORDER, CART>(TX, 64);
-  static bool configured = false;
+  static unsigned long long configured = 0;   // bit d: attribute set on device d
   auto kern = pencilMarchKernel<P, SOLVER, ORDER, DIR, TX, CART>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = pencil::ensureDynamicSmem(kern, smem, configured); e != cudaSuccess) return e;
   kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(a, chunk);
   return cudaGetLastError();
 }
@@ -543,9 +651,22 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
         vR[D::BXn] = bn;
       }
       const double A0 = ar0 * tab[chunk + r] * ar2;
-      pencil::solveInterface<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+      const bool keep = pencil::solveInterface<P, SOLVER, DIR>(vL, vR, eos, F, aux);
+      // 1-D HD Roe: the flux array of the reference persists between calls and a strong shock leaves the entry of
+      // the previous call (already area-weighted) in place, which CalcRightHandSide then weights again
+      constexpr bool STALE = (!P::mhd && P::ndim == 1 && SOLVER == SOLVER_ROE);
+      if constexpr (STALE) {
+        if (keep) {
+#pragma unroll
+          for (int nv = 0; nv < NV; nv++) F[nv] = a.staleFlux[nv * nx0 + c];
+        }
+      }
       mathBad |= pencil::fluxNotFinite<NV>(F, aux.cmax);
       pencil::finishInterface<P, SOLVER, DIR>(a, g, geo, A0, k, j, c, cell, vL, vR, F, aux);
+      if constexpr (STALE) {
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) a.staleFlux[nv * nx0 + c] = F[nv];
+      }
 #pragma unroll
       for (int nv = 0; nv < NV; nv++) fls[nv * 32 + lane] = F[nv];
       fls[NV * 32 + lane] = aux.cmax;
@@ -577,17 +698,13 @@ inline cudaError_t launchPencilRow(const SweepArgs &a, cudaStream_t stream) {
   const int nk = g.end[2] - g.beg[2] + 2 * ((P::ndim > 2) ? ext : 0);
   const long long ctasPerChunk = ((long long)nstrips * nk + WARPS - 1) / WARPS;
   int chunk = 64;
-  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * 148 * IDFX_ROW_MINB) chunk >>= 1;
+  while (chunk > 8 && ctasPerChunk * ((nj + chunk - 1) / chunk) < 4 * pencil::smCount() * IDFX_ROW_MINB) chunk >>= 1;
   if (chunk > nj) chunk = nj;
   const dim3 grid((unsigned)ctasPerChunk, (unsigned)((nj + chunk - 1) / chunk), 1);
-  static bool configured = false;
+  static unsigned long long configured = 0;   // bit d: attribute set on device d
   auto kern = pencilRowKernel<P, SOLVER, ORDER, WARPS, CART>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pencilRowSmem<P, ORDER, CART>(WARPS, 64));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = pencil::ensureDynamicSmem(kern, pencilRowSmem<P, ORDER, CART>(WARPS, 64), configured); e != cudaSuccess)
+    return e;
   kern<<<grid, WARPS * 32, pencilRowSmem<P, ORDER, CART>(WARPS, chunk), stream>>>(a, chunk, nstrips);
   return cudaGetLastError();
 }

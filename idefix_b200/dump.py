@@ -75,7 +75,7 @@ def _write_field(fh, name, arr, typ):
 
 def writeDump(filename, data, vc_names, Vc, Vs=None, t=0.0, dt=0.0, number=0, version="2.2.02-b200"):
     """Write the interior of Vc (nvar,k,j,i; only the entries named in vc_names, skipping None)
-    and Vs (ndim,k,j,i) of DataBlock ``data`` in the reference's dump format."""
+    and Vs (ndim,k,j,i) of DataBlock ``data`` in the reference's dump format (``number`` = N of dump.N.dmp)."""
     grid = data.mygrid
     nd = data.defs.dimensions
     with open(filename, "wb") as fh:
@@ -96,7 +96,8 @@ def writeDump(filename, data, vc_names, Vc, Vs=None, t=0.0, dt=0.0, number=0, ve
             for d in range(nd):
                 o = [1 if e == d else 0 for e in range(3)]
                 fields[f"Vs-BX{d + 1}s"] = Vs[d, kb:ke + o[2], jb:je + o[1], ib:ie + o[0]].transpose(2, 1, 0)
-        scalars = {"time": (t, 0), "dt": (dt, 0), "dumpFileNumber": (number, 2),
+        # dump.N stores N+1: the reference increments the counter before it writes the fields (dump.cpp:839)
+        scalars = {"time": (t, 0), "dt": (dt, 0), "dumpFileNumber": (number + 1, 2),
                    "geometry": (data.defs.geometry, 2),
                    "periodicity": ([int(grid.lbound[d] == 1) for d in range(3)], 2)}
         for name in sorted(list(fields) + list(scalars)):

@@ -72,9 +72,6 @@ class Fluid {
 #endif
     else if (s == "roe") mySolver = ROE;
     else IDEFIX_ERROR(std::string("Unknown ") + (MHD == YES ? "MHD" : "HD") + " solver type " + s);
-#if MHD == NO
-    if (mySolver == ROE) IDEFIX_ERROR("the HD Roe solver is outside the scope of this build");
-#endif
 #if MHD == YES
     if (input.CheckEntry("Hydro", "emf") >= 0) {
       const std::string e = input.Get<std::string>("Hydro", "emf", 0);

@@ -18,7 +18,6 @@ int main(int argc, char **argv) {
     DataBlock data(grid, input);
     TimeIntegrator Tint(input, data);
     Output output(input, data);
-    output.ncyclesPtr = &Tint.ncycles;
     Setup mysetup(input, grid, data, output);
     grid.ShowConfig();
     data.ShowConfig();

@@ -46,7 +46,6 @@ class Output {
   int vtkFileNumber{0}, dumpFileNumber{0};
   std::string vtkDir{"./"}, dumpDir{"./"};
   UserDefVariablesContainer userDefVariables;
-  long long *ncyclesPtr{nullptr};   // TimeIntegrator's cycle counter, stored in dumps
 
   Output(Input &input, DataBlock &data) {
     forceNoWrite = input.forceNoWrite;
@@ -141,6 +140,7 @@ class Output {
   void WriteDump(DataBlock &data) {
     const std::string name = dumpDir + idfxhost::numbered("dump", dumpFileNumber, "dmp");
     idfx::cout << "Dump: Write file " << name << "..." << std::flush;
+    dumpFileNumber++;   // before the scalars are emitted: dump.N stores N+1 (dump.cpp:839), Dump::Read takes it as is
     const auto t0 = std::chrono::steady_clock::now();
     DataBlockHost d(data);
     d.SyncFromDevice();
@@ -192,7 +192,6 @@ class Output {
     scalarI("vtkFileNumber", vtkFileNumber);
     scalarI("dumpFileNumber", dumpFileNumber);
     scalarI("geometry", GEOMETRY);
-    scalarI("ncycles", ncyclesPtr ? static_cast<int32_t>(*ncyclesPtr) : 0);
     const int32_t per[3] = {data.mygrid->lbound[0] == periodic, data.mygrid->lbound[1] == periodic,
                             data.mygrid->lbound[2] == periodic};
     entries["periodicity"] = [&]() { WriteField(f, "periodicity", 2, {3}, per); };
@@ -200,7 +199,6 @@ class Output {
     const double zero = 0.0;
     WriteField(f, "eof", 0, {1}, &zero);
     std::fclose(f);
-    dumpFileNumber++;
     idfx::cout << "done in " << std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() << " s."
                << std::endl;
   }
@@ -274,8 +272,7 @@ class Output {
       else if (field == "dumpLast") dumpLast = dv[0];
       else if (field == "analysisLast") analysisLast = dv[0];
       else if (field == "vtkFileNumber") vtkFileNumber = iv[0];
-      else if (field == "dumpFileNumber") dumpFileNumber = iv[0] + 1;
-      else if (field == "ncycles" && ncyclesPtr) *ncyclesPtr = iv[0];
+      else if (field == "dumpFileNumber") dumpFileNumber = iv[0];
     }
     std::fclose(f);
     d.SyncToDevice();

@@ -136,6 +136,10 @@ int idfx_get_ncycles(IdfxBlock *blk, long long *ncycles);
  * count == 0 (asserted by the parity tests and bench.py) means every quotient and root was the correctly
  * rounded IEEE value.  Build with `make FASTDIV=0` for a library that uses the ordinary operators only. */
 int idfx_math_exceptions(IdfxBlock *blk, unsigned int *count);
+/* Device self-test of the tensor-memory (TMEM) scratchpad the x2 / x3 sweeps keep their per-thread carry-over in
+ * (csrc/tmem.cuh): four co-resident CTAs per SM write, re-read and compare a data pattern.  *mismatches == 0 on a
+ * healthy sm_100a device.  No reference counterpart (the reference has no tensor-memory path). */
+int idfx_selftest_tmem(int device, long long *mismatches);
 /* number of kernels launched by this block since creation (bench "gpu_launches") */
 int idfx_launch_count(IdfxBlock *blk, long long *count);
 

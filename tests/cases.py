@@ -88,7 +88,7 @@ SHORT = [
 # (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
 # reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
 # fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
-PROBLEM_DIRS = {"sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
+PROBLEM_DIRS = {"sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
 
 
 def _sph(solver, emf=None, nstages=2):
@@ -179,13 +179,15 @@ FULL = [
 ]
 
 
-# Cases pinned for the CPU oracle only (the CUDA path does not implement them yet): the HD Roe
-# solver of the reference's default sod test, incl. its 1-D quirk of leaving the previous flux in place at strong
-# shocks (roeHD.hpp:312-328).  Not run by the GPU tests.
+# The HD Roe solver of the reference's default sod test (tests/test_roe_hd_iso_gpu.py on the GPU, tests/test_oracle.py
+# for the oracle).  sodstrong_*: a 1e5 pressure ratio drives interfaces through the solver's strong-shock switch,
+# which in one dimension leaves the flux of the previous call in place (roeHD.hpp:312-328) -- reproduced.
 ORACLE_SHORT = [
     Short("sod_roe_plm", "sod", 2, "sod_plm", _sod("roe"), (1, 20, 60)),
     Short("sod_roe_ppm_rk3", "sod", 4, "sod_ppm", _sod("roe", 3), (1, 40)),
     Short("sodiso_roe_plm", "sodiso", 2, "sodiso_plm", _sod("roe"), (1, 40)),
+    Short("sodstrong_roe_plm", "sodstrong", 2, "sodstrong_plm", _sod("roe"), (1, 10, 60)),
+    Short("sodstrong_roe_plm_rk3", "sodstrong", 2, "sodstrong_plm", _sod("roe", 3), (1, 40)),
 ]
 ORACLE_FULL = [
     Full("sod_roe", "sod", 2, _sod("roe"), "HD/sod/dump.ref.double.plm.idefix.ini.dmp", 0.0),

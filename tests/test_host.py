@@ -123,6 +123,8 @@ def test_dump_round_trip(tmp_path):
         if name.startswith(("Vc-", "Vs-")):
             assert np.array_equal(mine.data[name], arr), name
     assert mine.data["dt"][0] == 1e-4 and int(mine.data["geometry"][0]) == 1
+    # dump.N stores N+1 (dump.cpp:839), like the reference's own dump.0000
+    assert int(mine.data["dumpFileNumber"][0]) == int(ref.data["dumpFileNumber"][0]) == 1
     assert [int(v) for v in mine.data["periodicity"]] == [1, 1, 0]
     # and the reference's own reader accepts the header
     assert mine.header.startswith("Idefix ") and "Dump Data" in mine.header

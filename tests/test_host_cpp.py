@@ -90,6 +90,14 @@ def assert_same_fields(mine, gold):
     assert checked > 0
     for attr in ("x1", "x1l", "x1r", "x2", "x3"):
         assert np.array_equal(getattr(mine, attr), getattr(gold, attr))
+    # every scalar the reference registers (time, dt, output bookkeeping, file numbers, geometry, periodicity):
+    # a dump written here must restart the reference and vice versa (dump.cpp:628-810)
+    scalars = [n for n in gold.data if not n.startswith(("Vc-", "Vs-"))]
+    assert {"time", "dt", "dumpFileNumber", "dumpLast", "vtkFileNumber", "geometry", "periodicity"} <= set(scalars)
+    for name in scalars:
+        assert name in mine.data, name
+        assert np.array_equal(np.asarray(mine.data[name]), np.asarray(gold.data[name])), name
+    assert set(mine.data) == set(gold.data)
 
 
 @pytest.mark.gpu

@@ -1,12 +1,6 @@
-"""First-run GPU tests: (1) the HD Roe solver (riemann_roe_hd.cuh dispatched by the pencil sweeps); (2) the
-isothermal kernels against the ORACLE on random states (they are already verified on the GPU against the
-reference build's dumps through the C++ host, tests/test_host_cpp.py; the oracle learnt the isothermal EOS later).
-
-FIRST-RUN TESTS.  The wiring was written after the round's GPU budget was spent: the solver function itself is
-pinned on the CPU (host-compiled source vs oracle, tests/test_riemann_host.py; oracle vs the reference build and
-the shipped HD/sod Roe goldens, tests/test_oracle.py), but these kernels have not run on a device yet.  Every
-test here is therefore marked xfail(strict=False): a failure cannot mask the verified suite, a pass shows up as
-XPASS.  The file sorts last so that nothing else runs after it in the same process.  Remove the marker once green.
+"""GPU parity of (1) the HD Roe solver (riemann_roe_hd.cuh, the solver of the reference's default test/HD/sod run),
+including its 1-D strong-shock quirk (roeHD.hpp:312-328: the flux of the previous call stays in place -- sodstrong_*
+cases, reproduced through SweepArgs::staleFlux) and (2) the isothermal kernels against the CPU oracle on random states.
 """
 import os
 
@@ -24,8 +18,7 @@ from idefix_b200.grid import Definitions
 from test_oracle_gpu import RandomFlow, build, make_ini
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="written after the GPU budget of the round was spent: not run on a GPU yet (first-run tests)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 SHORT_ROE = [c for c in ORACLE_SHORT if c.setup in REGISTRY]
 
@@ -146,12 +139,17 @@ def test_isothermal_cuda_equals_oracle_bitwise(case, fused):
     d.close()
 
 
-def test_roe_hd_isothermal_through_cpp_host(tmp_path_factory, tmp_path):
-    """isothermal HD Roe through the C++ host layer (./idefix built from idefix_b200/host/problems/sodIso): the dumps
-    equal those of the reference's own build for the same ini"""
+HOST_ROE = [c for c in ORACLE_SHORT if c.setup not in REGISTRY]
+
+
+@pytest.mark.parametrize("case", HOST_ROE, ids=[c.name for c in HOST_ROE])
+def test_roe_hd_through_cpp_host(case, tmp_path_factory, tmp_path):
+    """HD Roe through the C++ host layer (./idefix built from idefix_b200/host/problems/{sodIso,sodStrong}): the dumps
+    equal those of the reference's own build for the same ini, bit for bit -- isothermal, and the strong blast tube
+    whose interfaces take the 1-D stale-flux branch"""
     import test_host_cpp as thc
     from cases import ini_for
-    case = [c for c in ORACLE_SHORT if c.name == "sodiso_roe_plm"][0]
+    assert len(HOST_ROE) >= 3
     exe = thc.binary(case.setup, case.order, tmp_path_factory)
     ncyc = max(case.cycles)
     thc.run_idefix(exe, str(tmp_path), ini_for(case, dump_every_cycle=True), "-maxcycles", str(ncyc))
