@@ -15,6 +15,7 @@
 
 #include "../../include/idefix_b200.h"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace {
 
@@ -74,6 +75,10 @@ struct IdfxBlock {
   unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   double *staleFlux = nullptr; // 1-D HD Roe: area-weighted flux of the previous call (roeHD.hpp:312-328)
+  // TMA descriptors of Vc for the sweep kernels (tma.cuh): boxes [nvar][32 cells] and [nvar][32 + 2H cells]
+  CUtensorMap tmMarch, tmRow;
+  bool haveTmMarch = false, haveTmRow = false;
+  int tmRowCells = 0;
   // steady-state cycle of the fused path captured as a CUDA graph (launch-bound small grids: ~40 launches per cycle)
   cudaGraphExec_t cycleGraph = nullptr;
   long long cycleGraphLaunches = 0;
@@ -371,6 +376,10 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
   a.doInvDt = 1;
   a.fluxRho = b->fluxRho;
   a.staleFlux = b->staleFlux;
+  a.tmapMarch = b->haveTmMarch ? &b->tmMarch : nullptr;
+  a.tmapRow = b->haveTmRow ? &b->tmRow : nullptr;
+  a.tmapNvar = b->cfg.nvar;
+  a.tmapRowCells = b->tmRowCells;
   a.mathFlag = b->mathFlag;
   a.validateInputs = b->vcFieldFresh ? 0 : 1;   // our own stage epilogue already validated what it wrote
   return a;
@@ -759,6 +768,11 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
       rc = rc || devAlloc(b, &e.ezi, n) || devAlloc(b, &e.eyi, n) || devAlloc(b, &e.svx, n);
       rc = rc || devAlloc(b, &e.axL, n) || devAlloc(b, &e.axR, n) || devAlloc(b, &e.dxL, n) || devAlloc(b, &e.dxR, n);
     }
+  }
+  if (!rc && !std::getenv("IDFX_NO_TMA")) {   // A/B switch: per-lane cp.async loads only
+    b->tmRowCells = 32 + 2 * ((desc->order == 4) ? 2 : 1);
+    b->haveTmMarch = tma::encodeCellBox(&b->tmMarch, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, 32);
+    b->haveTmRow = tma::encodeCellBox(&b->tmRow, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, b->tmRowCells);
   }
   rc = rc || devAlloc(b, &b->state, 4);
   rc = rc || devAlloc(b, &b->redBits, 2);

@@ -21,6 +21,7 @@
 #define IDFX_SWEEP_PENCIL_CUH_
 
 #include "sweep.cuh"
+#include "tma.cuh"
 #include "tmem.cuh"
 
 // IDFX_TMEM = 1: the x2 / x3 marches keep their per-thread carry-over (left state of the next interface, flux and
@@ -140,44 +141,56 @@ IDFX_D void reportMathFlag(const SweepArgs &a, bool bad) {
 
 // =================================================================================================
 // x2 / x3 sweeps: a thread owns one (i, perpendicular) column and marches along the sweep direction.
+// Shared memory is organised per WARP (stencil ring [slot][nvar][32], normal field [2][32]) so that a ring
+// slot is exactly one TMA box and a warp never waits for another one.
 // =================================================================================================
 template <class P, int ORDER, bool CART>
+constexpr int pencilMarchDoublesPerWarp() {
+  return ((CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * P::nvar   // stencil ring
+          + 2                                                                  // normal field at the interface (x2)
+          + (IDFX_TMEM ? 0 : P::nvar + (P::nvar + 1)))                         // carry-over when it is not in TMEM
+         * 32;
+}
+template <class P, int ORDER, bool CART>
 constexpr size_t pencilMarchSmem(int TX, int chunk) {
-  return sizeof(double) * ((size_t)TX * ((CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * P::nvar   // stencil ring
-                                         + (IDFX_TMEM ? 0 : P::nvar)        // left state of the next interface
-                                         + (IDFX_TMEM ? 0 : (P::nvar + 1))  // previous interface: flux + signal speed
-                                         + 2)                               // normal field at the interface (x2)
+  return sizeof(double) * ((size_t)(TX / 32) * pencilMarchDoublesPerWarp<P, ORDER, CART>()
                            + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * (chunk + 2)
-                           + (IDFX_TMEM ? 2 : 0));                          // TMEM base address slot
+                           + (size_t)(TX / 32) * pencil::Halo<ORDER>::W        // one mbarrier per warp and ring slot
+                           + 2);                                               // TMEM base address slot
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART>
-__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencilMarchKernel(const SweepArgs a, const int chunk) {
+__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
+    pencilMarchKernel(const SweepArgs a, const int chunk, const __grid_constant__ CUtensorMap vcBoxes) {
   static_assert(DIR == JDIR || DIR == KDIR, "the marching kernel sweeps along x2 or x3");
   constexpr int NV = P::nvar;
   using D = Dirs<P, DIR>;
   constexpr bool LATE = CART;   // prefetch after the reconstruction (no cell behind the stencil is needed)
   constexpr int H = pencil::Halo<ORDER>::H, W = LATE ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W;
   constexpr int PDIR = (DIR == JDIR) ? KDIR : JDIR;  // the other perpendicular direction
+  constexpr int WARPS = TX / 32;
+  constexpr int PERWARP = pencilMarchDoublesPerWarp<P, ORDER, CART>();
+  constexpr int TROWS = CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN;
 
-  extern __shared__ double smem[];
-  const int tx = threadIdx.x;
-  double *ring = smem + tx;                         // ring[(slot * NV + nv) * TX]
+  extern __shared__ __align__(128) double smem[];
+  const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
+  double *wbase = smem + warp * PERWARP;
+  double *ring = wbase + lane;                      // ring[(slot * NV + nv) * 32]
+  double *vsb = wbase + W * NV * 32 + lane;         // vsb[buf * 32]
 #if IDFX_TMEM
   // carry-over in tensor memory: columns [2 nv, 2 nv + 1] = left state nv, [2 NV + 2 nv, ..] = previous flux nv,
   // [4 NV, 4 NV + 1] = previous signal speed
   constexpr int TCOLS = (4 * NV + 2 <= 32) ? 32 : 64;
   constexpr unsigned T_VLS = 0, T_FPREV = 2 * NV, T_CMAX = 4 * NV;
-  double *vsb = smem + W * NV * TX + tx;            // vsb[buf * TX]
-  double *tab = smem + (size_t)TX * (W * NV + 2);   // tab[row * (chunk+2) + r]
 #else
-  double *vls = smem + W * NV * TX + tx;            // vls[nv * TX]
-  double *fprev = vls + NV * TX;                    // fprev[nv * TX]
-  double *vsb = fprev + (NV + 1) * TX;              // vsb[buf * TX]
-  double *tab = smem + (size_t)TX * (W * NV + NV + (NV + 1) + 2);   // tab[row * (chunk+2) + r]
+  double *vls = wbase + (W * NV + 2) * 32 + lane;   // vls[nv * 32]
+  double *fprev = vls + NV * 32;                    // fprev[nv * 32]
 #endif
+  double *tab = smem + WARPS * PERWARP;             // tab[row * (chunk+2) + r]
   const int tlen = chunk + 2;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(tab + TROWS * tlen) + warp * pencil::Halo<ORDER>::W;
   const unsigned ringS = pencil::smemAddr(ring), vsbS = pencil::smemAddr(vsb);
+  const unsigned ringWarpS = pencil::smemAddr(wbase), barS = pencil::smemAddr(bars);
 
   const DevGrid &g = a.g;
   const int ext = a.perpExt;
@@ -199,9 +212,14 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       tab[(pencil::T_W + 5) * tlen + r] = g.dm[DIR][c];
     }
   }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < W; s++) tma::barrierInit(barS + 8 * s, 1);
+    tma::fenceBarrierInit();
+  }
 #if IDFX_TMEM
-  unsigned *tslot = reinterpret_cast<unsigned *>(tab + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * tlen);
-  const unsigned tbase = tmem::allocate<TCOLS>(tslot);   // contains the __syncthreads that publishes tab
+  unsigned *tslot = reinterpret_cast<unsigned *>(tab + TROWS * tlen + WARPS * pencil::Halo<ORDER>::W);
+  const unsigned tbase = tmem::allocate<TCOLS>(tslot);   // contains the __syncthreads that publishes tab / barriers
 #else
   __syncthreads();
 #endif
@@ -227,6 +245,33 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
   const long long cell0 = (DIR == JDIR) ? cidx(g, p, 0, i) : cidx(g, 0, p, i);
   const long long face0 = DIR * g.vsn + ((DIR == JDIR) ? sidx(g, p, 0, i) : sidx(g, 0, p, i));
   const bool columnInterior = columnValid && (i >= g.beg[0]) && (i < g.end[0]) && (p >= g.beg[PDIR]) && (p < g.end[PDIR]);
+  // TMA serves warps whose 32 columns are 32 consecutive cells of one x1 row (all but the few that wrap around
+  // the end of a row, and the tail of the last CTA); the others copy per lane
+  const int i0 = __shfl_sync(0xffffffffu, i, 0);
+  const bool useTma = (a.useTma != 0) && __all_sync(0xffffffffu, columnValid && (i == i0 + lane) &&
+                                                                    (p == __shfl_sync(0xffffffffu, p, 0)));
+  unsigned phases = 0;   // bit s: parity of the next completion of ring slot s (TMA path)
+
+  // primitives of cell `mc` along the march -> ring slot `slot` (all lanes call this convergently)
+  auto issueCell = [&](int slot, int mc) {
+    if (useTma) {
+      __syncwarp();   // every lane is done reading what the slot held
+      if (lane == 0) {
+        tma::barrierExpect(barS + 8 * slot, NV * 32 * 8);
+        tma::load4D(ringWarpS + slot * NV * 256, &vcBoxes, barS + 8 * slot, i0, (DIR == JDIR) ? mc : p, (DIR == JDIR) ? p : mc, 0);
+      }
+    } else {
+      const double *src = a.Vc + cell0 + (long long)mc * stride;
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (slot * NV + nv) * 256, src + nv * g.sn);
+    }
+  };
+  auto waitCell = [&](int slot) {
+    if (useTma) {
+      tma::barrierWait(barS + 8 * slot, (phases >> slot) & 1u);
+      phases ^= (1u << slot);
+    }
+  };
 
   const Eos eos{a.gamma, a.csiso};
   const double dt = *a.dt;
@@ -246,18 +291,13 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
   }
 
   // ---- prologue: cells mb-1-H .. mb+H, the normal field of the first interface ---------------------------
-  {
-    const double *src = a.Vc + cell0 + (long long)(mb - 1 - H) * stride;
 #pragma unroll
-    for (int c = 0; c < W; c++) {
-#pragma unroll
-      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (c * NV + nv) * TX * 8, src + nv * g.sn);
-      src += stride;
-    }
-  }
+  for (int c = 0; c < W; c++) issueCell(c, mb - 1 - H + c);
   if constexpr (P::mhd) pencil::cpAsync8s(vsbS, a.Vs + face0 + (long long)mb * vstride);
   pencil::cpAsyncCommit();
   pencil::cpAsyncWait<0>();
+#pragma unroll
+  for (int c = 0; c < W; c++) waitCell(c);
   // right-face values of cell mb-1 = left state of the first interface
   {
     const double dxc = tab[pencil::T_DX * tlen];
@@ -272,7 +312,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       double st[5];
       st[0] = st[4] = 0.0;
 #pragma unroll
-      for (int d = -H; d <= H; d++) st[2 + d] = ring[((H + d) * NV + nv) * TX];
+      for (int d = -H; d <= H; d++) st[2 + d] = ring[((H + d) * NV + nv) * 32];
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vl, vr;
       reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
@@ -280,35 +320,37 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       __syncwarp();
       tmem::store1(tbase + T_VLS + 2 * nv, vr);
 #else
-      vls[nv * TX] = vr;
+      vls[nv * 32] = vr;
 #endif
     }
   }
 
   bool mathBad = false;
   int q = 0;  // ring slot of cell m-H-1: free, receives cell m+H+1 (LATE: cell m+H, issued at the end of step m-1)
-  const double *pre = a.Vc + cell0 + (long long)(mb + H + (LATE ? 0 : 1)) * stride;
-  long long cellm = cell0 + (long long)mb * stride;
   if constexpr (LATE) {
     // cell mb+H completes the stencil of cell mb
-#pragma unroll
-    for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
+    issueCell(q, mb + H);
     pencil::cpAsyncCommit();
-    pre += stride;
   }
+  long long cellm = cell0 + (long long)mb * stride;
   for (int m = mb; m <= me; m++) {
     const int r = m - mb;
     if constexpr (!LATE) {
       // ---- prefetch what the next interface needs ----------------------------------------------------
       if (m < me) {
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
-        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
+        issueCell(q, m + H + 1);
+        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * 256, a.Vs + face0 + (long long)(m + 1) * vstride);
       }
       pencil::cpAsyncCommit();
       pencil::cpAsyncWait<1>();   // everything but the group just committed has landed
+      if (r > 0) {                // ... and so has the box issued one step ago (the prologue waited for its own)
+        int ql = q - 1;
+        if (ql < 0) ql += W;
+        waitCell(ql);
+      }
     } else {
       pencil::cpAsyncWait<0>();   // cell m+H and the normal field of interface m (issued one step ago)
+      waitCell(q);
     }
 
     // ---- cell m: face values; interface m: left state from cell m-1, right state from cell m -----------
@@ -327,7 +369,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       for (int d = -H; d <= H; d++) {
         int s = q + 1 + H + d;
         if (s >= W) s -= W;
-        so[d + H] = s * NV * TX;
+        so[d + H] = s * NV * 32;
       }
 #if IDFX_TMEM
       // left state = right-face values of cell m-1, parked in tensor memory one step ago
@@ -352,7 +394,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         double st[5];
         st[0] = st[4] = 0.0;
 #pragma unroll
-        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * TX];
+        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * 32];
         const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
         double vr;
         reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
@@ -360,8 +402,8 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         __syncwarp();
         tmem::store1(tbase + T_VLS + 2 * nv, vr);
 #else
-        vL[nv] = vls[nv * TX];
-        vls[nv * TX] = vr;
+        vL[nv] = vls[nv * 32];
+        vls[nv * 32] = vr;
 #endif
       }
     }
@@ -370,14 +412,13 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       if (m < me) {
         int qn = q + 1;
         if (qn >= W) qn -= W;
-#pragma unroll
-        for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (qn * NV + nv) * TX * 8, pre + nv * g.sn);
-        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
+        issueCell(qn, m + H + 1);
+        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * 256, a.Vs + face0 + (long long)(m + 1) * vstride);
       }
       pencil::cpAsyncCommit();
     }
     if constexpr (P::mhd) {
-      const double bn = vsb[(r & 1) * TX];
+      const double bn = vsb[(r & 1) * 32];
       vL[D::BXn] = bn;
       vR[D::BXn] = bn;
     }
@@ -417,14 +458,14 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
 #if !IDFX_TMEM
       double Fm[NV];
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * TX];
-      const double cmaxm = fprev[NV * TX];
+      for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * 32];
+      const double cmaxm = fprev[NV * 32];
 #endif
-      int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring)
-      if (sp < 0) sp += W;
-      const double *vprev = ring + sp * NV * TX;
+      int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring; never read when LATE: no
+      if (sp < 0) sp += W;      // source terms on cartesian grids, no primitive-to-conservative rebuild in x2 / x3)
+      const double *vprev = ring + sp * NV * 32;
       updateCell<typename P::Fast, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
-                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * TX]; });
+                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * 32]; });
     }
 #if IDFX_TMEM
     __syncwarp();
@@ -433,11 +474,10 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
     tmem::store1(tbase + T_CMAX, aux.cmax);
 #else
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) fprev[nv * TX] = F[nv];
-    fprev[NV * TX] = aux.cmax;
+    for (int nv = 0; nv < NV; nv++) fprev[nv * 32] = F[nv];
+    fprev[NV * 32] = aux.cmax;
 #endif
     q = (q + 1 == W) ? 0 : q + 1;
-    pre += stride;
     cellm += stride;
   }
   pencil::reportMathFlag(a, mathBad && columnValid);
@@ -466,7 +506,11 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
   static unsigned long long configured = 0;   // bit d: attribute set on device d
   auto kern = pencilMarchKernel<P, SOLVER, ORDER, DIR, TX, CART>;
   if (cudaError_t e = pencil::ensureDynamicSmem(kern, smem, configured); e != cudaSuccess) return e;
-  kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(a, chunk);
+  SweepArgs b = a;
+  const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(a.tmapMarch);
+  b.useTma = (map != nullptr && P::nvar == a.tmapNvar) ? 1 : 0;
+  static const CUtensorMap none = {};
+  kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(b, chunk, b.useTma ? *map : none);
   return cudaGetLastError();
 }
 
@@ -476,10 +520,14 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
 // Lane l holds cell c = cs - 1 + l; it reconstructs cell c, solves the interface on the LEFT face of
 // c with the right-face value of lane l-1, and updates cell c with the flux of lane l+1.
 // =================================================================================================
+// one row buffer = one TMA box [nvar][32 + 2H cells], padded to a multiple of 128 bytes (TMA destination alignment)
+template <class P, int ORDER>
+constexpr int pencilRowBufferDoubles() {
+  return (P::nvar * (32 + 2 * pencil::Halo<ORDER>::H) + 15) / 16 * 16;
+}
 template <class P, int ORDER>
 constexpr int pencilRowDoublesPerWarp() {
-  constexpr int H = pencil::Halo<ORDER>::H;
-  return 2 * P::nvar * (32 + 2 * H)   // two row buffers of primitives (current row, next row in flight)
+  return 2 * pencilRowBufferDoubles<P, ORDER>()   // two row buffers of primitives (current row, next row in flight)
          + P::nvar * 32               // right-face values
          + (P::nvar + 1) * 32         // fluxes + signal speed
          + 2 * 32;                    // normal field, double buffered
@@ -487,12 +535,12 @@ constexpr int pencilRowDoublesPerWarp() {
 
 template <class P, int ORDER, bool CART>
 constexpr size_t pencilRowSmem(int warps, int chunk) {
-  return sizeof(double) * ((size_t)warps * pencilRowDoublesPerWarp<P, ORDER>() + 2 * (size_t)chunk);
+  return sizeof(double) * ((size_t)warps * pencilRowDoublesPerWarp<P, ORDER>() + 2 * (size_t)chunk + 2 * (size_t)warps);
 }
 
 template <class P, int SOLVER, int ORDER, int WARPS, bool CART>
-__global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) pencilRowKernel(const SweepArgs a, const int chunk,
-                                                                                   const int nstrips) {
+__global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB))
+    pencilRowKernel(const SweepArgs a, const int chunk, const int nstrips, const __grid_constant__ CUtensorMap vcBoxes) {
   constexpr int DIR = IDIR;
   constexpr int NV = P::nvar;
   using D = Dirs<P, DIR>;
@@ -500,14 +548,23 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
   constexpr int RW = 32 + 2 * H;                      // cells per row buffer
   constexpr int STRIP = 30;                           // cells updated per warp and row
 
-  extern __shared__ double smem[];
+  constexpr int BUF = pencilRowBufferDoubles<P, ORDER>();   // doubles between the two row buffers
+  extern __shared__ __align__(128) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *wbase = smem + (size_t)warp * pencilRowDoublesPerWarp<P, ORDER>();
-  double *rows = wbase;                               // rows[(buf * NV + nv) * RW + x], x = cell - (cs-1-H)
-  double *vrs = rows + 2 * NV * RW;                   // vrs[nv * 32 + lane]
+  double *rows = wbase;                               // rows[buf * BUF + nv * RW + x], x = cell - (cs-1-H)
+  double *vrs = rows + 2 * BUF;                       // vrs[nv * 32 + lane]
   double *fls = vrs + NV * 32;                        // fls[nv * 32 + lane]
   double *vsb = fls + (NV + 1) * 32;                  // vsb[buf * 32 + lane]
   double *tab = smem + (size_t)WARPS * pencilRowDoublesPerWarp<P, ORDER>();   // tab[row * chunk + r]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(tab + 2 * chunk) + 2 * warp;   // one per row buffer
+  const unsigned barS = pencil::smemAddr(bars);
+  const bool useTma = (a.useTma != 0);
+  if (lane == 0) {
+    tma::barrierInit(barS, 1);
+    tma::barrierInit(barS + 8, 1);
+    tma::fenceBarrierInit();
+  }
 
   const DevGrid &g = a.g;
   const int ext = a.perpExt;
@@ -558,14 +615,23 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
   const bool ld1 = (lane < 2 * H) && (x0 + 32 + lane < nx0);
 
   const unsigned rowsS = pencil::smemAddr(rows), vsbS = pencil::smemAddr(vsb);
+  unsigned phases = 0;   // bit b: parity of the next completion of row buffer b (TMA path)
   auto issueRow = [&](int j, int buf) {
-    const long long rowBase = cidx(g, k, j, 0);
-    const unsigned dst = rowsS + (buf * NV * RW + lane) * 8;
-    const double *src = a.Vc + rowBase + x0 + lane;
+    if (useTma) {
+      // one box [nvar][RW cells] per warp and row; cells outside the array are zero-filled and never used
+      if (lane == 0) {
+        tma::barrierExpect(barS + 8 * buf, NV * RW * 8);
+        tma::load4D(rowsS + buf * BUF * 8, &vcBoxes, barS + 8 * buf, x0, j, k, 0);
+      }
+    } else {
+      const long long rowBase = cidx(g, k, j, 0);
+      const unsigned dst = rowsS + (buf * BUF + lane) * 8;
+      const double *src = a.Vc + rowBase + x0 + lane;
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) {   // all of them: the update rebuilds Uc from the cell's primitives
-      if (ld0) pencil::cpAsync8s(dst + nv * RW * 8, src + nv * g.sn);
-      if (ld1) pencil::cpAsync8s(dst + (nv * RW + 32) * 8, src + nv * g.sn + 32);
+      for (int nv = 0; nv < NV; nv++) {   // all of them: the update rebuilds Uc from the cell's primitives
+        if (ld0) pencil::cpAsync8s(dst + nv * RW * 8, src + nv * g.sn);
+        if (ld1) pencil::cpAsync8s(dst + (nv * RW + 32) * 8, src + nv * g.sn + 32);
+      }
     }
     if constexpr (P::mhd) {
       if (faceLane) pencil::cpAsync8s(vsbS + (buf * 32 + lane) * 8, a.Vs + DIR * g.vsn + sidx(g, k, j, c));
@@ -583,10 +649,14 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB)) 
     if (j + 1 < je) issueRow(j + 1, buf ^ 1);
     pencil::cpAsyncCommit();
     pencil::cpAsyncWait<1>();
+    if (useTma) {
+      tma::barrierWait(barS + 8 * buf, (phases >> buf) & 1u);
+      phases ^= (1u << buf);
+    }
     __syncwarp();   // the row buffer was filled by all lanes of the warp
 
     // ---- cell c: face values --------------------------------------------------------------------------
-    const double *row = rows + buf * NV * RW + H + lane;   // row[nv*RW + d] = cell c + d
+    const double *row = rows + buf * BUF + H + lane;   // row[nv*RW + d] = cell c + d
     double vL[NV], vR[NV];
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) {
@@ -705,7 +775,11 @@ inline cudaError_t launchPencilRow(const SweepArgs &a, cudaStream_t stream) {
   auto kern = pencilRowKernel<P, SOLVER, ORDER, WARPS, CART>;
   if (cudaError_t e = pencil::ensureDynamicSmem(kern, pencilRowSmem<P, ORDER, CART>(WARPS, 64), configured); e != cudaSuccess)
     return e;
-  kern<<<grid, WARPS * 32, pencilRowSmem<P, ORDER, CART>(WARPS, chunk), stream>>>(a, chunk, nstrips);
+  SweepArgs b = a;
+  const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(a.tmapRow);
+  b.useTma = (map != nullptr && P::nvar == a.tmapNvar && a.tmapRowCells == 32 + 2 * pencil::Halo<ORDER>::H) ? 1 : 0;
+  static const CUtensorMap none = {};
+  kern<<<grid, WARPS * 32, pencilRowSmem<P, ORDER, CART>(WARPS, chunk), stream>>>(b, chunk, nstrips, b.useTma ? *map : none);
   return cudaGetLastError();
 }
 

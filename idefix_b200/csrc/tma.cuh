@@ -1,0 +1,93 @@
+// tma.cuh -- tensor-memory-accelerator (TMA) loads of the sweep kernels: device wrappers + host-side descriptors.
+//
+// A warp of a sweep kernel needs, per marching step, one box of primitives: [nvar][1][1][32 (+2H) cells along x1].
+// With cp.async that is nvar (x2) LDGSTS per lane plus their 64-bit address arithmetic, and the copies allocate in
+// L1 on their way -- evicting the register spills that live there (ncu: every long-scoreboard stall of the sweeps
+// sits on an LDL).  One elected lane issues ONE cp.async.bulk.tensor instead (SASS: UTMALDG); the box goes
+// L2 -> shared memory without touching L1 and completes on a per-warp mbarrier.
+//
+// Descriptor limits (CUDA driver API, cuTensorMapEncodeTiled): base address 16-byte aligned, every stride a
+// multiple of 16 bytes (=> nx1 even for FP64 rows), box inner extent a multiple of 16 bytes.  Blocks that do not
+// qualify keep the per-lane cp.async path; so do warps whose 32 columns wrap around the end of an x1 row.
+#ifndef IDFX_TMA_CUH_
+#define IDFX_TMA_CUH_
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include "common.cuh"
+
+namespace tma {
+
+#define IDFX_TMA_DEV __device__ __forceinline__
+
+IDFX_TMA_DEV void barrierInit(unsigned bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals) : "memory");
+}
+// makes freshly initialised barriers visible to the async proxy
+IDFX_TMA_DEV void fenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders this thread's generic-proxy shared-memory accesses before subsequent async-proxy (TMA) accesses
+IDFX_TMA_DEV void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+IDFX_TMA_DEV void barrierExpect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// spins until the phase with the given parity of the barrier has completed
+IDFX_TMA_DEV void barrierWait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "IDFX_TMA_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra IDFX_TMA_DONE;\n"
+      "bra IDFX_TMA_WAIT;\n"
+      "IDFX_TMA_DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// box of a rank-4 tensor (x1, x2, x3, variable) -> shared memory, completion counted in bytes on `bar`
+IDFX_TMA_DEV void load4D(unsigned dstShared, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dstShared),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ---- host ------------------------------------------------------------------------------------------------
+// Descriptor of a (nvar, n3, n2, n1) FP64 array for boxes of `boxCells` cells along x1 and all `nvar` variables
+// of one (x2, x3) position.  Returns false when the array does not qualify (see the limits above) or the
+// driver entry point is unavailable; the caller then stays on the cp.async path.
+inline bool encodeCellBox(CUtensorMap *out, const double *base, int n1, int n2, int n3, int nvar, int boxCells) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    cudaGetLastError();
+  }
+  if (!encode) return false;
+  if ((reinterpret_cast<unsigned long long>(base) & 15ull) || (n1 & 1) || boxCells > 256 || nvar > 256 ||
+      ((boxCells * 8) & 15))
+    return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)n1, (cuuint64_t)n2, (cuuint64_t)n3, (cuuint64_t)nvar};
+  const cuuint64_t strides[3] = {(cuuint64_t)n1 * 8, (cuuint64_t)n1 * n2 * 8, (cuuint64_t)n1 * n2 * n3 * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)boxCells, 1, 1, (cuuint32_t)nvar};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double *>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tma
+
+#endif  // IDFX_TMA_CUH_
