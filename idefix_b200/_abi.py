@@ -99,6 +99,12 @@ SYMBOLS = {
     "idfx_set_stream": (C.c_int, [_h, C.c_void_p]),
     "idfx_timing": (C.c_int, [_h, C.c_int, _pd]),
     "idfx_selftest_tmem": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)]),
+    "idfx_selftest_tma": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)]),
+    "idfx_p2p_mailbox": (C.c_int, [_h, C.POINTER(C.c_void_p), C.c_void_p]),
+    "idfx_p2p_connect": (C.c_int, [_h, C.c_int, C.c_int, (C.c_void_p * 2) * 3, (C.c_void_p * 2) * 3,
+                                   C.POINTER(C.c_void_p)]),
+    "idfx_p2p_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
+    "idfx_p2p_timeouts": (C.c_int, [_h, C.POINTER(C.c_ulonglong)]),
 }
 
 _lib = None

@@ -69,6 +69,13 @@ struct IdfxBlock {
   double *haloSend[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   double *haloRecv[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   double *haloPeer[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  // peer-to-peer exchange through device mailboxes (idfx_p2p_connect): no host callback, graph-capturable
+  bool p2p = false;
+  int p2pRank = 0, p2pWorld = 1;
+  unsigned long long *mailbox = nullptr, *p2pSeq = nullptr;
+  unsigned int *p2pTicket = nullptr;
+  unsigned long long *peerMailbox[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  unsigned long long *allMailbox[idfxk::P2P_MAX_RANKS] = {};
   std::vector<std::vector<double>> hostCoords;  // owned copies of the descriptor's coordinate arrays
   double wc[2] = {0, 0}, w0[2] = {0, 0};
   bool ownStream = true;
@@ -414,13 +421,44 @@ int readState(IdfxBlock *b) {
 
 bool needsExchange(const IdfxBlock *b, int dir) { return b->nproc[dir] > 1; }
 
+// a side exchanges ghosts with another block when it is internal, or periodic with nproc[dir] > 1
+// (mpi.cpp:262-266: MPI_PROC_NULL neighbours on physical boundaries)
+bool sideFacesBlock(const IdfxBlock *b, int dir, int side) {
+  const int type = side == 0 ? b->desc.lbound[dir] : b->desc.rbound[dir];
+  return type == IDFX_BC_INTERNAL || (type == IDFX_BC_PERIODIC && b->nproc[dir] > 1);
+}
+
+// Mpi::ExchangeX1/X2/X3 as two kernels over peer memory (boundary.cu: haloP2PKernel)
+int p2pExchange(IdfxBlock *b, int dir) {
+  idfxk::P2PChannel ch;
+  ch.dir = dir;
+  for (int s = 0; s < 2; s++) {
+    ch.active[s] = sideFacesBlock(b, dir, s) ? 1 : 0;
+    ch.peerRecv[s] = b->haloPeer[dir][s];
+    ch.localRecv[s] = b->haloRecv[dir][s];
+    ch.peerMailbox[s] = b->peerMailbox[dir][s];
+    if (ch.active[s] && (!ch.peerRecv[s] || !ch.peerMailbox[s] || !ch.localRecv[s]))
+      return fail("peer-to-peer halo exchange: a neighbour of this block has not been connected (idfx_p2p_connect)");
+  }
+  ch.mailbox = b->mailbox;
+  ch.seq = b->p2pSeq;
+  ch.ticket = b->p2pTicket;
+  KTRY(idfxk::haloP2P(b->cfg, b->g, b->Vc, b->Vs, true, ch, b->stream, &b->launches));
+  KTRY(idfxk::haloP2P(b->cfg, b->g, b->Vc, b->Vs, false, ch, b->stream, &b->launches));
+  return 0;
+}
+
 // Boundary::EnforceBoundaryDir (boundary.hpp:287-385) + ReconstructNormalField (:408-530) of one direction
 int enforceBoundaryDirImpl(IdfxBlock *b, int dir, double t, bool tKnown) {
   const IdfxBlockDesc &d = b->desc;
   {
     if (needsExchange(b, dir)) {
-      if (!b->haloFn) return fail("nproc > 1 in a direction but no halo exchange has been enrolled");
-      b->haloFn(b, dir, b->haloData);
+      if (b->p2p) {
+        if (p2pExchange(b, dir)) return 1;
+      } else {
+        if (!b->haloFn) return fail("nproc > 1 in a direction but no halo exchange has been enrolled");
+        b->haloFn(b, dir, b->haloData);
+      }
     }
     for (int side = 0; side < 2; side++) {
       const int type = side == 0 ? d.lbound[dir] : d.rbound[dir];
@@ -537,7 +575,19 @@ int timestepReduceImpl(IdfxBlock *b) {
 // MPI_Iallreduce(MIN) of timeIntegrator.cpp:318: the enrolled hook reduces the device scalar in place
 // across blocks, enqueued on the block's stream (a non-negative double orders like its bit pattern)
 void crossBlockReduce(IdfxBlock *b, double *devValue, int op) {
-  if (b->reduceFn && b->nproc[0] * b->nproc[1] * b->nproc[2] > 1) b->reduceFn(b, devValue, op, b->reduceData);
+  if (b->nproc[0] * b->nproc[1] * b->nproc[2] <= 1) return;
+  if (b->p2p) {
+    idfxk::P2PReduce r;
+    r.rank = b->p2pRank;
+    r.world = b->p2pWorld;
+    r.mailbox = b->mailbox;
+    r.seq = b->p2pSeq;
+    for (int q = 0; q < idfxk::P2P_MAX_RANKS; q++) r.allMailbox[q] = b->allMailbox[q];
+    idfxk::p2pAllReduce(r, devValue, op == IDFX_REDUCE_MIN ? 0 : 1, b->stream);
+    b->launches++;
+  } else if (b->reduceFn) {
+    b->reduceFn(b, devValue, op, b->reduceData);
+  }
 }
 
 // TimeIntegrator::Cycle as a sequence of the reference's own steps (timeIntegrator.cpp:246-414)
@@ -588,7 +638,7 @@ int cycleReferenceOrder(IdfxBlock *b) {
     }
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
-                           b->stream));
+                           b->mathFlag, b->stream));
   b->launches++;
   return 0;
 }
@@ -628,7 +678,7 @@ int cycleFused(IdfxBlock *b, bool lastOfBatch) {
     b->vcFieldFresh = !b->userBc;   // a user boundary function may write anywhere
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
-                           b->stream));
+                           b->mathFlag, b->stream));
   b->launches++;
   return 0;
 }
@@ -771,7 +821,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   }
   if (!rc && !std::getenv("IDFX_NO_TMA")) {   // A/B switch: per-lane cp.async loads only
     b->tmRowCells = 32 + 2 * ((desc->order == 4) ? 2 : 1);
-    b->haveTmMarch = tma::encodeCellBox(&b->tmMarch, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, 32);
+    b->haveTmMarch = tma::encodeCellBox(&b->tmMarch, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, 34);   // MARCH_BOX
     b->haveTmRow = tma::encodeCellBox(&b->tmRow, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, b->tmRowCells);
   }
   rc = rc || devAlloc(b, &b->state, 4);
@@ -1081,8 +1131,10 @@ namespace {
 // replayed, which removes the per-launch CPU cost that dominates small grids (2-D 1024^2: ~40 launches of
 // ~15 us each per 0.7 ms cycle).  Only for a single block without host callbacks on a capturable stream.
 bool graphEligible(const IdfxBlock *b, int ncycles) {
-  return b->useGraph && b->fused && ncycles >= 4 && !b->userBc && !b->haloFn && !b->timing && b->stream != nullptr &&
-         b->nproc[0] * b->nproc[1] * b->nproc[2] == 1;
+  const bool single = b->nproc[0] * b->nproc[1] * b->nproc[2] == 1;
+  // a decomposed block qualifies when its exchanges and reductions are the library's own peer-to-peer kernels
+  return b->useGraph && b->fused && ncycles >= 4 && !b->userBc && !b->timing && b->stream != nullptr &&
+         ((single && !b->haloFn) || b->p2p);
 }
 }  // namespace
 
@@ -1196,13 +1248,6 @@ int idfx_halo_buffer_size(IdfxBlock *b, int dir, size_t *ndoubles) {
   return 0;
 }
 
-// a side exchanges ghosts with another block when it is internal, or periodic with nproc[dir] > 1
-// (mpi.cpp:262-266: MPI_PROC_NULL neighbours on physical boundaries)
-static bool sideFacesBlock(const IdfxBlock *b, int dir, int side) {
-  const int type = side == 0 ? b->desc.lbound[dir] : b->desc.rbound[dir];
-  return type == IDFX_BC_INTERNAL || (type == IDFX_BC_PERIODIC && b->nproc[dir] > 1);
-}
-
 static int ensureHaloBuffers(IdfxBlock *b, int dir) {
   if (b->haloSend[dir][0]) return 0;
   const long long n = idfxk::haloBufferSize(b->cfg, b->g, dir);
@@ -1262,6 +1307,76 @@ int idfx_halo_ipc_handle(IdfxBlock *b, int dir, int side, void *handle64) {
   CUDA_TRY(cudaIpcGetMemHandle(&h, b->haloRecv[dir][side]));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
   std::memcpy(handle64, &h, 64);
+  return 0;
+}
+
+// ---- peer-to-peer exchange through device mailboxes ------------------------------------------------------------------
+static int ensureMailbox(IdfxBlock *b) {
+  if (b->mailbox) return 0;
+  if (devAlloc(b, &b->mailbox, idfxk::P2P_MB_WORDS) || devAlloc(b, &b->p2pSeq, idfxk::P2P_SEQ_WORDS) ||
+      devAlloc(b, &b->p2pTicket, 2))
+    return 1;
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_p2p_mailbox(IdfxBlock *b, void **mailbox, void *ipc_handle64) {
+  cudaSetDevice(b->desc.device);
+  if (ensureMailbox(b)) return 1;
+  if (mailbox) *mailbox = b->mailbox;
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, b->mailbox));
+    std::memcpy(ipc_handle64, &h, 64);
+  }
+  return 0;
+}
+
+int idfx_p2p_connect(IdfxBlock *b, int rank, int world, void *const peer_recv[3][2], void *const peer_mailbox[3][2],
+                     void *const *all_mailbox) {
+  cudaSetDevice(b->desc.device);
+  if (world < 1 || world > idfxk::P2P_MAX_RANKS || rank < 0 || rank >= world)
+    return fail("idfx_p2p_connect: rank / world out of range");
+  if (ensureMailbox(b)) return 1;
+  dropCycleGraph(b);
+  for (int d = 0; d < b->desc.ndim; d++) {
+    if (b->nproc[d] <= 1) continue;
+    if (ensureHaloBuffers(b, d)) return 1;
+    for (int s = 0; s < 2; s++) {
+      if (!sideFacesBlock(b, d, s)) continue;
+      if (!peer_recv[d][s] || !peer_mailbox[d][s]) return fail("idfx_p2p_connect: missing neighbour pointers");
+      b->haloPeer[d][s] = (double *)peer_recv[d][s];
+      b->peerMailbox[d][s] = (unsigned long long *)peer_mailbox[d][s];
+    }
+  }
+  for (int q = 0; q < world; q++) {
+    if (!all_mailbox || !all_mailbox[q]) return fail("idfx_p2p_connect: missing mailbox of a block of the domain");
+    b->allMailbox[q] = (unsigned long long *)all_mailbox[q];
+  }
+  b->p2pRank = rank;
+  b->p2pWorld = world;
+  b->p2p = true;
+  return 0;
+}
+
+int idfx_p2p_timeouts(IdfxBlock *b, unsigned long long *count) {
+  cudaSetDevice(b->desc.device);
+  *count = 0;
+  if (!b->p2pSeq) return 0;
+  CUDA_TRY(cudaMemcpyAsync(count, b->p2pSeq + idfxk::P2P_SEQ_TIMEOUTS, sizeof(*count), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int idfx_p2p_enable_peer_access(int device, int peer_device) {
+  if (device == peer_device) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  int can = 0;
+  CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) return fail("device cannot access its peer's memory");
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(cudaGetErrorString(e));
+  cudaGetLastError();
   return 0;
 }
 

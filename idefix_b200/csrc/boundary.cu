@@ -275,6 +275,201 @@ int idfxk::haloUnpack(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs
   return haloTransfer<false>(c, g, Vc, Vs, dir, side, const_cast<double *>(buf), st, launches);
 }
 
+// =================================================================================================
+// Peer-to-peer halo exchange (replaces Mpi::ExchangeX1/X2/X3, src/mpi.cpp:247-846, on one NVLink/NVSwitch box).
+//
+// One SEND kernel and one RECEIVE kernel per direction, for both sides and for Vc + every Vs component at once:
+//   send:    wait until the neighbours have consumed the previous message of each channel (ack flags in OUR mailbox),
+//            store the slabs straight into the neighbours' receive buffers over NVLink (the reference's buffer
+//            layout, mpi.cpp:79-134), then the last CTA to finish publishes the message number in the NEIGHBOURS'
+//            mailboxes (system-scope release);
+//   receive: spin on the message numbers in OUR mailbox (system-scope acquire), copy the received slabs into the
+//            ghost zones, then the last CTA acknowledges in the neighbours' mailboxes.
+// Message numbers live in device memory and are advanced by the kernels themselves, so the pair is identical launch
+// for launch and a whole RK cycle including its exchanges can be captured in a CUDA graph; nothing synchronises with
+// the host.  A neighbour that lags simply keeps the spinning CTAs waiting; since every block runs the same
+// send -> receive sequence, a wait is always for something the neighbour does without waiting for us (no deadlock).
+// =================================================================================================
+struct HaloSeg {
+  double *arr;            // Vc or Vs
+  long long sj, sk, sn;   // strides of arr
+  VarList vars;
+  Box box;                // cells / faces that travel
+  long long offset;       // first element of this segment in the flat index space of the plan
+  long long count;        // elements of this segment
+  long long bufOffset;    // first element of this segment inside its side's message buffer
+  int side;               // 0: left, 1: right
+  __host__ __device__ long long sideOffset() const { return bufOffset; }
+};
+struct HaloPlan {
+  int nseg;
+  long long total;
+  HaloSeg seg[8];
+};
+
+__device__ __forceinline__ unsigned long long loadAcquireSys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void storeReleaseSys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *flag >= want.  A neighbour that never answers (crashed process, blocks of one host thread driven in
+// the wrong order) must not hang the device for ever: after ~2^27 polls (tens of seconds) the wait gives up and
+// counts a time-out in the block's counters (idfx_p2p_timeouts), which the host turns into an error.
+__device__ __forceinline__ void waitAtLeast(const unsigned long long *flag, unsigned long long want,
+                                            unsigned long long *seq) {
+  unsigned int polls = 0;
+  while (loadAcquireSys(flag) < want) {
+    __nanosleep(polls < 64 ? 32 : 256);
+    if (++polls > (1u << 27)) {
+      atomicAdd(seq + idfxk::P2P_SEQ_TIMEOUTS, 1ull);
+      break;
+    }
+  }
+}
+
+template <bool SEND>
+__global__ void __launch_bounds__(256) haloP2PKernel(HaloPlan plan, idfxk::P2PChannel ch) {
+  using namespace idfxk;
+  // ---- wait: acknowledgements of everything sent so far / arrival of the next message ----------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) {
+      if (!ch.active[s]) continue;
+      if (SEND) {
+        const unsigned long long sent = ch.seq[P2P_SEQ_SEND + 2 * ch.dir + s];
+        waitAtLeast(ch.mailbox + P2P_MB_ACK + 2 * ch.dir + s, sent, ch.seq);
+      } else {
+        const unsigned long long want = ch.seq[P2P_SEQ_RECV + 2 * ch.dir + s] + 1;
+        waitAtLeast(ch.mailbox + P2P_MB_DATA + 2 * ch.dir + s, want, ch.seq);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- copy ---------------------------------------------------------------------------------------------------
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < plan.total; e += (long long)gridDim.x * blockDim.x) {
+    int sg = 0;
+    while (sg + 1 < plan.nseg && e >= plan.seg[sg].offset + plan.seg[sg].count) sg++;
+    const HaloSeg &g = plan.seg[sg];
+    const long long l = e - g.offset;
+    const int n0 = g.box.hi[0] - g.box.lo[0], n1 = g.box.hi[1] - g.box.lo[1], n2 = g.box.hi[2] - g.box.lo[2];
+    const int ii = (int)(l % n0);
+    const int jj = (int)((l / n0) % n1);
+    const int kk = (int)((l / ((long long)n0 * n1)) % n2);
+    const int n = (int)(l / ((long long)n0 * n1 * n2));
+    const long long a = g.vars.v[n] * g.sn + (long long)(g.box.lo[2] + kk) * g.sk + (long long)(g.box.lo[1] + jj) * g.sj +
+                        (g.box.lo[0] + ii);
+    // position inside the side's own message buffer
+    const long long pos = l + g.sideOffset();
+    if (SEND) ch.peerRecv[g.side][pos] = g.arr[a];
+    else g.arr[a] = ch.localRecv[g.side][pos];
+  }
+  // ---- publish: the last CTA to finish advances the message numbers and raises the neighbours' flags -----------------
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int *ticket = ch.ticket + (SEND ? 0 : 1);
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *ticket = 0u;
+      __threadfence_system();
+      for (int s = 0; s < 2; s++) {
+        if (!ch.active[s]) continue;
+        unsigned long long *counter = ch.seq + (SEND ? P2P_SEQ_SEND : P2P_SEQ_RECV) + 2 * ch.dir + s;
+        const unsigned long long m = *counter + 1;
+        *counter = m;
+        // our side-s slab fills the neighbour's ghost side 1-s; its data / ack flags are indexed by ITS side
+        storeReleaseSys(ch.peerMailbox[s] + (SEND ? P2P_MB_DATA : P2P_MB_ACK) + 2 * ch.dir + (1 - s), m);
+      }
+    }
+  }
+}
+
+// All-reduce (min / max) of one non-negative double over the blocks of the domain through the mailboxes: every
+// block stores its value into slot [rank] of every mailbox, then reads all slots of its own.  Replaces
+// MPI_Iallreduce(MIN) of timeIntegrator.cpp:318 (dt) and the MPI_MAX of checkDivB.hpp.  One CTA, one thread per block
+// of the domain; slots are double-buffered by the parity of the reduction number (a block cannot be two reductions
+// ahead of another one, since finishing a reduction needs everybody's contribution to it).
+__global__ void p2pAllReduceKernel(idfxk::P2PReduce r, double *value, int op) {
+  using namespace idfxk;
+  __shared__ double vals[P2P_MAX_RANKS];
+  const int t = threadIdx.x;
+  const unsigned long long m = r.seq[P2P_SEQ_REDUCE] + 1;
+  const int par = (int)(m & 1ull);
+  if (t < r.world) {
+    unsigned long long *dst = r.allMailbox[t] + P2P_MB_REDUCE + 4 * r.rank + 2 * par;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(*value);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(bits) : "memory");
+    __threadfence_system();
+    storeReleaseSys(dst + 1, m);
+    const unsigned long long *src = r.mailbox + P2P_MB_REDUCE + 4 * t + 2 * par;
+    waitAtLeast(src + 1, m, r.seq);
+    vals[t] = __longlong_as_double((long long)loadAcquireSys(src));
+  }
+  __syncthreads();
+  if (t == 0) {
+    double v = vals[0];
+    for (int q = 1; q < r.world; q++) v = (op == 0) ? fmin(v, vals[q]) : fmax(v, vals[q]);
+    *value = v;
+    r.seq[P2P_SEQ_REDUCE] = m;
+  }
+}
+
+int idfxk::haloP2P(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, bool send, const P2PChannel &ch,
+                   cudaStream_t st, long long *launches) {
+  HaloPlan plan;
+  plan.nseg = 0;
+  plan.total = 0;
+  for (int side = 0; side < 2; side++) {
+    if (!ch.active[side]) continue;
+    long long bufOffset = 0;   // same layout inside a side's buffer as haloTransfer (mpi.cpp:79-134)
+    auto add = [&](double *arr, long long sj, long long sk, long long sn, const VarList &vars, const Box &b) {
+      if (emptyBox(b) || vars.n == 0) return;
+      HaloSeg &sg = plan.seg[plan.nseg++];
+      sg.arr = arr;
+      sg.sj = sj;
+      sg.sk = sk;
+      sg.sn = sn;
+      sg.vars = vars;
+      sg.box = b;
+      sg.side = side;
+      sg.count = boxCount(b) * vars.n;
+      sg.offset = plan.total;
+      sg.bufOffset = bufOffset;
+      plan.total += sg.count;
+      bufOffset += sg.count;
+    };
+    add(Vc, g.sj, g.sk, g.sn, haloVars(c), haloBox(g, ch.dir, side, -1, send));
+    if (c.mhd) {
+      for (int comp = 0; comp < g.ndim; comp++) {
+        VarList one;
+        one.n = 1;
+        one.v[0] = comp;
+        add(Vs, g.vsj, g.vsk, g.vsn, one, haloBox(g, ch.dir, side, comp, send));
+      }
+    }
+  }
+  if (plan.nseg == 0) return 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // few CTAs per SM: a receive kernel may spin while the neighbour is still busy, and must leave room for whatever
+  // else shares the device (a second block of the same process, the other stream of an overlapped exchange)
+  long long blocks = (plan.total + 2047) / 2048;
+  if (blocks > 2LL * sms) blocks = 2LL * sms;
+  if (blocks < 1) blocks = 1;
+  if (send) haloP2PKernel<true><<<(unsigned)blocks, 256, 0, st>>>(plan, ch);
+  else haloP2PKernel<false><<<(unsigned)blocks, 256, 0, st>>>(plan, ch);
+  (*launches)++;
+  return (int)cudaGetLastError();
+}
+
+int idfxk::p2pAllReduce(const P2PReduce &r, double *devValue, int op, cudaStream_t st) {
+  p2pAllReduceKernel<<<1, P2P_MAX_RANKS, 0, st>>>(r, devValue, op);
+  return (int)cudaGetLastError();
+}
+
 // Boundary::EnforcePeriodic / EnforceReflective / EnforceOutflow for one side
 int idfxk::enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side,
                                    int type, cudaStream_t st, long long *launches) {

@@ -74,13 +74,43 @@ int haloPack(const PhysCfg &c, const DevGrid &g, const double *Vc, const double 
 int haloUnpack(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side, const double *buf,
                cudaStream_t st, long long *launches);
 
+// ---- peer-to-peer halo exchange and reduction through device mailboxes (boundary.cu) ------------------------------
+constexpr int P2P_MAX_RANKS = 64;
+// mailbox of a block (64-bit words, written by its neighbours / by every block of the domain):
+//   DATA[2 dir + side]  number of the last message that landed in the receive buffer of ghost side `side`
+//   ACK [2 dir + side]  number of the last message of OUR side-`side` slab the neighbour has unpacked
+//   REDUCE[4 rank + 2 parity + {0: value bits, 1: reduction number}]
+enum : int { P2P_MB_DATA = 0, P2P_MB_ACK = 6, P2P_MB_REDUCE = 12, P2P_MB_WORDS = 12 + 4 * P2P_MAX_RANKS };
+// private counters of a block (device memory, advanced by the kernels: graph replays stay valid)
+enum : int { P2P_SEQ_SEND = 0, P2P_SEQ_RECV = 6, P2P_SEQ_REDUCE = 12, P2P_SEQ_TIMEOUTS = 13, P2P_SEQ_WORDS = 16 };
+struct P2PChannel {
+  int dir;
+  int active[2];                       // side exchanges with another block
+  double *peerRecv[2];                 // neighbour's receive buffer our side-s slab is stored into
+  const double *localRecv[2];          // our receive buffer of ghost side s
+  unsigned long long *mailbox;         // ours
+  unsigned long long *peerMailbox[2];  // the neighbour's on side s
+  unsigned long long *seq;             // our counters
+  unsigned int *ticket;                // [2] last-CTA-done tickets (send, receive)
+};
+struct P2PReduce {
+  int rank, world;
+  unsigned long long *mailbox, *seq;
+  unsigned long long *allMailbox[P2P_MAX_RANKS];
+};
+// one kernel: both sides, Vc + every Vs component; send = true stores into the neighbours, false unpacks
+int haloP2P(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, bool send, const P2PChannel &ch, cudaStream_t st,
+            long long *launches);
+// in-place min (op 0) / max (op 1) of *devValue over all blocks
+int p2pAllReduce(const P2PReduce &r, double *devValue, int op, cudaStream_t st);
+
 // ---- reductions (reduce.cu) ----------------------------------------------------
 // min over the interior of 1/InvDt, written as ordered bits to *outBits (must be preset to +inf bits)
 int timestepReduce(const DevGrid &g, const double *invDt, unsigned long long *outBits, cudaStream_t st);
 // device-side dt control (timeIntegrator.cpp:313-323,380-408); state: [0]=t [1]=dt [2]=t0 [3]=tstop
 int dtControlBegin(double *state, unsigned long long *dtMinBits, cudaStream_t st);
 int dtControlEnd(double *state, unsigned long long *dtMinBits, double cfl, double cflMaxVar, double fixedDt,
-                 long long *ncycles, int *status, cudaStream_t st);
+                 long long *ncycles, int *status, const unsigned int *mathFlag, cudaStream_t st);
 int stageTimeAdvance(double *state, int stage, double wc, double w0, cudaStream_t st);
 int checkDivB(const PhysCfg &c, const DevGrid &g, const double *Vs, unsigned long long *outBits, cudaStream_t st);
 int checkNan(const PhysCfg &c, const DevGrid &g, const double *Vc, const double *Vs, int *count, cudaStream_t st);

@@ -132,7 +132,10 @@ __global__ void stageTimeKernel(double *state, int stage, double wc, double w0) 
 
 // timeIntegrator.cpp:380-408
 __global__ void dtEndKernel(double *state, const unsigned long long *dtMinBits, double cfl, double cflMaxVar,
-                            double fixedDt, long long *ncycles, int *status) {
+                            double fixedDt, long long *ncycles, int *status, const unsigned int *mathFlag) {
+  // the sweeps of this cycle left the validated envelope of their branch-free divisions / roots (fastmath.cuh):
+  // the state is no longer guaranteed to be the reference's, the host must stop (status bit 2)
+  if (mathFlag != nullptr && *mathFlag != 0u) *status |= 4;
   const double dt = state[1];
   state[0] = state[2] + dt;
   if (fixedDt > 0.0) {
@@ -179,8 +182,8 @@ int idfxk::stageTimeAdvance(double *state, int stage, double wc, double w0, cuda
   return (int)cudaGetLastError();
 }
 int idfxk::dtControlEnd(double *state, unsigned long long *dtMinBits, double cfl, double cflMaxVar, double fixedDt,
-                        long long *ncycles, int *status, cudaStream_t st) {
-  dtEndKernel<<<1, 1, 0, st>>>(state, dtMinBits, cfl, cflMaxVar, fixedDt, ncycles, status);
+                        long long *ncycles, int *status, const unsigned int *mathFlag, cudaStream_t st) {
+  dtEndKernel<<<1, 1, 0, st>>>(state, dtMinBits, cfl, cflMaxVar, fixedDt, ncycles, status, mathFlag);
   return (int)cudaGetLastError();
 }
 

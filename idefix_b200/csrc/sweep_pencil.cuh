@@ -144,12 +144,19 @@ IDFX_D void reportMathFlag(const SweepArgs &a, bool bad) {
 // Shared memory is organised per WARP (stencil ring [slot][nvar][32], normal field [2][32]) so that a ring
 // slot is exactly one TMA box and a warp never waits for another one.
 // =================================================================================================
+// A ring slot is one TMA box [nvar][MARCH_BOX cells]: 32 cells of the warp + 2, because an FP64 box must start at an
+// even x1 index (tma.cuh) and the warp's first column may be odd.  Slots are padded to 128 bytes (TMA destination).
+constexpr int MARCH_BOX = 34;
+template <class P>
+constexpr int pencilMarchSlotDoubles() {
+  return (P::nvar * MARCH_BOX + 15) / 16 * 16;
+}
 template <class P, int ORDER, bool CART>
 constexpr int pencilMarchDoublesPerWarp() {
-  return ((CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * P::nvar   // stencil ring
-          + 2                                                                  // normal field at the interface (x2)
-          + (IDFX_TMEM ? 0 : P::nvar + (P::nvar + 1)))                         // carry-over when it is not in TMEM
-         * 32;
+  return (CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * pencilMarchSlotDoubles<P>()   // stencil ring
+         + (2                                                                  // normal field at the interface (x2)
+            + (IDFX_TMEM ? 0 : P::nvar + (P::nvar + 1)))                       // carry-over when it is not in TMEM
+               * 32;
 }
 template <class P, int ORDER, bool CART>
 constexpr size_t pencilMarchSmem(int TX, int chunk) {
@@ -174,22 +181,22 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
 
   extern __shared__ __align__(128) double smem[];
   const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
+  constexpr int SLOT = pencilMarchSlotDoubles<P>(), MW = MARCH_BOX;
   double *wbase = smem + warp * PERWARP;
-  double *ring = wbase + lane;                      // ring[(slot * NV + nv) * 32]
-  double *vsb = wbase + W * NV * 32 + lane;         // vsb[buf * 32]
+  double *vsb = wbase + W * SLOT + lane;            // vsb[buf * 32]
 #if IDFX_TMEM
   // carry-over in tensor memory: columns [2 nv, 2 nv + 1] = left state nv, [2 NV + 2 nv, ..] = previous flux nv,
   // [4 NV, 4 NV + 1] = previous signal speed
   constexpr int TCOLS = (4 * NV + 2 <= 32) ? 32 : 64;
   constexpr unsigned T_VLS = 0, T_FPREV = 2 * NV, T_CMAX = 4 * NV;
 #else
-  double *vls = wbase + (W * NV + 2) * 32 + lane;   // vls[nv * 32]
+  double *vls = wbase + W * SLOT + 2 * 32 + lane;   // vls[nv * 32]
   double *fprev = vls + NV * 32;                    // fprev[nv * 32]
 #endif
   double *tab = smem + WARPS * PERWARP;             // tab[row * (chunk+2) + r]
   const int tlen = chunk + 2;
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(tab + TROWS * tlen) + warp * pencil::Halo<ORDER>::W;
-  const unsigned ringS = pencil::smemAddr(ring), vsbS = pencil::smemAddr(vsb);
+  const unsigned vsbS = pencil::smemAddr(vsb);
   const unsigned ringWarpS = pencil::smemAddr(wbase), barS = pencil::smemAddr(bars);
 
   const DevGrid &g = a.g;
@@ -251,19 +258,25 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
   const bool useTma = (a.useTma != 0) && __all_sync(0xffffffffu, columnValid && (i == i0 + lane) &&
                                                                     (p == __shfl_sync(0xffffffffu, p, 0)));
   unsigned phases = 0;   // bit s: parity of the next completion of ring slot s (TMA path)
+  // ring[slot * SLOT + nv * MW] = this lane's cell; a TMA box starts at the even index at or below the warp's first
+  // column, so the lanes sit one entry further when that column is odd
+  const int boxShift = useTma ? (i0 & 1) : 0;
+  double *ring = wbase + boxShift + lane;
+  const unsigned ringS = pencil::smemAddr(ring);
 
   // primitives of cell `mc` along the march -> ring slot `slot` (all lanes call this convergently)
   auto issueCell = [&](int slot, int mc) {
     if (useTma) {
       __syncwarp();   // every lane is done reading what the slot held
       if (lane == 0) {
-        tma::barrierExpect(barS + 8 * slot, NV * 32 * 8);
-        tma::load4D(ringWarpS + slot * NV * 256, &vcBoxes, barS + 8 * slot, i0, (DIR == JDIR) ? mc : p, (DIR == JDIR) ? p : mc, 0);
+        tma::barrierExpect(barS + 8 * slot, NV * MW * 8);
+        tma::load4D(ringWarpS + slot * SLOT * 8, &vcBoxes, barS + 8 * slot, i0 - boxShift, (DIR == JDIR) ? mc : p,
+                    (DIR == JDIR) ? p : mc, 0);
       }
     } else {
       const double *src = a.Vc + cell0 + (long long)mc * stride;
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (slot * NV + nv) * 256, src + nv * g.sn);
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (slot * SLOT + nv * MW) * 8, src + nv * g.sn);
     }
   };
   auto waitCell = [&](int slot) {
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       double st[5];
       st[0] = st[4] = 0.0;
 #pragma unroll
-      for (int d = -H; d <= H; d++) st[2 + d] = ring[((H + d) * NV + nv) * 32];
+      for (int d = -H; d <= H; d++) st[2 + d] = ring[(H + d) * SLOT + nv * MW];
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vl, vr;
       reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       for (int d = -H; d <= H; d++) {
         int s = q + 1 + H + d;
         if (s >= W) s -= W;
-        so[d + H] = s * NV * 32;
+        so[d + H] = s * SLOT;
       }
 #if IDFX_TMEM
       // left state = right-face values of cell m-1, parked in tensor memory one step ago
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
         double st[5];
         st[0] = st[4] = 0.0;
 #pragma unroll
-        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * 32];
+        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * MW];
         const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
         double vr;
         reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
@@ -463,9 +476,9 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
 #endif
       int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring; never read when LATE: no
       if (sp < 0) sp += W;      // source terms on cartesian grids, no primitive-to-conservative rebuild in x2 / x3)
-      const double *vprev = ring + sp * NV * 32;
+      const double *vprev = ring + sp * SLOT;
       updateCell<typename P::Fast, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
-                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * 32]; });
+                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * MW]; });
     }
 #if IDFX_TMEM
     __syncwarp();
@@ -508,7 +521,7 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
   if (cudaError_t e = pencil::ensureDynamicSmem(kern, smem, configured); e != cudaSuccess) return e;
   SweepArgs b = a;
   const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(a.tmapMarch);
-  b.useTma = (map != nullptr && P::nvar == a.tmapNvar) ? 1 : 0;
+  b.useTma = (map != nullptr && P::nvar == a.tmapNvar) ? 1 : 0;   // block.cu encodes this map with MARCH_BOX cells
   static const CUtensorMap none = {};
   kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(b, chunk, b.useTma ? *map : none);
   return cudaGetLastError();

@@ -7,8 +7,11 @@
 // L2 -> shared memory without touching L1 and completes on a per-warp mbarrier.
 //
 // Descriptor limits (CUDA driver API, cuTensorMapEncodeTiled): base address 16-byte aligned, every stride a
-// multiple of 16 bytes (=> nx1 even for FP64 rows), box inner extent a multiple of 16 bytes.  Blocks that do not
-// qualify keep the per-lane cp.async path; so do warps whose 32 columns wrap around the end of an x1 row.
+// multiple of 16 bytes (=> nx1 even for FP64 rows), box inner extent a multiple of 16 bytes.  And, measured on the
+// B200 (idfx_selftest_tma under compute-sanitizer): the FIRST ELEMENT of a box must itself sit on a 16-byte boundary,
+// i.e. an FP64 box must start at an even x1 index -- an odd start coordinate is an illegal-instruction fault.  Boxes
+// are therefore 32 + 2 cells wide and start at the even index at or below the first cell a warp needs.  Blocks that
+// do not qualify keep the per-lane cp.async path; so do warps whose 32 columns wrap around the end of an x1 row.
 #ifndef IDFX_TMA_CUH_
 #define IDFX_TMA_CUH_
 
@@ -31,19 +34,29 @@ IDFX_TMA_DEV void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::ct
 IDFX_TMA_DEV void barrierExpect(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// spins until the phase with the given parity of the barrier has completed
-IDFX_TMA_DEV void barrierWait(unsigned bar, unsigned parity) {
+// one poll: true when the phase with the given parity of the barrier has completed
+IDFX_TMA_DEV bool barrierTryWait(unsigned bar, unsigned parity) {
+  unsigned ok;
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "IDFX_TMA_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra IDFX_TMA_DONE;\n"
-      "bra IDFX_TMA_WAIT;\n"
-      "IDFX_TMA_DONE:\n"
-      "}" ::"r"(bar),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// waits for the phase with the given parity.  A copy that never completes (a box the hardware rejects -- the issuing
+// lane then dies with an illegal-instruction fault while the other lanes keep polling --, a byte count that does not
+// match the box) must surface as an error, not as a hung device: after ~2 s of polling the kernel traps.
+IDFX_TMA_DEV void barrierWait(unsigned bar, unsigned parity) {
+  if (barrierTryWait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!barrierTryWait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 32)) __trap();
+  }
 }
 
 // box of a rank-4 tensor (x1, x2, x3, variable) -> shared memory, completion counted in bytes on `bar`

@@ -79,6 +79,12 @@ class TimeIntegrator {
       msg << "dt = " << data.dt << " is too small.";
       throw std::runtime_error(msg.str());
     }
+    if (flags & 4)
+      throw std::runtime_error(
+          "the sweeps met operands outside the validated range of their branch-free FP64 divisions / square roots "
+          "(zero-crossing, subnormal, beyond 2^+-140, infinite or NaN: idfx_math_exceptions > 0); the state is no "
+          "longer guaranteed to be bit-identical with the reference.  Rebuild libidefix_b200.so with FASTDIV=0 for "
+          "this regime.");
     if (ncycles % checkNanPeriodicity == 0 && data.CheckNan() > 0)
       throw std::runtime_error("Nan found after integration cycle");
   }

@@ -120,6 +120,10 @@ def run(data, tint, tstop, maxcycles=-1, fused=True, check_every=64):
             raise RuntimeError(f"dt = {dt.value} is too small.")
         if flags.value & 2:
             raise IdefixError("Your guessed first_dt is too large.\nTry to reduce first_dt in the ini file.")
+        if flags.value & 4:
+            raise RuntimeError("the sweeps left the validated range of their branch-free FP64 divisions / square roots "
+                               "(idfx_math_exceptions > 0): results no longer guaranteed bit-identical with the "
+                               "reference; rebuild libidefix_b200.so with FASTDIV=0 for this regime")
     check(lib().idfx_get_ncycles(h, C.byref(n)))
     tint.ncycles = n.value
     return n.value

@@ -121,7 +121,10 @@ int idfx_check_nan(IdfxBlock *blk, int *nan_count);                  /* Fluid::C
  * (no host round trip); results are identical to the granular sequence. */
 int idfx_cycles(IdfxBlock *blk, int ncycles);
 /* One cycle, host-synchronous: returns the new t and dt like Cycle() leaves them
- * in DataBlock::t/dt.  status_flags: bit0 dt<1e-15, bit1 first_dt too large. */
+ * in DataBlock::t/dt.  status_flags: bit0 dt<1e-15, bit1 first_dt too large, bit2 the sweeps left the
+ * validated envelope of their branch-free FP64 divisions / square roots (idfx_math_exceptions > 0: operands that
+ * are subnormal, beyond 2^+-140, infinite or NaN) -- the results are no longer guaranteed to be the reference's
+ * and the host layers stop the run; a library built with `make FASTDIV=0` has no such envelope. */
 int idfx_cycle(IdfxBlock *blk, double *t, double *dt, int *status_flags);
 /* Limit dt so that the run ends at tstop (main.cpp:191). Negative disables. */
 int idfx_set_tstop(IdfxBlock *blk, double tstop);
@@ -140,6 +143,10 @@ int idfx_math_exceptions(IdfxBlock *blk, unsigned int *count);
  * (csrc/tmem.cuh): four co-resident CTAs per SM write, re-read and compare a data pattern.  *mismatches == 0 on a
  * healthy sm_100a device.  No reference counterpart (the reference has no tensor-memory path). */
 int idfx_selftest_tmem(int device, long long *mismatches);
+/* Device self-test of the TMA loads of the sweeps (csrc/tma.cuh): rank-4 FP64 boxes [nvar][1][1][cells] per warp,
+ * completion on a per-warp mbarrier, boxes crossing the array bounds (zero fill), compared element by element with
+ * plain loads.  *mismatches == 0 on a healthy device; -2 = the driver refused the tensor-map descriptor. */
+int idfx_selftest_tma(int device, long long *mismatches);
 /* number of kernels launched by this block since creation (bench "gpu_launches") */
 int idfx_launch_count(IdfxBlock *blk, long long *count);
 
@@ -185,6 +192,32 @@ int idfx_halo_ipc_handle(IdfxBlock *blk, int dir, int side, void *handle64);
 int idfx_halo_open_ipc(IdfxBlock *blk, const void *handle64, double **ptr);
 /* tell the block that `dir` has more than one block (nproc[dir] > 1) */
 int idfx_set_nproc(IdfxBlock *blk, const int nproc[3]);
+
+/* ---- peer-to-peer exchange over NVLink / NVSwitch, no host in the loop ------------------------
+ * Replaces Mpi::ExchangeX1/X2/X3 (src/mpi.cpp:247-846) and the MPI_Iallreduce of the time step
+ * (src/timeIntegrator.cpp:318,357-359) for the blocks of ONE box: per direction one kernel stores
+ * both slabs straight into the neighbours' receive buffers and raises a message number in their
+ * device "mailbox", a second one waits for the incoming numbers and fills the ghost zones; the dt
+ * minimum travels through the same mailboxes.  Once connected, idfx_set_boundaries / idfx_cycles
+ * need no halo or reduce callback and the whole cycle (exchanges included) replays as a CUDA graph.
+ *
+ * idfx_p2p_mailbox: device pointer of this block's mailbox and (ipc_handle64 != NULL) its 64-byte
+ *   cudaIpcMemHandle_t for blocks living in other processes (open it with idfx_halo_open_ipc).
+ * idfx_p2p_connect: rank / world = position of this block in the domain (rank = xproc[0] +
+ *   nproc[0]*(xproc[1] + nproc[1]*xproc[2]), the reference's Cartesian communicator, grid.cpp:222-223);
+ *   peer_recv[dir][side] = receive buffer (idfx_halo_buffers) of ghost side 1-side of the neighbour
+ *   on `side`; peer_mailbox[dir][side] = that neighbour's mailbox; all_mailbox[world] = every block's
+ *   mailbox (own included).  Pointers must be valid on this block's device (same process with peer
+ *   access enabled, or cudaIpcOpenMemHandle).  Call idfx_set_nproc first.
+ * Blocks driven by ONE host thread must be given their work with the non-blocking idfx_cycles on
+ * every block before any of them is synchronised (a block's receive kernel waits for its neighbour). */
+int idfx_p2p_mailbox(IdfxBlock *blk, void **mailbox, void *ipc_handle64);
+int idfx_p2p_connect(IdfxBlock *blk, int rank, int world, void *const peer_recv[3][2],
+                     void *const peer_mailbox[3][2], void *const *all_mailbox);
+/* number of waits on a neighbour that gave up (tens of seconds without an answer): non-zero = the exchange is broken */
+int idfx_p2p_timeouts(IdfxBlock *blk, unsigned long long *count);
+/* cudaDeviceEnablePeerAccess(device -> peer_device) for blocks of one process on several GPUs */
+int idfx_p2p_enable_peer_access(int device, int peer_device);
 
 #ifdef __cplusplus
 }

@@ -195,6 +195,31 @@ ORACLE_FULL = [
 ]
 
 
+# BASELINE.json configurations at (or, for C4 / C5, as close as one reference CPU run in this container allows to) the
+# sizes they are quoted on.  Fixtures: tests/golden/config_size/<name>.json = SHA-256 of every dumped field after N
+# cycles of the reference's own build (tests/golden/make_config_size.py); GPU test: tests/test_config_size_gpu.py.
+CONFIG_SIZE = [
+    Short("c1_sod_hllc_500", "sod", 2, "sod_plm", _sod("hllc"), (5, 100)),
+    Short("c2_ot2d_1024", "ot2d", 2, "ot2d_plm", _ot2d(1024, "hlld", "uct_hlld"), (3,)),
+    Short("c3_lw_128_hlld_ppm_rk3", "linearwave", 4, "lw_ppm", _lw(128, 128, 128, "hlld", 3, 1), (3,)),
+    Short("c4_ot3d_256", "ot3d", 2, "ot3d_plm", _ot3d(256, 256, 256), (3,)),
+]
+
+
+def _sph_sized(n1, n2, n3, solver):
+    o = _grid(["1", "1.0", str(n1), "l", "10.0"], ["1", "0.785398163397448", str(n2), "u", "2.356194490192345"],
+              ["1", "0.0", str(n3), "u", "6.283185307179586"])
+    o[("Hydro", "solver")] = solver
+    return o
+
+
+# C5 physics (spherical, log-r, Roe + LimO3 + uct_contact) at the reduced size SURVEY 8(d) names, through the C++ host
+CONFIG_SIZE_HOST = [
+    Short("c5_sph_96x48x96_roe_limo3", "sph", 3, "sph_limo3", _sph_sized(96, 48, 96, "roe"), (3,)),
+]
+CONFIG_SIZE = CONFIG_SIZE + CONFIG_SIZE_HOST
+
+
 def ini_for(case, dump_every_cycle=False):
     """ini text of a case = the set-up's default ini with the case's overrides applied"""
     import os

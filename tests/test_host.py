@@ -220,3 +220,5 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["higher_is_better"] is True and line["cpu_baseline"]["kind"] == "reference"
     assert line["e2e"] == {"value": line["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("test/MHD/OrszagTang3D")
+    # the arm describes what it ran (one OpenMP process on a bounded block), not the GPU arm's decomposition
+    assert "decomposition" not in line["config"] and "halo" not in line["config"] and line["config"]["block"] == 32

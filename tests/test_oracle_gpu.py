@@ -255,3 +255,24 @@ def test_two_blocks_on_one_gpu_peer_halo_bitwise():
     for d in datas:
         assert d.math_exceptions() == 0
         d.close()
+
+
+def test_fast_division_envelope_violation_stops_the_run():
+    """A state outside the validated envelope of the branch-free FP64 divisions (fastmath.cuh: every primitive zero or
+    of magnitude 2^-140 .. 2^140) must not go unnoticed: the cycle's status carries bit 2 and the host layer raises
+    (no silent loss of reference parity); idfx_math_exceptions counts the offending cells."""
+    import ctypes as C
+    from idefix_b200.timeintegrator import run
+    s = build(2, 2, True, (16, 12), "hlld", "uct_contact", 2, "periodic", seed=77)
+    s.InitFlow(s.data)
+    host = s.data.host_mirror
+    host.Vc[s.data.hydro.PRS, :, 5, 7] = 1.0e-200      # a near-vacuum cell: far below 2^-140
+    host.SyncToDevice()
+    s.data.SetBoundaries()
+    t, dt, flags = C.c_double(), C.c_double(), C.c_int()
+    _abi.check(_abi.lib().idfx_cycle(s.data._handle, C.byref(t), C.byref(dt), C.byref(flags)))
+    assert flags.value & 4, flags.value
+    assert s.data.math_exceptions() > 0
+    with pytest.raises(RuntimeError, match="validated range"):
+        run(s.data, s.tint, 1.0, fused=True, maxcycles=3)
+    s.data.close()
