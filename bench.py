@@ -380,7 +380,9 @@ def main_gpu(args):
         if world > 1:
             from idefix_b200.halo import HaloExchanger
             ex = HaloExchanger(setup.data, nproc, xproc, mode=args.halo)
-        setup.initialise()
+        setup.InitFlow(setup.data)
+        barrier()   # the first exchange should not wait for a rank still filling its initial condition
+        setup.data.SetBoundaries()
         return setup, ex
 
     setup, exchanger = make_block(b)

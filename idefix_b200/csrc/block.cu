@@ -82,9 +82,9 @@ struct IdfxBlock {
   unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   double *staleFlux = nullptr; // 1-D HD Roe: area-weighted flux of the previous call (roeHD.hpp:312-328)
-  // TMA descriptors of Vc for the sweep kernels (tma.cuh): boxes [nvar][32 cells] and [nvar][32 + 2H cells]
-  CUtensorMap tmMarch, tmRow;
-  bool haveTmMarch = false, haveTmRow = false;
+  // TMA descriptor of Vc for the x1 sweep (tma.cuh): boxes [nvar][32 + 2H cells]
+  CUtensorMap tmRow;
+  bool haveTmRow = false;
   int tmRowCells = 0;
   // steady-state cycle of the fused path captured as a CUDA graph (launch-bound small grids: ~40 launches per cycle)
   cudaGraphExec_t cycleGraph = nullptr;
@@ -383,7 +383,6 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
   a.doInvDt = 1;
   a.fluxRho = b->fluxRho;
   a.staleFlux = b->staleFlux;
-  a.tmapMarch = b->haveTmMarch ? &b->tmMarch : nullptr;
   a.tmapRow = b->haveTmRow ? &b->tmRow : nullptr;
   a.tmapNvar = b->cfg.nvar;
   a.tmapRowCells = b->tmRowCells;
@@ -819,9 +818,8 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
       rc = rc || devAlloc(b, &e.axL, n) || devAlloc(b, &e.axR, n) || devAlloc(b, &e.dxL, n) || devAlloc(b, &e.dxR, n);
     }
   }
-  if (!rc && !std::getenv("IDFX_NO_TMA")) {   // A/B switch: per-lane cp.async loads only
+  if (!rc && !std::getenv("IDFX_NO_TMA")) {   // A/B switch: per-lane cp.async loads in the x1 sweep
     b->tmRowCells = 32 + 2 * ((desc->order == 4) ? 2 : 1);
-    b->haveTmMarch = tma::encodeCellBox(&b->tmMarch, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, 34);   // MARCH_BOX
     b->haveTmRow = tma::encodeCellBox(&b->tmRow, b->Vc, g.nx[0], g.nx[1], g.nx[2], b->cfg.nvar, b->tmRowCells);
   }
   rc = rc || devAlloc(b, &b->state, 4);
@@ -1338,6 +1336,7 @@ int idfx_p2p_connect(IdfxBlock *b, int rank, int world, void *const peer_recv[3]
   if (world < 1 || world > idfxk::P2P_MAX_RANKS || rank < 0 || rank >= world)
     return fail("idfx_p2p_connect: rank / world out of range");
   if (ensureMailbox(b)) return 1;
+  KTRY(idfxk::p2pPreload());
   dropCycleGraph(b);
   for (int d = 0; d < b->desc.ndim; d++) {
     if (b->nproc[d] <= 1) continue;

@@ -465,6 +465,17 @@ int idfxk::haloP2P(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, b
   return (int)cudaGetLastError();
 }
 
+// Forces the (lazily loaded) peer-to-peer kernels into the context now: loading a kernel for its first launch may
+// need the device to drain, which never happens while a receive kernel is waiting for a neighbour whose work the same
+// host thread has not enqueued yet.
+int idfxk::p2pPreload() {
+  cudaFuncAttributes at;
+  cudaError_t e = cudaFuncGetAttributes(&at, haloP2PKernel<true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, haloP2PKernel<false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, p2pAllReduceKernel);
+  return (int)e;
+}
+
 int idfxk::p2pAllReduce(const P2PReduce &r, double *devValue, int op, cudaStream_t st) {
   p2pAllReduceKernel<<<1, P2P_MAX_RANKS, 0, st>>>(r, devValue, op);
   return (int)cudaGetLastError();

@@ -95,10 +95,10 @@ struct SweepArgs {
   unsigned int *mathFlag;   // incremented by threads whose branch-free division / sqrt failed a range check (fastmath.cuh)
   double *fluxRho;    // when tracers are on: raw Riemann mass flux of every interface of this sweep (else null)
   double *Uc0;        // fused path, first stage: also save the rebuilt Uc as the "begin" state (may be null)
-  // TMA (tma.cuh): HOST pointers to the block's CUtensorMap descriptors of Vc (boxes of 32 cells for the x2 / x3
-  // marches, 32 + 2H cells for the x1 rows), null when Vc does not qualify; the launchers pass the descriptor by
-  // value and set useTma.  tmapNvar = number of variables a box carries.
-  const void *tmapMarch, *tmapRow;
+  // TMA (tma.cuh): HOST pointer to the block's CUtensorMap descriptor of Vc for the x1 sweep (boxes of 32 + 2H cells
+  // x all variables), null when Vc does not qualify; the launcher passes the descriptor by value and sets useTma.
+  // tmapNvar = number of variables a box carries.
+  const void *tmapRow;
   int tmapNvar, tmapRowCells;
   int useTma;
   double *staleFlux;  // 1-D HD Roe only: (nvar, nx0) area-weighted flux of the previous call (roeHD.hpp:312-328), else null

@@ -101,6 +101,7 @@ struct P2PReduce {
 // one kernel: both sides, Vc + every Vs component; send = true stores into the neighbours, false unpacks
 int haloP2P(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, bool send, const P2PChannel &ch, cudaStream_t st,
             long long *launches);
+int p2pPreload();
 // in-place min (op 0) / max (op 1) of *devValue over all blocks
 int p2pAllReduce(const P2PReduce &r, double *devValue, int op, cudaStream_t st);
 

@@ -141,63 +141,44 @@ IDFX_D void reportMathFlag(const SweepArgs &a, bool bad) {
 
 // =================================================================================================
 // x2 / x3 sweeps: a thread owns one (i, perpendicular) column and marches along the sweep direction.
-// Shared memory is organised per WARP (stencil ring [slot][nvar][32], normal field [2][32]) so that a ring
-// slot is exactly one TMA box and a warp never waits for another one.
 // =================================================================================================
-// A ring slot is one TMA box [nvar][MARCH_BOX cells]: 32 cells of the warp + 2, because an FP64 box must start at an
-// even x1 index (tma.cuh) and the warp's first column may be odd.  Slots are padded to 128 bytes (TMA destination).
-constexpr int MARCH_BOX = 34;
-template <class P>
-constexpr int pencilMarchSlotDoubles() {
-  return (P::nvar * MARCH_BOX + 15) / 16 * 16;
-}
-template <class P, int ORDER, bool CART>
-constexpr int pencilMarchDoublesPerWarp() {
-  return (CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * pencilMarchSlotDoubles<P>()   // stencil ring
-         + (2                                                                  // normal field at the interface (x2)
-            + (IDFX_TMEM ? 0 : P::nvar + (P::nvar + 1)))                       // carry-over when it is not in TMEM
-               * 32;
-}
 template <class P, int ORDER, bool CART>
 constexpr size_t pencilMarchSmem(int TX, int chunk) {
-  return sizeof(double) * ((size_t)(TX / 32) * pencilMarchDoublesPerWarp<P, ORDER, CART>()
+  return sizeof(double) * ((size_t)TX * ((CART ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W) * P::nvar   // stencil ring
+                                         + (IDFX_TMEM ? 0 : P::nvar)        // left state of the next interface
+                                         + (IDFX_TMEM ? 0 : (P::nvar + 1))  // previous interface: flux + signal speed
+                                         + 2)                               // normal field at the interface (x2)
                            + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * (chunk + 2)
-                           + (size_t)(TX / 32) * pencil::Halo<ORDER>::W        // one mbarrier per warp and ring slot
-                           + 2);                                               // TMEM base address slot
+                           + (IDFX_TMEM ? 2 : 0));                          // TMEM base address slot
 }
 
 template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART>
-__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
-    pencilMarchKernel(const SweepArgs a, const int chunk, const __grid_constant__ CUtensorMap vcBoxes) {
+__global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencilMarchKernel(const SweepArgs a, const int chunk) {
   static_assert(DIR == JDIR || DIR == KDIR, "the marching kernel sweeps along x2 or x3");
   constexpr int NV = P::nvar;
   using D = Dirs<P, DIR>;
   constexpr bool LATE = CART;   // prefetch after the reconstruction (no cell behind the stencil is needed)
   constexpr int H = pencil::Halo<ORDER>::H, W = LATE ? pencil::Halo<ORDER>::WL : pencil::Halo<ORDER>::W;
   constexpr int PDIR = (DIR == JDIR) ? KDIR : JDIR;  // the other perpendicular direction
-  constexpr int WARPS = TX / 32;
-  constexpr int PERWARP = pencilMarchDoublesPerWarp<P, ORDER, CART>();
-  constexpr int TROWS = CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN;
 
-  extern __shared__ __align__(128) double smem[];
-  const int tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
-  constexpr int SLOT = pencilMarchSlotDoubles<P>(), MW = MARCH_BOX;
-  double *wbase = smem + warp * PERWARP;
-  double *vsb = wbase + W * SLOT + lane;            // vsb[buf * 32]
+  extern __shared__ double smem[];
+  const int tx = threadIdx.x;
+  double *ring = smem + tx;                         // ring[(slot * NV + nv) * TX]
 #if IDFX_TMEM
   // carry-over in tensor memory: columns [2 nv, 2 nv + 1] = left state nv, [2 NV + 2 nv, ..] = previous flux nv,
   // [4 NV, 4 NV + 1] = previous signal speed
   constexpr int TCOLS = (4 * NV + 2 <= 32) ? 32 : 64;
   constexpr unsigned T_VLS = 0, T_FPREV = 2 * NV, T_CMAX = 4 * NV;
+  double *vsb = smem + W * NV * TX + tx;            // vsb[buf * TX]
+  double *tab = smem + (size_t)TX * (W * NV + 2);   // tab[row * (chunk+2) + r]
 #else
-  double *vls = wbase + W * SLOT + 2 * 32 + lane;   // vls[nv * 32]
-  double *fprev = vls + NV * 32;                    // fprev[nv * 32]
+  double *vls = smem + W * NV * TX + tx;            // vls[nv * TX]
+  double *fprev = vls + NV * TX;                    // fprev[nv * TX]
+  double *vsb = fprev + (NV + 1) * TX;              // vsb[buf * TX]
+  double *tab = smem + (size_t)TX * (W * NV + NV + (NV + 1) + 2);   // tab[row * (chunk+2) + r]
 #endif
-  double *tab = smem + WARPS * PERWARP;             // tab[row * (chunk+2) + r]
   const int tlen = chunk + 2;
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(tab + TROWS * tlen) + warp * pencil::Halo<ORDER>::W;
-  const unsigned vsbS = pencil::smemAddr(vsb);
-  const unsigned ringWarpS = pencil::smemAddr(wbase), barS = pencil::smemAddr(bars);
+  const unsigned ringS = pencil::smemAddr(ring), vsbS = pencil::smemAddr(vsb);
 
   const DevGrid &g = a.g;
   const int ext = a.perpExt;
@@ -219,14 +200,9 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       tab[(pencil::T_W + 5) * tlen + r] = g.dm[DIR][c];
     }
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < W; s++) tma::barrierInit(barS + 8 * s, 1);
-    tma::fenceBarrierInit();
-  }
 #if IDFX_TMEM
-  unsigned *tslot = reinterpret_cast<unsigned *>(tab + TROWS * tlen + WARPS * pencil::Halo<ORDER>::W);
-  const unsigned tbase = tmem::allocate<TCOLS>(tslot);   // contains the __syncthreads that publishes tab / barriers
+  unsigned *tslot = reinterpret_cast<unsigned *>(tab + (size_t)(CART ? pencil::T_ROWS_CART : pencil::T_ROWS_GEN) * tlen);
+  const unsigned tbase = tmem::allocate<TCOLS>(tslot);   // contains the __syncthreads that publishes tab
 #else
   __syncthreads();
 #endif
@@ -252,39 +228,6 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
   const long long cell0 = (DIR == JDIR) ? cidx(g, p, 0, i) : cidx(g, 0, p, i);
   const long long face0 = DIR * g.vsn + ((DIR == JDIR) ? sidx(g, p, 0, i) : sidx(g, 0, p, i));
   const bool columnInterior = columnValid && (i >= g.beg[0]) && (i < g.end[0]) && (p >= g.beg[PDIR]) && (p < g.end[PDIR]);
-  // TMA serves warps whose 32 columns are 32 consecutive cells of one x1 row (all but the few that wrap around
-  // the end of a row, and the tail of the last CTA); the others copy per lane
-  const int i0 = __shfl_sync(0xffffffffu, i, 0);
-  const bool useTma = (a.useTma != 0) && __all_sync(0xffffffffu, columnValid && (i == i0 + lane) &&
-                                                                    (p == __shfl_sync(0xffffffffu, p, 0)));
-  unsigned phases = 0;   // bit s: parity of the next completion of ring slot s (TMA path)
-  // ring[slot * SLOT + nv * MW] = this lane's cell; a TMA box starts at the even index at or below the warp's first
-  // column, so the lanes sit one entry further when that column is odd
-  const int boxShift = useTma ? (i0 & 1) : 0;
-  double *ring = wbase + boxShift + lane;
-  const unsigned ringS = pencil::smemAddr(ring);
-
-  // primitives of cell `mc` along the march -> ring slot `slot` (all lanes call this convergently)
-  auto issueCell = [&](int slot, int mc) {
-    if (useTma) {
-      __syncwarp();   // every lane is done reading what the slot held
-      if (lane == 0) {
-        tma::barrierExpect(barS + 8 * slot, NV * MW * 8);
-        tma::load4D(ringWarpS + slot * SLOT * 8, &vcBoxes, barS + 8 * slot, i0 - boxShift, (DIR == JDIR) ? mc : p,
-                    (DIR == JDIR) ? p : mc, 0);
-      }
-    } else {
-      const double *src = a.Vc + cell0 + (long long)mc * stride;
-#pragma unroll
-      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (slot * SLOT + nv * MW) * 8, src + nv * g.sn);
-    }
-  };
-  auto waitCell = [&](int slot) {
-    if (useTma) {
-      tma::barrierWait(barS + 8 * slot, (phases >> slot) & 1u);
-      phases ^= (1u << slot);
-    }
-  };
 
   const Eos eos{a.gamma, a.csiso};
   const double dt = *a.dt;
@@ -304,13 +247,18 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
   }
 
   // ---- prologue: cells mb-1-H .. mb+H, the normal field of the first interface ---------------------------
+  {
+    const double *src = a.Vc + cell0 + (long long)(mb - 1 - H) * stride;
 #pragma unroll
-  for (int c = 0; c < W; c++) issueCell(c, mb - 1 - H + c);
+    for (int c = 0; c < W; c++) {
+#pragma unroll
+      for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (c * NV + nv) * TX * 8, src + nv * g.sn);
+      src += stride;
+    }
+  }
   if constexpr (P::mhd) pencil::cpAsync8s(vsbS, a.Vs + face0 + (long long)mb * vstride);
   pencil::cpAsyncCommit();
   pencil::cpAsyncWait<0>();
-#pragma unroll
-  for (int c = 0; c < W; c++) waitCell(c);
   // right-face values of cell mb-1 = left state of the first interface
   {
     const double dxc = tab[pencil::T_DX * tlen];
@@ -325,7 +273,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       double st[5];
       st[0] = st[4] = 0.0;
 #pragma unroll
-      for (int d = -H; d <= H; d++) st[2 + d] = ring[(H + d) * SLOT + nv * MW];
+      for (int d = -H; d <= H; d++) st[2 + d] = ring[((H + d) * NV + nv) * TX];
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vl, vr;
       reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
@@ -333,37 +281,35 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       __syncwarp();
       tmem::store1(tbase + T_VLS + 2 * nv, vr);
 #else
-      vls[nv * 32] = vr;
+      vls[nv * TX] = vr;
 #endif
     }
   }
 
   bool mathBad = false;
   int q = 0;  // ring slot of cell m-H-1: free, receives cell m+H+1 (LATE: cell m+H, issued at the end of step m-1)
+  const double *pre = a.Vc + cell0 + (long long)(mb + H + (LATE ? 0 : 1)) * stride;
+  long long cellm = cell0 + (long long)mb * stride;
   if constexpr (LATE) {
     // cell mb+H completes the stencil of cell mb
-    issueCell(q, mb + H);
+#pragma unroll
+    for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
     pencil::cpAsyncCommit();
+    pre += stride;
   }
-  long long cellm = cell0 + (long long)mb * stride;
   for (int m = mb; m <= me; m++) {
     const int r = m - mb;
     if constexpr (!LATE) {
       // ---- prefetch what the next interface needs ----------------------------------------------------
       if (m < me) {
-        issueCell(q, m + H + 1);
-        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * 256, a.Vs + face0 + (long long)(m + 1) * vstride);
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (q * NV + nv) * TX * 8, pre + nv * g.sn);
+        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
       }
       pencil::cpAsyncCommit();
       pencil::cpAsyncWait<1>();   // everything but the group just committed has landed
-      if (r > 0) {                // ... and so has the box issued one step ago (the prologue waited for its own)
-        int ql = q - 1;
-        if (ql < 0) ql += W;
-        waitCell(ql);
-      }
     } else {
       pencil::cpAsyncWait<0>();   // cell m+H and the normal field of interface m (issued one step ago)
-      waitCell(q);
     }
 
     // ---- cell m: face values; interface m: left state from cell m-1, right state from cell m -----------
@@ -382,7 +328,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       for (int d = -H; d <= H; d++) {
         int s = q + 1 + H + d;
         if (s >= W) s -= W;
-        so[d + H] = s * SLOT;
+        so[d + H] = s * NV * TX;
       }
 #if IDFX_TMEM
       // left state = right-face values of cell m-1, parked in tensor memory one step ago
@@ -407,7 +353,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
         double st[5];
         st[0] = st[4] = 0.0;
 #pragma unroll
-        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * MW];
+        for (int d = -H; d <= H; d++) st[2 + d] = ring[so[d + H] + nv * TX];
         const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
         double vr;
         reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
@@ -415,8 +361,8 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
         __syncwarp();
         tmem::store1(tbase + T_VLS + 2 * nv, vr);
 #else
-        vL[nv] = vls[nv * 32];
-        vls[nv * 32] = vr;
+        vL[nv] = vls[nv * TX];
+        vls[nv * TX] = vr;
 #endif
       }
     }
@@ -425,13 +371,14 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
       if (m < me) {
         int qn = q + 1;
         if (qn >= W) qn -= W;
-        issueCell(qn, m + H + 1);
-        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * 256, a.Vs + face0 + (long long)(m + 1) * vstride);
+#pragma unroll
+        for (int nv = 0; nv < NV; nv++) pencil::cpAsync8s(ringS + (qn * NV + nv) * TX * 8, pre + nv * g.sn);
+        if constexpr (P::mhd) pencil::cpAsync8s(vsbS + ((r + 1) & 1) * TX * 8, a.Vs + face0 + (long long)(m + 1) * vstride);
       }
       pencil::cpAsyncCommit();
     }
     if constexpr (P::mhd) {
-      const double bn = vsb[(r & 1) * 32];
+      const double bn = vsb[(r & 1) * TX];
       vL[D::BXn] = bn;
       vR[D::BXn] = bn;
     }
@@ -471,14 +418,14 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
 #if !IDFX_TMEM
       double Fm[NV];
 #pragma unroll
-      for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * 32];
-      const double cmaxm = fprev[NV * 32];
+      for (int nv = 0; nv < NV; nv++) Fm[nv] = fprev[nv * TX];
+      const double cmaxm = fprev[NV * TX];
 #endif
-      int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring; never read when LATE: no
-      if (sp < 0) sp += W;      // source terms on cartesian grids, no primitive-to-conservative rebuild in x2 / x3)
-      const double *vprev = ring + sp * SLOT;
+      int sp = sc - 1;          // slot of cell m-1 (its primitives are still in the ring)
+      if (sp < 0) sp += W;
+      const double *vprev = ring + sp * NV * TX;
       updateCell<typename P::Fast, DIR>(a, g, geo, eos, dt, dV, tab[pencil::T_DX * tlen + r], kc, jc, i, cellm - stride, Fm, F,
-                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * MW]; });
+                         cmaxm, aux.cmax, [&](int nv) { return vprev[nv * TX]; });
     }
 #if IDFX_TMEM
     __syncwarp();
@@ -487,10 +434,11 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB))
     tmem::store1(tbase + T_CMAX, aux.cmax);
 #else
 #pragma unroll
-    for (int nv = 0; nv < NV; nv++) fprev[nv * 32] = F[nv];
-    fprev[NV * 32] = aux.cmax;
+    for (int nv = 0; nv < NV; nv++) fprev[nv * TX] = F[nv];
+    fprev[NV * TX] = aux.cmax;
 #endif
     q = (q + 1 == W) ? 0 : q + 1;
+    pre += stride;
     cellm += stride;
   }
   pencil::reportMathFlag(a, mathBad && columnValid);
@@ -519,11 +467,7 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
   static unsigned long long configured = 0;   // bit d: attribute set on device d
   auto kern = pencilMarchKernel<P, SOLVER, ORDER, DIR, TX, CART>;
   if (cudaError_t e = pencil::ensureDynamicSmem(kern, smem, configured); e != cudaSuccess) return e;
-  SweepArgs b = a;
-  const CUtensorMap *map = reinterpret_cast<const CUtensorMap *>(a.tmapMarch);
-  b.useTma = (map != nullptr && P::nvar == a.tmapNvar) ? 1 : 0;   // block.cu encodes this map with MARCH_BOX cells
-  static const CUtensorMap none = {};
-  kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(b, chunk, b.useTma ? *map : none);
+  kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(a, chunk);
   return cudaGetLastError();
 }
 

@@ -1,17 +1,19 @@
 // tma.cuh -- tensor-memory-accelerator (TMA) loads of the sweep kernels: device wrappers + host-side descriptors.
 //
-// A warp of a sweep kernel needs, per marching step, one box of primitives: [nvar][1][1][32 (+2H) cells along x1].
-// With cp.async that is nvar (x2) LDGSTS per lane plus their 64-bit address arithmetic, and the copies allocate in
-// L1 on their way -- evicting the register spills that live there (ncu: every long-scoreboard stall of the sweeps
-// sits on an LDL).  One elected lane issues ONE cp.async.bulk.tensor instead (SASS: UTMALDG); the box goes
+// A warp of the x1 sweep needs, per row, one box of primitives: [nvar][1][1][32 + 2H cells along x1].
+// With cp.async that is 2 x nvar predicated LDGSTS per lane plus their 64-bit address arithmetic, and the copies
+// allocate in L1 on their way -- evicting the register spills that live there (ncu: every long-scoreboard stall of
+// the sweeps sits on an LDL).  One elected lane issues ONE cp.async.bulk.tensor instead (SASS: UTMALDG); the box goes
 // L2 -> shared memory without touching L1 and completes on a per-warp mbarrier.
+// (The x2 / x3 marches keep per-lane cp.async: their TMA variant -- one box per ring slot, issued in the middle of a
+// step between tcgen05 accesses -- never completed on the device in this round's experiments and was withdrawn.)
 //
 // Descriptor limits (CUDA driver API, cuTensorMapEncodeTiled): base address 16-byte aligned, every stride a
 // multiple of 16 bytes (=> nx1 even for FP64 rows), box inner extent a multiple of 16 bytes.  And, measured on the
 // B200 (idfx_selftest_tma under compute-sanitizer): the FIRST ELEMENT of a box must itself sit on a 16-byte boundary,
 // i.e. an FP64 box must start at an even x1 index -- an odd start coordinate is an illegal-instruction fault.  Boxes
-// are therefore 32 + 2 cells wide and start at the even index at or below the first cell a warp needs.  Blocks that
-// do not qualify keep the per-lane cp.async path; so do warps whose 32 columns wrap around the end of an x1 row.
+// of the x1 sweep start at cell 30 * strip, which is even by construction.  An array narrower than the box is accepted
+// by the encoder but the copy never completes.  Blocks that do not qualify keep the per-lane cp.async path.
 #ifndef IDFX_TMA_CUH_
 #define IDFX_TMA_CUH_
 
@@ -88,8 +90,10 @@ inline bool encodeCellBox(CUtensorMap *out, const double *base, int n1, int n2, 
     cudaGetLastError();
   }
   if (!encode) return false;
+  // (a box wider than the array itself -- tiny test grids -- is accepted by the encoder but never completes on the
+  // device: measured, idfx_selftest_tma / tests/test_oracle_gpu.py)
   if ((reinterpret_cast<unsigned long long>(base) & 15ull) || (n1 & 1) || boxCells > 256 || nvar > 256 ||
-      ((boxCells * 8) & 15))
+      ((boxCells * 8) & 15) || n1 < boxCells)
     return false;
   const cuuint64_t dims[4] = {(cuuint64_t)n1, (cuuint64_t)n2, (cuuint64_t)n3, (cuuint64_t)nvar};
   const cuuint64_t strides[3] = {(cuuint64_t)n1 * 8, (cuuint64_t)n1 * n2 * 8, (cuuint64_t)n1 * n2 * n3 * 8};
