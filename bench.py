@@ -367,7 +367,7 @@ def main_gpu(args):
 
     # ---- parity gate: a short case of the same physics on these very ranks against the reference's dump ----------
     parity_res = None
-    if cfg["short"]:
+    if cfg["short"] and not args.no_parity:
         parity_res = short_case_parity(cfg, nproc, xproc, rank, world, local)
         if rank == 0 and not (parity_res["max_abs"] == 0.0 and parity_res["math_exceptions"] == 0):
             raise SystemExit(f"bench.py: parity gate failed before the timed region: {parity_res}")
@@ -559,7 +559,9 @@ def main():
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS), help="BASELINE.json configuration (default C4)")
     ap.add_argument("--block", type=int, default=0, help="interior cells per direction per GPU (default: the config's)")
     ap.add_argument("--emf", default=None, help="C4: EMF averaging ([Hydro] emf); default = the reference's default uct_contact")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--halo", default="p2p", choices=["nccl", "p2p"],
+                    help="N > 1: p2p = the library's own exchange kernels over NVLink peer memory (default), "
+                         "nccl = packed slabs through torch.distributed point-to-point")
     ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: K)")
     ap.add_argument("--e2e-upload-only", action="store_true",
                     help="e2e without the read-back of the evolved state (default: full state up AND down every step)")
@@ -567,6 +569,7 @@ def main():
     ap.add_argument("--cpu-block", type=int, default=0, help="block of the bounded CPU sample (default: the config's)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs under ncu only)")
     ap.add_argument("--no-stated", action="store_true", help="N > 1: skip the additional 256^3-per-GPU measurement")
     args = ap.parse_args()
     if args.gpus not in DECOMP:

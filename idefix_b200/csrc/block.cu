@@ -91,6 +91,13 @@ struct IdfxBlock {
   long long cycleGraphLaunches = 0;
   bool useGraph = true;
   bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
+  // overlap of the ghost-zone work with the update of the interior (fused path): the boundary conditions / halo
+  // exchange of the NEXT stage run on a side stream as soon as the cells they read (the shell: active cells within
+  // nghost of a face) have their new primitives, while the main stream converts the rest of the block
+  cudaStream_t sideStream = nullptr;
+  cudaEvent_t evShell = nullptr, evGhosts = nullptr;
+  bool overlap = true, forceOverlap = false;
+  bool ghostsDone = false;     // the ghost zones already hold the boundary conditions of the current Vc / Vs
   // per-kernel-class timing with CUDA events on the launching stream (idfx_timing)
   bool timing = false;
   std::vector<cudaEvent_t> evPool;      // pairs: [2n] start, [2n+1] stop
@@ -642,34 +649,113 @@ int cycleReferenceOrder(IdfxBlock *b) {
   return 0;
 }
 
+// ghost zones of the current state: Boundary::SetBoundaries + the ghost shell of ReconstructVcField
+int fillGhosts(IdfxBlock *b) {
+  if (setBoundariesCore(b, 0.0, false)) return 1;
+  // the active cells already hold the face average when the previous step on this block was our own
+  // stage epilogue (b->vcFieldFresh): only the ghost cells changed with the boundary conditions
+  return reconstructVc(b, b->Vc, b->vcFieldFresh ? 1 : 0);
+}
+
+// The stage epilogue, and -- overlapped with it -- the ghost zones of the next stage.  The boundary kernels and the
+// halo exchange only READ the shell (active cells within nghost of a face, plus the faces of Vs, which the epilogue
+// does not write) and only WRITE ghost cells, which the epilogue does not touch: once the shell is converted they
+// run on the side stream while the main stream converts the core of the block.
+int epilogueAndGhosts(IdfxBlock *b, int stage, double wc, double w0, int keepUc, bool reduceDt) {
+  const IdfxBlockDesc &d = b->desc;
+  const DevGrid &g = b->g;
+  auto epi = [&](const int *lo, const int *hi) -> int {
+    KTRY(idfxk::stageEpilogue(b->cfg, g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, keepUc, b->stream,
+                              b->mathFlag, lo, hi, reduceDt ? b->invDt : nullptr, reduceDt ? b->redBits : nullptr));
+    b->launches++;
+    return 0;
+  };
+  int core_lo[3], core_hi[3];
+  // worth it only when there is a neighbour to wait for: on a single block the ghost fill is 0.6 ms of tiny kernels,
+  // and running them beside the bandwidth-bound epilogue (plus the six thin shell launches) costs slightly more than
+  // it hides (measured, profiles/r2_overlap_ab.md).  IDFX_OVERLAP=1 forces it on.
+  const bool multi = b->nproc[0] * b->nproc[1] * b->nproc[2] > 1;
+  bool haveCore = b->overlap && (multi || b->forceOverlap) && b->cfg.ntr == 0 && !b->userBc && !b->haloFn;
+  for (int a = 0; a < 3; a++) {
+    const int w = (a < d.ndim) ? g.ng[a] : 0;
+    core_lo[a] = g.beg[a] + w;
+    core_hi[a] = g.end[a] - w;
+    if (core_hi[a] - core_lo[a] < 8 * w) haveCore = false;   // small blocks: nothing worth overlapping
+  }
+  if (!haveCore) {
+    TimeScope ts(b, TIME_EPILOGUE);
+    return epi(nullptr, nullptr);
+  }
+  {
+    TimeScope ts(b, TIME_EPILOGUE);
+    // shell = six disjoint slabs: x3 slabs span the whole active (x1, x2) extent, x2 slabs the core in x3, x1 slabs
+    // the core in x2 and x3
+    for (int a = d.ndim - 1; a >= 0; a--) {
+      for (int side = 0; side < 2; side++) {
+        int lo[3], hi[3];
+        for (int e = 0; e < 3; e++) {
+          lo[e] = (e > a) ? core_lo[e] : g.beg[e];
+          hi[e] = (e > a) ? core_hi[e] : g.end[e];
+        }
+        if (side == 0) hi[a] = core_lo[a];
+        else lo[a] = core_hi[a];
+        if (epi(lo, hi)) return 1;
+      }
+    }
+  }
+  b->vcFieldFresh = true;
+  CUDA_TRY(cudaEventRecord(b->evShell, b->stream));
+  CUDA_TRY(cudaStreamWaitEvent(b->sideStream, b->evShell, 0));
+  {
+    cudaStream_t main = b->stream;
+    b->stream = b->sideStream;          // the boundary / exchange launchers enqueue on b->stream
+    const int rc = fillGhosts(b);
+    b->stream = main;
+    if (rc) return 1;
+  }
+  CUDA_TRY(cudaEventRecord(b->evGhosts, b->sideStream));
+  {
+    TimeScope ts(b, TIME_EPILOGUE);
+    if (epi(core_lo, core_hi)) return 1;
+  }
+  CUDA_TRY(cudaStreamWaitEvent(b->stream, b->evGhosts, 0));
+  b->ghostsDone = true;
+  return 0;
+}
+
 // The same cycle with the point-wise steps folded into the sweeps / CT / one epilogue.
 int cycleFused(IdfxBlock *b, bool lastOfBatch) {
   const IdfxBlockDesc &d = b->desc;
   KTRY(idfxk::dtControlBegin(b->state, b->redBits, b->stream));
   b->launches++;
   for (int stage = 0; stage < d.nstages; stage++) {
-    if (setBoundariesCore(b, 0.0, false)) return 1;
-    // the active cells already hold the face average when the previous step on this block was our own
-    // stage epilogue (b->vcFieldFresh): only the ghost cells changed with the boundary conditions
-    if (reconstructVc(b, b->Vc, b->vcFieldFresh ? 1 : 0)) return 1;
+    if (!b->ghostsDone) {
+      if (fillGhosts(b)) return 1;
+    }
+    b->ghostsDone = false;
     if (evolveStageImpl(b, stage)) return 1;
     const double wc = stage > 0 ? b->wc[stage - 1] : 0.0, w0 = stage > 0 ? b->w0[stage - 1] : 0.0;
     KTRY(idfxk::stageTimeAdvance(b->state, stage, wc, w0, b->stream));
     b->launches++;
-    if (stage == 0 && !(d.fixed_dt > 0.0)) {
-      if (timestepReduceImpl(b)) return 1;
-      crossBlockReduce(b, (double *)b->redBits, IDFX_REDUCE_MIN);
-    }
-    {
+    // DataBlock::ComputeTimestep after the first stage (timeIntegrator.cpp:313-323): min(1 / InvDt) is reduced by the
+    // epilogue kernel of this stage, which passes over every active cell anyway
+    const bool reduceDt = (stage == 0 && !(d.fixed_dt > 0.0));
+    // Uc is rebuilt from Vc by the x1 sweep of the next stage, so its write-back (8 of the 24-29 doubles the
+    // epilogue moves per cell) is only needed where somebody can look at it: after the last stage of the last
+    // cycle of this call, or when the tracer kernels need Uc(RHO)
+    const bool last = lastOfBatch && stage == d.nstages - 1;
+    const int keepUc = (b->cfg.ntr > 0 || last) ? 1 : 0;
+    if (last) {
+      // nothing follows inside this call: the caller gets the state back (and may change it before the next one)
       TimeScope ts(b, TIME_EPILOGUE);
-      // Uc is rebuilt from Vc by the x1 sweep of the next stage, so its write-back (8 of the 24-29 doubles this
-      // kernel moves per cell) is only needed where somebody can look at it: after the last stage of the last
-      // cycle of this call, or when the tracer kernels need Uc(RHO)
-      const int keepUc = (b->cfg.ntr > 0 || (lastOfBatch && stage == d.nstages - 1)) ? 1 : 0;
       KTRY(idfxk::stageEpilogue(b->cfg, b->g, b->Vc, b->Uc, b->Vs, b->Uc0, d.gamma, stage > 0 ? 1 : 0, wc, w0, keepUc,
-                                b->stream, b->mathFlag));
+                                b->stream, b->mathFlag, nullptr, nullptr, reduceDt ? b->invDt : nullptr,
+                                reduceDt ? b->redBits : nullptr));
+      b->launches++;
+    } else {
+      if (epilogueAndGhosts(b, stage, wc, w0, keepUc, reduceDt)) return 1;
     }
-    b->launches++;
+    if (reduceDt) crossBlockReduce(b, (double *)b->redBits, IDFX_REDUCE_MIN);
     if (b->cfg.ntr > 0) {   // RK combination + Tracer::ConvertConsToPrim with the final Uc(RHO)
       KTRY(idfxk::tracerConsToPrim(b->cfg, b->g, b->Vc, b->Uc, b->Uc0, stage > 0 ? 1 : 0, wc, w0, 1, b->stream));
       b->launches++;
@@ -754,6 +840,11 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   setupPhys(b);
   CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   if (std::getenv("IDFX_NO_GRAPH")) b->useGraph = false;   // A/B switch: always launch the cycle kernel by kernel
+  if (std::getenv("IDFX_NO_OVERLAP")) b->overlap = false;  // A/B switch: boundaries strictly before the sweeps
+  if (std::getenv("IDFX_OVERLAP")) b->forceOverlap = true; // ... or overlapped even on a single block
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->sideStream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&b->evShell, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&b->evGhosts, cudaEventDisableTiming));
 
   DevGrid &g = b->g;
   std::memset(&g, 0, sizeof(g));
@@ -870,6 +961,9 @@ int idfx_block_destroy(IdfxBlock *b) {
   for (void *p : b->allocs) cudaFree(p);
   if (b->hostState) cudaFreeHost(b->hostState);
   for (cudaEvent_t e : b->evPool) cudaEventDestroy(e);
+  if (b->evShell) cudaEventDestroy(b->evShell);
+  if (b->evGhosts) cudaEventDestroy(b->evGhosts);
+  if (b->sideStream) cudaStreamDestroy(b->sideStream);
   if (b->stream && b->ownStream) cudaStreamDestroy(b->stream);
   delete b;
   return 0;
@@ -1140,6 +1234,7 @@ int idfx_cycles(IdfxBlock *b, int ncycles) {
   cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
   // the caller holds device pointers to the state (idfx_field_info) and may have changed it since the last call
   b->vcFieldFresh = false;
+  b->ghostsDone = false;
   if (graphEligible(b, ncycles)) {
     if (cycleFused(b, false)) return 1;                       // first cycle: eager (full validation of the inputs)
     int done = 1;

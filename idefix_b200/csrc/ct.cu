@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(TBX *TBY, 4)
     ex1c = Ex1[c];
     ex2c = Ex2[c];
   }
+#pragma unroll 2
   for (int k = k0; k < k1; k++, c += sk, s += g.vsk) {
     double rhsx1 = 0.0, rhsx2 = 0.0, rhsx3 = 0.0;
     double ex1p = 0.0, ex2p = 0.0;   // plane k+1

@@ -48,9 +48,13 @@ int copy(double *dst, const double *src, long long n, cudaStream_t st);
 // dst = wl*dst + wr*src (stateContainer.cpp:91-98)
 int addAndStore(double *dst, const double *src, long long n, double wl, double wr, cudaStream_t st);
 // fused stage epilogue over the interior: RK combine of Uc, Uc(B) <- Vs, Vc <- C2P(Uc)
+// over the box [lo, hi) of cells (null: the whole interior)
 int stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs, const double *Uc0,
                   double gamma, int combine, double wc, double w0, int keepUc, cudaStream_t st,
-                  unsigned int *mathFlag = nullptr);
+                  unsigned int *mathFlag = nullptr, const int *lo = nullptr, const int *hi = nullptr,
+                  const double *invDt = nullptr, unsigned long long *dtMinBits = nullptr);
+// invDt / dtMinBits non-null: also reduce min(1 / InvDt) over the box into *dtMinBits (ordered bits), i.e.
+// DataBlock::ComputeTimestep folded into the epilogue of the first stage
 
 // ---- passive tracers (tracer.cu) ------------------------------------------------
 // Tracer::CalcFlux + CalcRightHandSide of one direction from the mass flux the sweep stored

@@ -13,6 +13,12 @@ namespace {
 
 constexpr int TB = 256;
 
+// box [lo, hi) of cells
+struct CellBox {
+  int lo[3], hi[3];
+};
+
+
 inline int blocksFor(long long n) { return (int)((n + TB - 1) / TB); }
 
 // run F<P>::run(args...) for the Phys matching c
@@ -78,9 +84,6 @@ __global__ void consToPrimKernel(DevGrid g, double *__restrict__ Vc, double *__r
 // V(BXn) = 0.5*(Vs(n,.) + Vs(n,.+1)) for the CT components, over the box [lo, hi) of cells
 // (the whole block, or one ghost slab: the boundary conditions never touch a face of an active cell, so
 // after our own stage epilogue the active cells already hold exactly these values)
-struct CellBox {
-  int lo[3], hi[3];
-};
 __global__ void reconstructVcFieldKernel(DevGrid g, const double *__restrict__ Vs, double *__restrict__ V, int bx1,
                                          CellBox b) {
   const int i = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,39 +121,64 @@ __global__ void addAndStoreKernel(double *__restrict__ d, const double *__restri
 template <class P>
 __global__ void stageEpilogueKernel(DevGrid g, double *__restrict__ Vc, double *__restrict__ Uc,
                                     const double *__restrict__ Vs, const double *__restrict__ Uc0, Eos eos,
-                                    int combine, double wc, double w0, int keepUc, unsigned int *mathFlag) {
-  const int ni = g.end[0] - g.beg[0], nj = g.end[1] - g.beg[1], nk = g.end[2] - g.beg[2];
+                                    int combine, double wc, double w0, int keepUc, unsigned int *mathFlag, CellBox box,
+                                    const double *__restrict__ invDt, unsigned long long *dtMinBits) {
+  const int ni = box.hi[0] - box.lo[0], nj = box.hi[1] - box.lo[1], nk = box.hi[2] - box.lo[2];
   const long long t = (long long)blockIdx.x * TB + threadIdx.x;
-  if (t >= (long long)ni * nj * nk) return;
-  const int i = g.beg[0] + (int)(t % ni);
-  const int j = g.beg[1] + (int)((t / ni) % nj);
-  const int k = g.beg[2] + (int)(t / ((long long)ni * nj));
-  const long long c = cidx(g, k, j, i);
-  double u[P::nvar], v[P::nvar];
-  if constexpr (P::mhd) {
-    const long long s = sidx(g, k, j, i);
-    u[P::BX1] = 0.5 * (Vs[s] + Vs[s + 1]);
-    if constexpr (P::ndim >= 2) u[P::BX2] = 0.5 * (Vs[g.vsn + s] + Vs[g.vsn + s + g.vsj]);
-    if constexpr (P::ndim == 3) u[P::BX3] = 0.5 * (Vs[2 * g.vsn + s] + Vs[2 * g.vsn + s + g.vsk]);
-  }
+  const bool valid = t < (long long)ni * nj * nk;
+  double dtCell = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+  if (valid) {
+    const int i = box.lo[0] + (int)(t % ni);
+    const int j = box.lo[1] + (int)((t / ni) % nj);
+    const int k = box.lo[2] + (int)(t / ((long long)ni * nj));
+    const long long c = cidx(g, k, j, i);
+    double u[P::nvar], v[P::nvar];
+    if constexpr (P::mhd) {
+      const long long s = sidx(g, k, j, i);
+      u[P::BX1] = 0.5 * (Vs[s] + Vs[s + 1]);
+      if constexpr (P::ndim >= 2) u[P::BX2] = 0.5 * (Vs[g.vsn + s] + Vs[g.vsn + s + g.vsj]);
+      if constexpr (P::ndim == 3) u[P::BX3] = 0.5 * (Vs[2 * g.vsn + s] + Vs[2 * g.vsn + s + g.vsk]);
+    }
 #pragma unroll
-  for (int nv = 0; nv < P::nvar; nv++) {
-    if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
-    double x = Uc[nv * g.sn + c];
-    if (combine) x = wc * x + w0 * Uc0[nv * g.sn + c];
-    u[nv] = x;
-  }
-  consToPrim<P>(v, u, eos);
-  // the primitives the next sweeps start from must lie in the validated envelope of the branch-free
-  // division / square root (fastmath.cuh); free here, this kernel is bandwidth-bound
-  bool bad = false;
+    for (int nv = 0; nv < P::nvar; nv++) {
+      if (P::mhd && nv >= P::BX1 && nv < P::BX1 + P::ndim) continue;
+      double x = Uc[nv * g.sn + c];
+      if (combine) x = wc * x + w0 * Uc0[nv * g.sn + c];
+      u[nv] = x;
+    }
+    consToPrim<P>(v, u, eos);
+    // the primitives the next sweeps start from must lie in the validated envelope of the branch-free
+    // division / square root (fastmath.cuh); free here, this kernel is bandwidth-bound
+    bool bad = false;
 #pragma unroll
-  for (int nv = 0; nv < P::nvar; nv++) {
-    Vc[nv * g.sn + c] = v[nv];
-    if (keepUc) Uc[nv * g.sn + c] = u[nv];
-    bad |= !idfxStateInRange(v[nv]);
+    for (int nv = 0; nv < P::nvar; nv++) {
+      Vc[nv * g.sn + c] = v[nv];
+      if (keepUc) Uc[nv * g.sn + c] = u[nv];
+      bad |= !idfxStateInRange(v[nv]);
+    }
+    if (bad && mathFlag != nullptr) atomicAdd(mathFlag, 1u);
+    // DataBlock::ComputeTimestep (dataBlock.cpp:333-364) folded in: the sweeps of this stage have finished
+    // accumulating InvDt, its reciprocal is reduced here instead of in a pass of its own
+    if (invDt != nullptr) dtCell = 1.0 / invDt[c];
   }
-  if (bad && mathFlag != nullptr) atomicAdd(mathFlag, 1u);
+  if (invDt != nullptr) {
+    // warp shuffles, one shared-memory step per CTA, and an atomic only from CTAs that lower the running minimum
+    // (one atomic per warp on a single address would serialise in L2: measured +5 ms at 512^3)
+    __shared__ double warpMins[TB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dtCell = fmin(dtCell, __shfl_xor_sync(0xffffffffu, dtCell, o));
+    if ((threadIdx.x & 31) == 0) warpMins[threadIdx.x >> 5] = dtCell;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = warpMins[0];
+#pragma unroll
+      for (int w = 1; w < TB / 32; w++) m = fmin(m, warpMins[w]);
+      if (m >= 0.0) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+        if (bits < *reinterpret_cast<volatile unsigned long long *>(dtMinBits)) atomicMin(dtMinBits, bits);
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -218,9 +246,16 @@ int idfxk::addAndStore(double *dst, const double *src, long long n, double wl, d
 
 int idfxk::stageEpilogue(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, const double *Vs,
                          const double *Uc0, double gamma, int combine, double wc, double w0, int keepUc,
-                         cudaStream_t st, unsigned int *mathFlag) {
-  const long long n = (long long)(g.end[0] - g.beg[0]) * (g.end[1] - g.beg[1]) * (g.end[2] - g.beg[2]);
+                         cudaStream_t st, unsigned int *mathFlag, const int *lo, const int *hi, const double *invDt,
+                         unsigned long long *dtMinBits) {
+  CellBox box;
+  for (int d = 0; d < 3; d++) {
+    box.lo[d] = lo ? lo[d] : g.beg[d];
+    box.hi[d] = hi ? hi[d] : g.end[d];
+    if (box.hi[d] <= box.lo[d]) return 0;
+  }
+  const long long n = (long long)(box.hi[0] - box.lo[0]) * (box.hi[1] - box.lo[1]) * (box.hi[2] - box.lo[2]);
   const Eos eos{gamma, 0.0};
   PHYS_DISPATCH((stageEpilogueKernel<P><<<blocksFor(n), TB, 0, st>>>(g, Vc, Uc, Vs, Uc0, eos, combine, wc, w0,
-                                                                      keepUc, mathFlag)))
+                                                                      keepUc, mathFlag, box, invDt, dtMinBits)))
 }

@@ -51,6 +51,11 @@ METRICS = [
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe busy %"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+    ("sm__inst_executed_pipe_lsu.sum", "LSU instructions"),
+    ("smsp__inst_executed_op_local_ld.sum", "local loads (spill fills)"),
+    ("smsp__inst_executed_op_local_st.sum", "local stores (spills)"),
+    ("l1tex__t_sectors_pipe_lsu_mem_local_op_ld_lookup_hit.sum", "local load sectors hit in L1"),
+    ("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "local load sectors"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall: wait (fixed-latency dependency) / issue"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall: long scoreboard / issue"),
