@@ -50,6 +50,8 @@ class IdfxBlockDesc(C.Structure):
 USER_BOUNDARY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p)
 HALO_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p)
 REDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+STAGE_HOOK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_double, C.c_void_p)
+HOOK_INTERNAL_BOUNDARY, HOOK_EMF_BOUNDARY = 0, 1
 REDUCE_MIN, REDUCE_MAX = 0, 1
 
 # every symbol include/idefix_b200.h declares: name -> (restype, argtypes)
@@ -88,6 +90,7 @@ SYMBOLS = {
     "idfx_enroll_userdef_boundary": (C.c_int, [_h, USER_BOUNDARY_FN, C.c_void_p]),
     "idfx_enroll_halo_exchange": (C.c_int, [_h, HALO_FN, C.c_void_p]),
     "idfx_enroll_reduce": (C.c_int, [_h, REDUCE_FN, C.c_void_p]),
+    "idfx_enroll_stage_hook": (C.c_int, [_h, C.c_int, STAGE_HOOK_FN, C.c_void_p]),
     "idfx_halo_buffer_size": (C.c_int, [_h, C.c_int, C.POINTER(C.c_size_t)]),
     "idfx_halo_buffers": (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(_pd), C.POINTER(_pd)]),
     "idfx_halo_pack": (C.c_int, [_h, C.c_int]),

@@ -64,6 +64,10 @@ struct IdfxBlock {
   void *userBcData = nullptr;
   IdfxHaloFn haloFn = nullptr;
   void *haloData = nullptr;
+  double stageTime = 0.0;                              // t handed to idfx_evolve_stage (granular path)
+  bool stageTimeKnown = false;
+  IdfxStageHookFn stageHook[2] = {nullptr, nullptr};   // internal boundary, EMF boundary
+  void *stageHookData[2] = {nullptr, nullptr};
   IdfxReduceFn reduceFn = nullptr;
   void *reduceData = nullptr;
   double *haloSend[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -427,6 +431,21 @@ int readState(IdfxBlock *b) {
 
 bool needsExchange(const IdfxBlock *b, int dir) { return b->nproc[dir] > 1; }
 
+// a user hook of the stage (IdfxStageHook): the stream is drained, the callback runs with the current time, and the
+// device is drained again (the callback may have launched kernels on other streams)
+int callStageHook(IdfxBlock *b, int which, double t, bool tKnown) {
+  if (!b->stageHook[which]) return 0;
+  if (tKnown) {
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+  } else {
+    if (readState(b)) return 1;
+    t = b->hostState[0];
+  }
+  b->stageHook[which](b, t, b->stageHookData[which]);
+  CUDA_TRY(cudaDeviceSynchronize());
+  return 0;
+}
+
 // a side exchanges ghosts with another block when it is internal, or periodic with nproc[dir] > 1
 // (mpi.cpp:262-266: MPI_PROC_NULL neighbours on physical boundaries)
 bool sideFacesBlock(const IdfxBlock *b, int dir, int side) {
@@ -509,6 +528,10 @@ int enforceBoundaryDirImpl(IdfxBlock *b, int dir, double t, bool tKnown) {
 // Boundary::SetBoundaries without the final ReconstructVcField (boundary.hpp:252-275)
 int setBoundariesCore(IdfxBlock *b, double t, bool tKnown) {
   TimeScope ts(b, TIME_BOUNDARY);
+  if (b->stageHook[IDFX_HOOK_INTERNAL_BOUNDARY]) {   // boundary.hpp:243-251
+    b->vcFieldFresh = false;                          // the hook may have changed Vs anywhere
+    if (callStageHook(b, IDFX_HOOK_INTERNAL_BOUNDARY, t, tKnown)) return 1;
+  }
   for (int dir = 0; dir < b->desc.ndim; dir++)
     if (enforceBoundaryDirImpl(b, dir, t, tKnown)) return 1;
   return 0;
@@ -555,6 +578,8 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
 #else
                               b->cfg.BX1, b->stream, &b->launches, 1));
 #endif
+    // EnforceEMFBoundary (enforceEMFBoundary.hpp:29-30); granular callers passed the stage time to idfx_evolve_stage
+    if (callStageHook(b, IDFX_HOOK_EMF_BOUNDARY, b->stageTime, b->stageTimeKnown)) return 1;
     int mode = 0;
     double wc = 0, w0 = 0;
     if (fused && multi) {
@@ -675,7 +700,8 @@ int epilogueAndGhosts(IdfxBlock *b, int stage, double wc, double w0, int keepUc,
   // and running them beside the bandwidth-bound epilogue (plus the six thin shell launches) costs slightly more than
   // it hides (measured, profiles/r2_overlap_ab.md).  IDFX_OVERLAP=1 forces it on.
   const bool multi = b->nproc[0] * b->nproc[1] * b->nproc[2] > 1;
-  bool haveCore = b->overlap && (multi || b->forceOverlap) && b->cfg.ntr == 0 && !b->userBc && !b->haloFn;
+  bool haveCore = b->overlap && (multi || b->forceOverlap) && b->cfg.ntr == 0 && !b->userBc && !b->haloFn &&
+                  !b->stageHook[0] && !b->stageHook[1];
   for (int a = 0; a < 3; a++) {
     const int w = (a < d.ndim) ? g.ng[a] : 0;
     core_lo[a] = g.beg[a] + w;
@@ -1165,14 +1191,17 @@ int idfx_state_add_and_store(IdfxBlock *b, double wc, double w0) {
 
 int idfx_evolve_stage(IdfxBlock *b, double t, double dt) {
   cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
-  (void)t;
+  b->stageTime = t;
+  b->stageTimeKnown = true;
   // dt lives on the device; only touch it when the caller's value differs from the mirror
   if (readState(b)) return 1;
   if (b->hostState[1] != dt) {
     b->hostState[9] = dt;
     CUDA_TRY(cudaMemcpyAsync(b->state + 1, b->hostState + 9, sizeof(double), cudaMemcpyHostToDevice, b->stream));
   }
-  return evolveStageImpl(b, -1);
+  const int rc = evolveStageImpl(b, -1);
+  b->stageTimeKnown = false;
+  return rc;
 }
 
 int idfx_compute_timestep(IdfxBlock *b, double *dt_min) {
@@ -1226,7 +1255,7 @@ bool graphEligible(const IdfxBlock *b, int ncycles) {
   const bool single = b->nproc[0] * b->nproc[1] * b->nproc[2] == 1;
   // a decomposed block qualifies when its exchanges and reductions are the library's own peer-to-peer kernels
   return b->useGraph && b->fused && ncycles >= 4 && !b->userBc && !b->timing && b->stream != nullptr &&
-         ((single && !b->haloFn) || b->p2p);
+         !b->stageHook[0] && !b->stageHook[1] && ((single && !b->haloFn) || b->p2p);
 }
 }  // namespace
 
@@ -1316,6 +1345,16 @@ int idfx_enroll_userdef_boundary(IdfxBlock *b, IdfxUserBoundaryFn fn, void *user
   dropCycleGraph(b);
   b->userBc = fn;
   b->userBcData = user;
+  return 0;
+}
+int idfx_enroll_stage_hook(IdfxBlock *b, int which, IdfxStageHookFn fn, void *user) {
+  cudaSetDevice(b->desc.device);
+  if (which != IDFX_HOOK_INTERNAL_BOUNDARY && which != IDFX_HOOK_EMF_BOUNDARY) return fail("unknown stage hook");
+  if (which == IDFX_HOOK_EMF_BOUNDARY && !(b->cfg.mhd && b->desc.ndim >= 2))
+    return fail("EMF boundary hooks need constrained transport (MHD, DIMENSIONS >= 2)");
+  dropCycleGraph(b);
+  b->stageHook[which] = fn;
+  b->stageHookData[which] = user;
   return 0;
 }
 int idfx_enroll_reduce(IdfxBlock *b, IdfxReduceFn fn, void *user) {

@@ -21,7 +21,15 @@ using UserDefBoundaryFunc = void (*)(Fluid<Phys> *, int dir, BoundarySide side, 
 using UserDefBoundaryFuncOld = void (*)(DataBlock &, int dir, BoundarySide side, const real t);
 template <typename Phys>
 using InternalBoundaryFunc = void (*)(Fluid<Phys> *, const real t);
+using InternalBoundaryFuncOld = void (*)(DataBlock &, const real t);
+using EmfBoundaryFunc = void (*)(DataBlock &, const real t);
 using StepFunc = void (*)(DataBlock &, const real t, const real dt);
+
+// Stand-in for Fluid::emf (ConstrainedTransport, constrainedTransport.hpp:22-144): the corner EMFs a user EMF
+// boundary function rewrites
+struct ConstrainedTransport {
+  IdefixArray3D<real> ex, ey, ez;
+};
 
 enum Solver { TVDLF = IDFX_TVDLF, HLL = IDFX_HLL, HLLC = IDFX_HLLC, HLLD = IDFX_HLLD, ROE = IDFX_ROE };
 
@@ -48,8 +56,9 @@ class Fluid {
   std::vector<std::string> VcName, VsName;
   DataBlock *data{nullptr};
   std::unique_ptr<Boundary<Phys>> boundary;
+  std::unique_ptr<ConstrainedTransport> emf;   // corner EMFs (data.hydro->emf->ex ..., as in the reference)
   Solver mySolver{HLL};
-  int emf{IDFX_EMF_UCT_CONTACT};
+  int emfScheme{IDFX_EMF_UCT_CONTACT};         // [Hydro] emf
   real gamma{5.0 / 3.0};
   real csiso{0.0};
   bool haveTracer{false};
@@ -59,6 +68,10 @@ class Fluid {
   std::string prefix{"Hydro"};
   UserDefBoundaryFunc<Phys> userDefBoundaryFunc{nullptr};
   UserDefBoundaryFuncOld userDefBoundaryFuncOld{nullptr};
+  InternalBoundaryFunc<Phys> internalBoundaryFunc{nullptr};
+  InternalBoundaryFuncOld internalBoundaryFuncOld{nullptr};
+  EmfBoundaryFunc emfBoundaryFunc{nullptr};
+  bool haveInternalBoundary{false}, haveEmfBoundary{false};
 
   Fluid(Input &input, DataBlock *d) : data(d) {
     boundary = std::make_unique<Boundary<Phys>>(this);
@@ -75,14 +88,14 @@ class Fluid {
 #if MHD == YES
     if (input.CheckEntry("Hydro", "emf") >= 0) {
       const std::string e = input.Get<std::string>("Hydro", "emf", 0);
-      if (e == "arithmetic") emf = IDFX_EMF_ARITHMETIC;
-      else if (e == "uct0") emf = IDFX_EMF_UCT0;
-      else if (e == "uct_contact") emf = IDFX_EMF_UCT_CONTACT;
-      else if (e == "uct_hll") emf = IDFX_EMF_UCT_HLL;
-      else if (e == "uct_hlld") emf = IDFX_EMF_UCT_HLLD;
+      if (e == "arithmetic") emfScheme = IDFX_EMF_ARITHMETIC;
+      else if (e == "uct0") emfScheme = IDFX_EMF_UCT0;
+      else if (e == "uct_contact") emfScheme = IDFX_EMF_UCT_CONTACT;
+      else if (e == "uct_hll") emfScheme = IDFX_EMF_UCT_HLL;
+      else if (e == "uct_hlld") emfScheme = IDFX_EMF_UCT_HLLD;
       else IDEFIX_ERROR("Unknown EMF averaging scheme " + e);
       // constrainedTransport.hpp:254-259
-      if (emf == IDFX_EMF_UCT_HLLD && mySolver != HLLD)
+      if (emfScheme == IDFX_EMF_UCT_HLLD && mySolver != HLLD)
         IDEFIX_ERROR("uct_hlld averaging is only compatible with the HLLD Riemann solver");
     }
 #endif
@@ -121,12 +134,11 @@ class Fluid {
   // ---- enrolment (enroll.hpp:13-113) ------------------------------------------------------------
   void EnrollUserDefBoundary(UserDefBoundaryFunc<Phys> f);
   void EnrollUserDefBoundary(UserDefBoundaryFuncOld f);
-  template <typename F>
-  void EnrollInternalBoundary(F) { IDEFIX_ERROR("internal boundary functions are outside the scope of this build"); }
+  void EnrollInternalBoundary(InternalBoundaryFunc<Phys> f);      // enroll.hpp:33-50
+  void EnrollInternalBoundary(InternalBoundaryFuncOld f);
+  void EnrollEmfBoundary(EmfBoundaryFunc f);                      // enroll.hpp:71-78
   template <typename F>
   void EnrollUserSourceTerm(F) { IDEFIX_ERROR("user source terms are outside the scope of this build"); }
-  template <typename F>
-  void EnrollEmfBoundary(F) { IDEFIX_ERROR("user EMF boundaries are outside the scope of this build"); }
   template <typename F>
   void EnrollIsoSoundSpeed(F) { IDEFIX_ERROR("user-defined sound speeds are outside the scope of this build"); }
 
@@ -189,7 +201,7 @@ class DataBlock {
     d.geometry = GEOMETRY;
     d.order = ORDER;
     d.solver = hydro->mySolver;
-    d.emf = hydro->emf;
+    d.emf = hydro->emfScheme;
     d.nstages = nstages;
     for (int dir = 0; dir < 3; dir++) {
       d.np_int[dir] = np_int[dir];
@@ -233,6 +245,17 @@ class DataBlock {
 #if MHD == YES
     IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_VS, &p, n));
     hydro->Vs = IdefixArray4D<real>(p, n[0], n[1], n[2], n[3]);
+#if DIMENSIONS >= 2
+    hydro->emf = std::make_unique<ConstrainedTransport>();
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_EZ, &p, n));
+    hydro->emf->ez = IdefixArray3D<real>(p, n[1], n[2], n[3]);
+#if DIMENSIONS == 3
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_EX, &p, n));
+    hydro->emf->ex = IdefixArray3D<real>(p, n[1], n[2], n[3]);
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_EY, &p, n));
+    hydro->emf->ey = IdefixArray3D<real>(p, n[1], n[2], n[3]);
+#endif
+#endif
 #endif
     for (int dir = 0; dir < 3; dir++) {
       x[dir] = IdefixArray1D<real>("DataBlock_x", np_tot[dir]);
@@ -323,6 +346,36 @@ inline void userBoundaryTrampoline(IdfxBlock *, int dir, int side, double t, voi
 }
 }  // namespace idfxhost
 
+namespace idfxhost {
+template <typename Phys>
+inline void internalBoundaryTrampoline(IdfxBlock *, double t, void *user) {
+  auto *f = static_cast<Fluid<Phys> *>(user);
+  if (f->internalBoundaryFunc) f->internalBoundaryFunc(f, t);
+  else if (f->internalBoundaryFuncOld) f->internalBoundaryFuncOld(*f->data, t);
+}
+template <typename Phys>
+inline void emfBoundaryTrampoline(IdfxBlock *, double t, void *user) {
+  auto *f = static_cast<Fluid<Phys> *>(user);
+  if (f->emfBoundaryFunc) f->emfBoundaryFunc(*f->data, t);
+}
+}  // namespace idfxhost
+
+template <typename Phys> void Fluid<Phys>::EnrollInternalBoundary(InternalBoundaryFunc<Phys> f) {
+  haveInternalBoundary = true;
+  internalBoundaryFunc = f;
+  IDFX_ABI(idfx_enroll_stage_hook(data->handle, IDFX_HOOK_INTERNAL_BOUNDARY, &idfxhost::internalBoundaryTrampoline<Phys>, this));
+}
+template <typename Phys> void Fluid<Phys>::EnrollInternalBoundary(InternalBoundaryFuncOld f) {
+  haveInternalBoundary = true;
+  internalBoundaryFuncOld = f;
+  IDFX_ABI(idfx_enroll_stage_hook(data->handle, IDFX_HOOK_INTERNAL_BOUNDARY, &idfxhost::internalBoundaryTrampoline<Phys>, this));
+}
+template <typename Phys> void Fluid<Phys>::EnrollEmfBoundary(EmfBoundaryFunc f) {
+  haveEmfBoundary = true;
+  emfBoundaryFunc = f;
+  IDFX_ABI(idfx_enroll_stage_hook(data->handle, IDFX_HOOK_EMF_BOUNDARY, &idfxhost::emfBoundaryTrampoline<Phys>, this));
+}
+
 template <typename Phys> void Fluid<Phys>::EnrollUserDefBoundary(UserDefBoundaryFunc<Phys> f) {
   userDefBoundaryFunc = f;
   IDFX_ABI(idfx_enroll_userdef_boundary(data->handle, &idfxhost::userBoundaryTrampoline<Phys>, this));
@@ -349,7 +402,7 @@ template <typename Phys> void Fluid<Phys>::ShowConfig() {
   idfx::cout << "Fluid: Riemann solver: " << names[mySolver] << "." << std::endl;
 #if MHD == YES
   const char *emfs[] = {"Arithmetic", "UCT0", "UCT_CONTACT", "UCT_HLL", "UCT_HLLD"};
-  idfx::cout << "Fluid: EMF averaging: " << emfs[emf] << "." << std::endl;
+  idfx::cout << "Fluid: EMF averaging: " << emfs[emfScheme] << "." << std::endl;
 #endif
 }
 

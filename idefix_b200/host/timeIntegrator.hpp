@@ -55,7 +55,8 @@ class TimeIntegrator {
   void Cycle(DataBlock &data) {
     if (ncycles % cyclePeriod == 0) ShowLog(data);
     const bool hooks = data.haveUserStepFirst || data.haveUserStepLast || data.hydro->userDefBoundaryFunc ||
-                       data.hydro->userDefBoundaryFuncOld;
+                       data.hydro->userDefBoundaryFuncOld || data.hydro->haveInternalBoundary ||
+                       data.hydro->haveEmfBoundary;
     if (hooks) {
       CycleReferenceOrder(data);
       return;

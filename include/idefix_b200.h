@@ -160,6 +160,18 @@ int idfx_timing(IdfxBlock *blk, int mode, double *out);
 /* ---- callbacks --------------------------------------------------------------- */
 /* UserDefBoundaryFunc (boundary.hpp:28-35): invoked for sides declared userdef.
  * side: 0 left, 1 right.  The block's stream is synchronised around the call. */
+/* Host callbacks inside a stage, the user hooks of src/fluid/enroll.hpp:33,71:
+ *   IDFX_HOOK_INTERNAL_BOUNDARY  InternalBoundaryFunc: first thing in Boundary::SetBoundaries (boundary.hpp:243-251),
+ *                                may rewrite Vc / Vs anywhere (e.g. cap a velocity, floor a density);
+ *   IDFX_HOOK_EMF_BOUNDARY       EmfBoundaryFunc: in EnforceEMFBoundary (enforceEMFBoundary.hpp:29-30), between
+ *                                CalcCornerEMF and EvolveMagField, may rewrite the corner EMFs (IDFX_FIELD_EX/EY/EZ).
+ * The library synchronises its stream before the call and the device after it, so the callback may launch its own
+ * kernels on any stream (or touch the arrays through idfx_field_info pointers).  A block with a hook runs its
+ * cycles without CUDA-graph replay. */
+enum IdfxStageHook { IDFX_HOOK_INTERNAL_BOUNDARY = 0, IDFX_HOOK_EMF_BOUNDARY = 1 };
+typedef void (*IdfxStageHookFn)(IdfxBlock *blk, double t, void *user);
+int idfx_enroll_stage_hook(IdfxBlock *blk, int which, IdfxStageHookFn fn, void *user);
+
 typedef void (*IdfxUserBoundaryFn)(IdfxBlock *blk, int dir, int side, double t, void *user);
 int idfx_enroll_userdef_boundary(IdfxBlock *blk, IdfxUserBoundaryFn fn, void *user);
 /* Halo exchange hook, replaces Mpi::ExchangeX1/X2/X3 (mpi.cpp:247,449,646) for

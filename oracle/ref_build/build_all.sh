@@ -25,6 +25,8 @@ b sph_limo3    $P/SphericalMHD            YES 3
 b sph_plm      $P/SphericalMHD            YES 2
 b polar_plm    $P/PolarMHD                YES 2
 b sodiso_plm   $P/sodIso                  NO  2
+b sodstrong_plm $P/sodStrong              NO  2
+b othooks_plm  $P/otHooks                 YES 2 TPX
 b iso25d_plm   $P/IsoMHD25D               YES 2 TPX
 b iso25d_limo3 $P/IsoMHD25D               YES 3 TPX
 b sph25d_plm   $P/Spherical25D            YES 2 TPX

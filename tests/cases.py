@@ -88,7 +88,7 @@ SHORT = [
 # (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
 # reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
 # fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
-PROBLEM_DIRS = {"sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
+PROBLEM_DIRS = {"othooks": "otHooks", "sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
 
 
 def _sph(solver, emf=None, nstages=2):
@@ -135,6 +135,10 @@ HOST_SHORT = [
           {("Hydro", "solver"): "hll", ("TimeIntegrator", "nstages"): 2}, (1, 10)),
     Short("iso25d_tvdlf_arith_limo3", "iso25d", 3, "iso25d_limo3",
           {("Hydro", "solver"): "tvdlf", ("Hydro", "emf"): "arithmetic"}, (1, 10)),
+    # user hooks of the stage (enroll.hpp:33,71): internal boundary (density floor) and EMF boundary (scaled ez)
+    Short("othooks_identity", "othooks", 2, "othooks_plm", _ot2d(64, "hlld", "uct_hlld"), (1, 10)),
+    Short("othooks_floor_scaled_emf", "othooks", 2, "othooks_plm",
+          {**_ot2d(64, "hlld", "uct_contact", 3), ("Setup", "rhofloor"): "0.2215", ("Setup", "emfscale"): "0.75"}, (1, 10)),
 ]
 
 FULL = [

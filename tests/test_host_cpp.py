@@ -26,7 +26,7 @@ HOST = os.path.join(ROOT, "idefix_b200", "host")
 PROBLEMS = {"sod": ("sod", "NO"), "ot2d": ("OrszagTang", "YES"), "ot3d": ("OrszagTang3D", "YES"),
             "sodUserBC": ("sodUserBC", "NO"), "sph": ("SphericalMHD", "YES"), "polar": ("PolarMHD", "YES"),
             "sodiso": ("sodIso", "NO"), "iso25d": ("IsoMHD25D", "YES"), "sph25d": ("Spherical25D", "YES"),
-            "polarhd": ("PolarHD2D", "NO"), "sodstrong": ("sodStrong", "NO")}
+            "polarhd": ("PolarHD2D", "NO"), "sodstrong": ("sodStrong", "NO"), "othooks": ("otHooks", "YES")}
 
 
 def build(problem, order, tmp_path_factory):
