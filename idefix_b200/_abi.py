@@ -44,6 +44,7 @@ class IdfxBlockDesc(C.Structure):
         ("first_dt", C.c_double), ("fixed_dt", C.c_double),
         ("x", _pd * 3), ("xl", _pd * 3), ("xr", _pd * 3), ("dx", _pd * 3),
         ("ntracer", C.c_int),
+        ("shock_flattening", C.c_double),
     ]
 
 

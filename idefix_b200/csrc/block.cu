@@ -86,6 +86,7 @@ struct IdfxBlock {
   unsigned int *mathFlag = nullptr;   // device counter of failed fast-path range checks (fastmath.cuh)
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   double *staleFlux = nullptr; // 1-D HD Roe: area-weighted flux of the previous call (roeHD.hpp:312-328)
+  unsigned char *shockFlags = nullptr;   // [Hydro] shockFlattening: FlagShock per cell (shockFlattening.hpp)
   // TMA descriptor of Vc for the x1 sweep (tma.cuh): boxes [nvar][32 + 2H cells]
   CUtensorMap tmRow;
   bool haveTmRow = false;
@@ -340,6 +341,7 @@ int validate(const IdfxBlockDesc &d) {
   if (d.ndim < 1 || d.ndim > 3) return fail("ndim must be 1..3");
   if (d.ncomp < d.ndim || d.ncomp > 3) return fail("ncomp must satisfy ndim <= ncomp <= 3");
   if (d.order < 1 || d.order > 4) return fail("order must be 1..4");
+  if (d.shock_flattening < 0.0) return fail("shockFlattening needs a non-negative smoothing value");
   if (d.nstages < 1 || d.nstages > 3) return fail("nstages must be 1..3");
   if (d.ntracer < 0 || d.ntracer > 8) return fail("The number of passive tracers should be between 0 and 8");
   if (d.geometry < IDFX_CARTESIAN || d.geometry > IDFX_SPHERICAL) return fail("unknown geometry");
@@ -394,6 +396,7 @@ SweepArgs baseSweepArgs(IdfxBlock *b) {
   a.doInvDt = 1;
   a.fluxRho = b->fluxRho;
   a.staleFlux = b->staleFlux;
+  a.shockFlags = b->shockFlags;
   a.tmapRow = b->haveTmRow ? &b->tmRow : nullptr;
   a.tmapNvar = b->cfg.nvar;
   a.tmapRowCells = b->tmRowCells;
@@ -552,6 +555,10 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
   if (fused && b->cfg.ntr > 0) {
     // Tracer::ConvertPrimToCons (+ the "begin" copy on the first stage); the fluid part is done by the x1 sweep
     KTRY(idfxk::tracerPrimToCons(b->cfg, b->g, b->Vc, b->Uc, (fusedStage == 0 && multi) ? b->Uc0 : nullptr, b->stream));
+    b->launches++;
+  }
+  if (b->shockFlags) {   // RiemannSolver::CalcFlux<IDIR> (calcFlux.hpp:31-34): flag the shocks once per stage
+    KTRY(idfxk::findShock(b->cfg, b->g, b->Vc, b->shockFlags, d.shock_flattening, d.csiso, b->stream));
     b->launches++;
   }
   for (int dir = 0; dir < d.ndim; dir++) {
@@ -899,6 +906,7 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   rc = rc || devAlloc(b, &b->mathFlag, 1);
   if (b->cfg.ntr > 0) rc = rc || devAlloc(b, &b->fluxRho, b->nCells);
   if (!b->cfg.mhd && b->cfg.ndim == 1 && b->cfg.solver == SOLVER_ROE) rc = rc || devAlloc(b, &b->staleFlux, b->nCells * b->cfg.nvar);
+  if (desc->shock_flattening > 0.0) rc = rc || devAlloc(b, &b->shockFlags, b->nCells);
   rc = rc || devAlloc(b, &b->Vc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->Uc, b->nCells * nv);
   rc = rc || devAlloc(b, &b->invDt, b->nCells);

@@ -101,6 +101,7 @@ struct SweepArgs {
   const void *tmapRow;
   int tmapNvar, tmapRowCells;
   int useTma;
+  const unsigned char *shockFlags;   // shock flattening: 1 where the cell is flagged (shockFlattening.hpp), null = off
   double *staleFlux;  // 1-D HD Roe only: (nvar, nx0) area-weighted flux of the previous call (roeHD.hpp:312-328), else null
 };
 

@@ -43,6 +43,10 @@ int consToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc, doubl
 // cell-centred field from the staggered one over the whole block (boundary.hpp:389-404)
 int reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *Vs, double *V, cudaStream_t st,
                        int ghostsOnly = 0);
+// ShockFlattening::FindShock (shockFlattening.hpp:68-178): flags[c] = 1 in cells of converging flow whose pressure
+// jump exceeds smoothing * min(P) over the cell and its neighbours, on the box [beg - 1, end + 1) of every direction
+int findShock(const PhysCfg &c, const DevGrid &g, const double *Vc, unsigned char *flags, double smoothing, double csiso,
+              cudaStream_t st);
 int fill(double *p, long long n, double value, cudaStream_t st);
 int copy(double *dst, const double *src, long long n, cudaStream_t st);
 // dst = wl*dst + wr*src (stateContainer.cpp:91-98)

@@ -97,6 +97,73 @@ __global__ void reconstructVcFieldKernel(DevGrid g, const double *__restrict__ V
   if (g.ndim == 3) V[(bx1 + 2) * g.sn + c] = 0.5 * (Vs[2 * g.vsn + s] + Vs[2 * g.vsn + s + g.vsk]);
 }
 
+// shockFlattening.hpp:68-150.  Sums are associated as the reference's D_EXPAND writes them (left to right).
+template <int ND>
+__global__ void findShockKernel(DevGrid g, const double *__restrict__ Vc, unsigned char *__restrict__ flags, int vx1,
+                                int prs, int rho, double smoothing, double cs, CellBox b) {
+  const int i = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = b.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = b.lo[2] + blockIdx.z;
+  if (i >= b.hi[0] || j >= b.hi[1] || k >= b.hi[2]) return;
+  const long long c = cidx(g, k, j, i);
+  const long long sj = g.sj, sk = g.sk, sn = g.sn;
+  const double *v1 = Vc + (long long)vx1 * sn, *v2 = Vc + (long long)(vx1 + 1) * sn, *v3 = Vc + (long long)(vx1 + 2) * sn;
+  double divV;
+  if (g.geometry == GEO_CARTESIAN) {
+    divV = (v1[c + 1] - v1[c - 1]) / (2 * g.dx[0][i]);
+    if (ND >= 2) divV = divV + (v2[c + sj] - v2[c - sj]) / (2 * g.dx[1][j]);
+    if (ND == 3) divV = divV + (v3[c + sk] - v3[c - sk]) / (2 * g.dx[2][k]);
+  } else {
+    divV = (v1[c + 1] + v1[c]) * faceAreaDir(g, 0, k, j, i + 1) - (v1[c - 1] + v1[c]) * faceAreaDir(g, 0, k, j, i);
+    if (ND >= 2)
+      divV = divV + (v2[c + sj] + v2[c]) * faceAreaDir(g, 1, k, j + 1, i) - (v2[c - sj] + v2[c]) * faceAreaDir(g, 1, k, j, i);
+    if (ND == 3)
+      divV = divV + (v3[c + sk] + v3[c]) * faceAreaDir(g, 2, k + 1, j, i) - (v3[c - sk] + v3[c]) * faceAreaDir(g, 2, k, j, i);
+    divV = 0.5 * divV / cellVolume(g, k, j, i);
+  }
+  unsigned char flag = 0;
+  if (divV < 0.0) {
+    // pressure of a cell: Vc(PRS), or rho cs^2 for the isothermal equation of state
+    auto P = [&](long long cc) { return prs >= 0 ? Vc[(long long)prs * sn + cc] : Vc[(long long)rho * sn + cc] * cs * cs; };
+    double pmin = P(c);
+    double pR = P(c + 1), pL = P(c - 1);
+    if (prs >= 0) {   // shockFlattening.hpp:128-141 (min with i+1 first, then i-1)
+      pmin = fmin(pmin, pR);
+      pmin = fmin(pmin, pL);
+    } else {          // :104-108 (min with i-1 first)
+      pmin = fmin(pmin, pL);
+      pmin = fmin(pmin, pR);
+    }
+    double gradP = fabs(pR - pL);
+    if (ND >= 2) {
+      pR = P(c + sj);
+      pL = P(c - sj);
+      if (prs >= 0) {
+        pmin = fmin(pmin, pR);
+        pmin = fmin(pmin, pL);
+      } else {
+        pmin = fmin(pmin, pL);
+        pmin = fmin(pmin, pR);
+      }
+      gradP += fabs(pR - pL);
+    }
+    if (ND == 3) {
+      pR = P(c + sk);
+      pL = P(c - sk);
+      if (prs >= 0) {
+        pmin = fmin(pmin, pR);
+        pmin = fmin(pmin, pL);
+      } else {
+        pmin = fmin(pmin, pL);
+        pmin = fmin(pmin, pR);
+      }
+      gradP += fabs(pR - pL);
+    }
+    if (gradP > smoothing * pmin) flag = 1;
+  }
+  flags[c] = flag;
+}
+
 __global__ void fillKernel(double *p, long long n, double v) {
   const long long c = (long long)blockIdx.x * TB + threadIdx.x;
   if (c < n) p[c] = v;
@@ -228,6 +295,22 @@ int idfxk::reconstructVcField(const PhysCfg &c, const DevGrid &g, const double *
       launch(hi);
     }
   }
+  return (int)cudaGetLastError();
+}
+
+int idfxk::findShock(const PhysCfg &c, const DevGrid &g, const double *Vc, unsigned char *flags, double smoothing,
+                     double csiso, cudaStream_t st) {
+  CellBox b;
+  for (int d = 0; d < 3; d++) {
+    b.lo[d] = g.beg[d] - g.off[d];
+    b.hi[d] = g.end[d] + g.off[d];
+  }
+  const dim3 blk(64, 4, 1);
+  const dim3 grd((b.hi[0] - b.lo[0] + 63) / 64, (b.hi[1] - b.lo[1] + 3) / 4, b.hi[2] - b.lo[2]);
+  const int prs = c.iso ? -1 : c.ENG;
+  if (g.ndim == 1) findShockKernel<1><<<grd, blk, 0, st>>>(g, Vc, flags, c.MX1, prs, c.RHO, smoothing, csiso, b);
+  else if (g.ndim == 2) findShockKernel<2><<<grd, blk, 0, st>>>(g, Vc, flags, c.MX1, prs, c.RHO, smoothing, csiso, b);
+  else findShockKernel<3><<<grd, blk, 0, st>>>(g, Vc, flags, c.MX1, prs, c.RHO, smoothing, csiso, b);
   return (int)cudaGetLastError();
 }
 

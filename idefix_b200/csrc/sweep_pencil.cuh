@@ -123,6 +123,18 @@ IDFX_D bool cellOutOfRange(V vcAt) {
   for (int nv = 0; nv < NV; nv++) bad |= !idfxStateInRange(vcAt(nv));
   return bad;
 }
+// Shock flattening (extrapolateToFaces.hpp:98-104,141-147,182-189): in a flagged cell PLM and LimO3 use the
+// reference's MinModLim, which always returns zero, i.e. face values q0 + 0 and q0 - 0; PPM ignores the flag
+template <int ORDER>
+IDFX_D void flattenCell(bool flat, double q0, double &vl, double &vr) {
+  if constexpr (ORDER == 2 || ORDER == 3) {
+    if (flat) {
+      vr = q0 + 0.0;
+      vl = q0 - 0.0;
+    }
+  }
+}
+
 template <int NV>
 IDFX_D bool fluxNotFinite(const double *F, double cmax) {
   unsigned m = (unsigned)__double2hiint(cmax) & 0x7ff00000u;
@@ -277,6 +289,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vl, vr;
       reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
+      if (a.shockFlags != nullptr) pencil::flattenCell<ORDER>(a.shockFlags[cell0 + (long long)(mb - 1) * stride] != 0, st[2], vl, vr);
 #if IDFX_TMEM
       __syncwarp();
       tmem::store1(tbase + T_VLS + 2 * nv, vr);
@@ -330,6 +343,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         if (s >= W) s -= W;
         so[d + H] = s * NV * TX;
       }
+      const bool flat = (a.shockFlags != nullptr) && (a.shockFlags[cellm] != 0);
 #if IDFX_TMEM
       // left state = right-face values of cell m-1, parked in tensor memory one step ago
       tmem::Pending1 vlp[NV];
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
         double vr;
         reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
+        pencil::flattenCell<ORDER>(flat, st[2], vR[nv], vr);
 #if IDFX_TMEM
         __syncwarp();
         tmem::store1(tbase + T_VLS + 2 * nv, vr);
@@ -615,6 +630,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB))
     // ---- cell c: face values --------------------------------------------------------------------------
     const double *row = rows + buf * BUF + H + lane;   // row[nv*RW + d] = cell c + d
     double vL[NV], vR[NV];
+    const bool flat = (a.shockFlags != nullptr) && cellLoad && (a.shockFlags[cidx(g, k, j, c)] != 0);
 #pragma unroll
     for (int nv = 0; nv < NV; nv++) {
       if (P::mhd && nv == D::BXn) continue;
@@ -625,6 +641,7 @@ __global__ void __launch_bounds__(WARPS * 32, (ORDER == 4 ? 2 : IDFX_ROW_MINB))
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vr;
       reconstructCell<ORDER, true>(st, positive, regular, wc, dxc, vR[nv], vr);
+      pencil::flattenCell<ORDER>(flat, st[2], vR[nv], vr);
       vrs[nv * 32 + lane] = vr;
     }
     __syncwarp();

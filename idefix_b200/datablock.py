@@ -56,7 +56,11 @@ class Fluid:
             if self.nTracer < 1:
                 raise IdefixError("The number of passive tracers should be >= 1")
         self.haveTracer = self.nTracer > 0
-        for opt in ("shockFlattening", "viscosity", "resistivity", "ambipolar", "hall", "rotation",
+        # [Hydro] shockFlattening <smoothing> (riemannSolver.hpp:154-159)
+        self.shockFlattening = 0.0
+        if inp.CheckEntry("Hydro", "shockFlattening") >= 0:
+            self.shockFlattening = inp.Get(float, "Hydro", "shockFlattening", 0)
+        for opt in ("viscosity", "resistivity", "ambipolar", "hall", "rotation",
                     "gravity", "fargo", "TDiffusion", "bragViscosity", "bragTDiffusion", "drag"):
             if inp.CheckEntry("Hydro", opt) >= 0:
                 raise IdefixError(f"[Hydro] {opt} is outside the scope of this build (explicit Godunov path only)")
@@ -140,6 +144,7 @@ class DataBlock:
         d.gamma, d.csiso = self.hydro.gamma, self.hydro.csiso
         d.cfl, d.cfl_max_var, d.first_dt, d.fixed_dt = self.cfl, self.cfl_max_var, first_dt, self.fixed_dt
         d.ntracer = self.hydro.nTracer
+        d.shock_flattening = self.hydro.shockFlattening
         self._desc = d
         self._callbacks = []
         self._handle = None

@@ -63,6 +63,7 @@ class Fluid {
   real csiso{0.0};
   bool haveTracer{false};
   int nTracer{0};
+  real shockFlattening{0.0};   // [Hydro] shockFlattening <smoothing>, 0 = off
   bool haveSourceTerms{GEOMETRY != CARTESIAN};
   bool haveUserSourceTerm{false};
   std::string prefix{"Hydro"};
@@ -111,7 +112,9 @@ class Fluid {
       nTracer = input.Get<int>("Hydro", "tracer", 0);
       if (nTracer < 1) IDEFIX_ERROR("The number of passive tracers should be >= 1");
     }
-    const char *unsupported[] = {"shockFlattening", "viscosity", "resistivity", "ambipolar", "hall",
+    if (input.CheckEntry("Hydro", "shockFlattening") >= 0)   // riemannSolver.hpp:154-159
+      shockFlattening = input.Get<real>("Hydro", "shockFlattening", 0);
+    const char *unsupported[] = {"viscosity", "resistivity", "ambipolar", "hall",
                                  "rotation", "gravity", "fargo", "TDiffusion", "bragViscosity", "bragTDiffusion",
                                  "drag"};
     for (const char *opt : unsupported)
@@ -222,6 +225,7 @@ class DataBlock {
     d.first_dt = firstDt;
     d.fixed_dt = fixedDt;
     d.ntracer = hydro->nTracer;
+    d.shock_flattening = hydro->shockFlattening;
     IDFX_CUDA(cudaSetDevice(input.device));
     IDFX_ABI(idfx_block_create(&d, &handle));
     // user kernels (idefix_for) run on the legacy default stream.  The library gets a BLOCKING stream of its

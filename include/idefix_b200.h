@@ -77,6 +77,9 @@ typedef struct IdfxBlockDesc {
   const double *dx[3];
   int ntracer;         /* [Hydro] tracer N: passive tracers stored behind the fluid variables in
                           Vc / Uc, index nvar .. nvar+N-1 (fluid.hpp:315-323, tracer.hpp:58-125) */
+  double shock_flattening; /* [Hydro] shockFlattening <smoothing> (riemannSolver.hpp:154-159, shockFlattening.hpp):
+                          > 0 flags the cells of converging flow with |grad P| > smoothing * min(P) before the x1
+                          sweep of every stage; PLM / LimO3 drop to the reference's MinMod there.  0 = off */
 } IdfxBlockDesc;
 
 typedef struct IdfxBlock IdfxBlock;

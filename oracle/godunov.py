@@ -22,7 +22,7 @@ class OracleDesc(C.Structure):
                 ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
                 ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
                 ("dx", C.c_double * 3), ("ntracer", C.c_int), ("order", C.c_int), ("isothermal", C.c_int),
-                ("csiso", C.c_double)]
+                ("csiso", C.c_double), ("shock_flattening", C.c_double)]
 
 
 _lib = None
@@ -62,7 +62,7 @@ class Oracle:
     (n, k, j, i) like the reference's IdefixArray4D."""
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
-                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None):
+                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None, shock_flattening=0.0):
         if mhd and solver == "tvdlf" and emf in ("uct_hll", "uct_hlld"):
             raise ValueError("TVDLF-MHD stores no upwind coefficients for uct_hlld and extends its sweeps by one "
                              "cell only (tvdlfMHD.hpp:30-41, 226-229): not pinned by any reference run")
@@ -70,6 +70,7 @@ class Oracle:
         d.isothermal = int(csiso is not None)
         d.csiso = csiso or 0.0
         d.ntracer = ntracer
+        d.shock_flattening = shock_flattening
         d.order = order
         d.ndim, d.ncomp, d.mhd = ndim, ncomp, int(mhd)
         d.solver, d.emf, d.nstages = SOLVERS[solver], EMFS[emf or "uct_contact"], nstages
@@ -107,7 +108,8 @@ class Oracle:
                 inp.Get(int, "TimeIntegrator", "nstages", 0), grid.np_int, [names[grid.lbound[a]] for a in range(nd)],
                 setup.data.hydro.gamma, inp.Get(float, "TimeIntegrator", "CFL", 0), first_dt,
                 [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer,
-                order=defs.order, csiso=setup.data.hydro.csiso if defs.isothermal else None)
+                order=defs.order, csiso=setup.data.hydro.csiso if defs.isothermal else None,
+                shock_flattening=setup.data.hydro.shockFlattening)
         return o
 
     def set_state(self, Vc, Vs=None):

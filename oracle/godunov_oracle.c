@@ -39,6 +39,7 @@ typedef struct {
   int order;                 /* Idefix_RECONSTRUCTION: 2 PLM (van Leer), 3 LimO3, 4 PPM (0 is read as 2) */
   int isothermal;            /* ISOTHERMAL: no energy equation, p = csiso^2 rho (eos_isothermal, constant cs) */
   double csiso;              /* [Hydro] csiso constant <value> */
+  double shock_flattening;   /* [Hydro] shockFlattening <smoothing> (riemannSolver.hpp:154-159); 0 = off */
 } OracleDesc;
 
 typedef struct {
@@ -51,6 +52,7 @@ typedef struct {
   double *Vc, *Uc, *Uc0, *Vs, *Vs0, *Flux, *cMax, *InvDt;
   double *ex, *ey, *ez, *exj, *exk, *eyi, *eyk, *ezi, *ezj, *Ex1, *Ex2, *Ex3;
   double *svx, *svy, *svz, *aL[3], *aR[3], *dL[3], *dR[3];
+  unsigned char *flags;      /* ShockFlattening::flagArray (shockFlattening.hpp:26), 1 = FlagShock::Shock */
   double t, dt;
   long ncycles;
 } Oracle;
@@ -90,6 +92,7 @@ Oracle *oracle_create(const OracleDesc *d) {
   o->Flux = zalloc(n * (o->nvar + o->ntr));
   o->cMax = zalloc(n);
   o->InvDt = zalloc(n);
+  o->flags = (unsigned char *)calloc((size_t)n, 1);
   if (d->mhd) {
     o->Vs = zalloc(o->vn * d->ndim);
     o->Vs0 = zalloc(o->vn * d->ndim);
@@ -113,6 +116,7 @@ void oracle_destroy(Oracle *o) {
   double *all[] = {o->Vc, o->Uc, o->Uc0, o->Flux, o->cMax, o->InvDt, o->Vs, o->Vs0, o->ex, o->ey, o->ez,
                    o->exj, o->exk, o->eyi, o->eyk, o->ezi, o->ezj, o->Ex1, o->Ex2, o->Ex3, o->svx, o->svy, o->svz};
   for (unsigned q = 0; q < sizeof(all) / sizeof(all[0]); q++) free(all[q]);
+  free(o->flags);
   for (int a = 0; a < 3; a++) {
     free(o->aL[a]);
     free(o->aR[a]);
@@ -300,12 +304,20 @@ static void ppm_states(double vm2, double vm1, double v0, double vp1, double vp2
 /* ExtrapolatePrimVar on a regular grid (extrapolateToFaces.hpp:89-124 PLM, :173-246 LimO3, :247-307 PPM):
  * q points at cell i of the variable, s = stride along the sweep; interface i-1/2 gets vL from cell i-1
  * and vR from cell i.  positive = RHO or PRS (face values that must stay positive). */
+static void reconstruct_interface_flat(int order, const double *q, long s, int positive, double dx, double *vL,
+                                       double *vR, int flatL, int flatR);
 static void reconstruct_interface(int order, const double *q, long s, int positive, double dx, double *vL,
                                   double *vR) {
+  reconstruct_interface_flat(order, q, s, positive, dx, vL, vR, 0, 0);
+}
+/* flatL / flatR: shock flattening flags of cell i-1 / cell i (extrapolateToFaces.hpp:98-104,114-120,182-189,217-224):
+ * a flagged cell uses MinModLim -- which always returns zero -- for PLM and LimO3; PPM ignores them */
+static void reconstruct_interface_flat(int order, const double *q, long s, int positive, double dx, double *vL,
+                                       double *vR, int flatL, int flatR) {
   if (order == 3) {
     double dvm = q[-s] - q[-2 * s];
     double dvp = q[0] - q[-s];
-    double dv = dvp * lim_o3(dvp, dvm, dx);
+    double dv = flatL ? minmod_ref(dvp, dvm) : dvp * lim_o3(dvp, dvm, dx);
     *vL = q[-s] + 0.5 * dv;
     if (positive && *vL <= 0.0) {
       dv = minmod_ref(dvp, dvm);
@@ -313,7 +325,7 @@ static void reconstruct_interface(int order, const double *q, long s, int positi
     }
     dvm = dvp;
     dvp = q[s] - q[0];
-    dv = dvm * lim_o3(dvm, dvp, dx);
+    dv = flatR ? minmod_ref(dvp, dvm) : dvm * lim_o3(dvm, dvp, dx);
     *vR = q[0] - 0.5 * dv;
     if (positive && *vR <= 0.0) {
       dv = minmod_ref(dvp, dvm);
@@ -330,11 +342,11 @@ static void reconstruct_interface(int order, const double *q, long s, int positi
   } else {
     double dvm = q[-s] - q[-2 * s];
     double dvp = q[0] - q[-s];
-    double dv = van_leer(dvp, dvm);
+    double dv = flatL ? minmod_ref(dvp, dvm) : van_leer(dvp, dvm);
     *vL = q[-s] + 0.5 * dv;
     dvm = dvp;
     dvp = q[s] - q[0];
-    dv = van_leer(dvp, dvm);
+    dv = flatR ? minmod_ref(dvp, dvm) : van_leer(dvp, dvm);
     *vR = q[0] - 0.5 * dv;
   }
 }
@@ -1192,10 +1204,53 @@ void oracle_convert(Oracle *o, long n, double *u, double *v, double *u2) {
   }
 }
 
+/* ---- ShockFlattening::FindShock, cartesian branch: shockFlattening.hpp:68-150,166-178 ------------- */
+static void find_shock(Oracle *o) {
+  const OracleDesc *d = &o->d;
+  const double *Vc = o->Vc;
+  const long sn = o->sn, sj = o->sj, sk = o->sk;
+  const int VX1 = o->MX1;
+  for (int k = o->beg[2] - o->off[2]; k < o->end[2] + o->off[2]; k++)
+    for (int j = o->beg[1] - o->off[1]; j < o->end[1] + o->off[1]; j++)
+      for (int i = o->beg[0] - o->off[0]; i < o->end[0] + o->off[0]; i++) {
+        const long c = C(o, k, j, i);
+        o->flags[c] = 0;
+        double divV = (Vc[VX1 * sn + c + 1] - Vc[VX1 * sn + c - 1]) / (2 * d->dx[0]);
+        if (d->ndim >= 2) divV = divV + (Vc[(VX1 + 1) * sn + c + sj] - Vc[(VX1 + 1) * sn + c - sj]) / (2 * d->dx[1]);
+        if (d->ndim == 3) divV = divV + (Vc[(VX1 + 2) * sn + c + sk] - Vc[(VX1 + 2) * sn + c - sk]) / (2 * d->dx[2]);
+        if (divV < 0.0) {
+          double pmin, gradP;
+          const long str[3] = {1, sj, sk};
+          if (d->isothermal) {
+            const double cs = d->csiso;
+            pmin = Vc[o->RHO * sn + c] * cs * cs;
+            gradP = 0.0;
+            for (int a = 0; a < d->ndim; a++) {
+              const double pR = Vc[o->RHO * sn + c + str[a]] * cs * cs, pL = Vc[o->RHO * sn + c - str[a]] * cs * cs;
+              pmin = fmin(pmin, pL);
+              pmin = fmin(pmin, pR);
+              gradP += fabs(pR - pL);
+            }
+          } else {
+            const double *P = Vc + o->ENG * sn;
+            pmin = P[c];
+            gradP = 0.0;
+            for (int a = 0; a < d->ndim; a++) {
+              pmin = fmin(pmin, P[c + str[a]]);
+              pmin = fmin(pmin, P[c - str[a]]);
+              gradP += fabs(P[c + str[a]] - P[c - str[a]]);
+            }
+          }
+          if (gradP > d->shock_flattening * pmin) o->flags[c] = 1;
+        }
+      }
+}
+
 /* ---- RiemannSolver::CalcFlux<dir>: reconstruct (extrapolateToFaces.hpp:89-124), solve, store ------ */
 static void calc_flux(Oracle *o, int dir) {
   const OracleDesc *d = &o->d;
   const int nv = o->nvar;
+  if (dir == 0 && d->shock_flattening > 0.0) find_shock(o); /* calcFlux.hpp:31-34 */
   /* perpendicular extension of the face box: 0 for HD; 1 or nghost for MHD (hlldMHD.hpp:32-49) */
   int ext = 0;
   if (d->mhd) ext = (d->emf == EMF_UCT_HLL || d->emf == EMF_UCT_HLLD) ? d->nghost[dir] : 1;
@@ -1212,9 +1267,10 @@ static void calc_flux(Oracle *o, int dir) {
       for (int i = lo[0]; i < hi[0]; i++) {
         const long c = C(o, k, j, i);
         double vL[8], vR[8], F[8];
+        const int flatL = d->shock_flattening > 0.0 && o->flags[c - s], flatR = d->shock_flattening > 0.0 && o->flags[c];
         for (int n = 0; n < nv; n++)
-          reconstruct_interface(d->order, o->Vc + n * o->sn + c, s, n == o->RHO || n == o->ENG, d->dx[dir], &vL[n],
-                                &vR[n]);
+          reconstruct_interface_flat(d->order, o->Vc + n * o->sn + c, s, n == o->RHO || n == o->ENG, d->dx[dir], &vL[n],
+                                     &vR[n], flatL, flatR);
         Speeds sp = {0, 0, 0, 0};
         if (d->mhd) {
           vL[o->BX1 + dir] = vR[o->BX1 + dir] = o->Vs[dir * o->vn + S(o, k, j, i)];

@@ -78,6 +78,13 @@ SHORT = [
           {**_ot3d(16, 32, 16, solver="hll", emf="uct0", nstages=3), ("Hydro", "tracer"): "2"}, (1, 10)),
     Short("ot3d_roe_contact_plm", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, solver="roe"), (1, 10)),
     Short("ot3d_hll_uct0_plm_rk3", "ot3d", 2, "ot3d_plm", _ot3d(16, 32, 16, solver="hll", emf="uct0", nstages=3), (1, 10)),
+    # shock flattening ([Hydro] shockFlattening, shockFlattening.hpp): flagged cells fall back on the reference's MinMod
+    Short("sod_hllc_plm_flat", "sod", 2, "sod_plm", {**_sod("hllc"), ("Hydro", "shockFlattening"): "0.5"}, (1, 20, 60)),
+    Short("sod_hll_limo3_flat", "sod", 3, "sod_limo3", {**_sod("hll"), ("Hydro", "shockFlattening"): "0.2"}, (1, 40)),
+    Short("ot2d_hlld_ucthlld_plm_flat", "ot2d", 2, "ot2d_plm",
+          {**_ot2d(64, "hlld", "uct_hlld"), ("Hydro", "shockFlattening"): "0.0005"}, (1, 10)),
+    Short("ot3d_hlld_contact_plm_flat_rk3", "ot3d", 2, "ot3d_plm",
+          {**_ot3d(16, 32, 16, nstages=3), ("Hydro", "shockFlattening"): "0.001"}, (1, 10)),
     # C3 physics: linear waves, HLLD + PPM + RK3 has no shipped golden -> reference binary
     Short("lw_fast_hlld_ppm_rk3", "linearwave", 4, "lw_ppm", _lw(32, 16, 16, "hlld", 3, 1), (1, 10)),
     Short("lw_alfven_roe_limo3", "linearwave", 3, "lw_limo3", _lw(32, 16, 16, "roe", 2, 2), (1, 10)),
@@ -116,6 +123,10 @@ HOST_SHORT = [
     Short("sph_hll_uct0_plm", "sph", 2, "sph_plm", _sph("hll", "uct0"), (1, 10)),
     Short("sph_tvdlf_arith_limo3", "sph", 3, "sph_limo3", _sph("tvdlf", "arithmetic"), (1, 10)),
     Short("polar_hlld_contact_plm", "polar", 2, "polar_plm", _polar("hlld"), (1, 10)),
+    # shock flattening in curvilinear geometry (area-weighted divergence, shockFlattening.hpp:78-87)
+    Short("sph_hlld_contact_plm_flat", "sph", 2, "sph_plm", {**_sph("hlld"), ("Hydro", "shockFlattening"): "0.0002"}, (1, 10)),
+    Short("polar_hll_uct0_plm_flat", "polar", 2, "polar_plm",
+          {**_polar("hll", "uct0"), ("Hydro", "shockFlattening"): "0.0002"}, (1, 10)),
     Short("polar_hll_ucthll_plm_rk3", "polar", 2, "polar_plm", _polar("hll", "uct_hll", 3), (1, 10)),
     # isothermal EOS: HD tube, and 2.5-D MHD (COMPONENTS 3 > DIMENSIONS 2: B_z through Uc)
     Short("sodiso_hllc_plm", "sodiso", 2, "sodiso_plm", _sod("hllc"), (1, 20)),
