@@ -21,7 +21,7 @@ CARTESIAN, CYLINDRICAL, POLAR, SPHERICAL = 1, 2, 3, 4
 TVDLF, HLL, HLLC, HLLD, ROE = 0, 1, 2, 3, 4
 EMF_ARITHMETIC, EMF_UCT0, EMF_UCT_CONTACT, EMF_UCT_HLL, EMF_UCT_HLLD = 0, 1, 2, 3, 4
 BC_INTERNAL, BC_PERIODIC, BC_REFLECTIVE, BC_OUTFLOW, BC_SHEARINGBOX, BC_AXIS, BC_USERDEF, BC_UNDEFINED = range(8)
-FIELD_VC, FIELD_UC, FIELD_VS, FIELD_INVDT, FIELD_EX, FIELD_EY, FIELD_EZ, FIELD_UC0, FIELD_VS0 = range(9)
+FIELD_VC, FIELD_UC, FIELD_VS, FIELD_INVDT, FIELD_EX, FIELD_EY, FIELD_EZ, FIELD_UC0, FIELD_VS0, FIELD_VE, FIELD_VE0 = range(11)
 
 GEOMETRY_NAMES = {"CARTESIAN": CARTESIAN, "CYLINDRICAL": CYLINDRICAL, "POLAR": POLAR, "SPHERICAL": SPHERICAL}
 SOLVER_NAMES = {"tvdlf": TVDLF, "hll": HLL, "hllc": HLLC, "hlld": HLLD, "roe": ROE}
@@ -45,6 +45,7 @@ class IdfxBlockDesc(C.Structure):
         ("x", _pd * 3), ("xl", _pd * 3), ("xr", _pd * 3), ("dx", _pd * 3),
         ("ntracer", C.c_int),
         ("shock_flattening", C.c_double),
+        ("evolve_vector_potential", C.c_int),
     ]
 
 
@@ -80,6 +81,7 @@ SYMBOLS = {
     "idfx_evolve_stage": (C.c_int, [_h, C.c_double, C.c_double]),
     "idfx_compute_timestep": (C.c_int, [_h, _pd]),
     "idfx_check_divb": (C.c_int, [_h, _pd]),
+    "idfx_derive_vector_potential": (C.c_int, [_h]),
     "idfx_check_nan": (C.c_int, [_h, C.POINTER(C.c_int)]),
     "idfx_cycles": (C.c_int, [_h, C.c_int]),
     "idfx_cycle": (C.c_int, [_h, _pd, _pd, C.POINTER(C.c_int)]),

@@ -87,6 +87,8 @@ struct IdfxBlock {
   double *fluxRho = nullptr;   // mass flux of the current sweep, for the tracer kernels (only with tracers)
   double *staleFlux = nullptr; // 1-D HD Roe: area-weighted flux of the previous call (roeHD.hpp:312-328)
   unsigned char *shockFlags = nullptr;   // [Hydro] shockFlattening: FlagShock per cell (shockFlattening.hpp)
+  double *Ve = nullptr, *Ve0 = nullptr;  // EVOLVE_VECTOR_POTENTIAL: edge-centred potential (laid out like Vs) + "begin" copy
+  int nVe = 0;                           // components of Ve: 3 (AX1e, AX2e, AX3e) in 3-D, 1 (AX3e) in 2-D
   // TMA descriptor of Vc for the x1 sweep (tma.cuh): boxes [nvar][32 + 2H cells]
   CUtensorMap tmRow;
   bool haveTmRow = false;
@@ -342,6 +344,8 @@ int validate(const IdfxBlockDesc &d) {
   if (d.ncomp < d.ndim || d.ncomp > 3) return fail("ncomp must satisfy ndim <= ncomp <= 3");
   if (d.order < 1 || d.order > 4) return fail("order must be 1..4");
   if (d.shock_flattening < 0.0) return fail("shockFlattening needs a non-negative smoothing value");
+  if (d.evolve_vector_potential && !(d.mhd && d.ndim >= 2))
+    return fail("EVOLVE_VECTOR_POTENTIAL is not compatible with 1D MHD");   // fluid.hpp:549-551
   if (d.nstages < 1 || d.nstages > 3) return fail("nstages must be 1..3");
   if (d.ntracer < 0 || d.ntracer > 8) return fail("The number of passive tracers should be between 0 and 8");
   if (d.geometry < IDFX_CARTESIAN || d.geometry > IDFX_SPHERICAL) return fail("unknown geometry");
@@ -596,7 +600,15 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
         w0 = b->w0[fusedStage - 1];
       }
     }
-    KTRY(idfxk::evolveMagField(b->g, b->emf, b->Vs, b->Vs0, b->state + 1, 0, mode, wc, w0, b->stream, &b->launches));
+    if (b->Ve) {
+      // EVOLVE_VECTOR_POTENTIAL (evolveStage.hpp:78-81): Ve += -dt E, then Vs = curl Ve.  On the fused path the
+      // Runge-Kutta combination of Ve (StateContainer::AddAndStore) is folded into the first kernel, so the Vs derived
+      // here is already the one ConvertConsToPrim would derive after the combination
+      KTRY(idfxk::evolveVectorPotential(b->g, b->emf, b->Ve, b->Ve0, b->state + 1, mode, wc, w0, b->stream, &b->launches));
+      KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));
+    } else {
+      KTRY(idfxk::evolveMagField(b->g, b->emf, b->Vs, b->Vs0, b->state + 1, 0, mode, wc, w0, b->stream, &b->launches));
+    }
     if (!fused) {
       if (reconstructVc(b, b->Uc)) return 1;
     }
@@ -646,8 +658,9 @@ int cycleReferenceOrder(IdfxBlock *b) {
     if (d.nstages > 1 && stage == 0) {
       KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * (b->cfg.nvar + b->cfg.ntr), b->stream));
       b->launches++;
-      if (b->cfg.mhd) {
-        KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * d.ndim, b->stream));
+      if (b->cfg.mhd) {   // states["current"] holds Ve instead of Vs when the potential is evolved (fluid.hpp:548-559)
+        if (b->Ve) KTRY(idfxk::copy(b->Ve0, b->Ve, b->nVs * b->nVe, b->stream));
+        else KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * d.ndim, b->stream));
         b->launches++;
       }
     }
@@ -663,10 +676,12 @@ int cycleReferenceOrder(IdfxBlock *b) {
       KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * (b->cfg.nvar + b->cfg.ntr), wc, w0, b->stream));
       b->launches++;
       if (b->cfg.mhd) {
-        KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * d.ndim, wc, w0, b->stream));
+        if (b->Ve) KTRY(idfxk::addAndStore(b->Ve, b->Ve0, b->nVs * b->nVe, wc, w0, b->stream));
+        else KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * d.ndim, wc, w0, b->stream));
         b->launches++;
       }
     }
+    if (b->Ve) KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));   // convertConsToPrim.hpp:117-119
     if (reconstructVc(b, b->Uc)) return 1;
     KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, d.gamma, b->stream));
     b->launches++;
@@ -819,6 +834,14 @@ int fieldPtr(IdfxBlock *b, int field, double **p, int dims[4]) {
       dims[2] = g.nx[1] + g.off[1];
       dims[3] = g.nx[0] + g.off[0];
       break;
+    case IDFX_FIELD_VE:
+    case IDFX_FIELD_VE0:
+      *p = (field == IDFX_FIELD_VE) ? b->Ve : b->Ve0;
+      dims[0] = b->nVe;
+      dims[1] = g.nx[2] + g.off[2];
+      dims[2] = g.nx[1] + g.off[1];
+      dims[3] = g.nx[0] + g.off[0];
+      break;
     case IDFX_FIELD_INVDT: *p = b->invDt; break;
     case IDFX_FIELD_EX: *p = b->emf.ex; break;
     case IDFX_FIELD_EY: *p = b->emf.ey; break;
@@ -915,6 +938,11 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
   if (b->cfg.mhd) {
     rc = rc || devAlloc(b, &b->Vs, b->nVs * desc->ndim);
     if (desc->nstages > 1) rc = rc || devAlloc(b, &b->Vs0, b->nVs * desc->ndim);
+    if (desc->evolve_vector_potential) {
+      b->nVe = (desc->ndim == 3) ? 3 : 1;
+      rc = rc || devAlloc(b, &b->Ve, b->nVs * b->nVe);
+      if (desc->nstages > 1) rc = rc || devAlloc(b, &b->Ve0, b->nVs * b->nVe);
+    }
     DevEmf &e = b->emf;
     const long long n = b->nCells;
     const int nd = desc->ndim;
@@ -1161,8 +1189,17 @@ int idfx_prim_to_cons(IdfxBlock *b) {
   return 0;
 }
 
+int idfx_derive_vector_potential(IdfxBlock *b) {
+  cudaSetDevice(b->desc.device);
+  if (!b->Ve) return 0;
+  b->vcFieldFresh = false;
+  KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));
+  return 0;
+}
+
 int idfx_cons_to_prim(IdfxBlock *b) {
   cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
+  if (b->Ve) KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));   // convertConsToPrim.hpp:117-119
   if (reconstructVc(b, b->Uc)) return 1;
   KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
   b->launches++;
@@ -1179,7 +1216,8 @@ int idfx_state_copy(IdfxBlock *b) {
   KTRY(idfxk::copy(b->Uc0, b->Uc, b->nCells * (b->cfg.nvar + b->cfg.ntr), b->stream));
   b->launches++;
   if (b->cfg.mhd) {
-    KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * b->desc.ndim, b->stream));
+    if (b->Ve) KTRY(idfxk::copy(b->Ve0, b->Ve, b->nVs * b->nVe, b->stream));
+    else KTRY(idfxk::copy(b->Vs0, b->Vs, b->nVs * b->desc.ndim, b->stream));
     b->launches++;
   }
   return 0;
@@ -1191,7 +1229,8 @@ int idfx_state_add_and_store(IdfxBlock *b, double wc, double w0) {
   KTRY(idfxk::addAndStore(b->Uc, b->Uc0, b->nCells * (b->cfg.nvar + b->cfg.ntr), wc, w0, b->stream));
   b->launches++;
   if (b->cfg.mhd) {
-    KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * b->desc.ndim, wc, w0, b->stream));
+    if (b->Ve) KTRY(idfxk::addAndStore(b->Ve, b->Ve0, b->nVs * b->nVe, wc, w0, b->stream));
+    else KTRY(idfxk::addAndStore(b->Vs, b->Vs0, b->nVs * b->desc.ndim, wc, w0, b->stream));
     b->launches++;
   }
   return 0;

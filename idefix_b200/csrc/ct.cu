@@ -276,6 +276,88 @@ __global__ void __launch_bounds__(TBX *TBY, 4)
   }
 }
 
+// ConstrainedTransport::EvolveVectorPotential (evolveVectorPotential.hpp:17-44): Ve += -dt E on [beg, end + 1) of
+// the active directions.  mode as in evolveMagFieldKernel: 1 saves the old value in Ve0 (first stage of the fused
+// path), 2 folds StateContainer::AddAndStore in (Ve <- wc (Ve - dt E) + w0 Ve0).
+// Ve(comp, k, j, i) shares the layout of Vs; DIMENSIONS == 3: comp = AX1e, AX2e, AX3e; DIMENSIONS == 2: AX3e only.
+template <int ND>
+__global__ void evolveVectorPotentialKernel(DevGrid g, DevEmf e, double *__restrict__ Ve, double *__restrict__ Ve0,
+                                            const double *dtp, int mode, double wc, double w0, Box b) {
+  BOX_INDEX(b)
+  const double dt = *dtp;
+  const long long c = cidx(g, k, j, i);
+  const long long s = sidx(g, k, j, i);
+  const double *E[3] = {e.ex, e.ey, e.ez};
+  constexpr int NE = (ND == 3) ? 3 : 1;
+#pragma unroll
+  for (int n = 0; n < NE; n++) {
+    const double emf = (ND == 3) ? E[n][c] : e.ez[c];
+    const long long a = n * g.vsn + s;
+    const double old = Ve[a];
+    double upd = old + (-dt * emf);
+    if (mode == 1) Ve0[a] = old;
+    if (mode == 2) upd = wc * upd + w0 * Ve0[a];
+    Ve[a] = upd;
+  }
+}
+
+// ConstrainedTransport::ComputeMagFieldFromA (evolveVectorPotential.hpp:48-163): Vs = curl Ve, every geometry
+template <int ND>
+__global__ void magFieldFromAKernel(DevGrid g, const double *__restrict__ Ve, double *__restrict__ Vs, int haveAxis, Box b) {
+  BOX_INDEX(b)
+  const long long s = sidx(g, k, j, i);
+  const long long sj = g.vsj, sk = g.vsk;
+  const double *A1 = Ve, *A2 = Ve + g.vsn, *A3 = (ND == 3) ? Ve + 2 * g.vsn : Ve;   // AX1e, AX2e, AX3e
+  const double *dx1 = g.dx[0], *dx2 = g.dx[1], *dx3 = g.dx[2];
+  double b1 = 0.0, b2 = 0.0, b3 = 0.0;
+  const int geo = g.geometry;
+  if (geo == GEO_CARTESIAN) {
+    b1 = 0.0;
+    if (ND >= 2) b1 = b1 + 1 / dx2[j] * (A3[s + sj] - A3[s]);
+    if (ND == 3) b1 = b1 - 1 / dx3[k] * (A2[s + sk] - A2[s]);
+    if (ND >= 2) {
+      b2 = -1 / dx1[i] * (A3[s + 1] - A3[s]);
+      if (ND == 3) b2 = b2 + 1 / dx3[k] * (A1[s + sk] - A1[s]);
+    }
+    if (ND == 3) b3 = +1 / dx1[i] * (A2[s + 1] - A2[s]) - 1 / dx2[j] * (A1[s + sj] - A1[s]);
+  } else if (geo == GEO_CYLINDRICAL) {
+    const double *x1 = g.x[0], *x1p = g.xr[0], *x1m = g.xl[0];
+    b1 = +1 / dx2[j] * (A3[s + sj] - A3[s]);
+    if (ND >= 2) b2 = -(fabs(x1p[i]) * A3[s + 1] - fabs(x1m[i]) * A3[s]) / fabs(x1[i] * dx1[i]);
+  } else if (geo == GEO_POLAR) {
+    const double *x1 = g.x[0], *x1m = g.xl[0];
+    b1 = 0.0;
+    if (ND >= 2) b1 = b1 + 1 / (fabs(x1m[i]) * dx2[j]) * (A3[s + sj] - A3[s]);
+    if (ND == 3) b1 = b1 - 1 / dx3[k] * (A2[s + sk] - A2[s]);
+    if (ND >= 2) {
+      b2 = -1 / dx1[i] * (A3[s + 1] - A3[s]);
+      if (ND == 3) b2 = b2 + 1 / dx3[k] * (A1[s + sk] - A1[s]);
+    }
+    if (ND == 3)
+      b3 = 1 / (fabs(x1[i])) * ((x1m[i + 1] * A2[s + 1] - x1m[i] * A2[s]) / dx1[i] - (A1[s + sj] - A1[s]) / dx2[j]);
+  } else {  // spherical
+    const double *x1 = g.x[0], *x1m = g.xl[0];
+    const double dV2 = g.dmu[j];
+    const double Ax2p = fabs(g.sinx2m[j + 1]);
+    double Ax2m = fabs(g.sinx2m[j]);
+    b1 = 0.0;
+    if (ND >= 2) b1 = b1 + 1 / (x1m[i] * dV2) * (Ax2p * A3[s + sj] - Ax2m * A3[s]);
+    if (ND == 3) b1 = b1 - dx2[j] / (x1m[i] * dV2 * dx3[k]) * (A2[s + sk] - A2[s]);
+    if (ND >= 2) {
+      if (haveAxis) {
+        if (fabs(Ax2m) < 1e-12) Ax2m = 1.0;
+      }
+      b2 = -1 / (x1[i] * dx1[i]) * (x1m[i + 1] * A3[s + 1] - x1m[i] * A3[s]);
+      if (ND == 3) b2 = b2 + 1 / (x1[i] * Ax2m * dx3[k]) * (A1[s + sk] - A1[s]);
+    }
+    if (ND == 3)
+      b3 = +1 / (x1[i] * dx1[i]) * (x1m[i + 1] * A2[s + 1] - x1m[i] * A2[s]) - 1 / (x1[i] * dx2[j]) * (A1[s + sj] - A1[s]);
+  }
+  Vs[s] = b1;
+  if (ND >= 2) Vs[g.vsn + s] = b2;
+  if (ND == 3) Vs[2 * g.vsn + s] = b3;
+}
+
 Box cornerBox(const DevGrid &g, int extra) {
   Box b;
   for (int d = 0; d < 3; d++) {
@@ -359,6 +441,29 @@ int idfxk::evolveMagField(const DevGrid &g, const DevEmf &e, double *Vs, double 
     if (g.ndim == 2) evolveMagFieldKernel<2, false><<<grid, block, 0, st>>>(g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
     else evolveMagFieldKernel<3, false><<<grid, block, 0, st>>>(g, e, Vs, Vs0, dt, haveAxis, mode, wc, w0, b);
   }
+  (*launches)++;
+  return (int)cudaGetLastError();
+}
+
+// EvolveVectorPotential + (optionally) the RK combination of Ve
+int idfxk::evolveVectorPotential(const DevGrid &g, const DevEmf &e, double *Ve, double *Ve0, const double *dt, int mode,
+                                 double wc, double w0, cudaStream_t st, long long *launches) {
+  if (g.ndim == 1) return 0;
+  const dim3 block(TBX, TBY, 1);
+  Box b = cornerBox(g, 0);
+  if (g.ndim == 2) evolveVectorPotentialKernel<2><<<boxGrid(b), block, 0, st>>>(g, e, Ve, Ve0, dt, mode, wc, w0, b);
+  else evolveVectorPotentialKernel<3><<<boxGrid(b), block, 0, st>>>(g, e, Ve, Ve0, dt, mode, wc, w0, b);
+  (*launches)++;
+  return (int)cudaGetLastError();
+}
+
+// ComputeMagFieldFromA on [beg, end + 1) of the active directions
+int idfxk::magFieldFromA(const DevGrid &g, const double *Ve, double *Vs, int haveAxis, cudaStream_t st, long long *launches) {
+  if (g.ndim == 1) return 0;
+  const dim3 block(TBX, TBY, 1);
+  Box b = cornerBox(g, 0);
+  if (g.ndim == 2) magFieldFromAKernel<2><<<boxGrid(b), block, 0, st>>>(g, Ve, Vs, haveAxis, b);
+  else magFieldFromAKernel<3><<<boxGrid(b), block, 0, st>>>(g, Ve, Vs, haveAxis, b);
   (*launches)++;
   return (int)cudaGetLastError();
 }

@@ -36,6 +36,11 @@ int calcCornerEmf(const DevGrid &g, const DevEmf &e, const double *Vc, const dou
 int evolveMagField(const DevGrid &g, const DevEmf &e, double *Vs, double *Vs0, const double *dt, int haveAxis,
                    int mode, double wc, double w0, cudaStream_t st, long long *launches);
 
+// EVOLVE_VECTOR_POTENTIAL (evolveVectorPotential.hpp): Ve += -dt E (mode as evolveMagField), Vs = curl Ve
+int evolveVectorPotential(const DevGrid &g, const DevEmf &e, double *Ve, double *Ve0, const double *dt, int mode,
+                          double wc, double w0, cudaStream_t st, long long *launches);
+int magFieldFromA(const DevGrid &g, const double *Ve, double *Vs, int haveAxis, cudaStream_t st, long long *launches);
+
 // ---- point-wise kernels (pointwise.cu) ---------------------------------------
 struct Eos2 { double gamma, csiso; };
 int primToCons(const PhysCfg &c, const DevGrid &g, const double *Vc, double *Uc, double gamma, cudaStream_t st);

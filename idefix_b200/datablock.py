@@ -145,6 +145,7 @@ class DataBlock:
         d.cfl, d.cfl_max_var, d.first_dt, d.fixed_dt = self.cfl, self.cfl_max_var, first_dt, self.fixed_dt
         d.ntracer = self.hydro.nTracer
         d.shock_flattening = self.hydro.shockFlattening
+        d.evolve_vector_potential = int(bool(getattr(defs, "evolve_vector_potential", False)))
         self._desc = d
         self._callbacks = []
         self._handle = None
@@ -193,6 +194,11 @@ class DataBlock:
     # ---- forwards (dataBlock.hpp:120-160) ------------------------------------------------
     def SetBoundaries(self):
         check(lib().idfx_set_boundaries(self._handle, self.t))
+
+    def DeriveVectorPotential(self):
+        """dataBlock.cpp:366-373: Vs = curl Ve when the vector potential is the evolved variable (no-op otherwise)"""
+        if self._handle is not None:
+            check(lib().idfx_derive_vector_potential(self._handle))
 
     def ResetStage(self):
         self.hydro.ResetStage()
@@ -285,10 +291,14 @@ class DataBlockHost:
         self._Uc = None      # allocated on first access; an untouched mirror is all zeros
         self._InvDt = None
         self.Vs = None
+        self.Ve = None
         if data.defs.mhd:
             nd = data.defs.dimensions
             off = [1 if d < nd else 0 for d in range(3)]
             self.Vs = np.zeros((nd, n3 + off[2], n2 + off[1], n1 + off[0]))
+            if getattr(data.defs, "evolve_vector_potential", False):
+                # edge-centred potential, laid out like Vs: AX1e, AX2e, AX3e in 3-D, AX3e alone in 2-D (idefix.hpp:116-125)
+                self.Ve = np.zeros((3 if nd == 3 else 1, n3 + off[2], n2 + off[1], n1 + off[0]))
 
     @property
     def Uc(self):
@@ -324,6 +334,8 @@ class DataBlockHost:
             d.upload(_abi.FIELD_UC, self.Uc)
         if self._InvDt is not None or not fresh:
             d.upload(_abi.FIELD_INVDT, self.InvDt)
+        if self.Ve is not None:
+            d.upload(_abi.FIELD_VE, self.Ve)
         if self.Vs is not None:
             d.upload(_abi.FIELD_VS, self.Vs)
             if not fresh:
@@ -340,6 +352,8 @@ class DataBlockHost:
         self.InvDt = d.download(_abi.FIELD_INVDT)
         if self.Vs is not None:
             self.Vs = d.download(_abi.FIELD_VS)
+        if self.Ve is not None:
+            self.Ve = d.download(_abi.FIELD_VE)
 
     def MakeVsFromAmag(self, A):
         """Vs = curl(A) on the staggered mesh, cartesian / polar / spherical

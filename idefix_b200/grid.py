@@ -24,6 +24,7 @@ class Definitions:
     mhd: bool = False
     isothermal: bool = False
     order: int = 2          # Idefix_RECONSTRUCTION: 1 Constant, 2 Linear, 3 LimO3, 4 Parabolic
+    evolve_vector_potential: bool = False   # Idefix_EVOLVE_VECTOR_POTENTIAL (idefix.hpp:116-125)
 
     def __post_init__(self):
         if isinstance(self.geometry, str):

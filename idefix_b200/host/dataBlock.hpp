@@ -51,6 +51,8 @@ class Fluid {
  public:
   IdefixArray4D<real> Vc;      // primitive variables (nvar,k,j,i)
   IdefixArray4D<real> Vs;      // staggered field (ndim,k+1,j+1,i+1)
+  IdefixArray4D<real> Ve;      // edge-centred vector potential (only with EVOLVE_VECTOR_POTENTIAL)
+  std::vector<std::string> VeName;
   IdefixArray4D<real> Uc;      // conservative variables
   IdefixArray3D<real> InvDt;   // inverse time step accumulator
   std::vector<std::string> VcName, VsName;
@@ -128,6 +130,13 @@ class Fluid {
 #if MHD == YES
     for (int c = 0; c < COMPONENTS; c++) VcName.push_back("BX" + std::to_string(c + 1));
     for (int c = 0; c < DIMENSIONS; c++) VsName.push_back("BX" + std::to_string(c + 1) + "s");
+#ifdef EVOLVE_VECTOR_POTENTIAL
+#if DIMENSIONS < 3
+    VeName.push_back("AX3e");   // fluid.hpp:667-690
+#else
+    for (int c = 0; c < 3; c++) VeName.push_back("AX" + std::to_string(c + 1) + "e");
+#endif
+#endif
 #endif
     for (int n = 0; n < nTracer; n++) VcName.push_back("TR" + std::to_string(n));   // fluid.hpp:634
   }
@@ -226,6 +235,13 @@ class DataBlock {
     d.fixed_dt = fixedDt;
     d.ntracer = hydro->nTracer;
     d.shock_flattening = hydro->shockFlattening;
+#ifdef EVOLVE_VECTOR_POTENTIAL
+#if MHD == YES && DIMENSIONS >= 2
+    d.evolve_vector_potential = 1;
+#else
+    IDEFIX_ERROR("EVOLVE_VECTOR_POTENTIAL is not compatible with 1D MHD");   // fluid.hpp:549-551
+#endif
+#endif
     IDFX_CUDA(cudaSetDevice(input.device));
     IDFX_ABI(idfx_block_create(&d, &handle));
     // user kernels (idefix_for) run on the legacy default stream.  The library gets a BLOCKING stream of its
@@ -249,6 +265,10 @@ class DataBlock {
 #if MHD == YES
     IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_VS, &p, n));
     hydro->Vs = IdefixArray4D<real>(p, n[0], n[1], n[2], n[3]);
+#ifdef EVOLVE_VECTOR_POTENTIAL
+    IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_VE, &p, n));
+    hydro->Ve = IdefixArray4D<real>(p, n[0], n[1], n[2], n[3]);
+#endif
 #if DIMENSIONS >= 2
     hydro->emf = std::make_unique<ConstrainedTransport>();
     IDFX_ABI(idfx_field_info(handle, IDFX_FIELD_EZ, &p, n));
@@ -283,11 +303,12 @@ class DataBlock {
   void PushTime() { IDFX_ABI(idfx_set_time(handle, t, dt)); }
   void PullTime() { IDFX_ABI(idfx_get_time(handle, &t, &dt)); }
   void SetBoundaries() { IDFX_ABI(idfx_set_boundaries(handle, t)); }
+  // Vs = curl Ve when the vector potential is the evolved variable, a no-op otherwise (dataBlock.cpp:366-373)
+  void DeriveVectorPotential() { IDFX_ABI(idfx_derive_vector_potential(handle)); }
   void ResetStage() { hydro->ResetStage(); }
   void ConsToPrim() { hydro->ConvertConsToPrim(); }
   void PrimToCons() { hydro->ConvertPrimToCons(); }
   void EvolveStage() { hydro->EvolveStage(t, dt); }
-  void DeriveVectorPotential() {}
   void Validate() {
     if (CheckNan() > 0) IDEFIX_ERROR("DataBlock::Validate: the initial state contains NaNs");
   }

@@ -12,7 +12,7 @@ class DataBlockHost {
   IdefixHostArray3D<real> InvDt;
 #if MHD == YES
   IdefixHostArray4D<real> Vs;
-  IdefixHostArray4D<real> Ve;      // only with EVOLVE_VECTOR_POTENTIAL (outside the scope of this build)
+  IdefixHostArray4D<real> Ve;      // edge-centred vector potential, allocated with EVOLVE_VECTOR_POTENTIAL only
   IdefixHostArray3D<real> Ex1, Ex2, Ex3;   // corner EMFs
 #endif
   std::array<real, 3> xbeg{}, xend{};
@@ -48,6 +48,9 @@ class DataBlockHost {
     InvDt = IdefixHostArray3D<real>("DataBlockHost_InvDt", np_tot[KDIR], np_tot[JDIR], np_tot[IDIR]);
 #if MHD == YES
     Vs = IdefixHostArray4D<real>("DataBlockHost_Vs", h.Vs.extent(0), h.Vs.extent(1), h.Vs.extent(2), h.Vs.extent(3));
+#ifdef EVOLVE_VECTOR_POTENTIAL
+    Ve = IdefixHostArray4D<real>("DataBlockHost_Ve", h.Ve.extent(0), h.Ve.extent(1), h.Ve.extent(2), h.Ve.extent(3));
+#endif
     Ex1 = IdefixHostArray3D<real>("DataBlockHost_Ex1", np_tot[KDIR], np_tot[JDIR], np_tot[IDIR]);
     Ex2 = IdefixHostArray3D<real>("DataBlockHost_Ex2", np_tot[KDIR], np_tot[JDIR], np_tot[IDIR]);
     Ex3 = IdefixHostArray3D<real>("DataBlockHost_Ex3", np_tot[KDIR], np_tot[JDIR], np_tot[IDIR]);
@@ -64,6 +67,9 @@ class DataBlockHost {
     IDFX_ABI(idfx_upload(data->handle, IDFX_FIELD_UC, Uc.data()));
 #if MHD == YES
     IDFX_ABI(idfx_upload(data->handle, IDFX_FIELD_VS, Vs.data()));
+#ifdef EVOLVE_VECTOR_POTENTIAL
+    IDFX_ABI(idfx_upload(data->handle, IDFX_FIELD_VE, Ve.data()));
+#endif
 #if DIMENSIONS >= 2
     IDFX_ABI(idfx_upload(data->handle, IDFX_FIELD_EZ, Ex3.data()));
 #endif
@@ -83,6 +89,9 @@ class DataBlockHost {
     IDFX_ABI(idfx_download(data->handle, IDFX_FIELD_UC, Uc.data()));
 #if MHD == YES
     IDFX_ABI(idfx_download(data->handle, IDFX_FIELD_VS, Vs.data()));
+#ifdef EVOLVE_VECTOR_POTENTIAL
+    IDFX_ABI(idfx_download(data->handle, IDFX_FIELD_VE, Ve.data()));
+#endif
 #endif
   }
 

@@ -111,6 +111,18 @@ using real = double;
 #define BX1s 0
 #define BX2s 1
 #define BX3s 2
+// edge-centred variables (idefix.hpp:116-125)
+#ifdef EVOLVE_VECTOR_POTENTIAL
+#if DIMENSIONS < 3
+#define AX1e 250
+#define AX2e 251
+#define AX3e 0
+#else
+#define AX1e 0
+#define AX2e 1
+#define AX3e 2
+#endif
+#endif
 #define AX1e 0
 #define AX2e 1
 #define AX3e 2

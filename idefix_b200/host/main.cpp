@@ -24,7 +24,10 @@ int main(int argc, char **argv) {
     Tint.ShowConfig();
 
     if (input.restartRequested) {
-      if (input.forceInitRequested) mysetup.InitFlow(data);
+      if (input.forceInitRequested) {
+        mysetup.InitFlow(data);
+        data.DeriveVectorPotential();
+      }
       idfx::cout << "Main: Restarting from dump file." << std::endl;
       if (!output.RestartFromDump(data, input.restartFileNumber)) {
         idfx::cout << "Main: restart aborted." << std::endl;
@@ -36,6 +39,7 @@ int main(int argc, char **argv) {
     if (!input.restartRequested) {
       idfx::cout << "Main: Creating initial conditions." << std::endl;
       mysetup.InitFlow(data);
+      data.DeriveVectorPotential();   // does something only when the vector potential is evolved (main.cpp:174)
       data.SetBoundaries();
       data.Validate();
       output.CheckForWrites(data);

@@ -177,6 +177,18 @@ class Output {
                    {data.np_int[0] + o[0], data.np_int[1] + o[1], data.np_int[2] + o[2]}, buf.data());
       };
     }
+#ifdef EVOLVE_VECTOR_POTENTIAL
+    // edge-centred: one more point in every active direction perpendicular to the component (dump.cpp:921-930)
+    for (int n = 0; n < static_cast<int>(data.hydro->VeName.size()); n++) {
+      entries["Ve-" + data.hydro->VeName[n]] = [&, n]() {
+        const int dirn = (DIMENSIONS < 3) ? 2 : n;
+        const int o[3] = {dirn != 0 && DIMENSIONS >= 1, dirn != 1 && DIMENSIONS >= 2, dirn != 2 && DIMENSIONS >= 3};
+        std::vector<double> buf = Interior(d, [&](int k, int j, int i) { return d.Ve(n, k, j, i); }, o[0], o[1], o[2]);
+        WriteField(f, "Ve-" + data.hydro->VeName[n], 0,
+                   {data.np_int[0] + o[0], data.np_int[1] + o[1], data.np_int[2] + o[2]}, buf.data());
+      };
+    }
+#endif
 #endif
     auto scalarD = [&](const std::string &nm, double v) {
       entries[nm] = [&, nm, v]() { WriteField(f, nm, 0, {1}, &v); };
@@ -266,6 +278,24 @@ class Output {
                 d.Vc(v, k, j, i) = dv[c++];
               }
             }
+#ifdef EVOLVE_VECTOR_POTENTIAL
+      } else if (field.rfind("Ve-", 0) == 0) {
+        const auto &list = data.hydro->VeName;
+        const auto it = std::find(list.begin(), list.end(), field.substr(3));
+        if (it == list.end()) {
+          IDEFIX_WARNING("Dump: ignoring unknown field " + field);
+          continue;
+        }
+        const int v = static_cast<int>(it - list.begin());
+        const int dirn = (DIMENSIONS < 3) ? 2 : v;
+        const int o[3] = {dirn != 0 && DIMENSIONS >= 1, dirn != 1 && DIMENSIONS >= 2, dirn != 2 && DIMENSIONS >= 3};
+        if (dims[0] != data.np_int[0] + o[0] || dims[1] != data.np_int[1] + o[1] || dims[2] != data.np_int[2] + o[2])
+          IDEFIX_ERROR("Dump: the grid of the restart file does not match the current grid");
+        long long c = 0;
+        for (int k = data.beg[2]; k < data.end[2] + o[2]; k++)
+          for (int j = data.beg[1]; j < data.end[1] + o[1]; j++)
+            for (int i = data.beg[0]; i < data.end[0] + o[0]; i++) d.Ve(v, k, j, i) = dv[c++];
+#endif
       } else if (field == "time") d.t = dv[0];
       else if (field == "dt") d.dt = dv[0];
       else if (field == "vtkLast") vtkLast = dv[0];

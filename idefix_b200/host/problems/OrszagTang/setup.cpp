@@ -19,8 +19,14 @@ void Setup::InitFlow(DataBlock &data) {
         host.Vc(PRS, k, j, i) = prs0;
         host.Vc(VX1, k, j, i) = -sy;
         host.Vc(VX2, k, j, i) = sin(twoPi * xc);
+#ifdef EVOLVE_VECTOR_POTENTIAL
+        // A_z on the cell corners: the potential is the evolved variable, the code derives the face field from it
+        const real xf = host.xl[IDIR](i), yf = host.xl[JDIR](j);
+        host.Ve(AX3e, k, j, i) = B0 / (2.0 * M_PI) * (cos(2.0 * M_PI * yf) + cos(4.0 * M_PI * xf) / 2.0);
+#else
         host.Vs(BX1s, k, j, i) = -B0 * sy;
         host.Vs(BX2s, k, j, i) = B0 * sin(4.0 * M_PI * xc);
+#endif
       }
     }
   }

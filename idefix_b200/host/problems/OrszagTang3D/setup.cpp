@@ -31,9 +31,17 @@ void Setup::InitFlow(DataBlock &data) {
         A(IDIR, k, j, i) = amp * cyl;
         A(JDIR, k, j, i) = amp * sin(twoPi * xf);
         A(KDIR, k, j, i) = amp * (cyl + cos(4.0 * M_PI * xf) / 2.0);
+#ifdef EVOLVE_VECTOR_POTENTIAL
+        // the potential itself is the evolved variable: hand it over, the code derives the face field
+        host.Ve(AX1e, k, j, i) = A(IDIR, k, j, i);
+        host.Ve(AX2e, k, j, i) = A(JDIR, k, j, i);
+        host.Ve(AX3e, k, j, i) = A(KDIR, k, j, i);
+#endif
       }
     }
   }
+#ifndef EVOLVE_VECTOR_POTENTIAL
   host.MakeVsFromAmag(A);
+#endif
   host.SyncToDevice();
 }

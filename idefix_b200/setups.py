@@ -32,9 +32,11 @@ class Setup:
     defs = None
     ini = ""
 
-    def __init__(self, order=2, overrides=None, nproc=(1, 1, 1), xproc=(0, 0, 0), device=0, ini=None):
+    def __init__(self, order=2, overrides=None, nproc=(1, 1, 1), xproc=(0, 0, 0), device=0, ini=None,
+                 vector_potential=False):
         d = self.defs
-        self.definitions = Definitions(d.dimensions, d.components, d.geometry, d.mhd, d.isothermal, order)
+        self.definitions = Definitions(d.dimensions, d.components, d.geometry, d.mhd, d.isothermal, order,
+                                       bool(vector_potential) or d.evolve_vector_potential)
         self.input = Input.from_string(ini if ini is not None else self.ini)
         for (block, name), vals in (overrides or {}).items():
             if vals is None:
@@ -47,8 +49,9 @@ class Setup:
         self.tstop = self.input.Get(float, "TimeIntegrator", "tstop", 0)
 
     def initialise(self):
-        """main.cpp:159-177: InitFlow, then SetBoundaries"""
+        """main.cpp:159-177: InitFlow, DeriveVectorPotential, then SetBoundaries"""
         self.InitFlow(self.data)
+        self.data.DeriveVectorPotential()
         self.data.SetBoundaries()
         return self
 
@@ -151,9 +154,14 @@ X2-end    periodic
         d.Vc[3] = 5.0 / (12.0 * math.pi)
         d.Vc[1] = np.broadcast_to(-fsin(2.0 * math.pi * y), (n3, n2, n1))
         d.Vc[2] = np.broadcast_to(fsin(2.0 * math.pi * x), (n3, n2, n1))
-        # the loops of the reference stop at np_tot: the last face of each staggered array stays 0
-        d.Vs[0][:n3, :n2, :n1] = np.broadcast_to(-B0 * fsin(2.0 * math.pi * y), (n3, n2, n1))
-        d.Vs[1][:n3, :n2, :n1] = np.broadcast_to(B0 * fsin(4.0 * math.pi * x), (n3, n2, n1))
+        if data.defs.evolve_vector_potential:   # setup.cpp:41-45: A_z on the cell corners
+            xl = d.xl[0][None, None, :]
+            yl = d.xl[1][None, :, None]
+            d.Ve[0][:n3, :n2, :n1] = B0 / (2.0 * math.pi) * (fcos(2.0 * math.pi * yl) + fcos(4.0 * math.pi * xl) / 2.0)
+        else:
+            # the loops of the reference stop at np_tot: the last face of each staggered array stays 0
+            d.Vs[0][:n3, :n2, :n1] = np.broadcast_to(-B0 * fsin(2.0 * math.pi * y), (n3, n2, n1))
+            d.Vs[1][:n3, :n2, :n1] = np.broadcast_to(B0 * fsin(4.0 * math.pi * x), (n3, n2, n1))
         d.SyncToDevice()
 
 
@@ -205,7 +213,10 @@ X3-end    periodic
             d.Vc[trg] = np.broadcast_to(np.where(x > 0.5, 1.0, 0.0), shape)
             if data.hydro.nTracer > 1:
                 d.Vc[trg + 1] = np.broadcast_to(np.where(z > 0.5, 1.0, 0.0), shape)
-        d.MakeVsFromAmag(Ve)
+        if data.defs.evolve_vector_potential:   # setup.cpp:217-223: the potential itself is the evolved variable
+            d.Ve[...] = Ve
+        else:
+            d.MakeVsFromAmag(Ve)
         d.SyncToDevice()
 
 

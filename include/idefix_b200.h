@@ -42,7 +42,10 @@ enum IdfxField {
   IDFX_FIELD_EY = 5,
   IDFX_FIELD_EZ = 6,
   IDFX_FIELD_UC0 = 7,    /* states["begin"] copy of Uc                                  */
-  IDFX_FIELD_VS0 = 8     /* states["begin"] copy of Vs                                  */
+  IDFX_FIELD_VS0 = 8,    /* states["begin"] copy of Vs                                  */
+  IDFX_FIELD_VE = 9,     /* EVOLVE_VECTOR_POTENTIAL: edge-centred vector potential, laid out like Vs:
+                            (3, n3+o3, n2+o2, n1+1) = AX1e, AX2e, AX3e in 3-D, (1, ...) = AX3e in 2-D */
+  IDFX_FIELD_VE0 = 10    /* states["begin"] copy of Ve                                  */
 };
 
 /* Compile-time configuration of the reference (definitions.hpp macros and CMake
@@ -80,6 +83,9 @@ typedef struct IdfxBlockDesc {
   double shock_flattening; /* [Hydro] shockFlattening <smoothing> (riemannSolver.hpp:154-159, shockFlattening.hpp):
                           > 0 flags the cells of converging flow with |grad P| > smoothing * min(P) before the x1
                           sweep of every stage; PLM / LimO3 drop to the reference's MinMod there.  0 = off */
+  int evolve_vector_potential; /* EVOLVE_VECTOR_POTENTIAL (Idefix_EVOLVE_VECTOR_POTENTIAL, idefix.hpp:116-125): the
+                          evolved magnetic variable is the edge-centred vector potential Ve (Ve += -dt E), the face
+                          field is derived from it (Vs = curl Ve, evolveVectorPotential.hpp); needs MHD, DIMENSIONS >= 2 */
 } IdfxBlockDesc;
 
 typedef struct IdfxBlock IdfxBlock;
@@ -116,6 +122,9 @@ int idfx_state_copy(IdfxBlock *blk);                  /* StateContainer::CopyFro
 int idfx_state_add_and_store(IdfxBlock *blk, double wc, double w0);  /* stateContainer.cpp:75-104              */
 int idfx_evolve_stage(IdfxBlock *blk, double t, double dt);          /* Fluid::EvolveStage evolveStage.hpp:41-90 */
 int idfx_compute_timestep(IdfxBlock *blk, double *dt_min);           /* DataBlock::ComputeTimestep dataBlock.cpp:333-364 */
+/* DataBlock::DeriveVectorPotential (dataBlock.cpp:366-373): Vs = curl Ve; what main() calls after InitFlow when the
+ * vector potential is the evolved variable (main.cpp:141-174).  No-op otherwise. */
+int idfx_derive_vector_potential(IdfxBlock *blk);
 int idfx_check_divb(IdfxBlock *blk, double *divb_max);               /* Fluid::CheckDivB checkDivB.hpp:15-68     */
 int idfx_check_nan(IdfxBlock *blk, int *nan_count);                  /* Fluid::CheckNan  checkNan.hpp:15-131     */
 

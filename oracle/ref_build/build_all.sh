@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")"
 J=${J:-8}
-b() { [ -x ../_ref/$1/idefix ] || make -s -j$J NAME=$1 SETUP=$2 MHD=$3 ORDER=$4 LOOP=$5; }
+b() { [ -x ../_ref/$1/idefix ] || make -s -j$J NAME=$1 SETUP=$2 MHD=$3 ORDER=$4 LOOP=$5 VP=$6; }
 make -s -j$J kokkos
 # core set: the CPU baseline of bench.py (ot3d_plm) and the smoke / headline parity cases
 b ot3d_plm     test/MHD/OrszagTang3D      YES 2
@@ -18,6 +18,9 @@ b lw_limo3     test/MHD/LinearWaveTest    YES 3
 b ot2d_limo3   test/MHD/OrszagTang        YES 3 TPX
 b ot2d_ppm     test/MHD/OrszagTang        YES 4 TPX
 b mhdsod_plm   test/MHD/sod               YES 2
+# EVOLVE_VECTOR_POTENTIAL builds (the reference's own OrszagTang set-ups carry the #ifdef branches)
+b ot2d_plm_vp  test/MHD/OrszagTang        YES 2 TPX 1
+b ot3d_plm_vp  test/MHD/OrszagTang3D      YES 2 "" 1
 b sod_limo3    test/HD/sod                NO  3
 b sod_ppm      test/HD/sod                NO  4
 P=$(cd ../../idefix_b200/host/problems && pwd)

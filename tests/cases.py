@@ -85,6 +85,12 @@ SHORT = [
           {**_ot2d(64, "hlld", "uct_hlld"), ("Hydro", "shockFlattening"): "0.0005"}, (1, 10)),
     Short("ot3d_hlld_contact_plm_flat_rk3", "ot3d", 2, "ot3d_plm",
           {**_ot3d(16, 32, 16, nstages=3), ("Hydro", "shockFlattening"): "0.001"}, (1, 10)),
+    # EVOLVE_VECTOR_POTENTIAL (evolveVectorPotential.hpp): reference binaries built with -DEVOLVE_VECTOR_POTENTIAL
+    # (ref name ending in _vp <=> the set-up is created with vector_potential=True)
+    Short("ot2d_hlld_ucthlld_plm_vp", "ot2d", 2, "ot2d_plm_vp", _ot2d(64, "hlld", "uct_hlld"), (1, 10)),
+    Short("ot2d_roe_contact_plm_rk3_vp", "ot2d", 2, "ot2d_plm_vp", _ot2d(64, "roe", "uct_contact", 3), (1, 10)),
+    Short("ot3d_hlld_contact_plm_vp", "ot3d", 2, "ot3d_plm_vp", _ot3d(16, 32, 16), (1, 10)),
+    Short("ot3d_hll_uct0_plm_rk3_vp", "ot3d", 2, "ot3d_plm_vp", _ot3d(16, 32, 16, solver="hll", emf="uct0", nstages=3), (1, 10)),
     # C3 physics: linear waves, HLLD + PPM + RK3 has no shipped golden -> reference binary
     Short("lw_fast_hlld_ppm_rk3", "linearwave", 4, "lw_ppm", _lw(32, 16, 16, "hlld", 3, 1), (1, 10)),
     Short("lw_alfven_roe_limo3", "linearwave", 3, "lw_limo3", _lw(32, 16, 16, "roe", 2, 2), (1, 10)),
@@ -185,6 +191,12 @@ FULL = [
     # the same shipped golden with the two tracers of the stock ini switched on: Vc-TR0 / Vc-TR1 are compared too
     Full("ot3d_hlld_contact_tracers", "ot3d", 2, {**_ot3d(32, 64, 32), ("Hydro", "tracer"): "2"},
          "MHD/OrszagTang3D/dump.ref.double.plm.idefix.ini.dmp", 1e-13),
+    # the reference's shipped vector-potential goldens (testme.py of test/MHD/OrszagTang with -vectPot)
+    Full("ot2d_hlld_hlld_vp", "ot2d_vp", 2, _ot2d(128, "hlld", "uct_hlld"),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld-hlld.ini.vectPot.dmp", 1e-12),
+    Full("ot2d_hlld_contact_vp", "ot2d_vp", 2, _ot2d(128, "hlld", None),
+         "MHD/OrszagTang/dump.ref.double.plm.idefix-hlld.ini.vectPot.dmp", 1e-12),
+    Full("ot2d_roe_vp", "ot2d_vp", 2, _ot2d(128, "roe", None), "MHD/OrszagTang/dump.ref.double.plm.idefix.ini.vectPot.dmp", 1e-12),
     Full("lw_fast_roe_plm", "linearwave", 2, _lw(64, 32, 32, "roe", 2, 1),
          "MHD/LinearWaveTest/dump.ref.double.plm.idefix-fast.ini.dmp", 1e-14),
     Full("lw_alfven_roe_ppm", "linearwave", 4, {**_lw(64, 32, 32, "roe", 3, 2), ("TimeIntegrator", "tstop"): "1.0"},
@@ -246,7 +258,8 @@ def ini_for(case, dump_every_cycle=False):
             inp.remove("Output", name)
     else:
         from idefix_b200.setups import REGISTRY
-        inp = Input.from_string(REGISTRY[case.setup].ini)
+        name = case.setup[:-3] if case.setup.endswith("_vp") else case.setup   # *_vp: the same set-up, vector potential
+        inp = Input.from_string(REGISTRY[name].ini)
     for (block, name), vals in case.overrides.items():
         if vals is None:
             inp.remove(block, name)

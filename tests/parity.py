@@ -10,8 +10,16 @@ from idefix_b200.timeintegrator import run
 REL_L1_TOL = 1e-12
 
 
+def wants_vector_potential(case):
+    """EVOLVE_VECTOR_POTENTIAL cases: SHORT cases name a reference binary built with the define (`*_vp`), FULL cases
+    a set-up `*_vp`"""
+    return getattr(case, "ref", "").endswith("_vp") or case.setup.endswith("_vp")
+
+
 def make(case, **kw):
-    return REGISTRY[case.setup](order=case.order, overrides=case.overrides, **kw).initialise()
+    name = case.setup[:-3] if case.setup.endswith("_vp") else case.setup
+    return REGISTRY[name](order=case.order, overrides=case.overrides, vector_potential=wants_vector_potential(case),
+                          **kw).initialise()
 
 
 def fields_of(setup):
@@ -28,6 +36,14 @@ def fields_of(setup):
         for dd in range(setup.definitions.dimensions):
             o = [1 if e == dd else 0 for e in range(3)]
             out[f"Vs-BX{dd + 1}s"] = Vs[dd, kb:ke + o[2], jb:je + o[1], ib:ie + o[0]].transpose(2, 1, 0)
+        if getattr(setup.definitions, "evolve_vector_potential", False):
+            # edge-centred: one more point in the active directions perpendicular to the component (dump.cpp:921-930)
+            Ve = d.download(_abi.FIELD_VE)
+            nd = setup.definitions.dimensions
+            comps = [(0, "AX1e", 0), (1, "AX2e", 1), (2, "AX3e", 2)] if nd == 3 else [(0, "AX3e", 2)]
+            for n, name, dirn in comps:
+                o = [1 if (e != dirn and e < nd) else 0 for e in range(3)]
+                out[f"Ve-{name}"] = Ve[n, kb:ke + o[2], jb:je + o[1], ib:ie + o[0]].transpose(2, 1, 0)
     return out
 
 

@@ -29,11 +29,11 @@ PROBLEMS = {"sod": ("sod", "NO"), "ot2d": ("OrszagTang", "YES"), "ot3d": ("Orsza
             "polarhd": ("PolarHD2D", "NO"), "sodstrong": ("sodStrong", "NO"), "othooks": ("otHooks", "YES")}
 
 
-def build(problem, order, tmp_path_factory):
+def build(problem, order, tmp_path_factory, vp=False):
     pdir, mhd = PROBLEMS[problem]
-    out = tmp_path_factory.mktemp(f"{problem}_o{order}") / "idefix"
+    out = tmp_path_factory.mktemp(f"{problem}_o{order}{'_vp' if vp else ''}") / "idefix"
     cmd = ["make", "-s", "-C", HOST, f"PROBLEM={os.path.join(HOST, 'problems', pdir)}", f"MHD={mhd}",
-           f"ORDER={order}", f"OUT={out}"]
+           f"ORDER={order}", f"OUT={out}"] + (["VP=1"] if vp else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     return str(out)
@@ -42,10 +42,10 @@ def build(problem, order, tmp_path_factory):
 _built = {}
 
 
-def binary(problem, order, tmp_path_factory):
-    key = (problem, order)
+def binary(problem, order, tmp_path_factory, vp=False):
+    key = (problem, order, vp)
     if key not in _built:
-        _built[key] = build(problem, order, tmp_path_factory)
+        _built[key] = build(problem, order, tmp_path_factory, vp)
     return _built[key]
 
 
@@ -112,6 +112,29 @@ def test_cpp_host_dumps_equal_reference_dumps(case, tmp_path_factory, tmp_path):
         gold = readDump(os.path.join(ROOT, "tests", "golden", "short", f"{case.name}.c{n:04d}.dmp"))
         assert_same_fields(mine, gold)
         assert float(mine.data["time"][0]) == float(gold.data["time"][0])
+
+
+VP_CASES = [c for c in SHORT if c.ref.endswith("_vp")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", VP_CASES, ids=[c.name for c in VP_CASES])
+def test_cpp_host_vector_potential_dumps_equal_reference_dumps(case, tmp_path_factory, tmp_path):
+    """EVOLVE_VECTOR_POTENTIAL through the C++ host (make VP=1): the problem set-ups carry the reference's own
+    #ifdef EVOLVE_VECTOR_POTENTIAL branch (d.Ve(AX3e, ...)); dumps incl. the Ve-AX?e fields equal the dumps of a
+    reference build with -DEVOLVE_VECTOR_POTENTIAL"""
+    assert len(VP_CASES) >= 4
+    exe = binary(case.setup, case.order, tmp_path_factory, vp=True)
+    ncyc = max(case.cycles)
+    run_idefix(exe, str(tmp_path), ini_for(case, dump_every_cycle=True), "-maxcycles", str(ncyc))
+    for n in (0,) + tuple(case.cycles):
+        mine = readDump(os.path.join(tmp_path, f"dump.{n:04d}.dmp"))
+        gold = readDump(os.path.join(ROOT, "tests", "golden", "short", f"{case.name}.c{n:04d}.dmp"))
+        assert any(k.startswith("Ve-") for k in gold.data)
+        for name, ref in gold.data.items():
+            if name.startswith(("Vc-", "Vs-", "Ve-")):
+                assert name in mine.data, name
+                assert np.array_equal(np.asarray(mine.data[name]), np.asarray(ref)), name
 
 
 @pytest.mark.gpu

@@ -23,6 +23,8 @@ def in_scope(case):
     emf = case.overrides.get(("Hydro", "emf"))
     if case.order not in (2, 3, 4) or solver not in ORACLE_SOLVERS:
         return False
+    if getattr(case, "ref", "").endswith("_vp") or case.setup.endswith("_vp"):
+        return False   # EVOLVE_VECTOR_POTENTIAL: pinned on the reference's own builds directly, not restated
     return emf in (None, "arithmetic", "uct0", "uct_contact", "uct_hll", "uct_hlld")
 
 
