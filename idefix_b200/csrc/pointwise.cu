@@ -229,8 +229,25 @@ __global__ void stageEpilogueKernel(DevGrid g, double *__restrict__ Vc, double *
     if (invDt != nullptr) dtCell = 1.0 / invDt[c];
   }
   if (invDt != nullptr) {
+#ifndef IDFX_DT_CTA
+    // Few cells lower the running minimum.  Every warp compares its cells with a cached copy of it -- possibly
+    // stale, hence larger, because the minimum only decreases: a stale copy costs a superfluous atomic, never a
+    // missed one -- and only warps that hold a lower value reduce and go to the atomic.  No barrier: a
+    // __syncthreads() here keeps whole CTAs of this streaming kernel resident until their slowest load returns.
+    // (One unconditional atomic per warp on a single address serialises in L2: measured +5 ms at 512^3.)
+    const unsigned long long mine = (dtCell >= 0.0) ? (unsigned long long)__double_as_longlong(dtCell) : ~0ull;
+    const unsigned long long seen = *dtMinBits;
+    if (__any_sync(0xffffffffu, mine < seen)) {
+      unsigned long long m = mine;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+        m = other < m ? other : m;
+      }
+      if ((threadIdx.x & 31) == 0) atomicMin(dtMinBits, m);
+    }
+#else
     // warp shuffles, one shared-memory step per CTA, and an atomic only from CTAs that lower the running minimum
-    // (one atomic per warp on a single address would serialise in L2: measured +5 ms at 512^3)
     __shared__ double warpMins[TB / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dtCell = fmin(dtCell, __shfl_xor_sync(0xffffffffu, dtCell, o));
@@ -245,6 +262,7 @@ __global__ void stageEpilogueKernel(DevGrid g, double *__restrict__ Vc, double *
         if (bits < *reinterpret_cast<volatile unsigned long long *>(dtMinBits)) atomicMin(dtMinBits, bits);
       }
     }
+#endif
   }
 }
 

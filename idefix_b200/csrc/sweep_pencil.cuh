@@ -164,7 +164,9 @@ constexpr size_t pencilMarchSmem(int TX, int chunk) {
                            + (IDFX_TMEM ? 2 : 0));                          // TMEM base address slot
 }
 
-template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART>
+// FLAT: the block has shock flattening on (a.shockFlags set).  A compile-time switch here, unlike in the x1 kernel:
+// testing the flag per step costs the marches 5 % (measured, profiles/r2_ab_experiments.md) even when it is off.
+template <class P, int SOLVER, int ORDER, int DIR, int TX, bool CART, bool FLAT>
 __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencilMarchKernel(const SweepArgs a, const int chunk) {
   static_assert(DIR == JDIR || DIR == KDIR, "the marching kernel sweeps along x2 or x3");
   constexpr int NV = P::nvar;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
       const bool positive = (nv == P::RHO) || (P::energy && nv == P::PRS);
       double vl, vr;
       reconstructCell<ORDER>(st, positive, regular, wc, dxc, vl, vr);
-      if (a.shockFlags != nullptr) pencil::flattenCell<ORDER>(a.shockFlags[cell0 + (long long)(mb - 1) * stride] != 0, st[2], vl, vr);
+      if constexpr (FLAT) pencil::flattenCell<ORDER>(a.shockFlags[cell0 + (long long)(mb - 1) * stride] != 0, st[2], vl, vr);
 #if IDFX_TMEM
       __syncwarp();
       tmem::store1(tbase + T_VLS + 2 * nv, vr);
@@ -343,7 +345,8 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
         if (s >= W) s -= W;
         so[d + H] = s * NV * TX;
       }
-      const bool flat = (a.shockFlags != nullptr) && (a.shockFlags[cellm] != 0);
+      bool flat = false;
+      if constexpr (FLAT) flat = a.shockFlags[cellm] != 0;
 #if IDFX_TMEM
       // left state = right-face values of cell m-1, parked in tensor memory one step ago
       tmem::Pending1 vlp[NV];
@@ -463,8 +466,11 @@ __global__ void __launch_bounds__(TX, (ORDER == 4 ? 2 : IDFX_MARCH_MINB)) pencil
 #endif
 }
 
-template <class P, int SOLVER, int ORDER, int DIR, bool CART>
+template <class P, int SOLVER, int ORDER, int DIR, bool CART, bool FLAT = false>
 inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
+  if constexpr (!FLAT && (ORDER == 2 || ORDER == 3)) {   // PPM and first order ignore the flags (flattenCell)
+    if (a.shockFlags != nullptr) return launchPencilMarch<P, SOLVER, ORDER, DIR, CART, true>(a, stream);
+  }
   constexpr int TX = 128;
   const DevGrid &g = a.g;
   constexpr int PDIR = (DIR == JDIR) ? KDIR : JDIR;
@@ -480,7 +486,7 @@ inline cudaError_t launchPencilMarch(const SweepArgs &a, cudaStream_t stream) {
   const dim3 grid((unsigned)ctasPerLayer, (unsigned)((nsweep + chunk - 1) / chunk), 1);
   const size_t smem = pencilMarchSmem<P, ORDER, CART>(TX, 64);
   static unsigned long long configured = 0;   // bit d: attribute set on device d
-  auto kern = pencilMarchKernel<P, SOLVER, ORDER, DIR, TX, CART>;
+  auto kern = pencilMarchKernel<P, SOLVER, ORDER, DIR, TX, CART, FLAT>;
   if (cudaError_t e = pencil::ensureDynamicSmem(kern, smem, configured); e != cudaSuccess) return e;
   kern<<<grid, TX, pencilMarchSmem<P, ORDER, CART>(TX, chunk), stream>>>(a, chunk);
   return cudaGetLastError();

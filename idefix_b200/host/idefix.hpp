@@ -123,9 +123,6 @@ using real = double;
 #define AX3e 2
 #endif
 #endif
-#define AX1e 0
-#define AX2e 1
-#define AX3e 2
 
 #if DIMENSIONS == 1
 #define IOFFSET 1
