@@ -97,6 +97,8 @@ struct IdfxBlock {
   cudaGraphExec_t cycleGraph = nullptr;
   long long cycleGraphLaunches = 0;
   bool useGraph = true;
+  // polar axis (axis.hpp:52-56): sides of x2 that lie on it, and whether x3 covers the full circle
+  bool haveAxis = false, axisLeft = false, axisRight = false, axisTwoPi = false;
   bool vcFieldFresh = false;   // active cells of Vc(BXn) equal the face average of Vs (set by the fused stage epilogue)
   // overlap of the ghost-zone work with the update of the interior (fused path): the boundary conditions / halo
   // exchange of the NEXT stage run on a side stream as soon as the cells they read (the shell: active cells within
@@ -365,8 +367,14 @@ int validate(const IdfxBlockDesc &d) {
     if (d.np_int[dir] < 1) return fail("np_int must be >= 1");
     const int lb = d.lbound[dir], rb = d.rbound[dir];
     for (int t : {lb, rb}) {
-      if (t == IDFX_BC_SHEARINGBOX || t == IDFX_BC_AXIS)
-        return fail("shearingbox / axis boundaries are outside the scope of this build");
+      if (t == IDFX_BC_SHEARINGBOX) return fail("shearingbox boundaries are outside the scope of this build");
+      if (t == IDFX_BC_AXIS) {
+        if (dir != 1) return fail("Axis Boundaries are only applicable to X2");   // grid.cpp:98-101
+        if (d.geometry != IDFX_SPHERICAL)
+          return fail("Axis boundary conditions are only designed to handle spherical geometry");   // axis.hpp:112-114
+        if (d.ndim == 3 && (d.lbound[2] == IDFX_BC_INTERNAL || d.rbound[2] == IDFX_BC_INTERNAL))
+          return fail("axis boundaries with a domain decomposition along X3 are outside the scope of this build");
+      }
       if (t < 0 || t >= IDFX_BC_UNDEFINED) return fail("undefined boundary condition");
     }
   }
@@ -506,6 +514,9 @@ int enforceBoundaryDirImpl(IdfxBlock *b, int dir, double t, bool tKnown) {
         case IDFX_BC_OUTFLOW:
           KTRY(idfxk::enforcePhysicalBoundary(b->cfg, b->g, b->Vc, b->Vs, dir, side, BC_OUTFLOW, b->stream, &b->launches));
           break;
+        case IDFX_BC_AXIS:   // boundary.hpp:313-314,359-360
+          KTRY(idfxk::enforceAxisBoundary(b->cfg, b->g, b->Vc, b->Vs, side, b->axisTwoPi ? 1 : 0, b->stream, &b->launches));
+          break;
         case IDFX_BC_USERDEF: {
           if (!b->userBc)
             return fail("No function has been enrolled to define your own boundary conditions");
@@ -526,7 +537,13 @@ int enforceBoundaryDirImpl(IdfxBlock *b, int dir, double t, bool tKnown) {
     if (b->cfg.mhd) {
       const int left = !(d.lbound[dir] == IDFX_BC_PERIODIC || d.lbound[dir] == IDFX_BC_INTERNAL);
       const int right = !(d.rbound[dir] == IDFX_BC_PERIODIC || d.rbound[dir] == IDFX_BC_INTERNAL);
-      KTRY(idfxk::reconstructNormalField(b->cfg, b->g, b->Vs, dir, left, right, b->stream, &b->launches));
+      // across an axis the phi direction is reversed (boundary.hpp:471-474, 3-D only)
+      const int signLeft = (dir == 1 && d.ndim == 3 && b->axisLeft) ? -1 : 1;
+      const int signRight = (dir == 1 && d.ndim == 3 && b->axisRight) ? -1 : 1;
+      KTRY(idfxk::reconstructNormalField(b->cfg, b->g, b->Vs, dir, left, right, b->stream, &b->launches, signLeft, signRight));
+      if (dir == 1 && b->haveAxis)   // boundary.hpp:496-499
+        KTRY(idfxk::axisRegularizeBx2s(b->g, b->Vs, b->axisTwoPi ? 1 : 0, b->axisLeft ? 1 : 0, b->axisRight ? 1 : 0, b->stream,
+                                       &b->launches));
     }
   }
   return 0;
@@ -591,6 +608,9 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
 #endif
     // EnforceEMFBoundary (enforceEMFBoundary.hpp:29-30); granular callers passed the stage time to idfx_evolve_stage
     if (callStageHook(b, IDFX_HOOK_EMF_BOUNDARY, b->stageTime, b->stageTimeKnown)) return 1;
+    if (b->haveAxis)   // enforceEMFBoundary.hpp:32-34
+      KTRY(idfxk::axisRegularizeEmf(b->g, b->emf.ex, b->emf.ez, b->axisTwoPi ? 1 : 0, b->axisLeft ? 1 : 0,
+                                    b->axisRight ? 1 : 0, b->stream, &b->launches));
     int mode = 0;
     double wc = 0, w0 = 0;
     if (fused && multi) {
@@ -605,9 +625,10 @@ int evolveStageImpl(IdfxBlock *b, int fusedStage) {
       // Runge-Kutta combination of Ve (StateContainer::AddAndStore) is folded into the first kernel, so the Vs derived
       // here is already the one ConvertConsToPrim would derive after the combination
       KTRY(idfxk::evolveVectorPotential(b->g, b->emf, b->Ve, b->Ve0, b->state + 1, mode, wc, w0, b->stream, &b->launches));
-      KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));
+      KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, b->haveAxis ? 1 : 0, b->stream, &b->launches));
     } else {
-      KTRY(idfxk::evolveMagField(b->g, b->emf, b->Vs, b->Vs0, b->state + 1, 0, mode, wc, w0, b->stream, &b->launches));
+      KTRY(idfxk::evolveMagField(b->g, b->emf, b->Vs, b->Vs0, b->state + 1, b->haveAxis ? 1 : 0, mode, wc, w0, b->stream,
+                                 &b->launches));
     }
     if (!fused) {
       if (reconstructVc(b, b->Uc)) return 1;
@@ -681,7 +702,7 @@ int cycleReferenceOrder(IdfxBlock *b) {
         b->launches++;
       }
     }
-    if (b->Ve) KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));   // convertConsToPrim.hpp:117-119
+    if (b->Ve) KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, b->haveAxis ? 1 : 0, b->stream, &b->launches));   // convertConsToPrim.hpp:117-119
     if (reconstructVc(b, b->Uc)) return 1;
     KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, d.gamma, b->stream));
     b->launches++;
@@ -722,7 +743,7 @@ int epilogueAndGhosts(IdfxBlock *b, int stage, double wc, double w0, int keepUc,
   // and running them beside the bandwidth-bound epilogue (plus the six thin shell launches) costs slightly more than
   // it hides (measured, profiles/r2_overlap_ab.md).  IDFX_OVERLAP=1 forces it on.
   const bool multi = b->nproc[0] * b->nproc[1] * b->nproc[2] > 1;
-  bool haveCore = b->overlap && (multi || b->forceOverlap) && b->cfg.ntr == 0 && !b->userBc && !b->haloFn &&
+  bool haveCore = b->overlap && (multi || b->forceOverlap) && b->cfg.ntr == 0 && !b->userBc && !b->haloFn && !b->haveAxis &&
                   !b->stageHook[0] && !b->stageHook[1];
   for (int a = 0; a < 3; a++) {
     const int w = (a < d.ndim) ? g.ng[a] : 0;
@@ -808,7 +829,8 @@ int cycleFused(IdfxBlock *b, bool lastOfBatch) {
       KTRY(idfxk::tracerConsToPrim(b->cfg, b->g, b->Vc, b->Uc, b->Uc0, stage > 0 ? 1 : 0, wc, w0, 1, b->stream));
       b->launches++;
     }
-    b->vcFieldFresh = !b->userBc;   // a user boundary function may write anywhere
+    // a user boundary function may write anywhere; the axis regularisation rewrites B_theta on an ACTIVE face
+    b->vcFieldFresh = !b->userBc && !b->haveAxis;
   }
   KTRY(idfxk::dtControlEnd(b->state, b->redBits, d.cfl, d.cfl_max_var, d.fixed_dt, b->ncyclesDev, b->statusDev,
                            b->mathFlag, b->stream));
@@ -894,6 +916,14 @@ int idfx_block_create(const IdfxBlockDesc *desc, IdfxBlock **out) {
     b->desc.dx[dir] = b->hostCoords[dir * 4 + 3].data();
   }
   setupPhys(b);
+  // Axis::Axis (axis.hpp:116-136): which sides of x2 lie on the polar axis, and whether x3 goes all the way round
+  b->axisLeft = desc->ndim >= 2 && desc->lbound[1] == IDFX_BC_AXIS;
+  b->axisRight = desc->ndim >= 2 && desc->rbound[1] == IDFX_BC_AXIS;
+  b->haveAxis = b->axisLeft || b->axisRight;
+  if (b->haveAxis) {
+    const int kb = desc->nghost[2], ke = desc->nghost[2] + desc->np_int[2];
+    b->axisTwoPi = std::fabs(b->desc.xr[2][ke - 1] - b->desc.xl[2][kb] - 2.0 * M_PI) < 1e-10;
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   if (std::getenv("IDFX_NO_GRAPH")) b->useGraph = false;   // A/B switch: always launch the cycle kernel by kernel
   if (std::getenv("IDFX_NO_OVERLAP")) b->overlap = false;  // A/B switch: boundaries strictly before the sweeps
@@ -1193,13 +1223,13 @@ int idfx_derive_vector_potential(IdfxBlock *b) {
   cudaSetDevice(b->desc.device);
   if (!b->Ve) return 0;
   b->vcFieldFresh = false;
-  KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));
+  KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, b->haveAxis ? 1 : 0, b->stream, &b->launches));
   return 0;
 }
 
 int idfx_cons_to_prim(IdfxBlock *b) {
   cudaSetDevice(b->desc.device);   // one process may drive blocks on several devices
-  if (b->Ve) KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, 0, b->stream, &b->launches));   // convertConsToPrim.hpp:117-119
+  if (b->Ve) KTRY(idfxk::magFieldFromA(b->g, b->Ve, b->Vs, b->haveAxis ? 1 : 0, b->stream, &b->launches));   // convertConsToPrim.hpp:117-119
   if (reconstructVc(b, b->Uc)) return 1;
   KTRY(idfxk::consToPrim(b->cfg, b->g, b->Vc, b->Uc, b->desc.gamma, b->stream));
   b->launches++;

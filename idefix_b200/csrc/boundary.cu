@@ -162,6 +162,65 @@ __global__ void reconstructNormalKernel(DevGrid g, double *__restrict__ Vs, int 
   }
 }
 
+// ---- polar axis of spherical grids (src/fluid/boundary/axis.cpp) ---------------------------------------------
+// Axis::EnforceAxisBoundary (axis.cpp:279-357): ghost cells across the axis come from the opposite meridian (full
+// 2 pi: k shifted by half the active cells) or from the same one (a fraction of 2 pi), mirrored in theta, with the
+// sign of the theta / phi components flipped (symmetryVc / symmetryVs, axis.hpp:128-162).
+__global__ void axisFillKernel(double *__restrict__ q, long long sj, long long sk, long long sn, Box b, int nvars,
+                               int jref, int offset, int signMask, int twoPi, int ngk, int nkint) {
+  const int i = b.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = b.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  const int nk = b.hi[2] - b.lo[2];
+  const int k = b.lo[2] + (int)(blockIdx.z % nk);
+  const int n = (int)(blockIdx.z / nk);
+  if (i >= b.hi[0] || j >= b.hi[1] || n >= nvars) return;
+  const int kcomp = twoPi ? ngk + ((k - ngk + nkint / 2) % nkint) : k;
+  const long long dst = n * sn + (long long)k * sk + (long long)j * sj + i;
+  const long long src = n * sn + (long long)kcomp * sk + (long long)(2 * jref - j + offset) * sj + i;
+  const double v = q[src];
+  q[dst] = ((signMask >> n) & 1) ? -1.0 * v : 1.0 * v;
+}
+
+// Axis::RegularizeBX2s (axis.cpp:362-395).  Full 2 pi: the reference is built with
+// AXIS_BX2S_USE_ATHENA_REGULARISATION (axis.hpp:21), i.e. FixBx2sAxisGhostAverage (axis.cpp:244-272): the value on
+// the axis is the mean of its two neighbours in theta, 3-D only, active k.  A fraction of 2 pi: zero on the axis.
+__global__ void axisBx2sKernel(DevGrid g, double *__restrict__ Vs, int twoPi, int left, int right) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.nx[0] || k >= g.nx[2]) return;
+  double *B2 = Vs + g.vsn;
+  for (int side = 0; side < 2; side++) {
+    if (!(side == 0 ? left : right)) continue;
+    const int jaxis = side == 0 ? g.beg[1] : g.end[1];
+    if (twoPi) {
+      if (g.ndim == 3 && k >= g.beg[2] && k < g.end[2])
+        B2[sidx(g, k, jaxis, i)] = 0.5 * (B2[sidx(g, k, jaxis - 1, i)] + B2[sidx(g, k, jaxis + 1, i)]);
+    } else {
+      B2[sidx(g, k, jaxis, i)] = 0.0;
+    }
+  }
+}
+
+// Axis::RegularizeEMFs (axis.cpp:26-84,160-177) on one side: the radial EMF on the axis is its mean around the pole
+// (full 2 pi, 3-D) or zero (fraction of 2 pi), the azimuthal EMF on the axis is zero.  One thread per radial index
+// adds the active k in ascending order, which is the order of the reference's atomic accumulation when it runs on
+// one thread (measured: descending or pairwise orders differ from it in the last bit; with several OpenMP threads
+// the reference itself is not reproducible here).
+__global__ void axisEmfKernel(DevGrid g, double *__restrict__ ex, double *__restrict__ ez, int jref, int twoPi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nx[0]) return;
+  if (g.ndim == 3) {
+    double value = 0.0;
+    if (twoPi) {
+      double sum = 0.0;
+      for (int k = g.beg[2]; k < g.end[2]; k++) sum += ex[cidx(g, k, jref, i)];
+      value = sum / ((double)(g.end[2] - g.beg[2]));
+    }
+    for (int k = 0; k < g.nx[2]; k++) ex[cidx(g, k, jref, i)] = value;
+  }
+  for (int k = 0; k < g.nx[2]; k++) ez[cidx(g, k, jref, i)] = 0.0;
+}
+
 // ---- halo pack / unpack ----------------------------------------------------------------------
 struct VarList {
   int n;
@@ -520,13 +579,65 @@ int idfxk::enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *V
 }
 
 int idfxk::reconstructNormalField(const PhysCfg &c, const DevGrid &g, double *Vs, int dir, int left, int right,
-                                  cudaStream_t st, long long *launches) {
+                                  cudaStream_t st, long long *launches, int signLeft, int signRight) {
   if (!c.mhd || (!left && !right)) return 0;
   const int p0 = (dir == 0) ? 1 : 0;
   const int p1 = (dir == 2) ? 1 : 2;
   const dim3 block(32, 4, 1);
   const dim3 grid((g.nx[p0] + 31) / 32, (g.nx[p1] + 3) / 4, 1);
-  reconstructNormalKernel<<<grid, block, 0, st>>>(g, Vs, dir, left, right, 1, 1);
+  reconstructNormalKernel<<<grid, block, 0, st>>>(g, Vs, dir, left, right, signLeft, signRight);
   (*launches)++;
+  return (int)cudaGetLastError();
+}
+
+// Axis::EnforceAxisBoundary for one side of x2
+int idfxk::enforceAxisBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int side, int twoPi,
+                               cudaStream_t st, long long *launches) {
+  const int jref = side == 0 ? g.beg[1] : g.end[1] - 1;
+  const int offset = side == 0 ? -1 : 1;
+  const int ngk = g.ng[2], nkint = g.end[2] - g.beg[2];
+  {
+    const Box b = ghostSlab(g, 1, side, -1);
+    int signMask = 0;   // VX2, VX3, BX2, BX3 change sign across the axis (axis.hpp:133-144); tracers do not
+    if (c.ncomp >= 2) signMask |= 1 << (c.MX1 + 1);
+    if (c.ncomp >= 3) signMask |= 1 << (c.MX1 + 2);
+    if (c.mhd && c.ncomp >= 2) signMask |= 1 << (c.BX1 + 1);
+    if (c.mhd && c.ncomp >= 3) signMask |= 1 << (c.BX1 + 2);
+    const int nall = c.nvar + c.ntr;
+    const dim3 blk = slabBlock(b);
+    axisFillKernel<<<boxGrid(b, nall, blk), blk, 0, st>>>(Vc, g.sj, g.sk, g.sn, b, nall, jref, offset, signMask, twoPi,
+                                                          ngk, nkint);
+    (*launches)++;
+  }
+  if (c.mhd) {
+    for (int comp = 0; comp < g.ndim; comp++) {
+      if (comp == 1) continue;   // the normal component is reconstructed from div B = 0 (axis.cpp:335)
+      const Box b = ghostSlab(g, 1, side, comp);
+      const dim3 blk = slabBlock(b);
+      axisFillKernel<<<boxGrid(b, 1, blk), blk, 0, st>>>(Vs + comp * g.vsn, g.vsj, g.vsk, 0, b, 1, jref, offset,
+                                                         comp == 0 ? 0 : 1, twoPi, ngk, nkint);
+      (*launches)++;
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+int idfxk::axisRegularizeBx2s(const DevGrid &g, double *Vs, int twoPi, int left, int right, cudaStream_t st,
+                              long long *launches) {
+  const dim3 block(32, 4, 1);
+  const dim3 grid((g.nx[0] + 31) / 32, (g.nx[2] + 3) / 4, 1);
+  axisBx2sKernel<<<grid, block, 0, st>>>(g, Vs, twoPi, left, right);
+  (*launches)++;
+  return (int)cudaGetLastError();
+}
+
+int idfxk::axisRegularizeEmf(const DevGrid &g, double *ex, double *ez, int twoPi, int left, int right, cudaStream_t st,
+                             long long *launches) {
+  for (int side = 0; side < 2; side++) {
+    if (!(side == 0 ? left : right)) continue;
+    const int jref = side == 0 ? g.beg[1] : g.end[1];
+    axisEmfKernel<<<(g.nx[0] + 63) / 64, 64, 0, st>>>(g, ex, ez, jref, twoPi);
+    (*launches)++;
+  }
   return (int)cudaGetLastError();
 }

@@ -79,7 +79,13 @@ int tracerConsToPrim(const PhysCfg &c, const DevGrid &g, double *Vc, double *Uc,
 int enforcePhysicalBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int dir, int side, int type,
                             cudaStream_t st, long long *launches);
 int reconstructNormalField(const PhysCfg &c, const DevGrid &g, double *Vs, int dir, int left, int right,
-                           cudaStream_t st, long long *launches);
+                           cudaStream_t st, long long *launches, int signLeft = 1, int signRight = 1);
+// polar axis of spherical grids (axis.cpp): ghost cells across the axis, B_theta on the axis, EMFs on the axis
+int enforceAxisBoundary(const PhysCfg &c, const DevGrid &g, double *Vc, double *Vs, int side, int twoPi, cudaStream_t st,
+                        long long *launches);
+int axisRegularizeBx2s(const DevGrid &g, double *Vs, int twoPi, int left, int right, cudaStream_t st, long long *launches);
+int axisRegularizeEmf(const DevGrid &g, double *ex, double *ez, int twoPi, int left, int right, cudaStream_t st,
+                      long long *launches);
 // halo pack / unpack (mpi.hpp:49-172, mpi.cpp:79-134)
 long long haloBufferSize(const PhysCfg &c, const DevGrid &g, int dir);
 int haloPack(const PhysCfg &c, const DevGrid &g, const double *Vc, const double *Vs, int dir, int side, double *buf,

@@ -161,8 +161,30 @@ class Grid:
                 xl[:] = xs
                 xr[:] = xe
             self.x[d], self.xl[d], self.xr[d], self.dx[d] = x, xl, xr, dx
+        # Axis treatment (gridHost.cpp:227-263): the domain must touch the axis, and the theta spacing is mirrored
+        # across it (ghost faces rebuilt outwards from the axis face; the cell centres keep their values)
         if self.haveAxis:
-            raise IdefixError("axis boundaries are outside the scope of this build")
+            if defs.geometry != _abi.SPHERICAL:
+                raise IdefixError("Axis boundaries only compatible with Spherical boundary conditions")
+            if defs.dimensions < 2:
+                raise IdefixError("Axis Boundaries requires at least two dimenions")
+            x, xl, xr, dx = self.x[1], self.xl[1], self.xr[1], self.dx[1]
+            if abs(self.xbeg[1]) > 1e-10 and self.lbound[1] == _abi.BC_AXIS:
+                raise IdefixError("Axis Boundaries requires your X2 domain to start at exactly x2=0.0")
+            if abs(self.xend[1] - math.pi) > 1e-10 and self.rbound[1] == _abi.BC_AXIS:
+                raise IdefixError("Axis Boundaries requires your X2 domain to end at exactly x2=Pi")
+            if self.lbound[1] == _abi.BC_AXIS:
+                jref = self.nghost[1]
+                for j in range(jref - 1, -1, -1):
+                    dx[j] = dx[2 * jref - j - 1]
+                    xl[j] = xl[j + 1] - dx[j]
+                    xr[j] = xl[j + 1]
+            if self.rbound[1] == _abi.BC_AXIS:
+                jref = self.nghost[1] + self.np_int[1] - 1
+                for j in range(jref + 1, self.np_tot[1]):
+                    dx[j] = dx[2 * jref - j + 1]
+                    xr[j] = xr[j - 1] + dx[j]
+                    xl[j] = xr[j - 1]
 
     # DataBlock::ExtractSubdomain (dataBlock.cpp:33-66, 162-190)
     def subdomain(self):

@@ -173,6 +173,7 @@ class DataBlock {
   real t{0.0}, dt{0.0};
   Grid *mygrid{nullptr};
   std::unique_ptr<Hydro> hydro;
+  bool haveAxis{false};          // an X2 boundary lies on the polar axis (dataBlock.cpp:43-50)
   bool haveUserStepFirst{false}, haveUserStepLast{false};
   StepFunc userStepFirst{nullptr}, userStepLast{nullptr};
   IdfxBlock *handle{nullptr};   // the C-ABI block behind this DataBlock
@@ -190,6 +191,7 @@ class DataBlock {
       end[dir] = nghost[dir] + np_int[dir];
       gbeg[dir] = nghost[dir];
       gend[dir] = nghost[dir] + np_int[dir];
+      if (grid.lbound[dir] == axis || grid.rbound[dir] == axis) haveAxis = true;
       lbound[dir] = grid.lbound[dir];
       rbound[dir] = grid.rbound[dir];
       xbeg[dir] = grid.xbeg[dir];
@@ -332,7 +334,16 @@ class DataBlock {
   void LaunchUserStepLast() {
     if (haveUserStepLast) userStepLast(*this, t, dt);
   }
-  void ShowConfig() { hydro->ShowConfig(); }
+  void ShowConfig() {
+    hydro->ShowConfig();
+    if (haveAxis) {   // axis.cpp:12-23
+      idfx::cout << "Axis: Axis regularisation ENABLED." << std::endl;
+      if (std::fabs(mygrid->xend[KDIR] - mygrid->xbeg[KDIR] - 2.0 * M_PI) < 1e-10)
+        idfx::cout << "Axis: Full 2pi regularisation around the axis." << std::endl;
+      else
+        idfx::cout << "Axis: Fractional (2pi/N) regularisation around the axis." << std::endl;
+    }
+  }
 };
 
 // ---- Fluid / Boundary members that need the complete DataBlock -----------------------------------------

@@ -41,7 +41,10 @@ class Grid {
         else if (name == "axis") t = axis;
         else if (name == "userdef") t = userdef;
         else IDEFIX_ERROR("Unknown boundary type " + name);
-        if (t == axis) IDEFIX_ERROR("axis boundaries are outside the scope of this build");
+        if (t == axis) {   // grid.cpp:98-104
+          if (dir != JDIR) IDEFIX_ERROR("Axis Boundaries are only applicable to X2");
+          haveAxis = true;
+        }
         if (t == shearingbox) IDEFIX_ERROR("shearing-box boundaries are outside the scope of this build");
         (side == 0 ? lbound : rbound)[dir] = t;
       }
@@ -169,6 +172,37 @@ class Grid {
           }
         }
         idx += P.size;
+      }
+    }
+    // Axis treatment (gridHost.cpp:227-263): the domain must touch the axis, and the theta spacing is mirrored
+    // across it (the ghost faces are rebuilt outwards from the axis face; the cell centres keep their values)
+    if (haveAxis) {
+#if GEOMETRY != SPHERICAL
+      IDEFIX_ERROR("Axis boundaries only compatible with Spherical boundary conditions");
+#endif
+#if DIMENSIONS < 2
+      IDEFIX_ERROR("Axis Boundaries requires at least two dimenions");
+#endif
+      const real smallNumber = 1e-10;
+      if ((std::fabs(xbeg[JDIR]) > smallNumber) && (lbound[JDIR] == axis))
+        IDEFIX_ERROR("Axis Boundaries requires your X2 domain to start at exactly x2=0.0");
+      if ((std::fabs(xend[JDIR] - M_PI) > smallNumber) && (rbound[JDIR] == axis))
+        IDEFIX_ERROR("Axis Boundaries requires your X2 domain to end at exactly x2=Pi");
+      if (lbound[JDIR] == axis) {
+        const int jref = nghost[JDIR];
+        for (int j = jref - 1; j >= 0; j--) {
+          dx[JDIR](j) = dx[JDIR](2 * jref - j - 1);
+          xl[JDIR](j) = xl[JDIR](j + 1) - dx[JDIR](j);
+          xr[JDIR](j) = xl[JDIR](j + 1);
+        }
+      }
+      if (rbound[JDIR] == axis) {
+        const int jref = nghost[JDIR] + np_int[JDIR] - 1;
+        for (int j = jref + 1; j < np_tot[JDIR]; j++) {
+          dx[JDIR](j) = dx[JDIR](2 * jref - j + 1);
+          xr[JDIR](j) = xr[JDIR](j - 1) + dx[JDIR](j);
+          xl[JDIR](j) = xr[JDIR](j - 1);
+        }
       }
     }
   }

@@ -101,7 +101,7 @@ SHORT = [
 # (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
 # reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
 # fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
-PROBLEM_DIRS = {"othooks": "otHooks", "sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
+PROBLEM_DIRS = {"axis": "AxisMHD", "othooks": "otHooks", "sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
 
 
 def _sph(solver, emf=None, nstages=2):
@@ -110,6 +110,18 @@ def _sph(solver, emf=None, nstages=2):
     o[("Hydro", "solver")] = solver
     o[("Hydro", "emf")] = emf
     o[("TimeIntegrator", "nstages")] = nstages
+    return o
+
+
+def _axis(solver, emf=None, nstages=2, x2=("0.0", "3.141592653589793"), x3=("0.0", "6.283185307179586"), beg="axis",
+          end="axis", n=(16, 16, 16)):
+    """problems/AxisMHD: a spherical shell with the polar axis inside the domain (axis.cpp): theta from 0 and / or to pi"""
+    o = _grid(["1", "1.0", str(n[0]), "l", "4.0"], ["1", x2[0], str(n[1]), "u", x2[1]], ["1", x3[0], str(n[2]), "u", x3[1]])
+    o[("Hydro", "solver")] = solver
+    o[("Hydro", "emf")] = emf
+    o[("TimeIntegrator", "nstages")] = nstages
+    o[("Boundary", "X2-beg")] = beg
+    o[("Boundary", "X2-end")] = end
     return o
 
 
@@ -129,6 +141,21 @@ HOST_SHORT = [
     Short("sph_hll_uct0_plm", "sph", 2, "sph_plm", _sph("hll", "uct0"), (1, 10)),
     Short("sph_tvdlf_arith_limo3", "sph", 3, "sph_limo3", _sph("tvdlf", "arithmetic"), (1, 10)),
     Short("polar_hlld_contact_plm", "polar", 2, "polar_plm", _polar("hlld"), (1, 10)),
+    # the polar axis inside the domain (axis.cpp): full 2 pi (ghosts from the opposite meridian, Ex1
+    # averaged around the pole, B_theta on the axis from its neighbours), a quarter of the circle (Ex1 = 0 and
+    # BX2s = 0 on the axis), an axis on one side only, and the vector-potential variant (Ex3 = 0 on the axis matters)
+    Short("axis_hlld_contact_plm", "axis", 2, "axis_plm", _axis("hlld"), (1, 10)),
+    Short("axis_hlld_ucthlld_plm_rk3", "axis", 2, "axis_plm", _axis("hlld", "uct_hlld", 3, n=(12, 20, 24)), (1, 10)),
+    Short("axis_quarter_hll_uct0_plm_rk3", "axis", 2, "axis_plm", _axis("hll", "uct0", 3, x3=("0.0", "1.5707963267948966")), (1, 10)),
+    Short("axis_north_roe_contact_limo3", "axis", 3, "axis_limo3",
+          _axis("roe", x2=("0.0", "1.5707963267948966"), end="outflow"), (1, 10)),
+    Short("axis_south_tvdlf_arith_plm", "axis", 2, "axis_plm",
+          _axis("tvdlf", "arithmetic", x2=("1.5707963267948966", "3.141592653589793"), beg="outflow"), (1, 10)),
+    Short("axis_hlld_contact_plm_vp", "axis", 2, "axis_plm_vp", _axis("hlld"), (1, 10)),
+    Short("axis_hlld_ucthlld_plm", "axis", 2, "axis_plm", _axis("hlld", "uct_hlld"), (1, 10)),
+    Short("axis_hll_contact_plm_rk3", "axis", 2, "axis_plm", _axis("hll", None, 3, n=(12, 20, 24)), (1, 10)),
+    Short("axis_south_hlld_contact_plm", "axis", 2, "axis_plm",
+          _axis("hlld", x2=("1.5707963267948966", "3.141592653589793"), beg="outflow"), (1, 10)),
     # shock flattening in curvilinear geometry (area-weighted divergence, shockFlattening.hpp:78-87)
     Short("sph_hlld_contact_plm_flat", "sph", 2, "sph_plm", {**_sph("hlld"), ("Hydro", "shockFlattening"): "0.0002"}, (1, 10)),
     Short("polar_hll_uct0_plm_flat", "polar", 2, "polar_plm",

@@ -33,7 +33,11 @@ def main():
         wanted = [0] + list(case.cycles)
         if all(os.path.exists(os.path.join(HERE, "short", f"{case.name}.c{n:04d}.dmp")) for n in wanted):
             continue
-        res = run_reference(case.ref, ini_for(case, dump_every_cycle=True), maxcycles=max(case.cycles), keep=True, timeout=600)
+        # Axis::SymmetrizeEx1Side adds the radial EMFs around the pole with atomics (axis.cpp:39-42): only a single
+        # thread gives a reproducible (ascending-k) order, and that is the order the CUDA kernel uses
+        threads = 1 if case.setup == "axis" else None
+        res = run_reference(case.ref, ini_for(case, dump_every_cycle=True), maxcycles=max(case.cycles), keep=True, timeout=600,
+                            threads=threads)
         for n in wanted:
             src = os.path.join(res["workdir"], f"dump.{n:04d}.dmp")
             shutil.copy(src, os.path.join(HERE, "short", f"{case.name}.c{n:04d}.dmp"))

@@ -90,6 +90,25 @@ def test_decomposition_boundaries():
         Grid(Input.from_string(txt), Definitions(2, 2), nproc=(3, 1, 1))
 
 
+def test_axis_boundaries_only_on_x2():
+    """grid.cpp:98-104: `axis` is accepted on X2 (the library then insists on spherical geometry), refused elsewhere"""
+    txt = ("[Grid]\nX1-grid 1 1.0 8 u 2.0\nX2-grid 1 0.0 8 u 3.141592653589793\nX3-grid 1 0.0 8 u 6.283185307179586\n"
+           "[Boundary]\nX1-beg outflow\nX1-end outflow\nX2-beg axis\nX2-end axis\nX3-beg periodic\nX3-end periodic\n")
+    sph = Definitions(3, 3, geometry=_abi.SPHERICAL, mhd=True)
+    g = Grid(Input.from_string(txt), sph)
+    assert g.haveAxis and g.lbound[1] == _abi.BC_AXIS and g.rbound[1] == _abi.BC_AXIS
+    # gridHost.cpp:246-262: theta spacing mirrored across the axis, ghost faces rebuilt outwards from the axis face
+    ng, n = g.nghost[1], g.np_int[1]
+    assert g.xl[1][ng] == 0.0 and g.xr[1][ng - 1] == 0.0 and g.xl[1][ng - 1] == -g.dx[1][ng]
+    assert g.xr[1][ng + n] == g.xr[1][ng + n - 1] + g.dx[1][ng + n - 1] and g.xl[1][ng + n] == g.xr[1][ng + n - 1]
+    with pytest.raises(_abi.IdefixError):   # only on X2
+        Grid(Input.from_string(txt.replace("X1-beg outflow", "X1-beg axis")), sph)
+    with pytest.raises(_abi.IdefixError):   # only in spherical geometry
+        Grid(Input.from_string(txt), Definitions(3, 3))
+    with pytest.raises(_abi.IdefixError):   # the domain must reach the axis
+        Grid(Input.from_string(txt.replace("8 u 3.141592653589793", "8 u 3.0")), sph)
+
+
 @pytest.mark.parametrize("case", SHORT, ids=[c.name for c in SHORT])
 def test_initial_conditions_match_reference_dump(case):
     """InitFlow of every set-up is bit-identical with the reference's dump.0000"""
