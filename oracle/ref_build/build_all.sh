@@ -26,6 +26,7 @@ b sod_ppm      test/HD/sod                NO  4
 P=$(cd ../../idefix_b200/host/problems && pwd)
 b sph_limo3    $P/SphericalMHD            YES 3
 b sph_plm      $P/SphericalMHD            YES 2
+b axisfluxtube_plm test/MHD/AxisFluxTube   YES 2
 b axis_plm     $P/AxisMHD                 YES 2
 b axis_limo3   $P/AxisMHD                 YES 3
 b axis_plm_vp  $P/AxisMHD                 YES 2 "" 1

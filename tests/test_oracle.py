@@ -81,6 +81,57 @@ def test_oracle_matches_shipped_golden(case):
     o.close()
 
 
+# ---- polar axis: the fixtures of tests/golden/short/axis_* come from reference builds with an axis; this pins such a
+# build (the reference's own test/MHD/AxisFluxTube, unmodified) on the golden dump the reference ships for it --------
+AXIS_FLUX_TUBE_INI = """[Grid]
+X1-grid    1  1.0  32  u  8.0
+X2-grid    1  0.0  32  u  3.141592653589793
+X3-grid    1  0.0  64  u  6.283185307179586
+[TimeIntegrator]
+CFL         0.8
+tstop       2.0
+first_dt    1.e-4
+nstages     2
+[Hydro]
+solver    hlld
+gamma     1.5
+[Boundary]
+X1-beg    outflow
+X1-end    userdef
+X2-beg    axis
+X2-end    axis
+X3-beg    periodic
+X3-end    periodic
+[Setup]
+Rtorus    2.0
+Ztorus    2.0
+Rin       0.4
+[Output]
+uservar    divB  Er
+dmp        2.0
+log        1000000
+"""
+
+
+def test_reference_build_with_axis_reproduces_shipped_golden():
+    """test/MHD/AxisFluxTube/testme.py: non-regression against dump.ref.double.plm.idefix.ini.dmp, tolerance 1e-14 on
+    the reference's metric (mean over fields of the RMS difference, pytools/idfx_test.py:414-428).  The set-up itself
+    cannot go through the product: its 1e-20 field decays through the range the branch-free division refuses"""
+    from oracle.ref_run import cleanup, have, run_reference
+    if not have("axisfluxtube_plm"):
+        pytest.skip("oracle/_ref/axisfluxtube_plm not built (oracle/ref_build/build_all.sh)")
+    res = run_reference("axisfluxtube_plm", AXIS_FLUX_TUBE_INI, keep=True, timeout=1200)
+    try:
+        mine = readDump(os.path.join(res["workdir"], "dump.0001.dmp"))
+        gold = readDump(os.path.join(GOLD, "reference", "MHD", "AxisFluxTube", "dump.ref.double.plm.idefix.ini.dmp"))
+        assert float(mine.data["time"][0]) == float(gold.data["time"][0]) == 2.0
+        errs = [np.sqrt(np.mean((np.asarray(mine.data[k]) - np.asarray(v)) ** 2)) for k, v in gold.data.items()
+                if k.startswith(("Vc-", "Vs-"))]
+        assert len(errs) == 8 and sum(errs) / len(errs) <= 1e-14
+    finally:
+        cleanup(res)
+
+
 # ---- isothermal EOS: the problems live in the C++ host layer (idefix_b200/host/problems); the oracle starts
 # from the reference's own cycle-0 dump of the case and must reproduce its later dumps bit for bit ---------------
 ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2, 3, 1, True, True)}
