@@ -22,7 +22,7 @@ class OracleDesc(C.Structure):
                 ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
                 ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
                 ("dx", C.c_double * 3), ("ntracer", C.c_int), ("order", C.c_int), ("isothermal", C.c_int),
-                ("csiso", C.c_double), ("shock_flattening", C.c_double)]
+                ("csiso", C.c_double), ("shock_flattening", C.c_double), ("evolve_vector_potential", C.c_int)]
 
 
 _lib = None
@@ -36,7 +36,7 @@ def lib():
         L = C.CDLL(LIB)
         L.oracle_create.restype = C.c_void_p
         L.oracle_create.argtypes = [C.POINTER(OracleDesc)]
-        for name in ("oracle_vc", "oracle_vs"):
+        for name in ("oracle_vc", "oracle_vs", "oracle_ve"):
             getattr(L, name).restype = C.POINTER(C.c_double)
             getattr(L, name).argtypes = [C.c_void_p]
         for name in ("oracle_time", "oracle_dt"):
@@ -45,6 +45,7 @@ def lib():
         L.oracle_nvar.argtypes = [C.c_void_p]
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_boundaries.argtypes = [C.c_void_p]
+        L.oracle_derive_vector_potential.argtypes = [C.c_void_p]
         L.oracle_cycle.argtypes = [C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5
         L.oracle_riemann.restype = None
@@ -62,7 +63,7 @@ class Oracle:
     (n, k, j, i) like the reference's IdefixArray4D."""
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
-                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None, shock_flattening=0.0):
+                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None, shock_flattening=0.0, vector_potential=False):
         if mhd and solver == "tvdlf" and emf in ("uct_hll", "uct_hlld"):
             raise ValueError("TVDLF-MHD stores no upwind coefficients for uct_hlld and extends its sweeps by one "
                              "cell only (tvdlfMHD.hpp:30-41, 226-229): not pinned by any reference run")
@@ -71,6 +72,7 @@ class Oracle:
         d.csiso = csiso or 0.0
         d.ntracer = ntracer
         d.shock_flattening = shock_flattening
+        d.evolve_vector_potential = int(bool(vector_potential) and mhd and ndim >= 2)
         d.order = order
         d.ndim, d.ncomp, d.mhd = ndim, ncomp, int(mhd)
         d.solver, d.emf, d.nstages = SOLVERS[solver], EMFS[emf or "uct_contact"], nstages
@@ -90,6 +92,10 @@ class Oracle:
             off = [1 if a < ndim else 0 for a in range(3)]
             self.Vs = np.ctypeslib.as_array(lib().oracle_vs(self.h),
                                             shape=(ndim, nt[2] + off[2], nt[1] + off[1], nt[0] + off[0]))
+        self.Ve = None
+        if d.evolve_vector_potential:   # AX1e, AX2e, AX3e in 3-D; AX3e alone in 2-D
+            self.Ve = np.ctypeslib.as_array(lib().oracle_ve(self.h),
+                                            shape=(3 if ndim == 3 else 1, nt[2] + off[2], nt[1] + off[1], nt[0] + off[0]))
 
     @classmethod
     def from_setup(cls, setup):
@@ -109,12 +115,17 @@ class Oracle:
                 setup.data.hydro.gamma, inp.Get(float, "TimeIntegrator", "CFL", 0), first_dt,
                 [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer,
                 order=defs.order, csiso=setup.data.hydro.csiso if defs.isothermal else None,
-                shock_flattening=setup.data.hydro.shockFlattening)
+                shock_flattening=setup.data.hydro.shockFlattening,
+                vector_potential=getattr(defs, "evolve_vector_potential", False))
         return o
 
-    def set_state(self, Vc, Vs=None):
+    def set_state(self, Vc, Vs=None, Ve=None):
+        """initial condition (InitFlow), then main.cpp:172-176: DeriveVectorPotential, SetBoundaries"""
         self.Vc[...] = Vc
-        if self.Vs is not None:
+        if self.Ve is not None:
+            self.Ve[...] = Ve
+            lib().oracle_derive_vector_potential(self.h)
+        elif self.Vs is not None:
             self.Vs[...] = Vs
         lib().oracle_set_boundaries(self.h)
 

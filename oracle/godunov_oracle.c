@@ -40,6 +40,7 @@ typedef struct {
   int isothermal;            /* ISOTHERMAL: no energy equation, p = csiso^2 rho (eos_isothermal, constant cs) */
   double csiso;              /* [Hydro] csiso constant <value> */
   double shock_flattening;   /* [Hydro] shockFlattening <smoothing> (riemannSolver.hpp:154-159); 0 = off */
+  int evolve_vector_potential; /* EVOLVE_VECTOR_POTENTIAL: the edge-centred potential Ve is the evolved variable */
 } OracleDesc;
 
 typedef struct {
@@ -52,6 +53,9 @@ typedef struct {
   double *Vc, *Uc, *Uc0, *Vs, *Vs0, *Flux, *cMax, *InvDt;
   double *ex, *ey, *ez, *exj, *exk, *eyi, *eyk, *ezi, *ezj, *Ex1, *Ex2, *Ex3;
   double *svx, *svy, *svz, *aL[3], *aR[3], *dL[3], *dR[3];
+  double *Ve, *Ve0;          /* EVOLVE_VECTOR_POTENTIAL: AX1e, AX2e, AX3e in 3-D, AX3e alone in 2-D (idefix.hpp:116-125),
+                                each laid out like a component of Vs (fluid.hpp:552-553) */
+  int nve;
   unsigned char *flags;      /* ShockFlattening::flagArray (shockFlattening.hpp:26), 1 = FlagShock::Shock */
   double t, dt;
   long ncycles;
@@ -105,6 +109,11 @@ Oracle *oracle_create(const OracleDesc *d) {
       o->dL[a] = zalloc(n);
       o->dR[a] = zalloc(n);
     }
+    if (d->evolve_vector_potential && d->ndim >= 2) {
+      o->nve = d->ndim == 3 ? 3 : 1;
+      o->Ve = zalloc(o->vn * o->nve);
+      o->Ve0 = zalloc(o->vn * o->nve);
+    }
   }
   o->t = 0.0;
   o->dt = d->first_dt;
@@ -117,6 +126,8 @@ void oracle_destroy(Oracle *o) {
                    o->exj, o->exk, o->eyi, o->eyk, o->ezi, o->ezj, o->Ex1, o->Ex2, o->Ex3, o->svx, o->svy, o->svz};
   for (unsigned q = 0; q < sizeof(all) / sizeof(all[0]); q++) free(all[q]);
   free(o->flags);
+  free(o->Ve);
+  free(o->Ve0);
   for (int a = 0; a < 3; a++) {
     free(o->aL[a]);
     free(o->aR[a]);
@@ -128,6 +139,7 @@ void oracle_destroy(Oracle *o) {
 
 double *oracle_vc(Oracle *o) { return o->Vc; }
 double *oracle_vs(Oracle *o) { return o->Vs; }
+double *oracle_ve(Oracle *o) { return o->Ve; }
 double oracle_time(Oracle *o) { return o->t; }
 double oracle_dt(Oracle *o) { return o->dt; }
 int oracle_nvar(Oracle *o) { return o->nvar + o->ntr; }
@@ -1519,6 +1531,47 @@ static void evolve_mag_field(Oracle *o) {
       }
 }
 
+/* ConstrainedTransport::EvolveVectorPotential, evolveVectorPotential.hpp:17-43 */
+static void evolve_vector_potential(Oracle *o) {
+  const int nd = o->d.ndim;
+  const double dt = o->dt;
+  double *A3 = o->Ve + (nd == 3 ? 2 : 0) * o->vn;
+  for (int k = o->beg[2]; k < o->end[2] + o->off[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1] + o->off[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0] + o->off[0]; i++) {
+        const long c = C(o, k, j, i), s = S(o, k, j, i);
+        if (nd == 3) {
+          o->Ve[s] += -dt * o->ex[c];
+          o->Ve[o->vn + s] += -dt * o->ey[c];
+        }
+        A3[s] += -dt * o->ez[c];
+      }
+}
+
+/* ConstrainedTransport::ComputeMagFieldFromA, cartesian: evolveVectorPotential.hpp:46-68 */
+static void mag_field_from_a(Oracle *o) {
+  const int nd = o->d.ndim;
+  const long vj = o->vj, vk = o->vk;
+  const double *dx = o->d.dx;
+  const double *A1 = o->Ve, *A2 = o->Ve + o->vn, *A3 = o->Ve + (nd == 3 ? 2 : 0) * o->vn;
+  for (int k = o->beg[2]; k < o->end[2] + o->off[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1] + o->off[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0] + o->off[0]; i++) {
+        const long s = S(o, k, j, i);
+        double b1 = 0.0 + 1 / dx[1] * (A3[s + vj] - A3[s]);
+        if (nd == 3) b1 = b1 - 1 / dx[2] * (A2[s + vk] - A2[s]);
+        double b2 = -1 / dx[0] * (A3[s + 1] - A3[s]);
+        if (nd == 3) b2 = b2 + 1 / dx[2] * (A1[s + vk] - A1[s]);
+        o->Vs[s] = b1;
+        o->Vs[o->vn + s] = b2;
+        if (nd == 3) o->Vs[2 * o->vn + s] = +1 / dx[0] * (A2[s + 1] - A2[s]) - 1 / dx[1] * (A1[s + vj] - A1[s]);
+      }
+}
+/* DataBlock::DeriveVectorPotential, dataBlock.cpp:367-373 (called after InitFlow, main.cpp:174) */
+void oracle_derive_vector_potential(Oracle *o) {
+  if (o->Ve) mag_field_from_a(o);
+}
+
 /* Boundary::ReconstructVcField, boundary.hpp:389-404 */
 static void reconstruct_vc_field(Oracle *o, double *V) {
   for (int k = 0; k < o->nx[2]; k++)
@@ -1667,7 +1720,8 @@ int oracle_cycle(Oracle *o) {
     }
     if (d->nstages > 1 && stage == 0) { /* StateContainer::CopyFrom */
       memcpy(o->Uc0, o->Uc, sizeof(double) * ncell);
-      if (nface) memcpy(o->Vs0, o->Vs, sizeof(double) * nface);
+      if (o->Ve) memcpy(o->Ve0, o->Ve, sizeof(double) * o->vn * o->nve); /* the state holds Ve instead of Vs, fluid.hpp:549-559 */
+      else if (nface) memcpy(o->Vs0, o->Vs, sizeof(double) * nface);
     }
     for (int dir = 0; dir < d->ndim; dir++) { /* EvolveStage, evolveStage.hpp:41-90 */
       calc_flux(o, dir);
@@ -1677,7 +1731,12 @@ int oracle_cycle(Oracle *o) {
     }
     if (d->mhd && d->ndim >= 2) {
       corner_emf(o);
-      evolve_mag_field(o);
+      if (o->Ve) { /* evolveStage.hpp:78-81 */
+        evolve_vector_potential(o);
+        mag_field_from_a(o);
+      } else {
+        evolve_mag_field(o);
+      }
       reconstruct_vc_field(o, o->Uc);
     }
     o->t += o->dt;
@@ -1685,9 +1744,14 @@ int oracle_cycle(Oracle *o) {
     if (stage > 0) { /* AddAndStore: wl*Vout + wr*Vin over whole arrays, stateContainer.cpp:91-98 */
       const double a = wc[stage - 1], b = w0[stage - 1];
       for (long c = 0; c < ncell; c++) o->Uc[c] = a * o->Uc[c] + b * o->Uc0[c];
-      for (long c = 0; c < nface; c++) o->Vs[c] = a * o->Vs[c] + b * o->Vs0[c];
+      if (o->Ve) {
+        for (long c = 0; c < o->vn * o->nve; c++) o->Ve[c] = a * o->Ve[c] + b * o->Ve0[c];
+      } else {
+        for (long c = 0; c < nface; c++) o->Vs[c] = a * o->Vs[c] + b * o->Vs0[c];
+      }
       o->t = a * o->t + b * t0;
     }
+    if (o->Ve) mag_field_from_a(o); /* convertConsToPrim.hpp:117-119 */
     if (d->mhd) reconstruct_vc_field(o, o->Uc); /* ConvertConsToPrim starts with it, convertConsToPrim.hpp:120 */
     for (long c = 0; c < o->sn; c++) {
       double v[8], u[8];

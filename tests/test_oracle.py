@@ -23,17 +23,18 @@ def in_scope(case):
     emf = case.overrides.get(("Hydro", "emf"))
     if case.order not in (2, 3, 4) or solver not in ORACLE_SOLVERS:
         return False
-    if getattr(case, "ref", "").endswith("_vp") or case.setup.endswith("_vp"):
-        return False   # EVOLVE_VECTOR_POTENTIAL: pinned on the reference's own builds directly, not restated
     return emf in (None, "arithmetic", "uct0", "uct_contact", "uct_hll", "uct_hlld")
 
 
 def oracle_for(case):
-    s = REGISTRY[case.setup](order=case.order, overrides=case.overrides, device=None)
+    # EVOLVE_VECTOR_POTENTIAL cases: SHORT cases name a reference binary built with the define, FULL cases a set-up *_vp
+    vp = getattr(case, "ref", "").endswith("_vp") or case.setup.endswith("_vp")
+    name = case.setup[:-3] if case.setup.endswith("_vp") else case.setup
+    s = REGISTRY[name](order=case.order, overrides=case.overrides, device=None, vector_potential=vp)
     s.InitFlow(s.data)
     host = s.data.host_mirror
     o = Oracle.from_setup(s)
-    o.set_state(host.Vc, host.Vs)
+    o.set_state(host.Vc, host.Vs, host.Ve)
     return s, o
 
 
@@ -50,11 +51,19 @@ def compare(s, o, dump):
             off = [1 if e == dd else 0 for e in range(3)]
             a = o.Vs[dd, kb:ke + off[2], jb:je + off[1], ib:ie + off[0]].transpose(2, 1, 0)
             worst = max(worst, float(np.abs(a - dump.data[f"Vs-BX{dd + 1}s"]).max()))
+    if o.Ve is not None:
+        # edge-centred: one more point in the active directions perpendicular to the component (dump.cpp:921-930)
+        nd = s.definitions.dimensions
+        comps = [(0, "AX1e", 0), (1, "AX2e", 1), (2, "AX3e", 2)] if nd == 3 else [(0, "AX3e", 2)]
+        for n, name, dirn in comps:
+            off = [1 if (e != dirn and e < nd) else 0 for e in range(3)]
+            a = o.Ve[n, kb:ke + off[2], jb:je + off[1], ib:ie + off[0]].transpose(2, 1, 0)
+            worst = max(worst, float(np.abs(a - dump.data[f"Ve-{name}"]).max()))
     return worst
 
 
 SHORT_IN = [c for c in SHORT + ORACLE_SHORT if in_scope(c) and c.setup in REGISTRY]
-FULL_IN = [c for c in FULL + ORACLE_FULL if in_scope(c) and c.setup in ("sod", "mhdsod", "ot2d")]
+FULL_IN = [c for c in FULL + ORACLE_FULL if in_scope(c) and c.setup in ("sod", "mhdsod", "ot2d", "ot2d_vp")]
 
 
 @pytest.mark.parametrize("case", SHORT_IN, ids=[c.name for c in SHORT_IN])
