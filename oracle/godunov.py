@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libgodunov_oracle.so")
 
 SOLVERS = {"tvdlf": 0, "hll": 1, "hllc": 2, "hlld": 3, "roe": 4}
 EMFS = {"arithmetic": 0, "uct0": 1, "uct_contact": 2, "uct_hll": 3, "uct_hlld": 4}
-BCS = {"periodic": 1, "outflow": 3}
+BCS = {"periodic": 1, "reflective": 2, "outflow": 3, "axis": 5}
 
 
 class OracleDesc(C.Structure):
@@ -22,7 +22,8 @@ class OracleDesc(C.Structure):
                 ("nstages", C.c_int), ("np_int", C.c_int * 3), ("nghost", C.c_int * 3), ("bc", C.c_int * 3),
                 ("gamma", C.c_double), ("cfl", C.c_double), ("cfl_max_var", C.c_double), ("first_dt", C.c_double),
                 ("dx", C.c_double * 3), ("ntracer", C.c_int), ("order", C.c_int), ("isothermal", C.c_int),
-                ("csiso", C.c_double), ("shock_flattening", C.c_double), ("evolve_vector_potential", C.c_int)]
+                ("csiso", C.c_double), ("shock_flattening", C.c_double), ("evolve_vector_potential", C.c_int),
+                ("geometry", C.c_int), ("bc_right", C.c_int * 3)]
 
 
 _lib = None
@@ -46,6 +47,8 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_boundaries.argtypes = [C.c_void_p]
         L.oracle_derive_vector_potential.argtypes = [C.c_void_p]
+        L.oracle_set_grid.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.oracle_set_grid.restype = None
         L.oracle_cycle.argtypes = [C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5
         L.oracle_riemann.restype = None
@@ -63,7 +66,10 @@ class Oracle:
     (n, k, j, i) like the reference's IdefixArray4D."""
 
     def __init__(self, ndim, ncomp, mhd, solver, emf, nstages, np_int, bc, gamma, cfl, first_dt, dx,
-                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None, shock_flattening=0.0, vector_potential=False):
+                 cfl_max_var=1.1, ntracer=0, order=2, csiso=None, shock_flattening=0.0, vector_potential=False, geometry=1, grid=None,
+                 bc_right=None):
+        """geometry 1 cartesian (uniform spacing dx), 3 polar, 4 spherical: `grid` = per direction the arrays (x, xl, xr, dx)
+        with ghosts, as GridHost::MakeGrid builds them; bc / bc_right: boundary type names of the left / right sides"""
         if mhd and solver == "tvdlf" and emf in ("uct_hll", "uct_hlld"):
             raise ValueError("TVDLF-MHD stores no upwind coefficients for uct_hlld and extends its sweeps by one "
                              "cell only (tvdlfMHD.hpp:30-41, 226-229): not pinned by any reference run")
@@ -80,7 +86,9 @@ class Oracle:
             d.np_int[a] = np_int[a] if a < ndim else 1
             d.nghost[a] = (3 if order == 4 else 2) if a < ndim else 0
             d.bc[a] = BCS[bc[a]] if a < ndim else 0
+            d.bc_right[a] = BCS[bc_right[a]] if (bc_right is not None and a < ndim) else 0
             d.dx[a] = dx[a]
+        d.geometry = geometry
         d.gamma, d.cfl, d.cfl_max_var, d.first_dt = gamma, cfl, cfl_max_var, first_dt
         self.desc = d
         self.h = lib().oracle_create(C.byref(d))
@@ -92,6 +100,13 @@ class Oracle:
             off = [1 if a < ndim else 0 for a in range(3)]
             self.Vs = np.ctypeslib.as_array(lib().oracle_vs(self.h),
                                             shape=(ndim, nt[2] + off[2], nt[1] + off[1], nt[0] + off[0]))
+        if geometry != 1:
+            if geometry not in (3, 4) or ntracer:
+                raise ValueError("curvilinear oracle: polar / spherical, no tracers")
+            for a in range(3):
+                arrs = [np.ascontiguousarray(q, float) for q in grid[a]]
+                assert all(len(q) == nt[a] for q in arrs)
+                lib().oracle_set_grid(self.h, a, *[q.ctypes.data for q in arrs])
         self.Ve = None
         if d.evolve_vector_potential:   # AX1e, AX2e, AX3e in 3-D; AX3e alone in 2-D
             self.Ve = np.ctypeslib.as_array(lib().oracle_ve(self.h),
@@ -101,9 +116,9 @@ class Oracle:
     def from_setup(cls, setup):
         """same configuration as an idefix_b200.setups.Setup built with device=None (host only)"""
         defs, inp, grid = setup.definitions, setup.input, setup.grid
-        if defs.order not in (2, 3, 4) or defs.geometry != 1:
-            raise ValueError("the C oracle restates PLM / LimO3 / PPM, cartesian only")
-        names = {1: "periodic", 3: "outflow"}
+        if defs.order not in (2, 3, 4) or defs.geometry not in (1, 3, 4):
+            raise ValueError("the C oracle restates PLM / LimO3 / PPM in cartesian, polar and spherical geometry")
+        names = {1: "periodic", 2: "reflective", 3: "outflow", 5: "axis"}
         nd = defs.dimensions
         emf = inp.Get(str, "Hydro", "emf", 0) if inp.CheckEntry("Hydro", "emf") >= 0 else "uct_contact"
         if defs.isothermal and defs.mhd and emf == "uct_hlld":
@@ -116,7 +131,9 @@ class Oracle:
                 [float(grid.dx[a][0]) for a in range(3)], ntracer=setup.data.hydro.nTracer,
                 order=defs.order, csiso=setup.data.hydro.csiso if defs.isothermal else None,
                 shock_flattening=setup.data.hydro.shockFlattening,
-                vector_potential=getattr(defs, "evolve_vector_potential", False))
+                vector_potential=getattr(defs, "evolve_vector_potential", False), geometry=defs.geometry,
+                grid=[(grid.x[a], grid.xl[a], grid.xr[a], grid.dx[a]) for a in range(3)],
+                bc_right=[names[grid.rbound[a]] for a in range(nd)])
         return o
 
     def set_state(self, Vc, Vs=None, Ve=None):

@@ -7,15 +7,17 @@
  * structure of the CUDA kernels, and is pinned against the reference's golden dumps and against
  * dumps written by the reference's own CPU build (tests/test_oracle.py).
  *
- * Scope (the north-star headline path): cartesian uniform grids, 1-3 dimensions (and 2.5-D: more components
- * than dimensions), adiabatic EOS, PLM (van Leer) / LimO3 / PPM reconstruction, HD solvers TVDLF / HLL / HLLC / Roe,
- * MHD solvers TVDLF / HLL / HLLD / Roe, constrained transport with arithmetic / uct0 / uct_contact / uct_hll / uct_hlld
- * averaging (PPM corner states when ORDER is 4), passive tracers, periodic and outflow boundaries (with
- * ReconstructNormalField on the outflow sides in MHD), RK1/2/3, CFL time-step control; and the isothermal
+ * Scope (the north-star path): cartesian uniform grids, and polar / spherical geometry on uniform, stretched and
+ * logarithmic grids (oracle_set_grid: area-weighted fluxes in angular-momentum form, geometric source terms,
+ * irregular-grid PLM, curvilinear EvolveMagField, reflective sides, the polar axis); 1-3 dimensions (and 2.5-D:
+ * more components than dimensions), adiabatic EOS, PLM (van Leer) / LimO3 / PPM reconstruction, shock flattening,
+ * HD solvers TVDLF / HLL / HLLC / Roe, MHD solvers TVDLF / HLL / HLLD / Roe, constrained transport with arithmetic /
+ * uct0 / uct_contact / uct_hll / uct_hlld averaging (PPM corner states when ORDER is 4), the vector potential as the
+ * evolved variable, passive tracers (cartesian), periodic / outflow / reflective / axis boundaries (with
+ * ReconstructNormalField on the non-periodic sides in MHD), RK1/2/3, CFL time-step control; and the isothermal
  * EOS (constant sound speed) for the same solvers.
- * Curvilinear geometry is pinned through the reference binaries and golden dumps only (tests/golden); the
- * isothermal uct_hlld coefficients are restated for solver-level cross-checks but pinned by no
- * reference run.
+ * The isothermal uct_hlld coefficients are restated for solver-level cross-checks but pinned by no reference run;
+ * cylindrical geometry is not restated (the reference does not compile for it at this commit).
  *
  * Every function cites the reference file:line (relative to the reference tree) it follows.
  * Compile with -O2 -ffp-contract=off: expression association follows the reference so results are
@@ -27,7 +29,8 @@
 
 enum { TVDLF = 0, HLL = 1, HLLC = 2, HLLD = 3, ROE = 4 };
 enum { EMF_ARITHMETIC = 0, EMF_UCT0 = 1, EMF_UCT_CONTACT = 2, EMF_UCT_HLL = 3, EMF_UCT_HLLD = 4 };
-enum { BC_PERIODIC = 1, BC_OUTFLOW = 3 };
+enum { BC_PERIODIC = 1, BC_REFLECTIVE = 2, BC_OUTFLOW = 3, BC_AXIS = 5 };   /* idefix.hpp:220 */
+enum { GEO_CARTESIAN = 1, GEO_CYLINDRICAL = 2, GEO_POLAR = 3, GEO_SPHERICAL = 4 }; /* idefix.hpp:97-100 */
 
 typedef struct {
   int ndim, ncomp, mhd, solver, emf, nstages;
@@ -41,6 +44,8 @@ typedef struct {
   double csiso;              /* [Hydro] csiso constant <value> */
   double shock_flattening;   /* [Hydro] shockFlattening <smoothing> (riemannSolver.hpp:154-159); 0 = off */
   int evolve_vector_potential; /* EVOLVE_VECTOR_POTENTIAL: the edge-centred potential Ve is the evolved variable */
+  int geometry;              /* 0 / 1 cartesian, 3 polar, 4 spherical: needs oracle_set_grid for every direction */
+  int bc_right[3];           /* boundary type of the right side when it differs from bc[] (0 = the same) */
 } OracleDesc;
 
 typedef struct {
@@ -53,6 +58,13 @@ typedef struct {
   double *Vc, *Uc, *Uc0, *Vs, *Vs0, *Flux, *cMax, *InvDt;
   double *ex, *ey, *ez, *exj, *exk, *eyi, *eyk, *ezi, *ezj, *Ex1, *Ex2, *Ex3;
   double *svx, *svy, *svz, *aL[3], *aR[3], *dL[3], *dR[3];
+  /* curvilinear / non-uniform grids: coordinates incl. ghosts (gridHost.cpp), geometry helpers (makeGeometry.cpp:91-130)
+   * and the weights of the irregular PLM reconstruction (extrapolateToFaces.hpp:43-71) */
+  int geo, curv, bcl[3], bcr[3];
+  double *gx[3], *gxl[3], *gxr[3], *gdx[3], *xgc[3];
+  double *rt, *sinx2m, *sinx2, *tanx2, *dmu;
+  double *wp[3], *wm[3], *cp[3], *cm[3], *dp[3], *dm[3];
+  int axis_left, axis_right, axis_twopi;   /* Axis::Axis, axis.hpp:116-136 */
   double *Ve, *Ve0;          /* EVOLVE_VECTOR_POTENTIAL: AX1e, AX2e, AX3e in 3-D, AX3e alone in 2-D (idefix.hpp:116-125),
                                 each laid out like a component of Vs (fluid.hpp:552-553) */
   int nve;
@@ -115,13 +127,139 @@ Oracle *oracle_create(const OracleDesc *d) {
       o->Ve0 = zalloc(o->vn * o->nve);
     }
   }
+  o->geo = d->geometry ? d->geometry : GEO_CARTESIAN;
+  o->curv = o->geo != GEO_CARTESIAN;
+  for (int a = 0; a < 3; a++) {
+    o->bcl[a] = d->bc[a];
+    o->bcr[a] = d->bc_right[a] ? d->bc_right[a] : d->bc[a];
+  }
   o->t = 0.0;
   o->dt = d->first_dt;
   return o;
 }
 
+/* ---- curvilinear grids -------------------------------------------------------------------------------------
+ * The block's coordinates (cell centres, left / right faces, widths, ghosts included) as GridHost::MakeGrid builds
+ * them; called once per direction before the first cycle when desc.geometry is not cartesian. */
+static void make_geometry(Oracle *o);
+void oracle_set_grid(Oracle *o, int dir, const double *x, const double *xl, const double *xr, const double *dx) {
+  const int n = o->nx[dir];
+  double **dst[4] = {&o->gx[dir], &o->gxl[dir], &o->gxr[dir], &o->gdx[dir]};
+  const double *src[4] = {x, xl, xr, dx};
+  for (int q = 0; q < 4; q++) {
+    free(*dst[q]);
+    *dst[q] = zalloc(n);
+    memcpy(*dst[q], src[q], sizeof(double) * n);
+  }
+  if (o->gx[0] && o->gx[1] && o->gx[2]) make_geometry(o);
+}
+
+/* DataBlock::MakeGeometry, makeGeometry.cpp:91-130 (geometrical centres, spherical helpers) and
+ * ExtrapolateToFaces::ComputePLMweights, extrapolateToFaces.hpp:43-71 */
+static void make_geometry(Oracle *o) {
+  const int geo = o->geo;
+  const double *x1 = o->gx[0], *x1m = o->gxl[0], *x1p = o->gxr[0], *dx1 = o->gdx[0];
+  const double *x2 = o->gx[1], *x2m = o->gxl[1], *x2p = o->gxr[1];
+  double **one[] = {&o->rt, &o->sinx2m, &o->sinx2, &o->tanx2, &o->dmu};
+  for (unsigned q = 0; q < 5; q++) free(*one[q]);
+  o->rt = zalloc(o->nx[0]);
+  o->sinx2m = zalloc(o->nx[1] + 1);
+  o->sinx2 = zalloc(o->nx[1]);
+  o->tanx2 = zalloc(o->nx[1]);
+  o->dmu = zalloc(o->nx[1]);
+  for (int a = 0; a < 3; a++) {
+    double **w[] = {&o->xgc[a], &o->wp[a], &o->wm[a], &o->cp[a], &o->cm[a], &o->dp[a], &o->dm[a]};
+    for (unsigned q = 0; q < 7; q++) {
+      free(*w[q]);
+      *w[q] = zalloc(o->nx[a]);
+    }
+  }
+  for (int i = 0; i < o->nx[0]; i++) {
+    if (geo == GEO_CARTESIAN) {
+      o->xgc[0][i] = x1[i];
+    } else if (geo == GEO_POLAR || geo == GEO_CYLINDRICAL) {
+      o->xgc[0][i] = x1[i] + dx1[i] * dx1[i] / (12.0 * x1[i]);
+    } else {
+      o->xgc[0][i] = x1[i] + 2.0 * x1[i] * dx1[i] * dx1[i] / (12.0 * x1[i] * x1[i] + dx1[i] * dx1[i]);
+      o->rt[i] = (x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / (x1p[i] * x1p[i] - x1m[i] * x1m[i]) / 1.5;
+    }
+  }
+  for (int j = 0; j < o->nx[1]; j++) {
+    if (geo != GEO_SPHERICAL) {
+      o->xgc[1][j] = x2[j];
+    } else {
+      const double xL = x2m[j], xR = x2p[j];
+      o->xgc[1][j] = (sin(xR) - sin(xL) + xL * cos(xL) - xR * cos(xR)) / (cos(xL) - cos(xR));
+      o->sinx2m[j] = sin(xL);
+      o->sinx2[j] = sin(x2[j]);
+      o->tanx2[j] = tan(x2[j]);
+      o->dmu[j] = fabs(cos(xL) - cos(xR));
+    }
+  }
+  for (int k = 0; k < o->nx[2]; k++) o->xgc[2][k] = o->gx[2][k];
+  for (int a = 0; a < 3; a++) {
+    const double *gc = o->xgc[a], *xr = o->gxr[a], *dx = o->gdx[a];
+    for (int i = 1; i < o->nx[a] - 1; i++) {
+      o->wp[a][i] = dx[i] / (gc[i + 1] - gc[i]);
+      o->wm[a][i] = dx[i] / (gc[i] - gc[i - 1]);
+      o->cp[a][i] = (gc[i + 1] - gc[i]) / (xr[i] - gc[i]);
+      o->cm[a][i] = (gc[i] - gc[i - 1]) / (gc[i] - xr[i - 1]);
+      o->dp[a][i] = (xr[i] - gc[i]) / dx[i];
+      o->dm[a][i] = (gc[i] - xr[i - 1]) / dx[i];
+    }
+  }
+  /* Axis::Axis, axis.hpp:116-136 */
+  o->axis_left = o->d.ndim >= 2 && o->bcl[1] == BC_AXIS;
+  o->axis_right = o->d.ndim >= 2 && o->bcr[1] == BC_AXIS;
+  o->axis_twopi = fabs(o->gxr[2][o->end[2] - 1] - o->gxl[2][o->beg[2]] - 2.0 * M_PI) < 1e-10;
+}
+
+/* cell volume and face areas, makeGeometry.cpp:66-84 and :139-211 (D_EXPAND: factors of the active dimensions only,
+ * multiplied left to right) */
+static double cell_volume(const Oracle *o, int k, int j, int i) {
+  const int nd = o->d.ndim;
+  const double *x1m = o->gxl[0], *x1p = o->gxr[0];
+  double v;
+  if (o->geo == GEO_POLAR) {
+    v = fabs(x1p[i] * x1p[i] - x1m[i] * x1m[i]) / 2.0;
+    if (nd >= 2) v = v * o->gdx[1][j];
+    if (nd == 3) v = v * o->gdx[2][k];
+  } else { /* spherical */
+    v = fabs(x1p[i] * x1p[i] * x1p[i] - x1m[i] * x1m[i] * x1m[i]) / 3.0;
+    if (nd >= 2) v = v * fabs(cos(o->gxl[1][j]) - cos(o->gxr[1][j]));
+    if (nd == 3) v = v * o->gdx[2][k];
+  }
+  return v;
+}
+static double face_area_curv(const Oracle *o, int dir, int k, int j, int i) {
+  const int nd = o->d.ndim, sph = o->geo == GEO_SPHERICAL;
+  const double *x1 = o->gx[0], *x1m = o->gxl[0], *x1p = o->gxr[0], *dx1 = o->gdx[0];
+  const double *x2m = o->gxl[1], *x2p = o->gxr[1], *dx2 = o->gdx[1], *dx3 = o->gdx[2];
+  double A;
+  if (dir == 0) {
+    if (sph) A = (i == o->nx[0]) ? x1p[i - 1] * x1p[i - 1] : x1m[i] * x1m[i];
+    else A = (i == o->nx[0]) ? fabs(x1p[i - 1]) : fabs(x1m[i]);
+    if (nd >= 2) A = A * (sph ? fabs(cos(x2m[j]) - cos(x2p[j])) : dx2[j]);
+    if (nd == 3) A = A * dx3[k];
+  } else if (dir == 1) {
+    A = sph ? x1[i] * dx1[i] : dx1[i];
+    if (nd >= 2) A = A * (sph ? ((j == o->nx[1]) ? fabs(sin(x2p[j - 1])) : fabs(sin(x2m[j]))) : 1.0);
+    if (nd == 3) A = A * dx3[k];
+  } else {
+    A = x1[i] * dx1[i];
+    if (nd >= 2) A = A * dx2[j];
+    if (nd == 3) A = A * 1.0;
+  }
+  return A;
+}
+
 void oracle_destroy(Oracle *o) {
   if (!o) return;
+  for (int a = 0; a < 3; a++) {
+    double *g[] = {o->gx[a], o->gxl[a], o->gxr[a], o->gdx[a], o->xgc[a], o->wp[a], o->wm[a], o->cp[a], o->cm[a], o->dp[a], o->dm[a]};
+    for (unsigned q = 0; q < sizeof(g) / sizeof(g[0]); q++) free(g[q]);
+  }
+  free(o->rt); free(o->sinx2m); free(o->sinx2); free(o->tanx2); free(o->dmu);
   double *all[] = {o->Vc, o->Uc, o->Uc0, o->Flux, o->cMax, o->InvDt, o->Vs, o->Vs0, o->ex, o->ey, o->ez,
                    o->exj, o->exk, o->eyi, o->eyk, o->ezi, o->ezj, o->Ex1, o->Ex2, o->Ex3, o->svx, o->svy, o->svz};
   for (unsigned q = 0; q < sizeof(all) / sizeof(all[0]); q++) free(all[q]);
@@ -360,6 +498,40 @@ static void reconstruct_interface_flat(int order, const double *q, long s, int p
     dvp = q[s] - q[0];
     dv = flatR ? minmod_ref(dvp, dvm) : van_leer(dvp, dvm);
     *vR = q[0] - 0.5 * dv;
+  }
+}
+
+/* generalised van Leer limiter for non-uniform grids, slopeLimiter.hpp:58-65 */
+static double van_leer_irr(double dvp, double dvm, double cp, double cm) {
+  return dvp * dvm > 0.0 ? dvp * dvm * (cp * dvm + cm * dvp) / (dvp * dvp + dvm * dvm + (cp + cm - 2.0) * dvp * dvm) : 0.0;
+}
+/* ExtrapolatePrimVar when the grid is not "regular cartesian" (every curvilinear geometry, grid.cpp:49-51):
+ * PLM with the weights of ComputePLMweights (extrapolateToFaces.hpp:125-171), LimO3 with the local cell widths
+ * (:173-246), PPM unchanged (:247-307).  idx = index along the sweep of the cell right of the interface. */
+static void reconstruct_interface_flat(int order, const double *q, long s, int positive, double dx, double *vL,
+                                       double *vR, int flatL, int flatR);
+static void reconstruct_interface_curv(const Oracle *o, int dir, int idx, const double *q, long s, int positive,
+                                       double *vL, double *vR, int flatL, int flatR) {
+  const int order = o->d.order;
+  if (order == 2) {
+    double dvm = q[-s] - q[-2 * s];
+    double dvp = q[0] - q[-s];
+    dvm *= o->wm[dir][idx - 1];
+    dvp *= o->wp[dir][idx - 1];
+    double dv = flatL ? minmod_ref(dvp, dvm) : van_leer_irr(dvp, dvm, o->cp[dir][idx - 1], o->cm[dir][idx - 1]);
+    *vL = q[-s] + o->dp[dir][idx - 1] * dv;
+    dvm = q[0] - q[-s];
+    dvp = q[s] - q[0];
+    dvm *= o->wm[dir][idx];
+    dvp *= o->wp[dir][idx];
+    dv = flatR ? minmod_ref(dvp, dvm) : van_leer_irr(dvp, dvm, o->cp[dir][idx], o->cm[dir][idx]);
+    *vR = q[0] - o->dm[dir][idx] * dv;
+  } else if (order == 3) {
+    double a, b;
+    reconstruct_interface_flat(3, q, s, positive, o->gdx[dir][idx - 1], vL, &a, flatL, flatR);
+    reconstruct_interface_flat(3, q, s, positive, o->gdx[dir][idx], &b, vR, flatL, flatR);
+  } else {
+    reconstruct_interface_flat(order, q, s, positive, 0.0, vL, vR, flatL, flatR);
   }
 }
 
@@ -1227,9 +1399,20 @@ static void find_shock(Oracle *o) {
       for (int i = o->beg[0] - o->off[0]; i < o->end[0] + o->off[0]; i++) {
         const long c = C(o, k, j, i);
         o->flags[c] = 0;
-        double divV = (Vc[VX1 * sn + c + 1] - Vc[VX1 * sn + c - 1]) / (2 * d->dx[0]);
-        if (d->ndim >= 2) divV = divV + (Vc[(VX1 + 1) * sn + c + sj] - Vc[(VX1 + 1) * sn + c - sj]) / (2 * d->dx[1]);
-        if (d->ndim == 3) divV = divV + (Vc[(VX1 + 2) * sn + c + sk] - Vc[(VX1 + 2) * sn + c - sk]) / (2 * d->dx[2]);
+        double divV;
+        if (o->curv) { /* area-weighted divergence, shockFlattening.hpp:83-91 */
+          const double *V1 = Vc + VX1 * sn, *V2 = Vc + (VX1 + 1) * sn, *V3 = Vc + (VX1 + 2) * sn;
+          divV = (V1[c + 1] + V1[c]) * face_area_curv(o, 0, k, j, i + 1) - (V1[c - 1] + V1[c]) * face_area_curv(o, 0, k, j, i);
+          if (d->ndim >= 2)
+            divV = divV + (V2[c + sj] + V2[c]) * face_area_curv(o, 1, k, j + 1, i) - (V2[c - sj] + V2[c]) * face_area_curv(o, 1, k, j, i);
+          if (d->ndim == 3)
+            divV = divV + (V3[c + sk] + V3[c]) * face_area_curv(o, 2, k + 1, j, i) - (V3[c - sk] + V3[c]) * face_area_curv(o, 2, k, j, i);
+          divV = 0.5 * divV / cell_volume(o, k, j, i);
+        } else {
+          divV = (Vc[VX1 * sn + c + 1] - Vc[VX1 * sn + c - 1]) / (2 * d->dx[0]);
+          if (d->ndim >= 2) divV = divV + (Vc[(VX1 + 1) * sn + c + sj] - Vc[(VX1 + 1) * sn + c - sj]) / (2 * d->dx[1]);
+          if (d->ndim == 3) divV = divV + (Vc[(VX1 + 2) * sn + c + sk] - Vc[(VX1 + 2) * sn + c - sk]) / (2 * d->dx[2]);
+        }
         if (divV < 0.0) {
           double pmin, gradP;
           const long str[3] = {1, sj, sk};
@@ -1280,9 +1463,15 @@ static void calc_flux(Oracle *o, int dir) {
         const long c = C(o, k, j, i);
         double vL[8], vR[8], F[8];
         const int flatL = d->shock_flattening > 0.0 && o->flags[c - s], flatR = d->shock_flattening > 0.0 && o->flags[c];
-        for (int n = 0; n < nv; n++)
-          reconstruct_interface_flat(d->order, o->Vc + n * o->sn + c, s, n == o->RHO || n == o->ENG, d->dx[dir], &vL[n],
-                                     &vR[n], flatL, flatR);
+        const int idx = dir == 0 ? i : (dir == 1 ? j : k);
+        for (int n = 0; n < nv; n++) {
+          if (o->curv)
+            reconstruct_interface_curv(o, dir, idx, o->Vc + n * o->sn + c, s, n == o->RHO || n == o->ENG, &vL[n], &vR[n],
+                                       flatL, flatR);
+          else
+            reconstruct_interface_flat(d->order, o->Vc + n * o->sn + c, s, n == o->RHO || n == o->ENG, d->dx[dir], &vL[n],
+                                       &vR[n], flatL, flatR);
+        }
         Speeds sp = {0, 0, 0, 0};
         if (d->mhd) {
           vL[o->BX1 + dir] = vR[o->BX1 + dir] = o->Vs[dir * o->vn + S(o, k, j, i)];
@@ -1299,7 +1488,157 @@ static void calc_flux(Oracle *o, int dir) {
 }
 
 /* ---- Fluid_CorrectFluxFunctor + Fluid_CalcRHSFunctor, cartesian: calcRightHandSide.hpp:152-195, 201-551 */
+/* curvilinear geometry: Fluid_CorrectFluxFunctor (calcRightHandSide.hpp:152-195) and Fluid_CalcRHSFunctor (:330-551),
+ * without Fargo / rotation / gravity / parabolic terms / grid coarsening */
+static void calc_rhs_curv(Oracle *o, int dir) {
+  const OracleDesc *d = &o->d;
+  const int nv = o->nvar, geo = o->geo, nc = d->ncomp;
+  const long s = dir == 0 ? 1 : (dir == 1 ? o->sj : o->sk);
+  const double *x1 = o->gx[0], *x1m = o->gxl[0];
+  /* iMPHI / iBPHI / iBTH of idefix.hpp:128-188 (-1: not defined for this geometry / number of components) */
+  int mphi = -1, bphi = -1, bth = -1;
+  if (geo == GEO_POLAR && nc >= 2) { mphi = o->MX1 + 1; bphi = o->BX1 + 1; }
+  if (geo == GEO_SPHERICAL && nc == 3) { mphi = o->MX1 + 2; bphi = o->BX1 + 2; }
+  if (geo == GEO_SPHERICAL && nc >= 2) bth = o->BX1 + 1;
+  if (!d->mhd) bphi = bth = -1;
+  int hi[3];
+  for (int a = 0; a < 3; a++) hi[a] = o->end[a] + (a == dir ? 1 : 0);
+  for (int k = o->beg[2]; k < hi[2]; k++)
+    for (int j = o->beg[1]; j < hi[1]; j++)
+      for (int i = o->beg[0]; i < hi[0]; i++) {
+        const double A = face_area_curv(o, dir, k, j, i);
+        for (int n = 0; n < nv; n++) {
+          double Ax = A;
+          if (dir == 0) {
+            if (geo == GEO_POLAR) {
+              if (n == mphi) Ax *= fabs(x1m[i]);   /* conserve angular momentum */
+              if (n == bphi) Ax = 1.0;
+            } else {
+              if (n == mphi) Ax *= fabs(x1m[i]);
+              if (n == bth || n == bphi) Ax = x1m[i];
+            }
+          } else if (dir == 1 && geo == GEO_SPHERICAL && nc == 3) {
+            if (n == mphi) Ax *= fabs(o->sinx2m[j]);
+            if (n == bphi) Ax = 1.0;
+          }
+          o->Flux[n * o->sn + C(o, k, j, i)] = o->Flux[n * o->sn + C(o, k, j, i)] * Ax;
+        }
+      }
+  const double dt = o->dt;
+  for (int k = o->beg[2]; k < o->end[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0]; i++) {
+        const long c = C(o, k, j, i);
+        const double dtdV = dt / cell_volume(o, k, j, i);
+        double rhs[8];
+        for (int n = 0; n < nv; n++) rhs[n] = -dtdV * (o->Flux[n * o->sn + c + s] - o->Flux[n * o->sn + c]);
+        if (dir == 0) {
+          if (mphi >= 0) rhs[mphi] = rhs[mphi] / x1[i];
+          if (d->mhd) {
+            if (geo == GEO_POLAR) {
+              if (bphi >= 0) rhs[bphi] = -dt / o->gdx[0][i] * (o->Flux[bphi * o->sn + c + 1] - o->Flux[bphi * o->sn + c]);
+            } else {
+              const double q = dt / (x1[i] * o->gdx[0][i]);
+              if (bth >= 0) rhs[bth] = -q * ((o->Flux[bth * o->sn + c + 1] - o->Flux[bth * o->sn + c]));
+              if (bphi >= 0) rhs[bphi] = -q * ((o->Flux[bphi * o->sn + c + 1] - o->Flux[bphi * o->sn + c]));
+            }
+          }
+        } else if (dir == 1 && geo == GEO_SPHERICAL && nc == 3) {
+          rhs[mphi] /= fabs(o->sinx2[j]);
+          if (d->mhd)
+            rhs[bphi] = -dt / (o->rt[i] * o->gdx[1][j]) * (o->Flux[bphi * o->sn + c + o->sj] - o->Flux[bphi * o->sn + c]);
+        }
+        const int ig = dir == 0 ? i : (dir == 1 ? j : k);
+        double dl = o->gdx[dir][ig];
+        if (geo == GEO_POLAR) {
+          if (dir == 1) dl = dl * x1[i];
+        } else {
+          if (dir == 1) dl = dl * o->rt[i];
+          else if (dir == 2) dl = dl * o->rt[i] * o->dmu[j] / o->gdx[1][j];
+        }
+        o->InvDt[c] = o->InvDt[c] + 0.5 * (o->cMax[c + s] + o->cMax[c]) / (dl);
+        for (int n = 0; n < nv; n++) {
+          if (d->mhd && n >= o->BX1 && n < o->BX1 + d->ndim) continue;
+          o->Uc[n * o->sn + c] = o->Uc[n * o->sn + c] + rhs[n];
+        }
+      }
+}
+
+/* Fluid_AddSourceTermsFunctor, addSourceTerms.hpp:96-192: curvature terms of polar and spherical geometry */
+static void add_source_terms(Oracle *o) {
+  const OracleDesc *d = &o->d;
+  const int nc = d->ncomp, RHO = o->RHO, MX1 = o->MX1, BX1 = o->BX1, geo = o->geo;
+  const double dt = o->dt;
+  for (int k = o->beg[2]; k < o->end[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0]; i++) {
+        const long c = C(o, k, j, i);
+        double v[8];
+        for (int n = 0; n < o->nvar; n++) v[n] = o->Vc[n * o->sn + c];
+        double c2Iso = 0.0;
+        if (d->isothermal) { c2Iso = d->csiso; c2Iso *= c2Iso; }
+        if (geo == GEO_POLAR) {
+          if (nc < 2) continue;   /* iVPHI undefined */
+          const double vphi = v[MX1 + 1] + 0.0;
+          double Sm = v[RHO] * vphi * vphi;
+          if (d->isothermal) Sm += v[RHO] * c2Iso;
+          else Sm += v[o->ENG];
+          if (d->mhd) {
+            Sm -= v[BX1 + 1] * v[BX1 + 1];
+            double b2 = v[BX1] * v[BX1];
+            if (nc >= 2) b2 = b2 + v[BX1 + 1] * v[BX1 + 1];
+            if (nc == 3) b2 = b2 + v[BX1 + 2] * v[BX1 + 2];
+            Sm += 0.5 * (b2);
+          }
+          o->Uc[MX1 * o->sn + c] += dt * Sm / o->gx[0][i];
+        } else {
+          const double vphi = (nc == 3 ? v[MX1 + 2] : 0.0) + 0.0;
+          double vv = 0.0;
+          if (nc >= 2) vv = vv + v[MX1 + 1] * v[MX1 + 1];
+          if (nc == 3) vv = vv + vphi * vphi;
+          double Sm = v[RHO] * (vv);
+          if (d->isothermal) Sm += 2.0 * v[RHO] * c2Iso;
+          else Sm += 2.0 * v[o->ENG];
+          if (d->mhd) {
+            double hs = 0.0;
+            if (nc >= 2) hs = hs + v[BX1 + 1] * v[BX1 + 1];
+            if (nc == 3) hs = hs + v[BX1 + 2] * v[BX1 + 2];
+            Sm -= hs;
+            double b2 = v[BX1] * v[BX1];
+            if (nc >= 2) b2 = b2 + v[BX1 + 1] * v[BX1 + 1];
+            if (nc == 3) b2 = b2 + v[BX1 + 2] * v[BX1 + 2];
+            Sm += b2;
+          }
+          o->Uc[MX1 * o->sn + c] += dt * Sm / o->rt[i];
+          if (nc >= 2) {
+            const double ct = 1.0 / o->tanx2[j];
+            double cc = 0.0;
+            cc = cc - v[MX1 + 1] * v[MX1];
+            if (nc == 3) cc = cc + ct * vphi * vphi;
+            Sm = v[RHO] * (cc);
+            if (d->isothermal) Sm += ct * c2Iso * v[RHO];
+            else Sm += ct * v[o->ENG];
+            if (d->mhd) {
+              double hs = 0.0;
+              hs = hs + v[BX1 + 1] * v[BX1];
+              if (nc == 3) hs = hs - ct * v[BX1 + 2] * v[BX1 + 2];
+              Sm += hs;
+              double b2 = v[BX1] * v[BX1];
+              b2 = b2 + v[BX1 + 1] * v[BX1 + 1];
+              if (nc == 3) b2 = b2 + v[BX1 + 2] * v[BX1 + 2];
+              Sm += 0.5 * ct * (b2);
+            }
+            o->Uc[(MX1 + 1) * o->sn + c] += dt * Sm / o->rt[i];
+          }
+        }
+      }
+}
+
 static void calc_rhs(Oracle *o, int dir) {
+  if (o->curv) {
+    calc_rhs_curv(o, dir);
+    return;
+  }
   const OracleDesc *d = &o->d;
   const int nv = o->nvar;
   const long s = dir == 0 ? 1 : (dir == 1 ? o->sj : o->sk);
@@ -1508,8 +1847,54 @@ static void corner_emf(Oracle *o) {
       }
 }
 
+/* EvolveMagField, polar and spherical: evolveMagField.hpp:81-121 */
+static void evolve_mag_field_curv(Oracle *o) {
+  const int nd = o->d.ndim, haveAxis = o->axis_left || o->axis_right;
+  const long sj = o->sj, sk = o->sk;
+  const double dt = o->dt;
+  const double *x1 = o->gx[0], *x1m = o->gxl[0], *dx1 = o->gdx[0], *dx2 = o->gdx[1], *dx3 = o->gdx[2];
+  const double *Ex1 = o->ex, *Ex2 = o->ey, *Ex3 = o->ez;
+  for (int k = o->beg[2]; k < o->end[2] + o->off[2]; k++)
+    for (int j = o->beg[1]; j < o->end[1] + o->off[1]; j++)
+      for (int i = o->beg[0]; i < o->end[0] + o->off[0]; i++) {
+        const long c = C(o, k, j, i), s = S(o, k, j, i);
+        double r1 = 0.0, r2 = 0.0, r3 = 0.0;
+        if (o->geo == GEO_POLAR) {
+          if (nd >= 2) r1 = r1 - dt / (fabs(x1m[i]) * dx2[j]) * (Ex3[c + sj] - Ex3[c]);
+          if (nd == 3) r1 = r1 + dt / dx3[k] * (Ex2[c + sk] - Ex2[c]);
+          if (nd >= 2) {
+            r2 = dt / dx1[i] * (Ex3[c + 1] - Ex3[c]);
+            if (nd == 3) r2 = r2 - dt / dx3[k] * (Ex1[c + sk] - Ex1[c]);
+          }
+          if (nd == 3)
+            r3 = dt / (fabs(x1[i])) * (-(x1m[i + 1] * Ex2[c + 1] - x1m[i] * Ex2[c]) / dx1[i] + (Ex1[c + sj] - Ex1[c]) / dx2[j]);
+        } else {
+          const double dV2 = o->dmu[j];
+          const double Ax2p = fabs(o->sinx2m[j + 1]);
+          double Ax2m = fabs(o->sinx2m[j]);
+          if (nd >= 2) r1 = r1 - dt / (x1m[i] * dV2) * (Ax2p * Ex3[c + sj] - Ax2m * Ex3[c]);
+          if (nd == 3) r1 = r1 + dt * dx2[j] / (x1m[i] * dV2 * dx3[k]) * (Ex2[c + sk] - Ex2[c]);
+          if (nd >= 2) {
+            /* the area vanishes on the axis, where Ex1(k+1) - Ex1(k) = 0 anyway: evolveMagField.hpp:108-113 */
+            if (haveAxis && fabs(Ax2m) < 1e-12) Ax2m = 1.0;
+            r2 = dt / (x1[i] * dx1[i]) * (x1m[i + 1] * Ex3[c + 1] - x1m[i] * Ex3[c]);
+            if (nd == 3) r2 = r2 - dt / (x1[i] * Ax2m * dx3[k]) * (Ex1[c + sk] - Ex1[c]);
+          }
+          if (nd == 3)
+            r3 = -dt / (x1[i] * dx1[i]) * (x1m[i + 1] * Ex2[c + 1] - x1m[i] * Ex2[c]) + dt / (x1[i] * dx2[j]) * (Ex1[c + sj] - Ex1[c]);
+        }
+        o->Vs[s] = o->Vs[s] + r1;
+        if (nd >= 2) o->Vs[o->vn + s] = o->Vs[o->vn + s] + r2;
+        if (nd == 3) o->Vs[2 * o->vn + s] = o->Vs[2 * o->vn + s] + r3;
+      }
+}
+
 /* EvolveMagField, cartesian: evolveMagField.hpp:61-74 */
 static void evolve_mag_field(Oracle *o) {
+  if (o->curv) {
+    evolve_mag_field_curv(o);
+    return;
+  }
   const int nd = o->d.ndim;
   const long sj = o->sj, sk = o->sk;
   const double dt = o->dt, *dx = o->d.dx;
@@ -1552,6 +1937,40 @@ static void evolve_vector_potential(Oracle *o) {
 static void mag_field_from_a(Oracle *o) {
   const int nd = o->d.ndim;
   const long vj = o->vj, vk = o->vk;
+  if (o->curv) { /* evolveVectorPotential.hpp:76-116 */
+    const double *B1 = o->Ve, *B2 = o->Ve + o->vn, *B3 = o->Ve + (nd == 3 ? 2 : 0) * o->vn; /* AX1e, AX2e, AX3e */
+    const double *x1 = o->gx[0], *x1m = o->gxl[0], *dx1 = o->gdx[0], *dx2 = o->gdx[1], *dx3 = o->gdx[2];
+    const int haveAxis = o->axis_left || o->axis_right;
+    for (int k = o->beg[2]; k < o->end[2] + o->off[2]; k++)
+      for (int j = o->beg[1]; j < o->end[1] + o->off[1]; j++)
+        for (int i = o->beg[0]; i < o->end[0] + o->off[0]; i++) {
+          const long s = S(o, k, j, i);
+          double b1 = 0.0, b2 = 0.0, b3 = 0.0;
+          if (o->geo == GEO_POLAR) {
+            b1 = 0.0 + 1 / (fabs(x1m[i]) * dx2[j]) * (B3[s + vj] - B3[s]);
+            if (nd == 3) b1 = b1 - 1 / dx3[k] * (B2[s + vk] - B2[s]);
+            b2 = -1 / dx1[i] * (B3[s + 1] - B3[s]);
+            if (nd == 3) b2 = b2 + 1 / dx3[k] * (B1[s + vk] - B1[s]);
+            if (nd == 3)
+              b3 = 1 / (fabs(x1[i])) * ((x1m[i + 1] * B2[s + 1] - x1m[i] * B2[s]) / dx1[i] - (B1[s + vj] - B1[s]) / dx2[j]);
+          } else {
+            const double dV2 = o->dmu[j];
+            const double Ax2p = fabs(o->sinx2m[j + 1]);
+            double Ax2m = fabs(o->sinx2m[j]);
+            b1 = 0.0 + 1 / (x1m[i] * dV2) * (Ax2p * B3[s + vj] - Ax2m * B3[s]);
+            if (nd == 3) b1 = b1 - dx2[j] / (x1m[i] * dV2 * dx3[k]) * (B2[s + vk] - B2[s]);
+            if (haveAxis && fabs(Ax2m) < 1e-12) Ax2m = 1.0;
+            b2 = -1 / (x1[i] * dx1[i]) * (x1m[i + 1] * B3[s + 1] - x1m[i] * B3[s]);
+            if (nd == 3) b2 = b2 + 1 / (x1[i] * Ax2m * dx3[k]) * (B1[s + vk] - B1[s]);
+            if (nd == 3)
+              b3 = +1 / (x1[i] * dx1[i]) * (x1m[i + 1] * B2[s + 1] - x1m[i] * B2[s]) - 1 / (x1[i] * dx2[j]) * (B1[s + vj] - B1[s]);
+          }
+          o->Vs[s] = b1;
+          o->Vs[o->vn + s] = b2;
+          if (nd == 3) o->Vs[2 * o->vn + s] = b3;
+        }
+    return;
+  }
   const double *dx = o->d.dx;
   const double *A1 = o->Ve, *A2 = o->Ve + o->vn, *A3 = o->Ve + (nd == 3 ? 2 : 0) * o->vn;
   for (int k = o->beg[2]; k < o->end[2] + o->off[2]; k++)
@@ -1665,7 +2084,186 @@ static void reconstruct_normal_field(Oracle *o, int dir) {
   }
 }
 
+/* ---- general boundaries (per-side types, reflective, polar axis, curvilinear areas) ------------------------------ */
+/* Boundary::EnforceReflective, boundary.hpp:676-736: mirror image, normal velocity and tangential field change sign */
+static void fill_reflective(Oracle *o, double *q, long qj, long qk, int dir, int side, const int *n_int, const int *n_tot,
+                            int flip) {
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; a++) {
+    const int g = o->d.nghost[a];
+    lo[a] = (a == dir) ? side * (g + n_int[a]) : 0;
+    hi[a] = (a == dir) ? g + side * (g + n_int[a]) : n_tot[a];
+  }
+  const int g = o->d.nghost[dir], nn = o->d.np_int[dir];
+  for (int k = lo[2]; k < hi[2]; k++)
+    for (int j = lo[1]; j < hi[1]; j++)
+      for (int i = lo[0]; i < hi[0]; i++) {
+        int r[3] = {i, j, k};
+        r[dir] = 2 * (g + side * nn) - r[dir] - 1;
+        const double ref = q[(long)r[2] * qk + (long)r[1] * qj + r[0]];
+        q[(long)k * qk + (long)j * qj + i] = flip ? -1.0 * ref : 1.0 * ref;
+      }
+}
+/* Axis::EnforceAxisBoundary, axis.cpp:279-357: ghost cells across the axis come from the opposite meridian (x3 spans
+ * 2 pi: k shifted by half the active cells) or from the same one, mirrored in theta */
+static void fill_axis(Oracle *o, double *q, long qj, long qk, int side, const int *n_int, const int *n_tot, int flip) {
+  const int g = o->d.nghost[1], gk = o->d.nghost[2], nk = o->d.np_int[2];
+  const int jref = side == 0 ? o->beg[1] : o->end[1] - 1, offset = side == 0 ? -1 : 1;
+  const int jlo = side * (g + n_int[1]), jhi = g + side * (g + n_int[1]);
+  for (int k = 0; k < n_tot[2]; k++)
+    for (int j = jlo; j < jhi; j++)
+      for (int i = 0; i < n_tot[0]; i++) {
+        const int kcomp = o->axis_twopi ? gk + ((k - gk + nk / 2) % nk) : k;
+        const double ref = q[(long)kcomp * qk + (long)(2 * jref - j + offset) * qj + i];
+        q[(long)k * qk + (long)j * qj + i] = flip ? -1 * ref : 1 * ref;
+      }
+}
+/* Boundary::ReconstructNormalField with the face areas of any geometry, boundary.hpp:408-530; across an axis the phi
+ * direction is reversed (:471-474, 3-D only) */
+static void reconstruct_normal_field_curv(Oracle *o, int dir) {
+  const int nd = o->d.ndim;
+  const int left = !(o->bcl[dir] == BC_PERIODIC), right = !(o->bcr[dir] == BC_PERIODIC);
+  double *B1 = o->Vs, *B2 = nd >= 2 ? o->Vs + o->vn : NULL, *B3 = nd == 3 ? o->Vs + 2 * o->vn : NULL;
+#define AR(d_, k_, j_, i_) (o->curv ? face_area_curv(o, d_, k_, j_, i_) : face_area(o, d_))
+  if (dir == 0) {
+    for (int k = 0; k < o->nx[2]; k++)
+      for (int j = 0; j < o->nx[1]; j++) {
+        if (left)
+          for (int i = o->beg[0] - 1; i >= 0; i--) {
+            double tr = 0.0;
+            if (nd >= 2) tr = tr + AR(1, k, j + 1, i) * B2[S(o, k, j + 1, i)] - AR(1, k, j, i) * B2[S(o, k, j, i)];
+            if (nd == 3) tr = tr + AR(2, k + 1, j, i) * B3[S(o, k + 1, j, i)] - AR(2, k, j, i) * B3[S(o, k, j, i)];
+            B1[S(o, k, j, i)] = 1.0 / AR(0, k, j, i) * (AR(0, k, j, i + 1) * B1[S(o, k, j, i + 1)] + (tr));
+          }
+        if (right)
+          for (int i = o->end[0]; i < o->nx[0]; i++) {
+            double tr = 0.0;
+            if (nd >= 2) tr = tr + AR(1, k, j + 1, i) * B2[S(o, k, j + 1, i)] - AR(1, k, j, i) * B2[S(o, k, j, i)];
+            if (nd == 3) tr = tr + AR(2, k + 1, j, i) * B3[S(o, k + 1, j, i)] - AR(2, k, j, i) * B3[S(o, k, j, i)];
+            B1[S(o, k, j, i + 1)] = 1.0 / AR(0, k, j, i + 1) * (AR(0, k, j, i) * B1[S(o, k, j, i)] - (tr));
+          }
+      }
+  } else if (dir == 1) {
+    const int signLeft = (nd == 3 && o->axis_left) ? -1 : 1, signRight = (nd == 3 && o->axis_right) ? -1 : 1;
+    for (int k = 0; k < o->nx[2]; k++)
+      for (int i = 0; i < o->nx[0]; i++) {
+        if (left)
+          for (int j = o->beg[1] - 1; j >= 0; j--) {
+            double tr = AR(0, k, j, i + 1) * B1[S(o, k, j, i + 1)] - AR(0, k, j, i) * B1[S(o, k, j, i)];
+            if (nd == 3) tr = tr + signLeft * (AR(2, k + 1, j, i) * B3[S(o, k + 1, j, i)] - AR(2, k, j, i) * B3[S(o, k, j, i)]);
+            B2[S(o, k, j, i)] = 1.0 / AR(1, k, j, i) * (AR(1, k, j + 1, i) * B2[S(o, k, j + 1, i)] + (tr));
+          }
+        if (right)
+          for (int j = o->end[1]; j < o->nx[1]; j++) {
+            double tr = AR(0, k, j, i + 1) * B1[S(o, k, j, i + 1)] - AR(0, k, j, i) * B1[S(o, k, j, i)];
+            if (nd == 3) tr = tr + signRight * (AR(2, k + 1, j, i) * B3[S(o, k + 1, j, i)] - AR(2, k, j, i) * B3[S(o, k, j, i)]);
+            B2[S(o, k, j + 1, i)] = 1.0 / AR(1, k, j + 1, i) * (AR(1, k, j, i) * B2[S(o, k, j, i)] - (tr));
+          }
+      }
+  } else {
+    for (int j = 0; j < o->nx[1]; j++)
+      for (int i = 0; i < o->nx[0]; i++) {
+        if (left)
+          for (int k = o->beg[2] - 1; k >= 0; k--) {
+            const double tr = AR(0, k, j, i + 1) * B1[S(o, k, j, i + 1)] - AR(0, k, j, i) * B1[S(o, k, j, i)] +
+                              AR(1, k, j + 1, i) * B2[S(o, k, j + 1, i)] - AR(1, k, j, i) * B2[S(o, k, j, i)];
+            B3[S(o, k, j, i)] = 1.0 / AR(2, k, j, i) * (AR(2, k + 1, j, i) * B3[S(o, k + 1, j, i)] + (tr));
+          }
+        if (right)
+          for (int k = o->end[2]; k < o->nx[2]; k++) {
+            const double tr = AR(0, k, j, i + 1) * B1[S(o, k, j, i + 1)] - AR(0, k, j, i) * B1[S(o, k, j, i)] +
+                              AR(1, k, j + 1, i) * B2[S(o, k, j + 1, i)] - AR(1, k, j, i) * B2[S(o, k, j, i)];
+            B3[S(o, k + 1, j, i)] = 1.0 / AR(2, k + 1, j, i) * (AR(2, k, j, i) * B3[S(o, k, j, i)] - (tr));
+          }
+      }
+  }
+#undef AR
+}
+/* Axis::RegularizeBX2s, axis.cpp:362-395 (the reference is built with AXIS_BX2S_USE_ATHENA_REGULARISATION: mean of the
+ * two neighbours in theta, 3-D, active k; a fraction of 2 pi: zero) */
+static void axis_regularize_bx2s(Oracle *o) {
+  double *B2 = o->Vs + o->vn;
+  for (int side = 0; side < 2; side++) {
+    if (!(side == 0 ? o->axis_left : o->axis_right)) continue;
+    const int jaxis = side == 0 ? o->beg[1] : o->end[1];
+    if (o->axis_twopi) {
+      if (o->d.ndim == 3)
+        for (int k = o->beg[2]; k < o->end[2]; k++)
+          for (int i = 0; i < o->nx[0]; i++)
+            B2[S(o, k, jaxis, i)] = 0.5 * (B2[S(o, k, jaxis - 1, i)] + B2[S(o, k, jaxis + 1, i)]);
+    } else {
+      for (int k = 0; k < o->nx[2]; k++)
+        for (int i = 0; i < o->nx[0]; i++) B2[S(o, k, jaxis, i)] = 0.0;
+    }
+  }
+}
+/* Axis::RegularizeEMFs, axis.cpp:26-84,160-177: Ex1 on the axis = its mean around the pole (atomics of the reference
+ * run on one thread: ascending k) or zero, Ex3 on the axis = 0 */
+static void axis_regularize_emfs(Oracle *o) {
+  for (int side = 0; side < 2; side++) {
+    if (!(side == 0 ? o->axis_left : o->axis_right)) continue;
+    const int jref = side == 0 ? o->beg[1] : o->end[1];
+    for (int i = 0; i < o->nx[0]; i++) {
+      if (o->d.ndim == 3) {
+        double value = 0.0;
+        if (o->axis_twopi) {
+          double sum = 0.0;
+          for (int k = o->beg[2]; k < o->end[2]; k++) sum += o->ex[C(o, k, jref, i)];
+          value = sum / ((double)o->d.np_int[2]);
+        }
+        for (int k = 0; k < o->nx[2]; k++) o->ex[C(o, k, jref, i)] = value;
+      }
+      for (int k = 0; k < o->nx[2]; k++) o->ez[C(o, k, jref, i)] = 0.0;
+    }
+  }
+}
+
+static void set_boundaries_general(Oracle *o) {
+  const OracleDesc *d = &o->d;
+  for (int dir = 0; dir < d->ndim; dir++) {
+    for (int side = 0; side < 2; side++) {
+      const int type = side == 0 ? o->bcl[dir] : o->bcr[dir];
+      for (int n = 0; n < o->nvar + o->ntr; n++) {
+        double *q = o->Vc + n * o->sn;
+        if (type == BC_REFLECTIVE) {
+          fill_reflective(o, q, o->sj, o->sk, dir, side, d->np_int, o->nx,
+                          n == o->MX1 + dir || (d->mhd && n >= o->BX1 && n != o->BX1 + dir));
+        } else if (type == BC_AXIS) { /* symmetryVc, axis.hpp:133-144: VX2, VX3, BX2, BX3 */
+          const int flip = (d->ncomp >= 2 && n == o->MX1 + 1) || (d->ncomp == 3 && n == o->MX1 + 2) ||
+                           (d->mhd && d->ncomp >= 2 && n == o->BX1 + 1) || (d->mhd && d->ncomp == 3 && n == o->BX1 + 2);
+          fill_axis(o, q, o->sj, o->sk, side, d->np_int, o->nx, flip);
+        } else {
+          fill_ghosts(o, q, o->sj, o->sk, dir, side, type, d->np_int, o->nx, n == o->MX1 + dir);
+        }
+      }
+      if (d->mhd) {
+        for (int comp = 0; comp < d->ndim; comp++) {
+          if (type != BC_PERIODIC && comp == dir) continue; /* normal component: ReconstructNormalField */
+          int n_int[3], n_tot[3];
+          for (int a = 0; a < 3; a++) {
+            n_int[a] = d->np_int[a] + (a == comp ? 1 : 0);
+            n_tot[a] = o->nx[a] + (a == comp ? 1 : 0);
+          }
+          double *q = o->Vs + comp * o->vn;
+          if (type == BC_REFLECTIVE) fill_reflective(o, q, o->vj, o->vk, dir, side, n_int, n_tot, 1);
+          else if (type == BC_AXIS) fill_axis(o, q, o->vj, o->vk, side, n_int, n_tot, comp != 0); /* symmetryVs */
+          else fill_ghosts(o, q, o->vj, o->vk, dir, side, type, n_int, n_tot, 0);
+        }
+      }
+    }
+    if (d->mhd && (o->bcl[dir] != BC_PERIODIC || o->bcr[dir] != BC_PERIODIC)) {
+      reconstruct_normal_field_curv(o, dir);
+      if (dir == 1 && (o->axis_left || o->axis_right)) axis_regularize_bx2s(o); /* boundary.hpp:496-499 */
+    }
+  }
+  if (d->mhd) reconstruct_vc_field(o, o->Vc);
+}
+
 static void set_boundaries(Oracle *o) {
+  if (o->curv) {
+    set_boundaries_general(o);
+    return;
+  }
   const OracleDesc *d = &o->d;
   for (int dir = 0; dir < d->ndim; dir++) {
     for (int side = 0; side < 2; side++) {
@@ -1729,8 +2327,10 @@ int oracle_cycle(Oracle *o) {
       calc_rhs(o, dir);
       if (o->ntr > 0) tracer_calc_rhs(o, dir);
     }
+    if (o->curv) add_source_terms(o); /* evolveStage.hpp:58-59 */
     if (d->mhd && d->ndim >= 2) {
       corner_emf(o);
+      if (o->axis_left || o->axis_right) axis_regularize_emfs(o); /* enforceEMFBoundary.hpp:32-34 */
       if (o->Ve) { /* evolveStage.hpp:78-81 */
         evolve_vector_potential(o);
         mag_field_from_a(o);

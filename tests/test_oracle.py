@@ -143,15 +143,24 @@ def test_reference_build_with_axis_reproduces_shipped_golden():
 
 # ---- isothermal EOS: the problems live in the C++ host layer (idefix_b200/host/problems); the oracle starts
 # from the reference's own cycle-0 dump of the case and must reproduce its later dumps bit for bit ---------------
-ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2, 3, 1, True, True)}
-ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ISO_DEFS]
+ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2, 3, 1, True, True),
+            # curvilinear problem directories (definitions.hpp of idefix_b200/host/problems/<dir>)
+            "sph": Definitions(3, 3, 4, True, False), "polar": Definitions(3, 3, 3, True, False),
+            "sph25d": Definitions(2, 3, 4, True, False), "polarhd": Definitions(2, 2, 3, False, False),
+            "axis": Definitions(3, 3, 4, True, False)}
+ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ("sodiso", "iso25d")]
+# geometric terms of polar / spherical grids, stretched and logarithmic spacing, reflective sides, the polar axis,
+# shock flattening with the area-weighted divergence
+CURV_IN = [c for c in HOST_SHORT if c.setup in ("sph", "polar", "sph25d", "polarhd", "axis")]
 
 
 class _FromDump(Setup):
     """host-only set-up whose initial condition is the interior of a reference dump"""
 
     def __init__(self, case, dump):
-        self.defs = ISO_DEFS[case.setup]
+        d = ISO_DEFS[case.setup]
+        self.defs = Definitions(d.dimensions, d.components, d.geometry, d.mhd, d.isothermal,
+                                evolve_vector_potential=case.ref.endswith("_vp"))
         self.dump = dump
         super().__init__(order=case.order, device=None, ini=ini_for(case))
 
@@ -164,6 +173,12 @@ class _FromDump(Setup):
         for dd in range(self.definitions.dimensions if self.definitions.mhd else 0):
             off = [1 if e == dd else 0 for e in range(3)]
             h.Vs[dd, kb:ke + off[2], jb:je + off[1], ib:ie + off[0]] = self.dump.data[f"Vs-BX{dd + 1}s"].transpose(2, 1, 0)
+        if h.Ve is not None:
+            nd = self.definitions.dimensions
+            comps = [(0, "AX1e", 0), (1, "AX2e", 1), (2, "AX3e", 2)] if nd == 3 else [(0, "AX3e", 2)]
+            for n, name, dirn in comps:
+                off = [1 if (e != dirn and e < nd) else 0 for e in range(3)]
+                h.Ve[n, kb:ke + off[2], jb:je + off[1], ib:ie + off[0]] = self.dump.data[f"Ve-{name}"].transpose(2, 1, 0)
         data.host_mirror = h
 
 
@@ -174,6 +189,28 @@ def test_isothermal_oracle_matches_reference_build_bitwise(case):
     s.InitFlow(s.data)
     o = Oracle.from_setup(s)
     o.set_state(s.data.host_mirror.Vc, s.data.host_mirror.Vs)
+    done = 0
+    for n in case.cycles:
+        o.cycle(n - done)
+        done = n
+        gold = readDump(os.path.join(GOLD, "short", f"{case.name}.c{n:04d}.dmp"))
+        worst = compare(s, o, gold)
+        assert worst == 0.0, f"{case.name}: max |oracle - reference| = {worst} after {n} cycles"
+        assert o.t == float(gold.data["time"][0])
+    o.close()
+
+
+@pytest.mark.parametrize("case", CURV_IN, ids=[c.name for c in CURV_IN])
+def test_curvilinear_oracle_matches_reference_build_bitwise(case):
+    """polar / spherical geometry (area-weighted fluxes, angular-momentum form, geometric sources, irregular PLM /
+    LimO3 / PPM, curvilinear EvolveMagField, reflective sides, the polar axis): the restatement starts from the
+    reference build's cycle-0 dump of the case and must reproduce its later dumps bit for bit"""
+    assert len(CURV_IN) >= 21
+    s = _FromDump(case, readDump(os.path.join(GOLD, "short", f"{case.name}.c0000.dmp")))
+    s.InitFlow(s.data)
+    o = Oracle.from_setup(s)
+    h = s.data.host_mirror
+    o.set_state(h.Vc, h.Vs, h.Ve)
     done = 0
     for n in case.cycles:
         o.cycle(n - done)
