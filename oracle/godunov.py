@@ -49,6 +49,12 @@ def lib():
         L.oracle_derive_vector_potential.argtypes = [C.c_void_p]
         L.oracle_set_grid.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.oracle_set_grid.restype = None
+        L.oracle_add_source_terms.argtypes = [C.c_void_p]
+        L.oracle_add_source_terms.restype = None
+        L.oracle_uc.argtypes = [C.c_void_p]
+        L.oracle_uc.restype = C.POINTER(C.c_double)
+        L.oracle_reconstruct_curv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_reconstruct_curv.restype = None
         L.oracle_cycle.argtypes = [C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5
         L.oracle_riemann.restype = None

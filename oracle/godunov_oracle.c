@@ -1634,6 +1634,15 @@ static void add_source_terms(Oracle *o) {
       }
 }
 
+/* entry points of the host-compiled product source tests (tests/test_riemann_host.py) */
+void oracle_add_source_terms(Oracle *o) { add_source_terms(o); }
+double *oracle_uc(Oracle *o) { return o->Uc; }
+/* irregular-grid reconstruction along a 1-D array of nx[dir] cells with the block's own weights:
+ * vL[i] / vR[i] = left / right state of interface i-1/2 */
+void oracle_reconstruct_curv(Oracle *o, int dir, const double *q, int positive, double *vL, double *vR) {
+  for (int i = 3; i < o->nx[dir] - 2; i++) reconstruct_interface_curv(o, dir, i, q + i, 1, positive, &vL[i], &vR[i], 0, 0);
+}
+
 static void calc_rhs(Oracle *o, int dir) {
   if (o->curv) {
     calc_rhs_curv(o, dir);

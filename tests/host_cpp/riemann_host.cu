@@ -156,3 +156,66 @@ extern "C" int idfx_host_convert(int ncomp, int mhd, int iso, double gamma, doub
 #undef IDFX_CASE
   return 1;
 }
+
+// ---- irregular-grid reconstruction (recon.cuh, every non-cartesian geometry): per-cell weights {wp, wm, cp, cm, dp, dm}
+// of extrapolateToFaces.hpp:43-71 and the local cell width (LimO3) ------------------------------------------------
+template <int ORDER>
+static void reconstructIrregularAll(long n, const double *q, int positive, const double *w6, const double *dx, double *vL,
+                                    double *vR) {
+  for (long i = 3; i < n - 2; i++) {
+    double lo[2], hi[2];
+    for (int side = 0; side < 2; side++) {
+      const long c = i - 1 + side;
+      const double st[5] = {q[c - 2], q[c - 1], q[c], q[c + 1], q[c + 2]};
+      const double wc[6] = {w6[6 * c], w6[6 * c + 1], w6[6 * c + 2], w6[6 * c + 3], w6[6 * c + 4], w6[6 * c + 5]};
+      reconstructCell<ORDER, false>(st, positive != 0, false, wc, dx[c], lo[side], hi[side]);
+    }
+    vL[i] = hi[0];
+    vR[i] = lo[1];
+  }
+}
+extern "C" int idfx_host_reconstruct_irregular(int order, long n, const double *q, int positive, const double *w6,
+                                               const double *dx, double *vL, double *vR) {
+  if (order == 2) reconstructIrregularAll<2>(n, q, positive, w6, dx, vL, vR);
+  else if (order == 3) reconstructIrregularAll<3>(n, q, positive, w6, dx, vL, vR);
+  else if (order == 4) reconstructIrregularAll<4>(n, q, positive, w6, dx, vL, vR);
+  else return 1;
+  return 0;
+}
+
+// ---- geometrical source terms of polar / spherical grids (sweep.cuh::geometricSource, addSourceTerms.hpp:96-192) ---
+// (sweep.cuh also holds updateCell, whose fire-and-forget accumulation is a device atomic: give the host pass of this
+// test build a plain stand-in so that the header compiles; updateCell itself is not called here)
+template <class T>
+static __host__ __device__ inline T idfxHostAtomicAdd(T *p, T v) {
+  const T old = *p;
+  *p = old + v;
+  return old;
+}
+#define atomicAdd idfxHostAtomicAdd
+#include "sweep.cuh"
+#undef atomicAdd
+
+template <class P>
+static void sourceAll(const DevGrid &g, const Eos &eos, double dt, long n, const double *v, const int *jj, const int *ii,
+                      double *s1, double *s2) {
+  for (long c = 0; c < n; c++) geometricSource<P>(g, v + c * P::nvar, eos, dt, jj[c], ii[c], s1[c], s2[c]);
+}
+// x1 / rt: per radial index, tanx2: per latitudinal index; the n cells are addressed by (jj, ii)
+extern "C" int idfx_host_geometric_source(int geometry, int ndim, int ncomp, int mhd, int iso, double gamma, double csiso,
+                                          double dt, long n, const double *v, const int *jj, const int *ii, const double *x1,
+                                          const double *rt, const double *tanx2, double *s1, double *s2) {
+  DevGrid g{};
+  g.geometry = geometry;
+  g.ndim = ndim;
+  g.x[0] = x1;
+  g.rt = rt;
+  g.tanx2 = tanx2;
+  const Eos eos{gamma, csiso};
+#define SRC_CASE(ND, NC, M, I) \
+  if (ndim == ND && ncomp == NC && mhd == M && iso == I) { sourceAll<Phys<ND, NC, (M != 0), (I != 0)>>(g, eos, dt, n, v, jj, ii, s1, s2); return 0; }
+  SRC_CASE(3, 3, 1, 0) SRC_CASE(2, 3, 1, 0) SRC_CASE(2, 2, 0, 0) SRC_CASE(3, 3, 0, 0) SRC_CASE(2, 2, 1, 0)
+  SRC_CASE(2, 3, 1, 1) SRC_CASE(2, 3, 0, 1)
+#undef SRC_CASE
+  return 1;
+}

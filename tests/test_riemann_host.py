@@ -29,6 +29,8 @@ def host_lib(tmp_path_factory):
                                       + [C.c_int, C.c_void_p])
     lib.idfx_host_reconstruct.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     lib.idfx_host_convert.argtypes = [C.c_int] * 3 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 3
+    lib.idfx_host_reconstruct_irregular.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    lib.idfx_host_geometric_source.argtypes = ([C.c_int] * 5 + [C.c_double] * 3 + [C.c_long] + [C.c_void_p] * 8)
     return lib
 
 
@@ -187,4 +189,97 @@ def test_conversion_source_equals_oracle_bitwise(host_lib, ncomp, mhd, iso):
         assert (uo != u).any(), "the pressure floor never fired"
     for a, b in ((uo, up), (vo, vp), (u2o, u2p)):
         assert (a.view(np.int64) == b.view(np.int64)).all()
+    o.close()
+
+
+# ---- curvilinear geometry: the oracle now restates it (pinned bitwise on the reference builds by tests/test_oracle.py),
+# so the product's irregular-grid reconstruction and geometric source terms can be checked on the CPU as well ----------
+def _spherical_oracle(n1, n2, ncomp=3, mhd=True, order=2, geometry=4, csiso=None, rng=None):
+    """a 2-D (r, theta) block on a randomly stretched grid; returns (oracle, coordinates with ghosts)"""
+    import math
+    ng = 3 if order == 4 else 2
+    grid = []
+    for a, (n, lo, hi) in enumerate(((n1, 1.0, 4.0), (n2, 0.3, 2.8), (1, 0.0, 1.0))):
+        g = ng if a < 2 else 0
+        w = rng.uniform(0.5, 1.5, n + 2 * g) if a < 2 else np.ones(1)
+        edges = np.concatenate([[0.0], np.cumsum(w)])
+        edges = lo + (hi - lo) * (edges - edges[g]) / (edges[g + n] - edges[g])
+        xl, xr = edges[:-1].copy(), edges[1:].copy()
+        grid.append((0.5 * (xl + xr), xl, xr, xr - xl))
+    o = Oracle(2, ncomp, mhd, "hll", "uct_contact", 2, [n1, n2, 1], ["outflow", "outflow"], 1.4, 0.5, 1e-4, [0.1, 0.1, 0.1],
+               order=order, geometry=geometry, grid=grid, csiso=csiso)
+    return o, grid, ng
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+@pytest.mark.parametrize("positive", [0, 1])
+def test_irregular_reconstruction_source_equals_oracle_bitwise(host_lib, order, positive):
+    """recon.cuh on a non-uniform grid (the PLM weights of extrapolateToFaces.hpp:43-71, LimO3 with the local cell width):
+    product source per cell vs the oracle per interface, on a randomly stretched spherical radial grid"""
+    rng = np.random.default_rng(11 + order)
+    n1 = 4000
+    o, grid, ng = _spherical_oracle(n1, 8, order=order, rng=rng)
+    x, xl, xr, dx = grid[0]
+    n = n1 + 2 * ng
+    # the weights as the product's host code forms them (block.cu::buildGeometry, spherical radial direction)
+    gc = x + 2.0 * x * dx * dx / (12.0 * x * x + dx * dx)
+    w6 = np.zeros((n, 6))
+    i = np.arange(1, n - 1)
+    w6[i, 0] = dx[i] / (gc[i + 1] - gc[i])
+    w6[i, 1] = dx[i] / (gc[i] - gc[i - 1])
+    w6[i, 2] = (gc[i + 1] - gc[i]) / (xr[i] - gc[i])
+    w6[i, 3] = (gc[i] - gc[i - 1]) / (gc[i] - xr[i - 1])
+    w6[i, 4] = (xr[i] - gc[i]) / dx[i]
+    w6[i, 5] = (gc[i] - xr[i - 1]) / dx[i]
+    q = np.cumsum(rng.standard_normal(n)) * 0.1 + np.sin(np.arange(n) * 0.05)
+    q[n // 2:n // 2 + 400] = 10.0 ** rng.uniform(-6, 2, 400)
+    if positive:
+        q = np.abs(q) + 1e-12
+    q = np.ascontiguousarray(q)
+    out = [np.zeros(n) for _ in range(4)]
+    oracle_lib().oracle_reconstruct_curv(o.h, 0, q.ctypes.data, positive, out[0].ctypes.data, out[1].ctypes.data)
+    assert host_lib.idfx_host_reconstruct_irregular(order, n, q.ctypes.data, positive, w6.ctypes.data,
+                                                    np.ascontiguousarray(dx).ctypes.data, out[2].ctypes.data,
+                                                    out[3].ctypes.data) == 0
+    assert np.abs(out[0]).sum() > 0
+    assert (out[0].view(np.int64) == out[2].view(np.int64)).all(), "left states differ"
+    assert (out[1].view(np.int64) == out[3].view(np.int64)).all(), "right states differ"
+    o.close()
+
+
+@pytest.mark.parametrize("geometry,ncomp,mhd,iso", [(4, 3, 1, 0), (4, 3, 1, 1), (3, 2, 0, 0), (3, 2, 1, 0), (4, 3, 0, 1)])
+def test_geometric_source_terms_equal_oracle_bitwise(host_lib, geometry, ncomp, mhd, iso):
+    """sweep.cuh::geometricSource (centrifugal / pressure / hoop-stress terms of polar and spherical grids) against the
+    oracle's restatement of addSourceTerms.hpp:96-192 on random states of a randomly stretched grid"""
+    import math
+    rng = np.random.default_rng(31 + geometry + ncomp + 2 * mhd + 4 * iso)
+    n1, n2 = 96, 64
+    o, grid, ng = _spherical_oracle(n1, n2, ncomp=ncomp, mhd=bool(mhd), geometry=geometry, csiso=0.7 if iso else None, rng=rng)
+    nvar = o.nvar
+    o.Vc[...] = rng.uniform(-1.5, 1.5, o.Vc.shape)
+    o.Vc[0] = 10.0 ** rng.uniform(-1.5, 1.0, o.Vc.shape[1:])
+    if not iso:
+        o.Vc[ncomp + 1] = 10.0 ** rng.uniform(-2.0, 1.0, o.Vc.shape[1:])
+    nt = o.Vc.shape
+    Uc = np.ctypeslib.as_array(oracle_lib().oracle_uc(o.h), shape=nt)
+    Uc[...] = 0.0
+    oracle_lib().oracle_add_source_terms(o.h)
+    first_dt = 1e-4   # the oracle's dt before its first cycle
+    jj, ii = np.meshgrid(np.arange(ng, ng + n2, dtype=np.int32), np.arange(ng, ng + n1, dtype=np.int32), indexing="ij")
+    jj, ii = np.ascontiguousarray(jj.ravel()), np.ascontiguousarray(ii.ravel())
+    v = np.ascontiguousarray(o.Vc[:, 0][:, jj, ii].T)          # (n, nvar)
+    x1, xl1, xr1, _ = grid[0]
+    rt = np.array([(p * p * p - m * m * m) / (p * p - m * m) / 1.5 for p, m in zip(xr1, xl1)])
+    tanx2 = np.array([math.tan(t) for t in grid[1][0]])
+    s1, s2 = np.zeros(len(jj)), np.zeros(len(jj))
+    assert host_lib.idfx_host_geometric_source(geometry, 2, ncomp, mhd, iso, 1.4, 0.7, first_dt, len(jj), v.ctypes.data,
+                                               jj.ctypes.data, ii.ctypes.data, np.ascontiguousarray(x1).ctypes.data,
+                                               rt.ctypes.data, tanx2.ctypes.data, s1.ctypes.data, s2.ctypes.data) == 0
+    ref1 = Uc[1, 0][jj, ii]
+    assert np.abs(ref1).sum() > 0
+    assert (ref1.view(np.int64) == s1.view(np.int64)).all(), "radial source differs"
+    if geometry == 4 and ncomp >= 2:
+        ref2 = Uc[2, 0][jj, ii]
+        assert np.abs(ref2).sum() > 0
+        assert (np.ascontiguousarray(ref2).view(np.int64) == s2.view(np.int64)).all(), "latitudinal source differs"
     o.close()
