@@ -55,6 +55,13 @@ def lib():
         L.oracle_uc.restype = C.POINTER(C.c_double)
         L.oracle_reconstruct_curv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_reconstruct_curv.restype = None
+        L.oracle_calc_rhs.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_calc_rhs.restype = None
+        for name in ("oracle_flux", "oracle_cmax", "oracle_invdt"):
+            getattr(L, name).restype = C.POINTER(C.c_double)
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.oracle_geometry.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_geometry.restype = None
         L.oracle_cycle.argtypes = [C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_void_p, C.c_int, C.c_long] + [C.c_void_p] * 5
         L.oracle_riemann.restype = None

@@ -1643,6 +1643,21 @@ void oracle_reconstruct_curv(Oracle *o, int dir, const double *q, int positive, 
   for (int i = 3; i < o->nx[dir] - 2; i++) reconstruct_interface_curv(o, dir, i, q + i, 1, positive, &vL[i], &vR[i], 0, 0);
 }
 
+static void calc_rhs(Oracle *o, int dir);
+void oracle_calc_rhs(Oracle *o, int dir) { calc_rhs(o, dir); }
+double *oracle_flux(Oracle *o) { return o->Flux; }
+double *oracle_cmax(Oracle *o) { return o->cMax; }
+double *oracle_invdt(Oracle *o) { return o->InvDt; }
+/* face areas along dir and cell volumes in the cell-centred layout (curvilinear blocks only) */
+void oracle_geometry(Oracle *o, int dir, double *area, double *vol) {
+  for (int k = 0; k < o->nx[2]; k++)
+    for (int j = 0; j < o->nx[1]; j++)
+      for (int i = 0; i < o->nx[0]; i++) {
+        area[C(o, k, j, i)] = face_area_curv(o, dir, k, j, i);
+        vol[C(o, k, j, i)] = cell_volume(o, k, j, i);
+      }
+}
+
 static void calc_rhs(Oracle *o, int dir) {
   if (o->curv) {
     calc_rhs_curv(o, dir);

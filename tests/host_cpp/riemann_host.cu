@@ -219,3 +219,80 @@ extern "C" int idfx_host_geometric_source(int geometry, int ndim, int ncomp, int
 #undef SRC_CASE
   return 1;
 }
+
+// ---- area weighting of the interface flux and the conservative update of a cell in curvilinear geometry
+// (sweep.cuh::areaWeightFlux + updateCell: calcRightHandSide.hpp:152-195, 330-551, addSourceTerms.hpp) ----------------
+// Arrays in the reference's layouts: Vc / Uc / Flux (nvar, k, j, i), InvDt / cMax / area / vol (k, j, i); area[c] = area
+// of the lower face of cell c along DIR.  Every active cell is updated in place like the sweeps do it.
+template <class P, int DIR>
+static void rhsAll(const DevGrid &g, const Eos &eos, double dt, int doSource, const double *Vc, double *Uc, double *invDt,
+                   const double *Flux, const double *cMax, const double *area, const double *vol) {
+  SweepArgs a{};
+  a.g = g;
+  a.Vc = Vc;
+  a.Uc = Uc;
+  a.invDt = invDt;
+  a.doInvDt = 1;
+  a.doSource = doSource;
+  const long long s = DIR == 0 ? 1 : (DIR == 1 ? g.sj : g.sk);
+  for (int k = g.beg[2]; k < g.end[2]; k++)
+    for (int j = g.beg[1]; j < g.end[1]; j++)
+      for (int i = g.beg[0]; i < g.end[0]; i++) {
+        const long long c = cidx(g, k, j, i);
+        double Fm[P::nvar], Fp[P::nvar];
+        for (int nv = 0; nv < P::nvar; nv++) {
+          Fm[nv] = Flux[nv * g.sn + c];
+          Fp[nv] = Flux[nv * g.sn + c + s];
+        }
+        areaWeightFlux<P, DIR>(g, g.geometry, area[c], k, j, i, Fm);
+        areaWeightFlux<P, DIR>(g, g.geometry, area[c + s], k + (DIR == 2), j + (DIR == 1), i + (DIR == 0), Fp);
+        const int idir = DIR == 0 ? i : (DIR == 1 ? j : k);
+        updateCell<P, DIR>(a, g, g.geometry, eos, dt, vol[c], g.dx[DIR][idir], k, j, i, c, Fm, Fp, cMax[c], cMax[c + s],
+                           [&](int nv) { return Vc[nv * g.sn + c]; });
+      }
+}
+template <class P>
+static int rhsByDir(int dir, const DevGrid &g, const Eos &eos, double dt, int doSource, const double *Vc, double *Uc,
+                    double *invDt, const double *Flux, const double *cMax, const double *area, const double *vol) {
+  if (dir == 0) rhsAll<P, 0>(g, eos, dt, doSource, Vc, Uc, invDt, Flux, cMax, area, vol);
+  else if (dir == 1) rhsAll<P, 1>(g, eos, dt, doSource, Vc, Uc, invDt, Flux, cMax, area, vol);
+  else if (dir == 2 && P::ndim == 3) rhsAll<P, (P::ndim == 3 ? 2 : 0)>(g, eos, dt, doSource, Vc, Uc, invDt, Flux, cMax, area, vol);
+  else return 1;
+  return 0;
+}
+// coords: x1, x1l, dx1, rt (n1 each), dx2, sinx2, sinx2m, dmu, tanx2 (n2 each), in this order
+extern "C" int idfx_host_curvilinear_rhs(int geometry, int ndim, int ncomp, int mhd, int iso, int dir, double gamma,
+                                         double csiso, double dt, int doSource, const int *nx, const int *ng,
+                                         const double *const *coords, const double *Vc, double *Uc, double *invDt,
+                                         const double *Flux, const double *cMax, const double *area, const double *vol) {
+  DevGrid g{};
+  g.geometry = geometry;
+  g.ndim = ndim;
+  for (int d = 0; d < 3; d++) {
+    g.nx[d] = nx[d];
+    g.ng[d] = ng[d];
+    g.beg[d] = ng[d];
+    g.end[d] = nx[d] - ng[d];
+    g.off[d] = d < ndim ? 1 : 0;
+  }
+  g.sj = nx[0];
+  g.sk = (long long)nx[0] * nx[1];
+  g.sn = g.sk * nx[2];
+  g.x[0] = coords[0];
+  g.xl[0] = coords[1];
+  g.dx[0] = coords[2];
+  g.rt = coords[3];
+  g.dx[1] = coords[4];
+  g.sinx2 = coords[5];
+  g.sinx2m = coords[6];
+  g.dmu = coords[7];
+  g.tanx2 = coords[8];
+  g.dx[2] = coords[9];
+  const Eos eos{gamma, csiso};
+#define RHS_CASE(ND, NC, M, I) \
+  if (ndim == ND && ncomp == NC && mhd == M && iso == I)  \
+    return rhsByDir<Phys<ND, NC, (M != 0), (I != 0)>>(dir, g, eos, dt, doSource, Vc, Uc, invDt, Flux, cMax, area, vol);
+  RHS_CASE(3, 3, 1, 0) RHS_CASE(2, 3, 1, 0) RHS_CASE(2, 2, 0, 0) RHS_CASE(3, 3, 0, 0) RHS_CASE(2, 3, 1, 1)
+#undef RHS_CASE
+  return 1;
+}

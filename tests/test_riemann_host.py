@@ -31,6 +31,7 @@ def host_lib(tmp_path_factory):
     lib.idfx_host_convert.argtypes = [C.c_int] * 3 + [C.c_double, C.c_double, C.c_long] + [C.c_void_p] * 3
     lib.idfx_host_reconstruct_irregular.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_int] + [C.c_void_p] * 4
     lib.idfx_host_geometric_source.argtypes = ([C.c_int] * 5 + [C.c_double] * 3 + [C.c_long] + [C.c_void_p] * 8)
+    lib.idfx_host_curvilinear_rhs.argtypes = ([C.c_int] * 6 + [C.c_double] * 3 + [C.c_int] + [C.c_void_p] * 10)
     return lib
 
 
@@ -282,4 +283,77 @@ def test_geometric_source_terms_equal_oracle_bitwise(host_lib, geometry, ncomp, 
         ref2 = Uc[2, 0][jj, ii]
         assert np.abs(ref2).sum() > 0
         assert (np.ascontiguousarray(ref2).view(np.int64) == s2.view(np.int64)).all(), "latitudinal source differs"
+    o.close()
+
+
+def _stretched_block(rng, geometry, ndim, ncomp, mhd, n=(10, 9, 8)):
+    """an oracle block of `ndim` dimensions in polar (3) / spherical (4) geometry on randomly stretched grids"""
+    ng = 2
+    grid, np_int = [], []
+    ranges = ((1.0, 3.0), (0.4, 2.6) if geometry == 4 else (0.0, 1.5), (0.0, 1.2))
+    for a in range(3):
+        na = n[a] if a < ndim else 1
+        g = ng if a < ndim else 0
+        w = rng.uniform(0.6, 1.4, na + 2 * g)
+        edges = np.concatenate([[0.0], np.cumsum(w)])
+        lo, hi = ranges[a]
+        edges = lo + (hi - lo) * (edges - edges[g]) / (edges[g + na] - edges[g])
+        xl, xr = edges[:-1].copy(), edges[1:].copy()
+        grid.append((0.5 * (xl + xr), xl, xr, xr - xl))
+        np_int.append(na)
+    o = Oracle(ndim, ncomp, mhd, "hll", "uct_contact", 2, np_int, ["outflow"] * ndim, 1.4, 0.5, 1e-4, [0.1, 0.1, 0.1],
+               geometry=geometry, grid=grid)
+    return o, grid, ng
+
+
+@pytest.mark.parametrize("geometry,ndim,ncomp,mhd", [(4, 3, 3, True), (3, 3, 3, True), (4, 2, 3, True), (3, 2, 2, False),
+                                                     (4, 3, 3, False)])
+def test_curvilinear_update_source_equals_oracle_bitwise(host_lib, geometry, ndim, ncomp, mhd):
+    """sweep.cuh::areaWeightFlux + updateCell (area weighting in angular-momentum form, the B_theta / B_phi flux factors,
+    the curvilinear right-hand side, the cell crossing time of the CFL estimate, geometric sources on the last sweep)
+    against the oracle's Fluid_CorrectFluxFunctor / Fluid_CalcRHSFunctor / AddSourceTerms on random data"""
+    import math
+    rng = np.random.default_rng(101 + 7 * geometry + ndim + ncomp + int(mhd))
+    o, grid, ng = _stretched_block(rng, geometry, ndim, ncomp, mhd)
+    L = oracle_lib()
+    shape = o.Vc.shape
+    ncell = int(np.prod(shape[1:]))
+    view = lambda ptr, shp: np.ctypeslib.as_array(ptr, shape=shp)   # noqa: E731
+    Uc, Flux = view(L.oracle_uc(o.h), shape), view(L.oracle_flux(o.h), shape)
+    cMax, InvDt = view(L.oracle_cmax(o.h), shape[1:]), view(L.oracle_invdt(o.h), shape[1:])
+    o.Vc[...] = rng.uniform(-1.5, 1.5, shape)
+    o.Vc[0] = 10.0 ** rng.uniform(-1.5, 1.0, shape[1:])
+    o.Vc[ncomp + 1] = 10.0 ** rng.uniform(-2.0, 1.0, shape[1:])
+    Uc[...] = rng.uniform(-2.0, 2.0, shape)
+    InvDt[...] = rng.uniform(0.0, 5.0, shape[1:])
+    mine_Uc, mine_InvDt = Uc.copy(), InvDt.copy()
+    start_Uc = Uc.copy()
+    x1, x1l, x1r, dx1 = grid[0]
+    x2, x2l, x2r, dx2 = grid[1]
+    coords = [x1, x1l, dx1, np.array([(p * p * p - m * m * m) / (p * p - m * m) / 1.5 for p, m in zip(x1r, x1l)]),
+              dx2, np.array([math.sin(t) for t in x2]), np.array([math.sin(t) for t in x2l]),
+              np.array([abs(math.cos(a) - math.cos(b)) for a, b in zip(x2l, x2r)]), np.array([math.tan(t) for t in x2]),
+              grid[2][3]]
+    coords = [np.ascontiguousarray(c, float) for c in coords]
+    cptr = (C.c_void_p * len(coords))(*[c.ctypes.data for c in coords])
+    nx = (C.c_int * 3)(shape[3], shape[2], shape[1])
+    ngs = (C.c_int * 3)(*[ng if a < ndim else 0 for a in range(3)])
+    area, vol = np.zeros(shape[1:]), np.zeros(shape[1:])
+    for dir in range(ndim):
+        raw = rng.uniform(-1.0, 1.0, shape)
+        cm = rng.uniform(0.1, 3.0, shape[1:])
+        Flux[...] = raw
+        cMax[...] = cm
+        L.oracle_geometry(o.h, dir, area.ctypes.data, vol.ctypes.data)
+        L.oracle_calc_rhs(o.h, dir)
+        assert host_lib.idfx_host_curvilinear_rhs(geometry, ndim, ncomp, int(mhd), 0, dir, 1.4, 0.0, 1e-4,
+                                                  int(dir == ndim - 1), nx, ngs, cptr, o.Vc.ctypes.data,
+                                                  mine_Uc.ctypes.data, mine_InvDt.ctypes.data, raw.ctypes.data,
+                                                  cm.ctypes.data, area.ctypes.data, vol.ctypes.data) == 0
+    L.oracle_add_source_terms(o.h)
+    active = tuple(slice(ng, -ng) if a < ndim else slice(None) for a in (2, 1, 0))
+    assert (Uc[(slice(None),) + active] != start_Uc[(slice(None),) + active]).mean() > 0.6   # the update did something
+    assert ncell > 0 and (Uc != mine_Uc).sum() == 0, np.argwhere(Uc != mine_Uc)[:5]
+    assert (InvDt.view(np.int64) == mine_InvDt.view(np.int64)).all()
+    assert (Uc.view(np.int64) == mine_Uc.view(np.int64)).all()
     o.close()
