@@ -232,10 +232,18 @@ X3-end    periodic
 """
 
 
-def test_cpp_host_input_and_grid_match_python_mirror(tmp_path):
+@pytest.mark.parametrize("with_axis", [False, True], ids=["reflective", "axis"])
+def test_cpp_host_input_and_grid_match_python_mirror(tmp_path, with_axis):
     """CPU-only: the C++ Input / Grid (ini grammar, patch types u / l / s+ / s-, Newton solve of the stretch
     factor, GetOrSet's ostream round trip of defaults) produce bit-identical coordinates and the same values as
-    the Python mirror, which tests/test_host.py pins against the reference's own grids"""
+    the Python mirror, which tests/test_host.py pins against the reference's own grids.  with_axis: theta from 0 to
+    pi on 16 cells between two axis boundaries -- the ghost spacing mirrored across the axis (gridHost.cpp:246-262),
+    where rebuilding the faces outwards from the axis changes the outermost one by an ulp"""
+    HOST_LOGIC_INI = globals()["HOST_LOGIC_INI"]
+    if with_axis:
+        HOST_LOGIC_INI = (HOST_LOGIC_INI.replace("X2-grid    1  0.3  7  u  2.8", "X2-grid    1  0.0  16  u  3.141592653589793")
+                          .replace("X2-beg    reflective", "X2-beg    axis").replace("X2-end    reflective", "X2-end    axis"))
+        assert "axis" in HOST_LOGIC_INI and "16  u" in HOST_LOGIC_INI
     from idefix_b200 import _abi
     from idefix_b200.grid import Definitions, Grid
     from idefix_b200.input import Input
@@ -269,6 +277,9 @@ def test_cpp_host_input_and_grid_match_python_mirror(tmp_path):
     for d in range(3):
         for i in range(g.np_tot[d]):
             assert got[(d, i)] == [float(g.x[d][i]), float(g.xl[d][i]), float(g.xr[d][i]), float(g.dx[d][i])], (d, i)
+    if with_axis:   # the mirrored ghosts differ from a plain continuation of the uniform grid (16 cells: by one ulp)
+        n, ng = g.np_int[1], g.nghost[1]
+        assert g.haveAxis and float(g.xr[1][ng + n + 1]) != 0.0 + (n + 2) * float(g.dx[1][ng])
     vals = {ln.split()[0]: ln.split()[1:] for ln in lines if ln.split()[0] in ("gamma", "cflmaxvar", "nstages", "solver", "check")}
     assert float.fromhex(vals["gamma"][0]) == inp.GetOrSet(float, "Hydro", "gamma", 0, 5.0 / 3.0) == 1.66667
     assert float.fromhex(vals["cflmaxvar"][0]) == 1.1 and vals["nstages"] == ["3"] and vals["solver"] == ["hlld"]
