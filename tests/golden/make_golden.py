@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_SHORT, SHORT, ini_for  # noqa: E402
+from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_ONLY_SHORT, ORACLE_SHORT, SHORT, ini_for  # noqa: E402
 from oracle.ref_run import cleanup, run_reference  # noqa: E402
 
 REFERENCE_GOLDENS = "/root/reference/reference"
@@ -27,7 +27,7 @@ REFERENCE_GOLDENS = "/root/reference/reference"
 def main():
     only = set(sys.argv[1:])
     os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
-    for case in SHORT + HOST_SHORT + ORACLE_SHORT:
+    for case in SHORT + HOST_SHORT + ORACLE_SHORT + ORACLE_ONLY_SHORT:
         if only and case.name not in only:
             continue
         wanted = [0] + list(case.cycles)
@@ -35,7 +35,7 @@ def main():
             continue
         # Axis::SymmetrizeEx1Side adds the radial EMFs around the pole with atomics (axis.cpp:39-42): only a single
         # thread gives a reproducible (ascending-k) order, and that is the order the CUDA kernel uses
-        threads = 1 if case.setup == "axis" else None
+        threads = 1 if case.setup in ("axis", "axis25d") else None
         res = run_reference(case.ref, ini_for(case, dump_every_cycle=True), maxcycles=max(case.cycles), keep=True, timeout=600,
                             threads=threads)
         for n in wanted:

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_SHORT, SHORT, ini_for
+from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_ONLY_SHORT, ORACLE_SHORT, SHORT, ini_for
 from idefix_b200.dump import readDump, vc_names
 from idefix_b200.datablock import DataBlockHost
 from idefix_b200.grid import Definitions
@@ -147,11 +147,12 @@ ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2
             # curvilinear problem directories (definitions.hpp of idefix_b200/host/problems/<dir>)
             "sph": Definitions(3, 3, 4, True, False), "polar": Definitions(3, 3, 3, True, False),
             "sph25d": Definitions(2, 3, 4, True, False), "polarhd": Definitions(2, 2, 3, False, False),
-            "axis": Definitions(3, 3, 4, True, False)}
+            "axis": Definitions(3, 3, 4, True, False), "axis25d": Definitions(2, 3, 4, True, False)}
 ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ("sodiso", "iso25d")]
 # geometric terms of polar / spherical grids, stretched and logarithmic spacing, reflective sides, the polar axis,
 # shock flattening with the area-weighted divergence
-CURV_IN = [c for c in HOST_SHORT if c.setup in ("sph", "polar", "sph25d", "polarhd", "axis")]
+CURV_IN = [c for c in HOST_SHORT if c.setup in ("sph", "polar", "sph25d", "polarhd", "axis")] + \
+    ORACLE_ONLY_SHORT
 
 
 class _FromDump(Setup):
@@ -205,7 +206,7 @@ def test_curvilinear_oracle_matches_reference_build_bitwise(case):
     """polar / spherical geometry (area-weighted fluxes, angular-momentum form, geometric sources, irregular PLM /
     LimO3 / PPM, curvilinear EvolveMagField, reflective sides, the polar axis): the restatement starts from the
     reference build's cycle-0 dump of the case and must reproduce its later dumps bit for bit"""
-    assert len(CURV_IN) >= 21
+    assert len(CURV_IN) >= 23
     s = _FromDump(case, readDump(os.path.join(GOLD, "short", f"{case.name}.c0000.dmp")))
     s.InitFlow(s.data)
     o = Oracle.from_setup(s)
