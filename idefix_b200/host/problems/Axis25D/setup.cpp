@@ -1,7 +1,7 @@
 // Axisymmetric flow along the polar axis of a rotating, magnetised shell: uniform velocity and field along z (both
 // regular on the axis), solid-body rotation, a toroidal field proportional to the cylindrical radius and a dense blob
-// on the northern axis.  Test infrastructure: built against the REFERENCE only (oracle/ref_build), to pin the
-// oracle's 2-D axis path (no average around the pole, B_theta = 0 and E_phi = 0 on the axis) on the CPU.
+// on the northern axis: the 2-D axis path (no average around the pole, B_theta = 0 and E_phi = 0 on the axis).
+// Compiles unchanged against the reference and against the B200 host layer.
 #include "idefix.hpp"
 #include "setup.hpp"
 

@@ -28,7 +28,7 @@ b sph_limo3    $P/SphericalMHD            YES 3
 b sph_plm      $P/SphericalMHD            YES 2
 b axisfluxtube_plm test/MHD/AxisFluxTube   YES 2
 b axis_plm     $P/AxisMHD                 YES 2
-b axis25d_plm  $(pwd)/problems/Axis25D    YES 2 TPX
+b axis25d_plm  $P/Axis25D                 YES 2 TPX
 b axis_limo3   $P/AxisMHD                 YES 3
 b axis_plm_vp  $P/AxisMHD                 YES 2 "" 1
 b polar_plm    $P/PolarMHD                YES 2

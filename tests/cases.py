@@ -101,8 +101,7 @@ SHORT = [
 # (idefix_b200/host/problems/<dir>: definitions.hpp + setup.cpp + idefix.ini, written against the
 # reference's user API) are compiled twice -- by oracle/ref_build against the REFERENCE sources (the
 # fixtures) and by idefix_b200/host against our host layer (the run under test, tests/test_host_cpp.py).
-ORACLE_PROBLEM_DIRS = {"axis25d": "Axis25D"}
-PROBLEM_DIRS = {"axis": "AxisMHD", "othooks": "otHooks", "sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
+PROBLEM_DIRS = {"axis": "AxisMHD", "axis25d": "Axis25D", "othooks": "otHooks", "sodstrong": "sodStrong", "sph": "SphericalMHD", "polar": "PolarMHD", "sodiso": "sodIso", "iso25d": "IsoMHD25D", "sph25d": "Spherical25D", "polarhd": "PolarHD2D"}
 
 
 def _sph(solver, emf=None, nstages=2):
@@ -153,6 +152,11 @@ HOST_SHORT = [
     Short("axis_south_tvdlf_arith_plm", "axis", 2, "axis_plm",
           _axis("tvdlf", "arithmetic", x2=("1.5707963267948966", "3.141592653589793"), beg="outflow"), (1, 10)),
     Short("axis_hlld_contact_plm_vp", "axis", 2, "axis_plm_vp", _axis("hlld"), (1, 10)),
+    # 2.5-D spherical block between two axis boundaries (problems/Axis25D): no average around the pole, B_theta = 0 and
+    # E_phi = 0 on the axis
+    Short("axis25d_hlld_contact_plm", "axis25d", 2, "axis25d_plm", {("Hydro", "solver"): "hlld"}, (1, 10)),
+    Short("axis25d_roe_uct0_plm_rk3", "axis25d", 2, "axis25d_plm",
+          {("Hydro", "solver"): "roe", ("Hydro", "emf"): "uct0", ("TimeIntegrator", "nstages"): 3}, (1, 10)),
     Short("axis_hlld_ucthlld_plm", "axis", 2, "axis_plm", _axis("hlld", "uct_hlld"), (1, 10)),
     Short("axis_hll_contact_plm_rk3", "axis", 2, "axis_plm", _axis("hll", None, 3, n=(12, 20, 24)), (1, 10)),
     Short("axis_south_hlld_contact_plm", "axis", 2, "axis_plm",
@@ -244,15 +248,6 @@ ORACLE_SHORT = [
     Short("sodstrong_roe_plm", "sodstrong", 2, "sodstrong_plm", _sod("roe"), (1, 10, 60)),
     Short("sodstrong_roe_plm_rk3", "sodstrong", 2, "sodstrong_plm", _sod("roe", 3), (1, 40)),
 ]
-# Cases of the ORACLE alone (tests/test_oracle.py, CPU): a 2.5-D spherical block between two axis boundaries -- the 2-D
-# axis path (no average around the pole, B_theta = 0 and E_phi = 0 on the axis) against a reference build of
-# oracle/ref_build/problems/Axis25D.  The CUDA path of this configuration was written with the 3-D axis work but has
-# not run on a device yet, so no GPU test lists these.
-ORACLE_ONLY_SHORT = [
-    Short("axis25d_hlld_contact_plm", "axis25d", 2, "axis25d_plm", {("Hydro", "solver"): "hlld"}, (1, 10)),
-    Short("axis25d_roe_uct0_plm_rk3", "axis25d", 2, "axis25d_plm",
-          {("Hydro", "solver"): "roe", ("Hydro", "emf"): "uct0", ("TimeIntegrator", "nstages"): 3}, (1, 10)),
-]
 ORACLE_FULL = [
     Full("sod_roe", "sod", 2, _sod("roe"), "HD/sod/dump.ref.double.plm.idefix.ini.dmp", 0.0),
     Full("sod_roe_ppm_rk3", "sod", 4, _sod("roe", 3), "HD/sod/dump.ref.double.ppm.idefix-rk3.ini.dmp", 0.0),
@@ -289,11 +284,7 @@ def ini_for(case, dump_every_cycle=False):
     import os
     from idefix_b200.input import Input
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if case.setup in ORACLE_PROBLEM_DIRS:   # reference-only problem directories (test infrastructure)
-        inp = Input(os.path.join(here, "oracle", "ref_build", "problems", ORACLE_PROBLEM_DIRS[case.setup], "idefix.ini"))
-        for name in ("dmp", "vtk"):
-            inp.remove("Output", name)
-    elif case.setup in PROBLEM_DIRS:
+    if case.setup in PROBLEM_DIRS:
         inp = Input(os.path.join(here, "idefix_b200", "host", "problems", PROBLEM_DIRS[case.setup], "idefix.ini"))
         for name in ("dmp", "vtk"):
             inp.remove("Output", name)

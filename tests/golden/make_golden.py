@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_ONLY_SHORT, ORACLE_SHORT, SHORT, ini_for  # noqa: E402
+from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_SHORT, SHORT, ini_for  # noqa: E402
 from oracle.ref_run import cleanup, run_reference  # noqa: E402
 
 REFERENCE_GOLDENS = "/root/reference/reference"
@@ -27,7 +27,7 @@ REFERENCE_GOLDENS = "/root/reference/reference"
 def main():
     only = set(sys.argv[1:])
     os.makedirs(os.path.join(HERE, "short"), exist_ok=True)
-    for case in SHORT + HOST_SHORT + ORACLE_SHORT + ORACLE_ONLY_SHORT:
+    for case in SHORT + HOST_SHORT + ORACLE_SHORT:
         if only and case.name not in only:
             continue
         wanted = [0] + list(case.cycles)

@@ -27,7 +27,7 @@ PROBLEMS = {"sod": ("sod", "NO"), "ot2d": ("OrszagTang", "YES"), "ot3d": ("Orsza
             "sodUserBC": ("sodUserBC", "NO"), "sph": ("SphericalMHD", "YES"), "polar": ("PolarMHD", "YES"),
             "sodiso": ("sodIso", "NO"), "iso25d": ("IsoMHD25D", "YES"), "sph25d": ("Spherical25D", "YES"),
             "polarhd": ("PolarHD2D", "NO"), "sodstrong": ("sodStrong", "NO"), "othooks": ("otHooks", "YES"),
-            "axis": ("AxisMHD", "YES")}
+            "axis": ("AxisMHD", "YES"), "axis25d": ("Axis25D", "YES")}
 
 
 def build(problem, order, tmp_path_factory, vp=False):

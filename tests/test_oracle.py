@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_ONLY_SHORT, ORACLE_SHORT, SHORT, ini_for
+from cases import FULL, HOST_SHORT, ORACLE_FULL, ORACLE_SHORT, SHORT, ini_for
 from idefix_b200.dump import readDump, vc_names
 from idefix_b200.datablock import DataBlockHost
 from idefix_b200.grid import Definitions
@@ -151,8 +151,7 @@ ISO_DEFS = {"sodiso": Definitions(1, 1, 1, False, True), "iso25d": Definitions(2
 ISO_IN = [c for c in HOST_SHORT + ORACLE_SHORT if c.setup in ("sodiso", "iso25d")]
 # geometric terms of polar / spherical grids, stretched and logarithmic spacing, reflective sides, the polar axis,
 # shock flattening with the area-weighted divergence
-CURV_IN = [c for c in HOST_SHORT if c.setup in ("sph", "polar", "sph25d", "polarhd", "axis")] + \
-    ORACLE_ONLY_SHORT
+CURV_IN = [c for c in HOST_SHORT if c.setup in ("sph", "polar", "sph25d", "polarhd", "axis", "axis25d")]
 
 
 class _FromDump(Setup):
